@@ -1,0 +1,264 @@
+"""Shared workload definitions for the parity suite.
+
+Every case is written ONCE against the reference's public operator API
+(`epg.T/E/S/D/X/...`, nested lists, `@`), and is built three times:
+  * with the unmodified reference (`tests/golden/make_golden.py`, build container only),
+  * with the CPU oracle through the thin adapter `tests/oracle_api.py`,
+  * with the product `epgpy_b200` (drop-in: same constructors).
+
+A case function takes the API namespace and returns a dict:
+  seq      nested list of operators
+  options  simulate(**options) keywords (max_nstate, kvalue)
+  density  None | list   -> init=StateMatrix(density=...)
+  jac      None | list of variable names -> probe=[ADC, Jacobian(jac)]
+  kvec     None | base shift vector (oracle only: collinear n-d shifts)
+The sizes are small enough for the reference/oracle to finish in seconds; the
+BASELINE.json configs are reproduced at reduced grid size (same operators).
+"""
+
+import numpy as np
+
+
+def _fisp_schedule(ntr, seed=0):
+    rng = np.random.RandomState(seed)
+    fa = 10 + 50 * np.abs(np.sin(np.arange(ntr) * np.pi / 200))
+    tr = rng.uniform(11, 16, ntr)
+    return fa, tr
+
+
+def readme_mse(epg):
+    """BASELINE configs[0] verbatim (reference README.md:52-74)"""
+    FA, ESP, Necho, T1, T2 = 120, 10, 20, 150, [30, 40, 50]
+    exc, rfc = epg.T(90, 90), epg.T(FA, 0)
+    rlx = epg.E(ESP / 2, T1, T2)
+    shift = epg.S(1, duration=ESP / 2)
+    seq = [exc] + [[shift, rlx, rfc, shift, rlx, epg.ADC]] * Necho
+    return dict(seq=seq)
+
+
+def mse_grid(epg, nT2=6, nB1=5, nT1=3):
+    """BASELINE configs[1] at reduced grid"""
+    T2 = np.linspace(20, 300, nT2)
+    B1 = np.linspace(0.5, 1.2, nB1)[None, :]
+    T1 = np.linspace(500, 3000, nT1)[None, None, :]
+    exc = epg.T(90 * B1, 90)
+    rfc = epg.T(180 * B1, 0)
+    rlx = epg.E(4.75, T1, T2)
+    sh = epg.S(1)
+    seq = [exc] + [[sh, rlx, rfc, sh, rlx, epg.ADC]] * 17
+    return dict(seq=seq)
+
+
+def fisp(epg, ntr=60, sizes=(3, 4, 2), max_nstate=None, g=None):
+    """BASELINE configs[2] at reduced size.
+    NOTE the axis sizes are pairwise different on purpose: the reference's in-place matmul
+    (epgpy/opmatrix.py:208-221) silently mis-aligns an operator axis i with grid axis i-1 when
+    their sizes coincide (e.g. 3x3x3 or 100x100x100), giving wrong signals; see DESIGN.md."""
+    fa, tr = _fisp_schedule(ntr)
+    T1 = np.linspace(300, 3000, sizes[0])
+    T2 = np.linspace(20, 300, sizes[1])[None, :]
+    B1 = np.linspace(0.7, 1.2, sizes[2])[None, None, :]
+    kw = {} if g is None else {"g": g}
+    seq = [epg.T(180, 0), epg.E(20, T1, T2, **kw)]
+    for i in range(ntr):
+        seq.append([epg.T(fa[i] * B1, 90), epg.E(3, T1, T2, **kw), epg.ADC,
+                    epg.E(tr[i] - 3, T1, T2, **kw), epg.S(1)])
+    opts = {} if max_nstate is None else {"max_nstate": max_nstate}
+    return dict(seq=seq, options=opts)
+
+
+def fisp_unbounded(epg):
+    return fisp(epg, 60)
+
+
+def fisp_bounded(epg):
+    return fisp(epg, 80, max_nstate=10)
+
+
+def bssfp_offres(epg, ntr=50):
+    """bSSFP variant of M3: no shift, off-resonance axis (n = 0 all along)"""
+    T1, T2 = 1000.0, np.array([40.0, 80.0, 120.0])
+    g = np.linspace(-0.1, 0.1, 11)[None, :]
+    rf1, rf2 = epg.T(30, 0), epg.T(30, 180)
+    rlx = epg.E(5, T1, T2, g)
+    seq = [[rf1, rlx], [rf2, rlx]] * (ntr // 2) + [[rf1, epg.ADC]]
+    return dict(seq=seq)
+
+
+def fisp_jac_global(epg, ntr=30):
+    """M3J(i): global variables B1, T1, T2"""
+    fa, tr = _fisp_schedule(ntr)
+    T1 = np.linspace(300, 3000, 2)
+    T2 = np.linspace(20, 300, 3)[None, :]
+    B1 = np.linspace(0.7, 1.2, 2)[None, None, :]
+    o1 = ["T1", "T2"]
+    seq = [epg.T(180, 0), epg.E(20, T1, T2, order1=o1)]
+    for i in range(ntr):
+        seq.append([epg.T(fa[i] * B1, 90, order1={"B1": {"alpha": fa[i]}}), epg.E(3, T1, T2, order1=o1), epg.ADC,
+                    epg.E(tr[i] - 3, T1, T2, order1=o1), epg.S(1)])
+    return dict(seq=seq, jac=["B1", "T1", "T2"])
+
+
+def fisp_jac_pulses(epg, ntr=16, max_nstate=10):
+    """M3J(ii): per-pulse flip-angle variables, bounded states (optim_mrf.py:96)"""
+    fa, tr = _fisp_schedule(ntr)
+    T1 = np.linspace(300, 3000, 2)
+    T2 = np.linspace(20, 300, 3)[None, :]
+    names = [f"alpha_{i:03d}" for i in range(ntr)]
+    seq = [epg.T(180, 90), epg.E(20, T1, T2)]
+    for i in range(ntr):
+        seq.append([epg.T(fa[i], 90, order1={names[i]: "alpha"}), epg.E(3, T1, T2), epg.ADC,
+                    epg.E(tr[i] - 3, T1, T2), epg.S(1)])
+    return dict(seq=seq, jac=["magnitude"] + names, options={"max_nstate": max_nstate})
+
+
+def mse_jac(epg):
+    """reference test/test_diff.py:282-331 chain, as a simulate() call"""
+    exc = epg.T(90, 90)
+    ref = epg.T(150, 0, order1="alpha")
+    relax = epg.E(5, 1e3, 35, order1="T2")
+    grad = epg.S(1)
+    seq = [exc] + [grad, relax, ref, grad, relax, epg.ADC] * 5
+    return dict(seq=seq, jac=["T2", "alpha"])
+
+
+def jac_all_params(epg):
+    """phi / tau / T1 / g derivatives with array coefficients (diff.py:556-568)"""
+    T2 = np.array([30.0, 50.0, 80.0])
+    g = np.array([[0.0, 0.02]])
+    c = np.array([[1.0], [2.0], [3.0]])  # coefficient arrays need the full grid ndim in the reference
+    rf = epg.T(40, [[15.0, 60.0]], order1={"a": {"alpha": c}, "p": {"phi": 1.0}})
+    rlx = epg.E(6.0, 800.0, T2, g, order1={"tau": {"tau": 1}, "T1": {"T1": 1}, "g": {"g": 1}, "a": {"T2": 0.5}})
+    ph = epg.Phi(20.0, order1={"p": {"phi": 2.0}})
+    pr = epg.P(2.0, g, order1={"g": "g", "tau": "tau"})
+    seq = [epg.T(90, 90)] + [rf, rlx, epg.S(1), ph, pr, epg.ADC] * 6
+    return dict(seq=seq, jac=["a", "p", "tau", "T1", "g", "missing"])
+
+
+def gre_diffusion(epg, ntr=40):
+    """BASELINE configs[3] at reduced size: RF spoiling, 3-d shift, isotropic D"""
+    T1 = np.array([600.0, 1200.0])
+    T2 = np.array([[40.0, 80.0, 120.0]])
+    seq = []
+    kv = [2, 1, -1]
+    for n in range(ntr):
+        ph = 117.0 * n * (n + 1) / 2
+        seq.append([epg.T(15, ph), epg.E(2, T1, T2), epg.Adc(phase=-ph), epg.E(8, T1, T2),
+                    epg.S(kv), epg.D(10, 2e-3, k=kv)])
+    return dict(seq=seq, options={"kvalue": 500.0}, kvec=kv)
+
+
+def gre_diffusion_1d(epg, ntr=30):
+    """1-d integer shifts, D with and without the ramp term, tensor-free; max_nstate"""
+    T2 = np.array([40.0, 80.0])
+    seq = [epg.T(90, 90)]
+    for n in range(ntr):
+        seq.append([epg.S(1), epg.D(3.0, 1.5e-3, k=1), epg.E(3, 900.0, T2), epg.D(2.0, 1.5e-3),
+                    epg.T(35, 0), epg.ADC])
+    return dict(seq=seq, options={"kvalue": 3000.0, "max_nstate": 12})
+
+
+def _mt_model():
+    T1, T2, khi, f = [779.0, 779.0], [45.0, 12e-3], 4.3e-3, [1 - 0.117, 0.117]
+    return T1, T2, khi, f
+
+
+def bssfp_mt(epg, ntr=40, noff=7):
+    """BASELINE configs[4] forward (examples/exchange/gre_exchange.py:163-175, model2)"""
+    T1, T2, khi, f = _mt_model()
+    kmat = epg.exchange_matrix(khi, densities=f)
+    FA, TR = 10, 5
+    offres = 1 / TR * np.linspace(-0.5, 0.5, noff)
+    sat = epg.R(rL=[0, 0.0316])
+    rf1 = epg.T([FA, 0], 0) @ sat
+    rf2 = epg.T([FA, 0], 180) @ sat
+    exg = epg.X(TR, kmat, T1=T1, T2=T2, g=[offres])
+    adc = epg.Adc(reduce=0)
+    seq = [[rf1, exg], [rf2, exg]] * (ntr // 2) + [[rf1, adc]]
+    return dict(seq=seq, density=f)
+
+
+def spgr_exchange(epg, ntr=30):
+    """two-pool water exchange SPGR with RF spoiling + shift (gre_exchange.py:73-87, model1)"""
+    T1, T2, khi, f = [1000.0, 500.0], [100.0, 20.0], 2e-3, [0.8, 0.2]
+    kmat = epg.exchange_matrix(khi, densities=f)
+    PH = np.array([50.0, 117.0, 150.0])  # 3 values: a 2-value axis hits a reference in-place matmul misalignment
+    exg = epg.X(5, kmat, T1=T1, T2=T2)
+    adc = epg.Adc(reduce=0)
+    seq = [[epg.T(10, [i * (i + 1) / 2 * PH]), adc, exg, epg.S(1)] for i in range(ntr)]
+    return dict(seq=seq, density=f, options={"max_nstate": 8})
+
+
+def hyperecho(epg, npulse=15):
+    """reference test/test_core.py:9-32 (shorter); probe both F0 and Z0 through two ADCs"""
+    grad = epg.S(1)
+    se1 = [grad, epg.T(10, 0), grad, epg.ADC, epg.Adc("Z0")]
+    se2 = [grad, epg.T(-10, 0), grad, epg.ADC, epg.Adc("Z0")]
+    seq = [epg.T(90, 90)] + se1 * npulse + [grad, epg.T(180, 0), grad] + se2 * npulse
+    return dict(seq=seq)
+
+
+def misc_ops(epg):
+    """Phi, P, R, SPOILER, RESET, PD, Wait, negative and multi-step shifts, Adc phase/weights/reduce"""
+    T2 = np.array([30.0, 60.0, 90.0])
+    g = np.array([[-0.05, 0.0, 0.02, 0.07]])
+    seq = [
+        epg.PD([1.0, 0.5, 2.0]), epg.T(70, 30), epg.S(2), epg.E(4, 700.0, T2, g), epg.Phi([[10.0, 20, 30, 40]]),
+        epg.Adc(phase=25.0), epg.T(120, [[0.0, 45, 90, 135]]), epg.S(-1), epg.P(3.0, g), epg.ADC,
+        epg.R(rT=0.1 + 0.3j, rL=0.05, r0=0.02), epg.S(-2), epg.Wait(2.0), epg.T(45, 10), epg.Adc("Z0"),
+        epg.SPOILER, epg.T(33, 77), epg.S(1), epg.E(5, 500.0, 50.0), epg.T(150, 0), epg.S(1), epg.ADC,
+        epg.RESET, epg.T(20, 90), epg.Adc(phase=[10.0, 20.0, 30.0]),
+    ]
+    return dict(seq=seq)
+
+
+def adc_reduce(epg):
+    """weights / reduce / phase on the read-out (reference test/test_functions.py:69-76)"""
+    T2 = np.array([[30.0], [40.0], [50.0]])
+    g = np.array([[-0.1, -0.05, 0, 0.05, 1]])
+    rlx = epg.E(10, 1000, T2, g=g)
+    adc = epg.Adc(reduce=1, weights=[[1, 2, 3, 4, 5]], phase=[5.0, 10.0, 15.0])
+    grad = epg.S(1, duration=10)
+    seq = [epg.T(90, 90), grad, rlx, epg.T(180, 0), grad, rlx, adc, grad, rlx, epg.T(170, 0), grad, rlx, adc]
+    return dict(seq=seq)
+
+
+CASES = {
+    "readme_mse": readme_mse,
+    "mse_grid": mse_grid,
+    "fisp_unbounded": fisp_unbounded,
+    "fisp_bounded": fisp_bounded,
+    "bssfp_offres": bssfp_offres,
+    "fisp_jac_global": fisp_jac_global,
+    "fisp_jac_pulses": fisp_jac_pulses,
+    "mse_jac": mse_jac,
+    "jac_all_params": jac_all_params,
+    "gre_diffusion": gre_diffusion,
+    "gre_diffusion_1d": gre_diffusion_1d,
+    "bssfp_mt": bssfp_mt,
+    "spgr_exchange": spgr_exchange,
+    "hyperecho": hyperecho,
+    "misc_ops": misc_ops,
+    "adc_reduce": adc_reduce,
+}
+
+
+def namespace(pkg):
+    """`epg`-like namespace of a reference-compatible package (+ exchange_matrix helper)"""
+    import types
+
+    core = pkg.core
+    ns = types.SimpleNamespace(**{k: getattr(core, k) for k in dir(core) if not k.startswith("_")})
+    ns.exchange_matrix = pkg.exchange.exchange_matrix
+    return ns
+
+
+def run_api(epg, case):
+    """run a case with a reference-compatible API (the reference itself or epgpy_b200)"""
+    opts = dict(case.get("options") or {})
+    if case.get("density") is not None:
+        opts["init"] = epg.StateMatrix(density=case["density"])
+    if case.get("jac"):
+        sig, jac = epg.simulate(case["seq"], probe=[None, epg.Jacobian(case["jac"])], **opts)
+        return np.asarray(sig), np.asarray(jac)
+    return np.asarray(epg.simulate(case["seq"], **opts)), None

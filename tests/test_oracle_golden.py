@@ -1,0 +1,134 @@
+"""Pins the CPU oracle against the golden vectors produced by the unmodified reference
+(tests/golden/make_golden.py) and against the reference's closed-form known answers."""
+
+import numpy as np
+import pytest
+
+import cases
+import oracle_api
+from oracle import epg_oracle as O
+
+RTOL = 1e-10  # FP64 parity bar of BASELINE.json north_star
+
+
+def rel_err(a, b):
+    a, b = np.broadcast_arrays(np.asarray(a), np.asarray(b))
+    assert a.shape == b.shape, (a.shape, b.shape)
+    scale = max(np.abs(b).max(), 1e-300)
+    return np.abs(a - b).max() / scale
+
+
+@pytest.mark.parametrize("name", sorted(cases.CASES))
+def test_case_matches_reference(name, golden):
+    ref = golden(name)
+    case = cases.CASES[name](oracle_api.epg)
+    sig, jac = oracle_api.run(case)
+    assert rel_err(sig, ref["signal"]) < RTOL
+    if "jacobian" in ref.files:
+        assert rel_err(jac, ref["jacobian"]) < RTOL
+    if "times" in ref.files:
+        assert np.allclose(np.asarray(O.adc_times(case["seq"]), dtype=float), ref["times"])
+    assert tuple(ref["shape"]) == O.get_shape(case["seq"])
+
+
+def test_primitives(golden):
+    p = golden("primitives")
+    a, ph, tau, T1, T2, g = (p[k] for k in ("alpha", "phi", "tau", "T1", "T2", "g"))
+    assert rel_err(O.rf_matrix(a, ph), p["rf"]) < 1e-14
+    assert rel_err(O.rf_matrix_dalpha(a, ph), p["rf_dalpha"]) < 1e-14
+    assert rel_err(O.rf_matrix_dphi(a, ph), p["rf_dphi"]) < 1e-14
+    arr, arr0 = O.relax_arrays(tau, T1, T2, g)
+    assert rel_err(arr, p["relax_arr"]) < 1e-14 and rel_err(arr0, p["relax_arr0"]) < 1e-14
+    for q in ("tau", "T1", "T2", "g"):
+        d, d0 = O.relax_d(q, tau, T1, T2, g)
+        assert rel_err(d, p[f"relax_d_{q}"]) < 1e-13
+        if f"relax_d0_{q}" in p.files:
+            assert rel_err(d0, p[f"relax_d0_{q}"]) < 1e-13
+    assert rel_err(O.precession_arrays(tau, g)[0], p["prec_arr"]) < 1e-14
+    assert rel_err(O.precession_d("tau", 3.7, g)[0], p["prec_d_tau"]) < 1e-14
+    assert rel_err(O.precession_d("g", 3.7, g)[0], p["prec_d_g"]) < 1e-14
+    e, e0 = O.evolution_arrays(0.1 + 0.2j, 0.3, 0.05)
+    assert rel_err(e, p["evol_arr"]) < 1e-14 and rel_err(e0, p["evol_arr0"]) < 1e-14
+    k1 = [[1e3, 2e3, -5e2], [0, 1e3, 2e3]]
+    k2 = [[2e3, 2.5e3, -1e3], [1e3, 1.5e3, 1.5e3]]
+    assert rel_err(O.bmatrix(1.5, k1), p["bmat_1"]) < 1e-14
+    assert rel_err(O.bmatrix(1.5, k1, k2), p["bmat_2"]) < 1e-14
+    DL, DT = O.diffusion_factors(p["bmat_1"], p["bmat_2"], p["Dten"])
+    assert rel_err(DL, p["diff_DL"]) < 1e-14 and rel_err(DT, p["diff_DT"]) < 1e-14
+    DL, DT = O.diffusion_factors(p["bmat_1"], p["bmat_2"], 1.3e-3)
+    assert rel_err(DL, p["diff_DL_iso"]) < 1e-14 and rel_err(DT, p["diff_DT_iso"]) < 1e-14
+    assert rel_err(O.kinetic_matrix(4.3e-3, densities=[0.883, 0.117]), p["kmat"]) < 1e-14
+    assert rel_err(O.kinetic_matrix([1e-3, 2e-3], ncomp=3), p["kmat3"]) < 1e-14
+    xop = O.X(5.0, p["kmat"], T1=[779.0, 779.0], T2=[45.0, 12e-3], g=[np.linspace(-0.1, 0.1, 5)])
+    xm, ax = O.exchange_matrices(xop)
+    assert ax == int(p["xaxis"]) and rel_err(xm, p["xmat"]) < 1e-12
+
+
+def test_single_operator_states(golden):
+    p = golden("primitives")
+    st = p["state0"]
+    n = (st.shape[-2] - 1) // 2
+    eq = np.zeros_like(st)
+    eq[..., n, 2] = 1
+    assert rel_err(O.apply_matrix(st, O.rf_matrix([30.0, 140.0], 25.0)), p["state_T"]) < 1e-14
+    arr, arr0 = O.relax_arrays(7.0, 600.0, [40.0, 90.0], 0.03)
+    assert rel_err(O.apply_diag(st, arr, eq, arr0), p["state_E"]) < 1e-14
+    assert rel_err(O.shift_int(O.resize(st, n + 1), 1), p["state_S+1"]) < 1e-14
+    assert rel_err(O.shift_int(O.resize(st, n + 2), -2), p["state_S-2"]) < 1e-14
+    assert rel_err(O.shift_int(st, 1), p["state_S+1_nmax3"]) < 1e-14
+    sp = st.copy()
+    sp[..., :2] = 0
+    assert rel_err(sp, p["state_SPOILER"]) < 1e-14
+    sim = O._Sim((2,), st, 1.0, None, 800.0, None)
+    O._apply_diffusion(sim, O.D(4.0, 2e-3), False)
+    assert rel_err(sim.states, p["state_D"]) < 1e-14
+    sim = O._Sim((2,), st, 1.0, None, 800.0, None)
+    O._apply_diffusion(sim, O.D(4.0, 2e-3, k=1), False)
+    assert rel_err(sim.states, p["state_Dk"]) < 1e-14
+
+
+# ---- closed-form known answers restated from the reference's unit tests
+
+
+def test_known_answers_transition():
+    """reference test/test_transition.py:8-56"""
+    st = np.array([[[0, 0, 1]]], dtype=complex)
+    assert np.allclose(O.apply_matrix(st, O.rf_matrix(90, 90)), [[[1, 1, 0]]])
+    assert np.allclose(O.apply_matrix(st, O.rf_matrix(90, 0)), [[[-1j, 1j, 0]]])
+    assert np.allclose(O.apply_matrix(st, O.rf_matrix(180, 0)), [[[0, 0, -1]]])
+    m = O.rf_matrix(33.0, 71.0)[0]
+    assert np.allclose(m, m[[1, 0, 2]][:, [1, 0, 2]].conj())
+
+
+def test_known_answers_evolution():
+    """reference test/test_evolution.py:8-58 (limits)"""
+    arr, arr0 = O.relax_arrays(10.0, 1e3, 1e2)
+    assert np.allclose(arr[0], [np.exp(-0.1), np.exp(-0.1), np.exp(-0.01)])
+    assert np.allclose(arr0[0], [0, 0, 1 - np.exp(-0.01)])
+    arr, _ = O.relax_arrays(1.0, 1e30, 1e30, 0.25)
+    assert np.allclose(arr[0], [1j, -1j, 1])
+
+
+def test_known_answer_hyperecho():
+    """reference test/test_core.py:9-32: F0=1, Z0=0 at the end of a 2x201-pulse hyper-echo"""
+    e = oracle_api.epg
+    grad = e.S(1)
+    se1 = [grad, e.T(10, 0), grad, e.ADC]
+    se2 = [grad, e.T(-10, 0), grad, e.ADC]
+    n = 201
+    seq = [e.T(90, 90)] + se1 * n + [grad, e.T(180, 0), grad] + se2 * n
+    sig = O.simulate(seq)
+    assert not np.allclose(sig[:-1], 1)
+    assert np.allclose(sig[-1], 1)
+
+
+def test_known_answer_diffusion_free():
+    """reference test/test_diffusion.py:107-146: exp(-k^2 tau D) and the (1/4+1/12) ramp factor"""
+    e = oracle_api.epg
+    kvalue, tau, Dc = 1e5, 1.0, 1e-3
+    seq = [e.T(90, 90), e.S(1), e.D(tau, Dc), e.S(-1), e.ADC]
+    sig = O.simulate(seq, kvalue=kvalue)
+    assert np.allclose(sig[0], np.exp(-(kvalue**2) * tau * Dc * 1e-9))
+    seq = [e.T(90, 90), e.S(1), e.D(tau, Dc, k=1), e.S(-1), e.ADC]
+    sig = O.simulate(seq, kvalue=kvalue)
+    assert np.allclose(sig[0], np.exp(-(kvalue**2) * tau * Dc * 1e-9 / 3))
