@@ -1,0 +1,477 @@
+// epgx.cu -- C ABI of libepgx.so (include/epgx.h): plan management, kernel selection and launch.
+// Host-side here is bookkeeping only; every arithmetic step of the EPG path runs in the sm_100a
+// kernels of epgx_ring.cuh / epgx_reg.cuh.  There is no CPU fallback.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "epgx_common.cuh"
+#include "epgx_ring.cuh"
+
+using namespace epgx;
+
+static thread_local std::string g_err;
+
+static int fail(int code, const std::string &msg) {
+  g_err = msg;
+  return code;
+}
+
+#define CUDA_TRY(expr)                                                                   \
+  do {                                                                                   \
+    cudaError_t e_ = (expr);                                                             \
+    if (e_ != cudaSuccess)                                                               \
+      return fail(EPGX_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));    \
+  } while (0)
+
+struct epgx_plan {
+  epgx_tape tape; // pointers redirected to the vectors below
+  std::vector<epgx_op> ops;
+  std::vector<epgx_segment> segs;
+  std::vector<double> coef64;
+  std::vector<float> coef32;
+  std::vector<int> pats; // [npattern][MAX_DIMS+1]
+  int64_t natoms;
+  epgx_config cfg;
+  // workspace layout (bytes)
+  int64_t off_ops, off_segs, off_pats, off_coef, ws_bytes;
+};
+
+static const int kSmemLimit = 227 * 1024;
+
+static int pow2ceil(int x) {
+  int p = 1;
+  while (p < x) p <<= 1;
+  return p;
+}
+
+static int nvt_choice(int nvar, int want) {
+  // instantiated tile sizes of the ring kernel
+  const int opts[3] = {0, 1, 3};
+  if (nvar == 0) return 0;
+  if (want > 0) {
+    for (int o : opts)
+      if (o == want) return o;
+  }
+  return nvar == 1 ? 1 : 3;
+}
+
+static double form_flops(int code, int flags, int npool) {
+  switch (code) {
+  case EPGX_OP_T_GEN: return 56;
+  case EPGX_OP_T_RE:
+  case EPGX_OP_T_IM: return 28;
+  case EPGX_OP_E: return (flags & EPGX_FLAG_G) ? 14 : 6;
+  case EPGX_OP_DIAG: return 18;
+  case EPGX_OP_MATRIX: return 66;
+  case EPGX_OP_D: return 6;
+  case EPGX_OP_X: return 3.0 * (8.0 * npool - 2.0); // per pool: 3 components x (N cmul + (N-1) cadd)
+  default: return 0;
+  }
+}
+
+static int choose_variant(epgx_plan *pl, int kernel, int lanes, int vars, int atoms) {
+  const epgx_tape &t = pl->tape;
+  epgx_config &c = pl->cfg;
+  const int rsz = t.dtype == EPGX_F64 ? 8 : 4;
+  const int C = t.max_order + 1;
+  int G = lanes > 0 ? pow2ceil(lanes) : pow2ceil((C + 3) / 4);
+  if (G > 256) G = 256;
+  int nvt = nvt_choice(t.nvar, vars);
+  int64_t per_atom;
+  for (;;) {
+    per_atom = (int64_t)(1 + nvt) * t.npool * 3 * C * 2 * rsz + (int64_t)t.npattern * 4;
+    if (per_atom <= kSmemLimit - 1024 || nvt <= 1) break;
+    nvt = nvt == 3 ? 1 : 0;
+  }
+  if (per_atom > kSmemLimit - 1024)
+    return fail(EPGX_ERR_CAPACITY, "state of one atom (" + std::to_string(per_atom) +
+                                       " bytes) exceeds the shared memory of an SM; use max_nstate or float32");
+  int A = atoms > 0 ? atoms : (128 / G > 0 ? 128 / G : 1);
+  int64_t budget = atoms > 0 ? kSmemLimit - 1024 : 110 * 1024;
+  if (per_atom > budget) budget = kSmemLimit - 1024;
+  while (A > 1 && A * per_atom > budget) --A;
+  while (A * G > 256) --A;
+  if (A < 1) A = 1;
+  c.kernel = 0;
+  (void)kernel;
+  c.lanes_per_atom = G;
+  c.slots_per_lane = 0;
+  c.vars_per_pass = nvt;
+  c.var_tiles = nvt ? (t.nvar + nvt - 1) / nvt : 1;
+  c.atoms_per_cta = A;
+  c.threads_per_cta = A * G;
+  c.smem_bytes = (int)(A * per_atom + 16);
+  c.ring = C;
+  return EPGX_OK;
+}
+
+extern "C" int epgx_version(void) { return EPGX_VERSION; }
+
+extern "C" const char *epgx_last_error(void) { return g_err.c_str(); }
+
+extern "C" int epgx_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+static int entry_reals(int code, int blk, int flags, const epgx_tape &t) {
+  switch (code) {
+  case EPGX_OP_T_GEN: return blk == 0 ? 6 : 0;
+  case EPGX_OP_T_RE:
+  case EPGX_OP_T_IM: return blk == 0 ? 4 : 0;
+  case EPGX_OP_E: return blk == 0 ? 2 : blk == 1 ? 1 : ((flags & EPGX_FLAG_G) ? 2 : 0);
+  case EPGX_OP_DIAG: return blk == 0 ? 8 : 0;
+  case EPGX_OP_MATRIX: return blk == 0 ? 18 : (blk == 1 && (flags & EPGX_FLAG_AFFINE)) ? 6 : 0;
+  case EPGX_OP_D: return blk == 0 ? 3 * (t.max_order + 1) : 0;
+  case EPGX_OP_X: return blk == 0 ? 4 * t.npool * t.npool : 0;
+  case EPGX_OP_PD: return blk == 0 ? 1 : 0;
+  case EPGX_OP_ADC: return (blk == 0 && (flags & EPGX_FLAG_SCALE)) ? 2 : 0;
+  default: return 0;
+  }
+}
+
+extern "C" int epgx_plan_create(const epgx_tape *t, epgx_plan **out) {
+  if (!t || !out) return fail(EPGX_ERR_INVALID, "null argument");
+  *out = nullptr;
+  if (t->dtype != EPGX_F64 && t->dtype != EPGX_F32) return fail(EPGX_ERR_INVALID, "bad dtype");
+  if (t->ndim < 1 || t->ndim > EPGX_MAX_DIMS) return fail(EPGX_ERR_INVALID, "ndim out of range");
+  if (t->npool < 1 || t->npool > EPGX_MAX_POOLS)
+    return fail(EPGX_ERR_UNSUPPORTED, "number of exchange pools must be 1.." + std::to_string(EPGX_MAX_POOLS));
+  if (t->npattern < 1 || t->npattern > EPGX_MAX_PATTERNS) return fail(EPGX_ERR_INVALID, "npattern out of range");
+  if (t->nop < 0 || t->nseg < 0 || t->ncoef < 1 || !t->coef || (t->nop && !t->ops) || (t->nseg && !t->segs))
+    return fail(EPGX_ERR_INVALID, "empty or null tape arrays");
+  if (t->ncoef >= (int64_t)1 << 31) return fail(EPGX_ERR_CAPACITY, "coefficient table too large (>= 2^31 reals)");
+  if (t->max_order < 0 || t->init_n < 0 || t->init_n > t->max_order || t->nvar < 0 || t->nadc < 0)
+    return fail(EPGX_ERR_INVALID, "bad order / variable counts");
+  int64_t natoms = 1;
+  for (int d = 0; d < t->ndim; ++d) {
+    if (t->shape[d] < 1) return fail(EPGX_ERR_INVALID, "bad grid shape");
+    natoms *= t->shape[d];
+    if (natoms >= (int64_t)1 << 31) return fail(EPGX_ERR_CAPACITY, "more than 2^31 atoms");
+  }
+  // largest entry offset reachable through each pattern
+  std::vector<int64_t> pat_span(t->npattern, 0);
+  for (int q = 0; q < t->npattern; ++q) {
+    int64_t span = 0;
+    for (int d = 0; d < t->ndim; ++d) {
+      if (t->stride[q][d] < 0) return fail(EPGX_ERR_INVALID, "negative pattern stride");
+      span += (int64_t)t->stride[q][d] * (t->shape[d] - 1);
+    }
+    if (t->pool_stride[q] < 0) return fail(EPGX_ERR_INVALID, "negative pool stride");
+    span += (int64_t)t->pool_stride[q] * (t->npool - 1);
+    pat_span[q] = span;
+  }
+  auto block_ok = [&](uint32_t off, int pat, int64_t reals) {
+    return pat >= 0 && pat < t->npattern && (int64_t)off + pat_span[pat] + reals <= t->ncoef;
+  };
+  if (!block_ok(t->init_off, t->init_pat, 6 * (int64_t)(t->init_n + 1)) || !block_ok(t->m0_off, t->m0_pat, 1))
+    return fail(EPGX_ERR_INVALID, "initial-state block out of range");
+  for (int64_t i = 0; i < t->nop; ++i) {
+    const epgx_op &o = t->ops[i];
+    if (o.code >= EPGX_OP_COUNT) return fail(EPGX_ERR_INVALID, "unknown opcode in record " + std::to_string(i));
+    for (int b = 0; b < 3; ++b) {
+      const int n = entry_reals(o.code, b, o.flags, *t);
+      if (n && !block_ok(o.off[b], o.pat[b], n))
+        return fail(EPGX_ERR_INVALID, "coefficient block out of range in record " + std::to_string(i));
+    }
+    if ((o.flags & EPGX_FLAG_INJECT) && (o.aux < 0 || o.aux >= t->nvar))
+      return fail(EPGX_ERR_INVALID, "injection into unknown variable in record " + std::to_string(i));
+    if (o.code == EPGX_OP_ADC) {
+      if ((o.flags & EPGX_FLAG_BASE) && (o.aux < 0 || o.aux >= t->nadc))
+        return fail(EPGX_ERR_INVALID, "ADC row out of range in record " + std::to_string(i));
+      if ((o.flags & EPGX_FLAG_PARTIALS) && (o.aux1 < 0 || o.aux1 >= t->njac))
+        return fail(EPGX_ERR_INVALID, "jacobian row out of range in record " + std::to_string(i));
+    }
+  }
+  double flops = 0, updates = 0;
+  for (int64_t i = 0; i < t->nseg; ++i) {
+    const epgx_segment &s = t->segs[i];
+    if (s.first < 0 || s.count < 0 || (int64_t)s.first + s.count > t->nop || s.nact < -1 || s.nact > t->max_order ||
+        s.shift < -1 || s.shift > 1 || s.n_old < 0 || s.n_new < s.n_old || s.n_new > t->max_order ||
+        s.n_new > s.n_old + 1)
+      return fail(EPGX_ERR_INVALID, "bad segment " + std::to_string(i));
+    for (int r = s.first; r < s.first + s.count; ++r) {
+      const epgx_op &o = t->ops[r];
+      const double f = form_flops(o.code, o.flags, t->npool) * t->npool * (s.nact + 1.0);
+      if (f == 0) continue;
+      double sets = 0;
+      if (o.flags & EPGX_FLAG_INJECT) sets = 1;
+      else sets = ((o.flags & EPGX_FLAG_BASE) ? 1 : 0) + ((o.flags & EPGX_FLAG_PARTIALS) ? t->nvar : 0);
+      flops += f * sets;
+      if (!(o.flags & EPGX_FLAG_INJECT) && (o.flags & EPGX_FLAG_BASE)) updates += s.nact + 1.0;
+    }
+    if (s.shift) updates += s.n_new + 1.0;
+  }
+
+  epgx_plan *pl = new (std::nothrow) epgx_plan();
+  if (!pl) return fail(EPGX_ERR_INVALID, "out of host memory");
+  pl->tape = *t;
+  pl->ops.assign(t->ops, t->ops + t->nop);
+  pl->segs.assign(t->segs, t->segs + t->nseg);
+  if (t->dtype == EPGX_F64) pl->coef64.assign(t->coef, t->coef + t->ncoef);
+  else {
+    pl->coef32.resize(t->ncoef);
+    for (int64_t i = 0; i < t->ncoef; ++i) pl->coef32[i] = (float)t->coef[i];
+  }
+  pl->pats.assign((size_t)t->npattern * (EPGX_MAX_DIMS + 1), 0);
+  for (int q = 0; q < t->npattern; ++q) {
+    for (int d = 0; d < t->ndim; ++d) pl->pats[q * (EPGX_MAX_DIMS + 1) + d] = t->stride[q][d];
+    pl->pats[q * (EPGX_MAX_DIMS + 1) + EPGX_MAX_DIMS] = t->pool_stride[q];
+  }
+  pl->tape.ops = pl->ops.data();
+  pl->tape.segs = pl->segs.data();
+  pl->tape.coef = nullptr;
+  pl->natoms = natoms;
+  memset(&pl->cfg, 0, sizeof(pl->cfg));
+  int rc = choose_variant(pl, 0, 0, 0, 0);
+  if (rc != EPGX_OK) {
+    delete pl;
+    return rc;
+  }
+  pl->cfg.updates_per_atom = updates;
+  // the base state is recomputed by every variable tile
+  pl->cfg.flops_per_atom = flops;
+  auto align = [](int64_t x) { return (x + 255) & ~(int64_t)255; };
+  const int rsz = t->dtype == EPGX_F64 ? 8 : 4;
+  pl->off_ops = 0;
+  pl->off_segs = align(pl->off_ops + (int64_t)sizeof(epgx_op) * (t->nop ? t->nop : 1));
+  pl->off_pats = align(pl->off_segs + (int64_t)sizeof(epgx_segment) * (t->nseg ? t->nseg : 1));
+  pl->off_coef = align(pl->off_pats + (int64_t)pl->pats.size() * 4);
+  pl->ws_bytes = align(pl->off_coef + t->ncoef * rsz);
+  *out = pl;
+  return EPGX_OK;
+}
+
+extern "C" int epgx_plan_destroy(epgx_plan *pl) {
+  delete pl;
+  return EPGX_OK;
+}
+
+extern "C" int epgx_plan_config(const epgx_plan *pl, epgx_config *cfg) {
+  if (!pl || !cfg) return fail(EPGX_ERR_INVALID, "null argument");
+  *cfg = pl->cfg;
+  return EPGX_OK;
+}
+
+extern "C" int epgx_plan_set_variant(epgx_plan *pl, int kernel, int lanes, int vars, int atoms) {
+  if (!pl) return fail(EPGX_ERR_INVALID, "null plan");
+  const double f = pl->cfg.flops_per_atom, u = pl->cfg.updates_per_atom;
+  int rc = choose_variant(pl, kernel, lanes, vars, atoms);
+  pl->cfg.flops_per_atom = f;
+  pl->cfg.updates_per_atom = u;
+  return rc;
+}
+
+extern "C" int epgx_plan_workspace_bytes(const epgx_plan *pl, int64_t *bytes) {
+  if (!pl || !bytes) return fail(EPGX_ERR_INVALID, "null argument");
+  *bytes = pl->ws_bytes;
+  return EPGX_OK;
+}
+
+extern "C" int epgx_plan_upload(const epgx_plan *pl, void *ws, void *stream) {
+  if (!pl || !ws) return fail(EPGX_ERR_INVALID, "null argument");
+  if ((uintptr_t)ws & 255) return fail(EPGX_ERR_INVALID, "workspace must be 256-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  char *w = (char *)ws;
+  const epgx_tape &t = pl->tape;
+  if (t.nop) CUDA_TRY(cudaMemcpyAsync(w + pl->off_ops, pl->ops.data(), sizeof(epgx_op) * t.nop, cudaMemcpyHostToDevice, st));
+  if (t.nseg)
+    CUDA_TRY(cudaMemcpyAsync(w + pl->off_segs, pl->segs.data(), sizeof(epgx_segment) * t.nseg, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(w + pl->off_pats, pl->pats.data(), pl->pats.size() * 4, cudaMemcpyHostToDevice, st));
+  if (t.dtype == EPGX_F64)
+    CUDA_TRY(cudaMemcpyAsync(w + pl->off_coef, pl->coef64.data(), t.ncoef * 8, cudaMemcpyHostToDevice, st));
+  else
+    CUDA_TRY(cudaMemcpyAsync(w + pl->off_coef, pl->coef32.data(), t.ncoef * 4, cudaMemcpyHostToDevice, st));
+  return EPGX_OK;
+}
+
+template <typename real, int NP, int NVT>
+static int launch_ring(const epgx_plan *pl, const KParams &kp, cudaStream_t st) {
+  const epgx_config &c = pl->cfg;
+  auto kern = ring_kernel<real, NP, NVT>;
+  CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, c.smem_bytes));
+  dim3 grid((unsigned)((kp.atom_count + c.atoms_per_cta - 1) / c.atoms_per_cta), (unsigned)c.var_tiles);
+  kern<<<grid, c.threads_per_cta, c.smem_bytes, st>>>(kp);
+  CUDA_TRY(cudaGetLastError());
+  return EPGX_OK;
+}
+
+template <typename real> static int dispatch_ring(const epgx_plan *pl, const KParams &kp, cudaStream_t st) {
+  const int np = pl->tape.npool, nvt = pl->cfg.vars_per_pass;
+#define CASE(NP_, NVT_) \
+  if (np == NP_ && nvt == NVT_) return launch_ring<real, NP_, NVT_>(pl, kp, st);
+  CASE(1, 0) CASE(1, 1) CASE(1, 3) CASE(2, 0) CASE(2, 1) CASE(2, 3)
+#undef CASE
+  return fail(EPGX_ERR_UNSUPPORTED, "no kernel instance for npool=" + std::to_string(np) + " vars_per_pass=" + std::to_string(nvt));
+}
+
+extern "C" int epgx_simulate(const epgx_plan *pl, const void *ws, int64_t atom_begin, int64_t atom_count, void *signal,
+                             void *jacobian, void *stream) {
+  if (!pl || !ws) return fail(EPGX_ERR_INVALID, "null argument");
+  if (atom_begin < 0 || atom_count < 0 || atom_begin + atom_count > pl->natoms)
+    return fail(EPGX_ERR_INVALID, "atom range out of the grid");
+  if (atom_count == 0) return EPGX_OK;
+  const epgx_tape &t = pl->tape;
+  if (t.nadc && !signal) return fail(EPGX_ERR_INVALID, "null signal buffer");
+  if (t.nvar && t.njac && !jacobian) return fail(EPGX_ERR_INVALID, "null jacobian buffer");
+  const char *w = (const char *)ws;
+  KParams kp;
+  memset(&kp, 0, sizeof(kp));
+  kp.ops = (const epgx_op *)(w + pl->off_ops);
+  kp.segs = (const epgx_segment *)(w + pl->off_segs);
+  kp.pats = (const int *)(w + pl->off_pats);
+  kp.coef = w + pl->off_coef;
+  kp.signal = signal;
+  kp.jac = jacobian;
+  kp.atom_begin = atom_begin;
+  kp.atom_count = atom_count;
+  for (int d = 0; d < t.ndim; ++d) kp.shape[d] = (int)t.shape[d];
+  kp.ndim = t.ndim;
+  kp.npattern = t.npattern;
+  kp.nseg = (int)t.nseg;
+  kp.G = pl->cfg.lanes_per_atom;
+  kp.A = pl->cfg.atoms_per_cta;
+  kp.C = pl->cfg.ring;
+  kp.nvar = t.nvar;
+  kp.init_off = t.init_off;
+  kp.m0_off = t.m0_off;
+  kp.init_pat = t.init_pat;
+  kp.m0_pat = t.m0_pat;
+  kp.init_n = t.init_n;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (t.dtype == EPGX_F64) return dispatch_ring<double>(pl, kp, st);
+  return dispatch_ring<float>(pl, kp, st);
+}
+
+extern "C" int epgx_simulate_host(const epgx_plan *pl, int device, int64_t atom_begin, int64_t atom_count, void *signal,
+                                  void *jacobian) {
+  if (!pl) return fail(EPGX_ERR_INVALID, "null plan");
+  int ndev = epgx_device_count();
+  if (ndev == 0) return fail(EPGX_ERR_NO_DEVICE, "no CUDA device: the epgx engine has no CPU fallback");
+  if (device < 0 || device >= ndev) return fail(EPGX_ERR_INVALID, "bad device index");
+  CUDA_TRY(cudaSetDevice(device));
+  const epgx_tape &t = pl->tape;
+  const int64_t csz = t.dtype == EPGX_F64 ? 16 : 8;
+  const int64_t sig_bytes = csz * t.nadc * atom_count * t.npool;
+  const int64_t jac_bytes = csz * t.njac * t.nvar * atom_count * t.npool;
+  void *ws = nullptr, *dsig = nullptr, *djac = nullptr;
+  int rc = EPGX_OK;
+  cudaError_t e = cudaMalloc(&ws, pl->ws_bytes);
+  if (e == cudaSuccess && sig_bytes) e = cudaMalloc(&dsig, sig_bytes);
+  if (e == cudaSuccess && jac_bytes) e = cudaMalloc(&djac, jac_bytes);
+  if (e != cudaSuccess) rc = fail(EPGX_ERR_CUDA, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+  if (rc == EPGX_OK) rc = epgx_plan_upload(pl, ws, nullptr);
+  if (rc == EPGX_OK) rc = epgx_simulate(pl, ws, atom_begin, atom_count, dsig, djac, nullptr);
+  if (rc == EPGX_OK && sig_bytes) {
+    e = cudaMemcpy(signal, dsig, sig_bytes, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) rc = fail(EPGX_ERR_CUDA, std::string("D2H signal: ") + cudaGetErrorString(e));
+  }
+  if (rc == EPGX_OK && jac_bytes) {
+    e = cudaMemcpy(jacobian, djac, jac_bytes, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) rc = fail(EPGX_ERR_CUDA, std::string("D2H jacobian: ") + cudaGetErrorString(e));
+  }
+  if (rc == EPGX_OK) {
+    e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) rc = fail(EPGX_ERR_CUDA, std::string("sync: ") + cudaGetErrorString(e));
+  }
+  cudaFree(ws);
+  cudaFree(dsig);
+  cudaFree(djac);
+  return rc;
+}
+
+// ---- Adc(reduce=axis): out[o][i] = sum_r in[o][r][i]   (probe.py:148-153)
+template <typename real2> __global__ void reduce_kernel(const real2 *in, real2 *out, long long nouter, long long nred, long long ninner) {
+  const long long total = nouter * ninner;
+  for (long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x; j < total; j += (long long)gridDim.x * blockDim.x) {
+    const long long o = j / ninner, i = j - o * ninner;
+    const real2 *src = in + o * nred * ninner + i;
+    real2 acc = src[0];
+    for (long long r = 1; r < nred; ++r) {
+      const real2 v = src[r * ninner];
+      acc.x += v.x;
+      acc.y += v.y;
+    }
+    out[j] = acc;
+  }
+}
+
+extern "C" int epgx_reduce(int dtype, const void *in, void *out, int64_t nouter, int64_t nred, int64_t ninner, void *stream) {
+  if (!in || !out || nouter < 0 || nred < 1 || ninner < 0) return fail(EPGX_ERR_INVALID, "bad reduce arguments");
+  const int64_t total = nouter * ninner;
+  if (total == 0) return EPGX_OK;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == EPGX_F64) reduce_kernel<double2><<<blocks, 256, 0, st>>>((const double2 *)in, (double2 *)out, nouter, nred, ninner);
+  else if (dtype == EPGX_F32) reduce_kernel<float2><<<blocks, 256, 0, st>>>((const float2 *)in, (float2 *)out, nouter, nred, ninner);
+  else return fail(EPGX_ERR_INVALID, "bad dtype");
+  CUDA_TRY(cudaGetLastError());
+  return EPGX_OK;
+}
+
+// ---- FMA roofline denominator: 8 independent dependent-FMA chains per thread
+template <typename real> __global__ void fma_kernel(real *out, int iters, real a, real b) {
+  real x[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) x[i] = real(threadIdx.x + i) * real(1e-3);
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) x[i] = x[i] * a + b;
+  }
+  real s = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += x[i];
+  if (s == real(123.456)) out[0] = s;
+}
+
+extern "C" int epgx_fma_peak(int device, int dtype, double seconds, double *tflops) {
+  if (!tflops) return fail(EPGX_ERR_INVALID, "null argument");
+  int ndev = epgx_device_count();
+  if (ndev == 0) return fail(EPGX_ERR_NO_DEVICE, "no CUDA device");
+  if (device < 0 || device >= ndev) return fail(EPGX_ERR_INVALID, "bad device index");
+  CUDA_TRY(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+  void *buf = nullptr;
+  CUDA_TRY(cudaMalloc(&buf, 64));
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  const int threads = 256, blocks = prop.multiProcessorCount * 8;
+  int iters = 2000;
+  double best = 0, spent = 0;
+  if (seconds <= 0) seconds = 0.2;
+  for (int rep = 0; rep < 200 && spent < seconds; ++rep) {
+    cudaEventRecord(e0);
+    if (dtype == EPGX_F64) fma_kernel<double><<<blocks, threads>>>((double *)buf, iters, 1.0000001, 1e-9);
+    else fma_kernel<float><<<blocks, threads>>>((float *)buf, iters, 1.0000001f, 1e-9f);
+    cudaEventRecord(e1);
+    cudaError_t e = cudaEventSynchronize(e1);
+    if (e != cudaSuccess) {
+      cudaFree(buf);
+      return fail(EPGX_ERR_CUDA, std::string("fma kernel: ") + cudaGetErrorString(e));
+    }
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    const double fl = 2.0 * 8 * 16 * (double)iters * threads * blocks;
+    const double tf = fl / (ms * 1e-3) / 1e12;
+    if (rep > 0 && tf > best) best = tf;
+    spent += ms * 1e-3;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(buf);
+  *tflops = best;
+  return EPGX_OK;
+}

@@ -1,0 +1,139 @@
+// epgx_common.cuh -- shared definitions of the epgx engine (sm_100a only).
+//
+// Arithmetic forms of the tape records.  Every form acts on ONE configuration order: the triple
+// (F+, F-, Z) held as six reals.  Reference formulas: epgpy/transition.py:114-196 (T and its
+// derivatives), evolution.py:220-256 (E/P/R), opscalar.py:213-232, opmatrix.py:199-221,
+// diffusion.py:60-79, exchange.py:89-120; see include/epgx.h for the coefficient layouts.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "epgx.h"
+
+namespace epgx {
+
+template <typename real> struct vec2;
+template <> struct vec2<float> { typedef float2 type; };
+template <> struct vec2<double> { typedef double2 type; };
+
+// one configuration order of one state set
+template <typename real> struct Tri {
+  real pr, pi, mr, mi, zr, zi;
+};
+
+template <typename real> __device__ __forceinline__ void tri_zero(Tri<real> &t) {
+  t.pr = t.pi = t.mr = t.mi = t.zr = t.zi = real(0);
+}
+
+template <typename real> __device__ __forceinline__ void tri_add(Tri<real> &t, const Tri<real> &s) {
+  t.pr += s.pr; t.pi += s.pi; t.mr += s.mr; t.mi += s.mi; t.zr += s.zr; t.zi += s.zi;
+}
+
+// F+' = a F+ + B F- + U Z ; F-' = conj(B) F+ + a F- + conj(U) Z ; Z' = -1/2 (conj(U) F+ + U F-) + w Z
+template <typename real>
+__device__ __forceinline__ Tri<real> form_t_gen(const Tri<real> &s, real a, real w, real Br, real Bi, real Ur, real Ui) {
+  Tri<real> o;
+  const real h = real(-0.5);
+  o.pr = a * s.pr + Br * s.mr - Bi * s.mi + Ur * s.zr - Ui * s.zi;
+  o.pi = a * s.pi + Br * s.mi + Bi * s.mr + Ur * s.zi + Ui * s.zr;
+  o.mr = a * s.mr + Br * s.pr + Bi * s.pi + Ur * s.zr + Ui * s.zi;
+  o.mi = a * s.mi + Br * s.pi - Bi * s.pr + Ur * s.zi - Ui * s.zr;
+  o.zr = w * s.zr + h * (Ur * s.pr + Ui * s.pi + Ur * s.mr - Ui * s.mi);
+  o.zi = w * s.zi + h * (Ur * s.pi - Ui * s.pr + Ur * s.mi + Ui * s.mr);
+  return o;
+}
+
+// B = b, U = u real (phi = +-90 deg): real and imaginary parts decouple
+template <typename real>
+__device__ __forceinline__ Tri<real> form_t_re(const Tri<real> &s, real a, real w, real b, real u) {
+  Tri<real> o;
+  const real hu = real(-0.5) * u;
+  o.pr = a * s.pr + b * s.mr + u * s.zr;
+  o.pi = a * s.pi + b * s.mi + u * s.zi;
+  o.mr = a * s.mr + b * s.pr + u * s.zr;
+  o.mi = a * s.mi + b * s.pi + u * s.zi;
+  o.zr = w * s.zr + hu * (s.pr + s.mr);
+  o.zi = w * s.zi + hu * (s.pi + s.mi);
+  return o;
+}
+
+// B = b real, U = -i u (phi = 0 / 180 deg)
+template <typename real>
+__device__ __forceinline__ Tri<real> form_t_im(const Tri<real> &s, real a, real w, real b, real u) {
+  Tri<real> o;
+  const real hu = real(0.5) * u;
+  o.pr = a * s.pr + b * s.mr + u * s.zi;
+  o.pi = a * s.pi + b * s.mi - u * s.zr;
+  o.mr = a * s.mr + b * s.pr - u * s.zi;
+  o.mi = a * s.mi + b * s.pi + u * s.zr;
+  o.zr = w * s.zr + hu * (s.pi - s.mi);
+  o.zi = w * s.zi - hu * (s.pr - s.mr);
+  return o;
+}
+
+// F+ *= (er + i ei), F- *= (er - i ei), Z *= e1     (er + i ei = e2 cis(2 pi g tau))
+template <typename real>
+__device__ __forceinline__ Tri<real> form_e_g(const Tri<real> &s, real e1, real er, real ei) {
+  Tri<real> o;
+  o.pr = er * s.pr - ei * s.pi;
+  o.pi = er * s.pi + ei * s.pr;
+  o.mr = er * s.mr + ei * s.mi;
+  o.mi = er * s.mi - ei * s.mr;
+  o.zr = e1 * s.zr;
+  o.zi = e1 * s.zi;
+  return o;
+}
+
+template <typename real>
+__device__ __forceinline__ Tri<real> form_e(const Tri<real> &s, real e1, real e2) {
+  Tri<real> o;
+  o.pr = e2 * s.pr; o.pi = e2 * s.pi; o.mr = e2 * s.mr; o.mi = e2 * s.mi;
+  o.zr = e1 * s.zr; o.zi = e1 * s.zi;
+  return o;
+}
+
+// generic diagonal: c = (aP.re, aP.im, aM.re, aM.im, aZ.re, aZ.im)
+template <typename real>
+__device__ __forceinline__ Tri<real> form_diag(const Tri<real> &s, const real *c) {
+  Tri<real> o;
+  o.pr = c[0] * s.pr - c[1] * s.pi;
+  o.pi = c[0] * s.pi + c[1] * s.pr;
+  o.mr = c[2] * s.mr - c[3] * s.mi;
+  o.mi = c[2] * s.mi + c[3] * s.mr;
+  o.zr = c[4] * s.zr - c[5] * s.zi;
+  o.zi = c[4] * s.zi + c[5] * s.zr;
+  return o;
+}
+
+// generic 3x3 complex, row-major m[18]
+template <typename real>
+__device__ __forceinline__ Tri<real> form_matrix(const Tri<real> &s, const real *m) {
+  Tri<real> o;
+  o.pr = m[0] * s.pr - m[1] * s.pi + m[2] * s.mr - m[3] * s.mi + m[4] * s.zr - m[5] * s.zi;
+  o.pi = m[0] * s.pi + m[1] * s.pr + m[2] * s.mi + m[3] * s.mr + m[4] * s.zi + m[5] * s.zr;
+  o.mr = m[6] * s.pr - m[7] * s.pi + m[8] * s.mr - m[9] * s.mi + m[10] * s.zr - m[11] * s.zi;
+  o.mi = m[6] * s.pi + m[7] * s.pr + m[8] * s.mi + m[9] * s.mr + m[10] * s.zi + m[11] * s.zr;
+  o.zr = m[12] * s.pr - m[13] * s.pi + m[14] * s.mr - m[15] * s.mi + m[16] * s.zr - m[17] * s.zi;
+  o.zi = m[12] * s.pi + m[13] * s.pr + m[14] * s.mi + m[15] * s.mr + m[16] * s.zi + m[17] * s.zr;
+  return o;
+}
+
+// kernel parameters (by value; < 4 KB)
+struct KParams {
+  const epgx_op *ops;
+  const epgx_segment *segs;
+  const void *coef;
+  const int *pats; // [npattern][EPGX_MAX_DIMS + 1]: axis strides then pool stride (reals)
+  void *signal;
+  void *jac;
+  long long atom_begin, atom_count;
+  int shape[EPGX_MAX_DIMS];
+  int ndim, npattern, nseg;
+  int G, A, C, nvar;
+  unsigned init_off, m0_off;
+  int init_pat, m0_pat, init_n;
+};
+
+template <typename real> __device__ __forceinline__ real ldc(const real *p) { return __ldg(p); }
+
+} // namespace epgx

@@ -1,0 +1,232 @@
+"""ctypes binding of libepgx.so (include/epgx.h) + device-buffer plumbing.
+
+torch is used for device memory, streams and (in multi-process runs) torch.distributed only; every
+arithmetic step of the EPG path is a launch of the hand-written sm_100a kernels through the C ABI.
+There is NO CPU fallback: without the shared library or without a CUDA device the calls raise.
+"""
+
+import ctypes
+import os
+import threading
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libepgx.so")
+
+MAX_DIMS, MAX_PATTERNS = 8, 64
+
+
+class EpgxError(RuntimeError):
+    pass
+
+
+class _Tape(ctypes.Structure):
+    _fields_ = [
+        ("dtype", ctypes.c_int32), ("ndim", ctypes.c_int32), ("shape", ctypes.c_int64 * MAX_DIMS),
+        ("npool", ctypes.c_int32), ("npattern", ctypes.c_int32),
+        ("stride", (ctypes.c_int32 * MAX_DIMS) * MAX_PATTERNS), ("pool_stride", ctypes.c_int32 * MAX_PATTERNS),
+        ("nop", ctypes.c_int64), ("ops", ctypes.c_void_p), ("nseg", ctypes.c_int64), ("segs", ctypes.c_void_p),
+        ("ncoef", ctypes.c_int64), ("coef", ctypes.c_void_p),
+        ("init_off", ctypes.c_uint32), ("m0_off", ctypes.c_uint32), ("init_pat", ctypes.c_uint8),
+        ("m0_pat", ctypes.c_uint8), ("rsv0", ctypes.c_uint8 * 2), ("init_n", ctypes.c_int32),
+        ("nadc", ctypes.c_int32), ("njac", ctypes.c_int32), ("nvar", ctypes.c_int32), ("max_order", ctypes.c_int32),
+        ("rsv", ctypes.c_int32 * 3),
+    ]
+
+
+class Config(ctypes.Structure):
+    _fields_ = [
+        ("kernel", ctypes.c_int32), ("lanes_per_atom", ctypes.c_int32), ("slots_per_lane", ctypes.c_int32),
+        ("vars_per_pass", ctypes.c_int32), ("var_tiles", ctypes.c_int32), ("atoms_per_cta", ctypes.c_int32),
+        ("threads_per_cta", ctypes.c_int32), ("smem_bytes", ctypes.c_int32), ("ring", ctypes.c_int32),
+        ("rsv", ctypes.c_int32 * 3), ("flops_per_atom", ctypes.c_double), ("updates_per_atom", ctypes.c_double),
+    ]
+
+    def asdict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_ if k != "rsv"}
+
+
+_lib = None
+_lock = threading.Lock()
+
+EXPORTS = [
+    "epgx_version", "epgx_device_count", "epgx_last_error", "epgx_plan_create", "epgx_plan_destroy",
+    "epgx_plan_config", "epgx_plan_set_variant", "epgx_plan_workspace_bytes", "epgx_plan_upload",
+    "epgx_simulate", "epgx_simulate_host", "epgx_reduce", "epgx_fma_peak",
+]
+
+
+def lib():
+    """load libepgx.so (built in-tree by __graft_entry__.build / csrc/build.py); raises if missing"""
+    global _lib
+    with _lock:
+        if _lib is None:
+            if not os.path.exists(LIB_PATH):
+                raise EpgxError(
+                    f"{LIB_PATH} not found: build it with `python -m epgpy_b200.build` (nvcc, sm_100a). "
+                    "There is no CPU fallback."
+                )
+            L = ctypes.CDLL(LIB_PATH)
+            vp, i64, i32 = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int
+            L.epgx_version.restype = i32
+            L.epgx_device_count.restype = i32
+            L.epgx_last_error.restype = ctypes.c_char_p
+            L.epgx_plan_create.argtypes = [ctypes.POINTER(_Tape), ctypes.POINTER(vp)]
+            L.epgx_plan_destroy.argtypes = [vp]
+            L.epgx_plan_config.argtypes = [vp, ctypes.POINTER(Config)]
+            L.epgx_plan_set_variant.argtypes = [vp, i32, i32, i32, i32]
+            L.epgx_plan_workspace_bytes.argtypes = [vp, ctypes.POINTER(i64)]
+            L.epgx_plan_upload.argtypes = [vp, vp, vp]
+            L.epgx_simulate.argtypes = [vp, vp, i64, i64, vp, vp, vp]
+            L.epgx_simulate_host.argtypes = [vp, i32, i64, i64, vp, vp]
+            L.epgx_reduce.argtypes = [i32, vp, vp, i64, i64, i64, vp]
+            L.epgx_fma_peak.argtypes = [i32, i32, ctypes.c_double, ctypes.POINTER(ctypes.c_double)]
+            _lib = L
+    return _lib
+
+
+def _check(rc):
+    if rc != 0:
+        msg = lib().epgx_last_error().decode(errors="replace")
+        exc = {-2: MemoryError, -4: NotImplementedError}.get(rc, EpgxError)
+        raise exc(f"epgx error {rc}: {msg}")
+
+
+DTYPES = {"f64": 0, "f32": 1, "float64": 0, "float32": 1, "complex128": 0, "complex64": 1}
+
+
+def norm_dtype(dtype):
+    key = np.dtype(dtype).name if not isinstance(dtype, str) else dtype
+    if key not in DTYPES:
+        raise ValueError(f"dtype must be float64 or float32, got {dtype!r}")
+    return "f64" if DTYPES[key] == 0 else "f32"
+
+
+class Plan:
+    """a lowered sequence registered with the engine (host object; owns the C plan)"""
+
+    def __init__(self, low):
+        self.low = low
+        L = lib()
+        t = _Tape()
+        t.dtype = DTYPES[low.dtype]
+        ashape = low.atom_shape
+        t.ndim = len(ashape)
+        for i, d in enumerate(ashape):
+            t.shape[i] = d
+        t.npool = low.npool
+        t.npattern = len(low.patterns)
+        for q, (strides, ps) in enumerate(low.patterns):
+            for i, s in enumerate(strides):
+                t.stride[q][i] = s
+            t.pool_stride[q] = ps
+        self._ops = np.ascontiguousarray(low.ops)
+        self._segs = np.ascontiguousarray(low.segs)
+        self._coef = np.ascontiguousarray(low.coef, dtype=np.float64)
+        t.nop, t.ops = len(self._ops), self._ops.ctypes.data
+        t.nseg, t.segs = len(self._segs), self._segs.ctypes.data
+        t.ncoef, t.coef = len(self._coef), self._coef.ctypes.data
+        t.init_off, t.init_pat = low.init_ref
+        t.m0_off, t.m0_pat = low.m0_ref
+        t.init_n = low.init_n
+        t.nadc, t.njac, t.nvar, t.max_order = low.nadc, low.njac, low.nvar, low.max_order
+        self._h = ctypes.c_void_p()
+        _check(L.epgx_plan_create(ctypes.byref(t), ctypes.byref(self._h)))
+        self._ws = {}  # device index -> workspace tensor
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h and _lib is not None:
+            _lib.epgx_plan_destroy(h)
+
+    @property
+    def handle(self):
+        return self._h
+
+    def config(self):
+        c = Config()
+        _check(lib().epgx_plan_config(self._h, ctypes.byref(c)))
+        return c.asdict()
+
+    def set_variant(self, kernel=0, lanes_per_atom=0, vars_per_pass=0, atoms_per_cta=0):
+        _check(lib().epgx_plan_set_variant(self._h, kernel, lanes_per_atom, vars_per_pass, atoms_per_cta))
+
+    def workspace_bytes(self):
+        n = ctypes.c_int64()
+        _check(lib().epgx_plan_workspace_bytes(self._h, ctypes.byref(n)))
+        return n.value
+
+    # ---- device side
+    def upload(self, device):
+        """H2D of tape + coefficient table (cached per device); returns the workspace tensor"""
+        import torch
+
+        dev = torch.device("cuda", device)
+        if device not in self._ws:
+            with torch.cuda.device(dev):
+                ws = torch.empty(self.workspace_bytes(), dtype=torch.uint8, device=dev)
+                st = torch.cuda.current_stream(dev).cuda_stream
+                _check(lib().epgx_plan_upload(self._h, ws.data_ptr(), st))
+            self._ws[device] = ws
+        return self._ws[device]
+
+    def run(self, device, atom_begin=0, atom_count=None, signal=None, jacobian=None):
+        """launch the fused kernel for an atom range on torch's current stream of `device`.
+        Returns (signal, jacobian) device tensors: complex [nadc][atoms][npool], [njac][nvar][atoms][npool]"""
+        import torch
+
+        require_cuda()
+        low = self.low
+        if atom_count is None:
+            atom_count = low.natoms - atom_begin
+        dev = torch.device("cuda", device)
+        cdt = torch.complex128 if low.dtype == "f64" else torch.complex64
+        with torch.cuda.device(dev):
+            ws = self.upload(device)
+            if signal is None:
+                signal = torch.empty((low.nadc, atom_count, low.npool), dtype=cdt, device=dev)
+            if jacobian is None and low.nvar and low.njac:
+                jacobian = torch.empty((low.njac, low.nvar, atom_count, low.npool), dtype=cdt, device=dev)
+            st = torch.cuda.current_stream(dev).cuda_stream
+            _check(lib().epgx_simulate(self._h, ws.data_ptr(), atom_begin, atom_count,
+                                       signal.data_ptr() if signal is not None and signal.numel() else None,
+                                       jacobian.data_ptr() if jacobian is not None and jacobian.numel() else None, st))
+        return signal, jacobian
+
+    def run_host(self, device, atom_begin, atom_count, signal, jacobian=None):
+        """epgx_simulate_host: the plain C-ABI call on HOST numpy buffers (alloc + H2D + run + D2H)"""
+        require_cuda()
+        _check(lib().epgx_simulate_host(self._h, device, atom_begin, atom_count,
+                                        signal.ctypes.data if signal is not None and signal.size else None,
+                                        jacobian.ctypes.data if jacobian is not None and jacobian.size else None))
+
+
+def require_cuda():
+    if lib().epgx_device_count() < 1:
+        raise EpgxError("no CUDA device visible: the epgx engine has no CPU fallback")
+
+
+def device_reduce(t, axis):
+    """sum a complex device tensor over one axis with the engine's reduction kernel (Adc(reduce=))"""
+    import torch
+
+    t = t.contiguous()
+    shape = list(t.shape)
+    nouter = int(np.prod(shape[:axis])) if axis else 1
+    nred = shape[axis]
+    ninner = int(np.prod(shape[axis + 1:])) if axis + 1 < len(shape) else 1
+    out = torch.empty(shape[:axis] + shape[axis + 1:], dtype=t.dtype, device=t.device)
+    with torch.cuda.device(t.device):
+        st = torch.cuda.current_stream(t.device).cuda_stream
+        _check(lib().epgx_reduce(0 if t.dtype == torch.complex128 else 1, t.data_ptr(), out.data_ptr(), nouter, nred,
+                                 ninner, st))
+    return out
+
+
+def fma_peak(device=0, dtype="f64", seconds=0.3):
+    """measured CUDA-core FMA throughput (TFLOP/s) -- the roofline denominator of this path"""
+    require_cuda()
+    out = ctypes.c_double()
+    _check(lib().epgx_fma_peak(device, DTYPES[norm_dtype(dtype)], seconds, ctypes.byref(out)))
+    return out.value

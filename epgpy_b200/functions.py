@@ -1,0 +1,239 @@
+"""simulate / get_adc_times / getshape / getnshift / modify -- the reference's driver API
+(epgpy/functions.py:14-170, 251-369) on top of the sm_100a engine.
+
+`simulate` lowers the sequence once (lowering.py), uploads the op-tape, launches ONE fused kernel per
+device for the whole sequence and all atoms, and copies the ADC samples back.  The reference instead
+runs a Python loop with 1-4 array passes per operator and a device->host copy per ADC
+(functions.py:173-192, probe.py:63-66).
+"""
+
+import logging
+
+import numpy as np
+
+from . import common, engine, lowering
+from . import operators as ops
+from .lowering import flatten_sequence
+from .statematrix import StateMatrix
+
+LOGGER = logging.getLogger(__name__)
+
+
+def getshape(sequence):
+    """overall grid shape defined by a sequence (epgpy/functions.py:14-17)"""
+    return common.broadcast_shapes(*[op.shape for op in flatten_sequence(sequence)], append=True)
+
+
+def getnshift(sequence):
+    """number of phase states required by a sequence (epgpy/functions.py:20-26)"""
+    return sum(op.nshift for op in flatten_sequence(sequence))
+
+
+def getkdim(sequence):
+    return max([getattr(op, "kdim", 1) for op in flatten_sequence(sequence)] + [1])
+
+
+def get_adc_times(sequence):
+    """ADC opening times: running sum of the operators' durations (epgpy/functions.py:38-47)"""
+    tim, times = 0, []
+    for op in flatten_sequence(sequence):
+        tim = tim + op.duration
+        if isinstance(op, ops.Probe):
+            times.append(tim)
+    return times
+
+
+def _devices(device):
+    import torch
+
+    if device is None:
+        return [torch.cuda.current_device()]
+    if isinstance(device, (list, tuple)):
+        return [int(torch.device(d).index if not isinstance(d, int) else d) for d in device]
+    if isinstance(device, int):
+        return [device]
+    d = torch.device(device)
+    return [d.index if d.index is not None else torch.cuda.current_device()]
+
+
+def run_lowered(low, plan=None, device=None, atom_range=None):
+    """run a lowered sequence on one or several devices of this process (atoms split in contiguous
+    slabs, no inter-device traffic); returns (signal, jacobian, plan) with signal a device tensor list
+    per device: [(begin, count, sig, jac)]"""
+    import torch
+
+    engine.require_cuda()
+    plan = plan or engine.Plan(low)
+    devs = _devices(device)
+    begin, count = atom_range if atom_range is not None else (0, low.natoms)
+    per = -(-count // len(devs))
+    parts = []
+    for i, d in enumerate(devs):
+        b = begin + i * per
+        c = min(per, begin + count - b)
+        if c <= 0:
+            continue
+        sig, jac = plan.run(d, b, c)
+        parts.append((d, b, c, sig, jac))
+    return parts, plan
+
+
+def _assemble(low, parts, asarray=True):
+    """device slabs -> per-probe host arrays shaped like the reference's output (nADC, *grid)"""
+    import torch
+
+    grid, ax, npool = tuple(low.grid), low.pool_axis, low.npool
+    store_shape = tuple(d for i, d in enumerate(grid) if i != ax) + ((npool,) if ax is not None else ())
+    order = [i for i in range(len(grid)) if i != ax] + ([ax] if ax is not None else [])  # grid axis of each storage axis
+    cdt = np.complex128 if low.dtype == "f64" else np.complex64
+
+    def to_grid(flat):
+        a = flat.reshape(store_shape)
+        if ax is not None:
+            a = np.moveaxis(a, -1, ax)
+        return a.reshape(grid)
+
+    sig_host = jac_host = sig_dev = None
+    if low.nadc:
+        sig_host = np.empty((low.nadc, low.natoms, npool), dtype=cdt)
+        for d, b, c, sig, jac in parts:
+            sig_host[:, b:b + c] = sig.cpu().numpy()
+        # reduction of rows on the device (probe.py:148-153)
+        if any(r.kind == "sig" and r.reduce is not None for rows in low.rows for r in rows):
+            sig_dev = parts[0][3] if len(parts) == 1 else torch.cat([p[3].to(parts[0][3].device) for p in parts], dim=1)
+    if low.nvar and low.njac:
+        jac_host = np.empty((low.njac, low.nvar, low.natoms, npool), dtype=cdt)
+        for d, b, c, sig, jac in parts:
+            jac_host[:, :, b:b + c] = jac.cpu().numpy()
+
+    values = [[] for _ in range(low.nprobe)]
+    for rows in low.rows:
+        for ip, row in enumerate(rows):
+            if row.kind == "sig":
+                if row.reduce is None:
+                    arr = to_grid(sig_host[row.index])
+                else:
+                    t = sig_dev[row.index].reshape(store_shape)
+                    red = list(range(len(grid))) if row.reduce is True else sorted({r % len(grid) for r in row.reduce})
+                    for s_ax in sorted((order.index(r) for r in red), reverse=True):
+                        t = engine.device_reduce(t, s_ax)
+                    arr = t.cpu().numpy()
+                    keep = [g for g in order if g not in red]
+                    arr = np.transpose(arr, np.argsort(keep)) if keep else arr.reshape(())[()]
+                if row.post is not None:
+                    arr = row.post(arr)
+                values[ip].append(arr)
+            else:
+                jrow, cols = row.jac
+                out = np.zeros(grid + (len(cols),), dtype=cdt)
+                for ic, (kind, vi) in enumerate(cols):
+                    if kind == "mag":
+                        out[..., ic] = to_grid(sig_host[row.index])
+                    elif kind == "var":
+                        out[..., ic] = to_grid(jac_host[jrow, vi])
+                if row.post is not None:
+                    out = row.post(out)
+                values[ip].append(out)
+    if asarray:
+        return tuple(np.asarray(v) for v in values)
+    return tuple(tuple(v) for v in values)
+
+
+def simulate(sequence, *, adc_time=False, init=None, squeeze=False, probe=None, callback=None, asarray=True,
+             disp=False, dtype="float64", device=None, propagate_nondiff=False, **options):
+    """simulate a sequence; values are returned at the probe operators (epgpy/functions.py:50-170)
+
+    Parameters (reference-compatible):
+        sequence: (nested) list of operators
+        init: None | 3-vector | (2n+1) x 3 array | StateMatrix
+        adc_time: also return the ADC opening times
+        probe: probe (or list of) superseding the in-sequence ones (None keeps the in-sequence probe)
+        asarray: return one ndarray per probe
+        **options: state-matrix options: max_nstate, kvalue
+    Engine parameters:
+        dtype: 'float64' (complex128 states, <= 1e-10 vs the reference) or 'float32' (complex64, ~1e-5)
+        device: CUDA device index, or a list of indices: atoms are split in contiguous slabs
+        propagate_nondiff: False reproduces the reference, whose D / X / SPOILER never touch the
+            order-1 partial states (epgpy/operator.py:96-104); True applies them to the partials too
+            (the exact chain rule).
+    Returns: values | (times, values) -- ndarray (nADC, *grid) per probe, a tuple if several probes
+    """
+    if squeeze:
+        raise NotImplementedError("Automatic sequence squeezing not implemented yet")
+    if callback:
+        raise NotImplementedError("`callback` needs the state matrix on the host after every operator; "
+                                  "the fused device path has no such hook")
+    low = lowering.lower(sequence, init=init, probe=probe, options=options, dtype=engine.norm_dtype(dtype),
+                         propagate_nondiff=propagate_nondiff)
+    LOGGER.info("Simulate sequence: num. operators: %d, shape: %s, max order: %d", len(low.ops), low.grid, low.max_order)
+    parts, plan = run_lowered(low, device=device)
+    values = _assemble(low, parts, asarray=asarray)
+    times = np.asarray(low.times) if asarray else low.times
+    if len(values) == 1:
+        values = values[0]
+    if adc_time:
+        return times, values
+    return values
+
+
+def apply_operators(operators, sm):
+    raise NotImplementedError(
+        "applying an operator to a StateMatrix outside `simulate` needs the whole state on the host; "
+        "the device path only returns probe values"
+    )
+
+
+# --------------------------------------------------------------------------------------------- #
+# modify (epgpy/functions.py:251-347): pure host helper
+# --------------------------------------------------------------------------------------------- #
+
+
+def default_modifier(op, **kwargs):
+    """handle 'T1', 'T2', 'g' and 'att' keywords (epgpy/functions.py:310-347)"""
+    if isinstance(op, ops.T):
+        att = kwargs.get("att")
+        if att is not None and not np.allclose(att, 1):
+            op = ops.T(op.alpha * att, op.phi, name=op.name, duration=op.duration)
+            op.name += "#"
+    if np.any(np.asarray(op.duration) > 0):
+        T1, T2, g = kwargs.get("T1"), kwargs.get("T2"), kwargs.get("g")
+        if T1 is None and T2 is None and g is None:
+            pass
+        elif T1 is None and T2 is None:
+            op = op * ops.P(op.duration, g, duration=0)
+            op.name = op[0].name + "*"
+        else:
+            T1 = 1e10 if T1 is None else T1
+            T2 = 1e10 if T2 is None else T2
+            g = 0 if g is None else g
+            op = op * ops.E(op.duration, T1, T2, g, duration=0)
+            op.name = op[0].name + "*"
+    return op
+
+
+def modify(sequence, modifier=None, *, expand=True, **params):
+    """insert duration-dependent relaxation / precession after timed operators (epgpy/functions.py:251-307)"""
+    shape = getshape(sequence)
+    names = list(params)
+    values = [common.asparam(v) for v in params.values()]
+    if values:
+        nd = max([np.ndim(v) for v in values] + [0])
+        values = [v if common.isscalar(v) else common.left(v, nd) for v in values]
+    if expand and (len(shape) > 1 or shape[0] > 1):
+        dims = tuple(range(len(shape)))
+        values = [v if common.isscalar(v) else np.expand_dims(v, dims) for v in values]
+    params = dict(zip(names, values))
+    if not modifier:
+        modifier = default_modifier
+        if not params:
+            return sequence
+    elif not callable(modifier):
+        raise TypeError("`modifier` must be a callable")
+    newseq, opdict = [], {}
+    for op in flatten_sequence(sequence):
+        if id(op) not in opdict:
+            opdict[id(op)] = modifier(op, **params)
+        newseq.append(opdict[id(op)])
+    if isinstance(sequence, ops.MultiOperator):
+        return ops.MultiOperator(newseq, name=sequence.name)
+    return newseq

@@ -1,0 +1,542 @@
+"""Lowering: flattened operator sequence -> op-tape for the sm_100a engine (include/epgx.h).
+
+Replaces the reference's interpretation strategy (one numpy/cupy array expression per operator per
+TR, epgpy/functions.py:173-192) by a one-off compilation on the host:
+
+  * grid shape        left-aligned broadcast of all operator shapes (functions.py:14-17)
+  * coefficient table one float64 block per operator parameter group, in the group's own
+                      un-broadcast shape; the left-aligned broadcasting rule becomes per-axis strides
+                      ("patterns")
+  * records           one per operator application (+ derivative injections, diff.py:264-288)
+  * segments          runs of records between two unit shifts; S(k) -> |k| unit shifts
+                      (shift.py:86-101), max_nstate truncation included
+  * order schedule    n_old / n_new / nact per segment, a pure function of the S operators.  Orders
+                      that can no longer reach k = 0 before the last ADC are not updated
+                      (`prune_unobservable`): their values never enter any returned sample.
+"""
+
+import numpy as np
+
+from . import common, operators as ops_mod
+from .exchange import X
+from .operators import (PD, Adc, D, DiffOperator, EmptyOperator, Jacobian, MultiOperator, Operator, Probe, Reset, S,
+                        Spoiler)
+from .statematrix import StateMatrix
+
+# opcodes / flags (include/epgx.h)
+OP_NOP, OP_T_GEN, OP_T_RE, OP_T_IM, OP_E, OP_DIAG, OP_MATRIX, OP_D, OP_X, OP_SPOIL, OP_PD, OP_ADC = range(12)
+F_BASE, F_PARTIALS, F_INJECT, F_G, F_AFFINE, F_Z0, F_SCALE = (1 << i for i in range(7))
+SEG_RESET = 1
+MAX_DIMS, MAX_PATTERNS, MAX_POOLS = 8, 64, 2
+
+OP_DTYPE = np.dtype([("code", "<u2"), ("flags", "<u2"), ("aux", "<i4"), ("off", "<u4", (3,)), ("pat", "u1", (3,)),
+                     ("rsv", "u1"), ("aux1", "<i4"), ("rsv1", "<i4")])
+SEG_DTYPE = np.dtype([("first", "<i4"), ("count", "<i4"), ("nact", "<i4"), ("shift", "<i4"), ("n_old", "<i4"),
+                      ("n_new", "<i4"), ("flags", "<i4"), ("rsv", "<i4")])
+assert OP_DTYPE.itemsize == 32 and SEG_DTYPE.itemsize == 32
+
+
+def flatten_sequence(seq, flatten_multi=True):
+    """flat list of operators from nested lists / MultiOperators (epgpy/functions.py:355-369)"""
+    seq = [seq] if isinstance(seq, Operator) else seq
+    out = []
+    for item in seq:
+        if isinstance(item, (list, tuple)):
+            out.extend(flatten_sequence(item))
+        elif flatten_multi and isinstance(item, MultiOperator):
+            out.extend(flatten_sequence(item.operators))
+        elif isinstance(item, Operator):
+            out.append(item)
+        else:
+            raise ValueError(f"Invalid operator: {item}")
+    return out
+
+
+class Row:
+    """one output row (one probe at one ADC)"""
+
+    def __init__(self, kind, index, reduce=None, post=None, jac=None):
+        self.kind, self.index, self.reduce, self.post, self.jac = kind, index, reduce, post, jac
+
+
+class Lowered:
+    """the lowered sequence + everything needed to assemble the outputs"""
+
+    def nbytes_out(self, natoms=None, dtype=None):
+        natoms = self.natoms if natoms is None else natoms
+        csz = 16 if (dtype or self.dtype) == "f64" else 8
+        return csz * natoms * self.npool * (self.nadc + self.njac * self.nvar)
+
+
+class _Builder:
+    def __init__(self, grid, pool_axis):
+        self.grid = tuple(grid)
+        self.pool_axis = pool_axis
+        self.atom_axes = [i for i in range(len(grid)) if i != pool_axis]
+        self.chunks, self.ncoef = [], 0
+        self.patterns = {}
+        self.records = []
+        self.cache = {}
+
+    def pattern(self, strides, pool_stride):
+        key = (tuple(int(s) for s in strides), int(pool_stride))
+        if key not in self.patterns:
+            if len(self.patterns) >= MAX_PATTERNS:
+                raise NotImplementedError(f"more than {MAX_PATTERNS} distinct parameter broadcast patterns in one sequence")
+            self.patterns[key] = len(self.patterns)
+        return self.patterns[key]
+
+    def block(self, arr):
+        """register a coefficient block `lead + (entry,)`; returns (offset, pattern)"""
+        arr = np.ascontiguousarray(arr, dtype=np.float64)
+        lead = arr.shape[:-1]
+        if len(lead) > len(self.grid):
+            raise ValueError(f"Incompatible shapes: parameter {lead} vs grid {self.grid}")
+        es = np.array(arr.strides, dtype=np.int64) // 8
+        strides, pool_stride = [], 0
+        for i in range(len(self.grid)):
+            s = 0
+            if i < len(lead) and lead[i] != 1:
+                if lead[i] != self.grid[i]:
+                    raise ValueError(f"Incompatible shapes: parameter {lead} vs grid {self.grid}")
+                s = int(es[i])
+            if i == self.pool_axis:
+                pool_stride = s
+            else:
+                strides.append(s)
+        off = self.ncoef
+        self.chunks.append(arr.reshape(-1))
+        self.ncoef += arr.size
+        return off, self.pattern(strides, pool_stride)
+
+    def record(self, code, flags, blocks=(), aux=0, aux1=0):
+        rec = np.zeros((), dtype=OP_DTYPE)
+        rec["code"], rec["flags"], rec["aux"], rec["aux1"] = code, flags, aux, aux1
+        for i, b in enumerate(blocks):
+            if b is not None:
+                rec["off"][i], rec["pat"][i] = b
+        self.records.append(rec)
+        return len(self.records) - 1
+
+
+def _scale_block(blk, coeff):
+    coeff = np.asarray(coeff)
+    if coeff.ndim == 0:
+        return blk * float(coeff) if not np.iscomplexobj(coeff) else _cmul_block(blk, coeff)
+    if np.iscomplexobj(coeff):
+        raise NotImplementedError("complex chain-rule coefficients")
+    nd = max(blk.ndim - 1, coeff.ndim)
+    return common.left(blk, nd, tail=1) * common.left(coeff, nd)[..., None]
+
+
+def _cmul_block(blk, z):
+    raise NotImplementedError("complex chain-rule coefficients")
+
+
+def _emit_form(bld, form, flags, aux=0):
+    """emit one record for a coefficient form; returns nothing"""
+    kind = form[0]
+    if kind == "tgen":
+        blk = form[1]
+        Bi, Ur, Ui = blk[..., 3], blk[..., 4], blk[..., 5]
+        if not np.any(Bi) and not np.any(Ui):
+            bld.record(OP_T_RE, flags, [bld.block(blk[..., [0, 1, 2, 4]])], aux)
+        elif not np.any(Bi) and not np.any(Ur):
+            b4 = blk[..., [0, 1, 2, 5]].copy()
+            b4[..., 3] *= -1  # U = -i u
+            bld.record(OP_T_IM, flags, [bld.block(b4)], aux)
+        else:
+            bld.record(OP_T_GEN, flags, [bld.block(blk)], aux)
+    elif kind == "e":
+        _, b0, b1, b2, affine = form
+        fl = flags | (F_G if b2 is not None else 0) | (F_AFFINE if affine else 0)
+        bld.record(OP_E, fl, [bld.block(b0), bld.block(b1), None if b2 is None else bld.block(b2)], aux)
+    elif kind == "diag":
+        _, blk, affine = form
+        bld.record(OP_DIAG, flags | (F_AFFINE if affine else 0), [bld.block(blk)], aux)
+    elif kind == "matrix":
+        _, blk, blk0 = form
+        bld.record(OP_MATRIX, flags | (F_AFFINE if blk0 is not None else 0),
+                   [bld.block(blk), None if blk0 is None else bld.block(blk0)], aux)
+    else:
+        raise ValueError(kind)
+
+
+def _scaled_form(form, coeff):
+    kind = form[0]
+    if np.ndim(coeff) == 0 and coeff == 1:
+        return form
+    if kind == "tgen":
+        return ("tgen", _scale_block(form[1], coeff))
+    if kind == "diag":
+        return ("diag", _scale_block(form[1], coeff), form[2])
+    if kind == "matrix":
+        return ("matrix", _scale_block(form[1], coeff), None if form[2] is None else _scale_block(form[2], coeff))
+    raise ValueError(kind)
+
+
+def _unit_vector(vectors):
+    """common integer base vector of collinear integer shift vectors"""
+    base = None
+    for v in vectors:
+        v = np.asarray(v)
+        if not np.issubdtype(v.dtype, np.integer):
+            raise NotImplementedError(
+                "float shifts (the reference's shift-merge / shift-prune methods, epgpy/shift.py:367-542) are outside the hot path"
+            )
+        if v.shape[:-1] not in ((), (1,)):
+            raise NotImplementedError("per-atom shift vectors are outside the hot path")
+        v = v.reshape(-1)
+        if base is None:
+            base = v // np.gcd.reduce(np.abs(v))
+    return base
+
+
+def _multiple(v, base):
+    v = np.asarray(v).reshape(-1)
+    if len(v) < len(base):
+        v = np.pad(v, (0, len(base) - len(v)))
+    elif len(v) > len(base):
+        raise NotImplementedError("shift vectors of different dimensions in one sequence")
+    i = int(np.argmax(np.abs(base)))
+    m, r = divmod(int(v[i]), int(base[i]))
+    if r or not np.array_equal(m * base, v):
+        raise NotImplementedError(
+            "non-collinear n-d shifts (the reference's general shift-nd method, epgpy/shift.py:297-364) are outside the hot path"
+        )
+    return m
+
+
+def lower(sequence, *, init=None, probe=None, options=None, dtype="f64", propagate_nondiff=False,
+          prune_unobservable=True):
+    """sequence -> Lowered"""
+    options = dict(options or {})
+    seq = flatten_sequence(sequence)
+    if not any(isinstance(op, Probe) for op in seq):
+        raise ValueError("Cannot simulate sequence without at least one Probe/ADC operator")
+    for key in ("kgrid",):
+        if options.get(key):
+            raise NotImplementedError(f"state-matrix option `{key}` belongs to the shift-merge method, outside the hot path")
+
+    # ---- initial state
+    if init is None:
+        init = [0, 0, 1]
+    if isinstance(init, StateMatrix):
+        sm = init
+        options = {**sm.options, **options}
+        kvalue = options.pop("kvalue", sm.kvalue)
+    else:
+        kvalue = options.pop("kvalue", 1.0)
+        sm = StateMatrix(init)
+    max_nstate = options.pop("max_nstate", None) or None
+    options.pop("tvalue", None)
+    options.pop("prune", None)
+    if options:
+        raise TypeError(f"unknown simulate option(s): {sorted(options)}")
+
+    # ---- probes (functions.py:118-127, 184-189)
+    probes = None
+    if probe:
+        probes = list(probe) if isinstance(probe, (tuple, list)) else [probe]
+        probes = [pb if isinstance(pb, (Probe, type(None))) else Probe(pb) for pb in probes]
+
+    # ---- grid
+    grid = common.broadcast_shapes(*[op.shape for op in seq], sm.shape, append=True)
+    if len(grid) > MAX_DIMS:
+        raise NotImplementedError(f"more than {MAX_DIMS} grid axes")
+    xops = [op for op in seq if isinstance(op, X)]
+    pool_axis, npool = None, 1
+    if xops:
+        axes = {(op.axis, op.ncomp) for op in xops}
+        if len(axes) > 1:
+            raise NotImplementedError("exchange operators along different axes in one sequence")
+        pool_axis, npool = axes.pop()
+        if npool > MAX_POOLS:
+            raise NotImplementedError(f"exchange between more than {MAX_POOLS} compartments")
+        if pool_axis >= len(grid) or grid[pool_axis] != npool:
+            raise RuntimeError("Invalid state matrix shape")
+    atom_shape = tuple(d for i, d in enumerate(grid) if i != pool_axis) or (1,)
+    bld = _Builder(grid, pool_axis)
+
+    # ---- derivative variables: only those a Jacobian probe asks for
+    jprobes = [pb for pb in (probes or []) if isinstance(pb, Jacobian)]
+    jprobes += [op for op in seq if isinstance(op, Jacobian)] if probes is None else []
+    defined = []
+    for op in seq:
+        for var in getattr(op, "order1", None) or {}:
+            if var not in defined:
+                defined.append(var)
+    wanted = {v for pb in jprobes for v in pb.variables if v != "magnitude"}
+    variables = [v for v in defined if v in wanted]
+    vindex = {v: i for i, v in enumerate(variables)}
+    nvar = len(variables)
+
+    # ---- shifts: 1-d integers, or collinear integer vectors
+    vecs = [op.k for op in seq if isinstance(op, S) and not common.isscalar(op.k)]
+    base = _unit_vector(vecs) if vecs else None
+
+    def shift_count(op):
+        if base is None:
+            return int(op.k)
+        return _multiple([op.k] if common.isscalar(op.k) else op.k, base)
+
+    # ---- order schedule: maximum order of the whole tape
+    init_n = sm.nstate
+    n, max_order = init_n, init_n
+    for op in seq:
+        if isinstance(op, S):
+            cap = max_nstate or op.nmax or None
+            n = n + abs(shift_count(op)) if cap is None else min(n + abs(shift_count(op)), max(cap, 0))
+            max_order = max(max_order, n)
+        elif isinstance(op, Reset):
+            n = 0
+    if init_n > max_order:
+        max_order = init_n
+
+    # ---- init / equilibrium blocks (half storage: orders 0..init_n)
+    st = sm.states
+    half = st[..., init_n:, :]
+    init_blk = np.stack([half[..., 0].real, half[..., 0].imag, half[..., 1].real, half[..., 1].imag,
+                         half[..., 2].real, half[..., 2].imag], axis=-1).reshape(half.shape[:-2] + (6 * (init_n + 1),))
+    init_ref = bld.block(init_blk)
+    m0_ref = bld.block(np.asarray(sm.density, dtype=float)[..., None])
+
+    # ---- wavenumbers for D (diffusion.py:60-79): K(m) = m * base * kvalue [rad/m]
+    kdim = 1 if base is None else len(base)
+    bvec = np.ones(1) if base is None else base.astype(float)
+
+    def diffusion_block(op):
+        m = np.arange(0, max_order + 1, dtype=float)
+        tau = np.asarray(op.tau, dtype=float) * 1e-3
+        Kp = m[:, None] * bvec[None, :] * kvalue * 1e-3   # order +m
+        if op.k is None:
+            sh = np.zeros(kdim)
+        else:
+            sh = np.asarray(op.k, dtype=float).reshape(-1)
+            if len(sh) != kdim:
+                raise ValueError("Incompatible numbers of dimensions for k1 and k2")
+            sh = sh * kvalue * 1e-3
+        Dm = np.asarray(op.D, dtype=float)
+        if Dm.ndim == 0:
+            Dm = float(Dm) * np.eye(kdim)
+        elif Dm.shape[-2:] != (kdim, kdim) or Dm.ndim != 2:
+            raise NotImplementedError("D must be a scalar or one kdim x kdim matrix per operator")
+
+        def trace_bd(k2, shv):
+            """Tr(b D) / tau of a linear change (k2 - shv) -> k2  (diffusion.py:86-123)"""
+            k1 = k2 - shv
+            kd = k2 - k1
+            q = np.einsum("mi,ij,mj->m", k1, Dm, k1)
+            if np.allclose(kd, 0):
+                return q
+            return q + 0.5 * np.einsum("mi,ij,mj->m", k1, Dm, kd) + 0.5 * np.einsum("mi,ij,mj->m", kd, Dm, k1) \
+                + np.einsum("mi,ij,mj->m", kd, Dm, kd) / 3
+
+        tP = trace_bd(Kp, sh)     # F+ at order +m
+        tM = trace_bd(-Kp, sh)    # F-(m) carries the F+ factor of order -m
+        tL = np.einsum("mi,ij,mj->m", Kp, Dm, Kp)
+        rows = np.stack([tP, tM, tL], axis=-1).reshape(-1)      # [3 * (max_order + 1)]
+        tau = np.atleast_1d(tau)
+        return np.exp(-tau[..., None] * rows)
+
+    # ---- walk the sequence
+    segs = []
+    rows_out = []          # per ADC op: list of Row (one per probe)
+    times, tic = [], 0
+    nadc = njac = 0
+    n = init_n
+    alive = False          # any partial state non-zero so far
+    seg_first = 0
+
+    def close_segment(shift, n_old, n_new, flags=0):
+        nonlocal seg_first
+        seg = np.zeros((), dtype=SEG_DTYPE)
+        seg["first"], seg["count"] = seg_first, len(bld.records) - seg_first
+        seg["nact"], seg["shift"], seg["n_old"], seg["n_new"], seg["flags"] = n_old, shift, n_old, n_new, flags
+        segs.append(seg)
+        seg_first = len(bld.records)
+
+    def part_flag():
+        return F_PARTIALS if (nvar and alive) else 0
+
+    for op in seq:
+        if isinstance(op, Jacobian) and probes is not None:
+            pass  # an in-sequence Jacobian is a probe like any other
+        if isinstance(op, S):
+            m = shift_count(op)
+            cap = max_nstate or op.nmax or None
+            for _ in range(abs(m)):
+                n_new = n + 1 if cap is None else min(n + 1, max(cap, 0))
+                close_segment(1 if m > 0 else -1, n, n_new)
+                n = n_new
+        elif isinstance(op, (X, D, Spoiler)):
+            fl = F_BASE | (part_flag() if propagate_nondiff else 0)
+            if isinstance(op, Spoiler):
+                bld.record(OP_SPOIL, fl)
+            elif isinstance(op, D):
+                key = (id(op), "D")
+                if key not in bld.cache:
+                    bld.cache[key] = bld.block(diffusion_block(op))
+                bld.record(OP_D, fl, [bld.cache[key]])
+            else:
+                key = (id(op), "X")
+                if key not in bld.cache:
+                    # mat[..., dst(ax), src(ax+1), ..., 3] -> entry (mT[dst][src], mL[dst][src]) complex
+                    mat = np.moveaxis(op.mat, (op.axis, op.axis + 1), (-3, -2))  # [..., dst, src, 3]
+                    ent = np.stack([mat[..., 0].real, mat[..., 0].imag], axis=-1).reshape(mat.shape[:-3] + (-1,))
+                    enl = np.stack([mat[..., 2].real, mat[..., 2].imag], axis=-1).reshape(mat.shape[:-3] + (-1,))
+                    blk = np.concatenate([ent, enl], axis=-1)
+                    # re-insert a singleton pool axis so that lead axes line up with the grid
+                    blk = np.expand_dims(blk, op.axis) if blk.ndim - 1 >= op.axis else blk
+                    bld.cache[key] = bld.block(blk)
+                    dens = np.broadcast_to(common.left(sm.density, len(grid)), grid)
+                    khi = np.asarray(op.khi, dtype=float)
+                    chk = np.einsum("...i,...i->...", khi, np.moveaxis(dens[..., None], op.axis, -1))
+                    if not np.allclose(chk, 0):
+                        raise RuntimeError("Exchange matrix `khi` does not conserve total magnetization")
+                bld.record(OP_X, fl, [bld.cache[key]])
+        elif isinstance(op, PD):
+            if nvar and alive and not propagate_nondiff:
+                raise NotImplementedError("PD after a differentiated operator needs propagate_nondiff=True")
+            bld.record(OP_PD, F_BASE, [bld.block(np.atleast_1d(np.asarray(op.pd, dtype=float))[..., None])])
+            if op.reset:
+                close_segment(0, n, n, SEG_RESET)
+        elif isinstance(op, Reset):
+            if nvar and alive and not propagate_nondiff:
+                raise NotImplementedError("RESET after a differentiated operator needs propagate_nondiff=True")
+            close_segment(0, n, n, SEG_RESET)
+            n = 0
+        elif isinstance(op, DiffOperator):
+            key = (id(op), "form")
+            if key not in bld.cache:
+                bld.cache[key] = op._form()
+            form = bld.cache[key]
+            inj = [(vindex[var], param, coeff) for var, pc in op.order1.items() if var in vindex
+                   for param, coeff in pc.items()] if nvar else []
+            if not inj:
+                _emit_or_reuse(bld, op, form, F_BASE | part_flag())
+            else:
+                if alive:
+                    _emit_or_reuse(bld, op, form, F_PARTIALS)
+                for vi, param, coeff in inj:
+                    _emit_form(bld, _scaled_form(op._dform(param), coeff), F_INJECT, aux=vi)
+                alive = True
+                _emit_or_reuse(bld, op, form, F_BASE)
+        elif isinstance(op, Probe):
+            pass
+        elif isinstance(op, (EmptyOperator, ops_mod.System)):
+            pass
+        else:
+            raise NotImplementedError(f"operator {op!r} ({type(op).__name__}) has no device implementation")
+
+        tic = tic + op.duration
+        if isinstance(op, Probe):
+            rows = []
+            for pb in (probes or [op]):
+                eff = pb or op
+                phase = getattr(op, "phase", None) if isinstance(op, Adc) else None
+                custom_post = None
+                if not isinstance(op, Adc) and getattr(op, "_post", None):
+                    custom_post = op._post
+                if isinstance(eff, Jacobian):
+                    attr = eff.probe
+                    fl = (F_Z0 if attr == "Z0" else 0)
+                    blocks = []
+                    if phase is not None:
+                        ph = np.exp(1j * np.asarray(phase, dtype=float) * common.DEG)
+                        ph = np.atleast_1d(ph)
+                        blocks = [bld.block(np.stack([ph.real, ph.imag], axis=-1))]
+                        fl |= F_SCALE
+                    need_mag = "magnitude" in eff.variables
+                    cols = [("mag", None) if v == "magnitude" else ("var", vindex[v]) if v in vindex else ("zero", None)
+                            for v in eff.variables]
+                    srow = jrow = -1
+                    if need_mag:
+                        srow, nadc = nadc, nadc + 1
+                        fl |= F_BASE
+                    if nvar:
+                        jrow, njac = njac, njac + 1
+                        fl |= F_PARTIALS
+                    if fl & (F_BASE | F_PARTIALS):
+                        bld.record(OP_ADC, fl, blocks, aux=max(srow, 0), aux1=max(jrow, 0))
+                    rows.append(Row("jac", srow, post=custom_post, jac=(jrow, cols)))
+                else:
+                    attr = eff.attr
+                    if attr not in ("F0", "Z0"):
+                        raise NotImplementedError(f"Adc('{attr}'): only F0 and Z0 can be probed on the device")
+                    red = eff.reduce
+                    red = None if (red is None or red is False) else red
+                    if red is not None and red is not True and isinstance(red, (int, np.integer)):
+                        red = (int(red),)
+                    scale = None
+                    if eff.weights is not None:
+                        scale = np.asarray(eff.weights, dtype=complex)
+                    host_post = custom_post
+                    if phase is not None:
+                        if red is None:
+                            ph = np.exp(1j * np.asarray(phase, dtype=float) * common.DEG)
+                            if scale is None:
+                                scale = ph
+                            else:
+                                a, b = common.expand_left(np.atleast_1d(scale), np.atleast_1d(ph))
+                                scale = a * b
+                        else:
+                            host_post = op._post
+                    fl = F_BASE | (F_Z0 if attr == "Z0" else 0)
+                    blocks = []
+                    if scale is not None:
+                        scale = np.atleast_1d(scale)
+                        blocks = [bld.block(np.stack([scale.real, scale.imag], axis=-1))]
+                        fl |= F_SCALE
+                    bld.record(OP_ADC, fl, blocks, aux=nadc)
+                    rows.append(Row("sig", nadc, reduce=red, post=host_post))
+                    nadc += 1
+            rows_out.append(rows)
+            times.append(tic)
+
+    close_segment(0, n, n)
+
+    # ---- prune orders that cannot reach k = 0 before the last read-out
+    recs = np.array(bld.records, dtype=OP_DTYPE) if bld.records else np.zeros(0, dtype=OP_DTYPE)
+    segs = np.array(segs, dtype=SEG_DTYPE)
+    if prune_unobservable:
+        reach = -1
+        for i in range(len(segs) - 1, -1, -1):
+            s = segs[i]
+            if s["flags"] & SEG_RESET:
+                reach = -1
+            elif reach >= 0:
+                reach += abs(int(s["shift"]))
+            r = recs[s["first"]:s["first"] + s["count"]]
+            if np.any(r["code"] == OP_ADC):
+                reach = max(reach, 0)
+            segs[i]["nact"] = min(int(s["n_old"]), reach)
+
+    low = Lowered()
+    low.dtype = dtype
+    low.grid, low.atom_shape, low.pool_axis, low.npool = grid, atom_shape, pool_axis, npool
+    low.natoms = int(np.prod(atom_shape))
+    low.patterns = sorted(bld.patterns, key=bld.patterns.get)
+    low.ops, low.segs = recs, segs
+    low.coef = np.concatenate(bld.chunks) if bld.chunks else np.zeros(1)
+    low.init_ref, low.m0_ref, low.init_n = init_ref, m0_ref, init_n
+    low.nadc, low.njac, low.nvar, low.max_order = nadc, njac, nvar, max_order
+    low.variables = variables
+    low.rows, low.times = rows_out, times
+    low.nprobe = len(probes) if probes else 1
+    low.keepalive = seq
+    return low
+
+
+def _emit_or_reuse(bld, op, form, flags):
+    """records of the same operator object reuse its coefficient blocks (operators are reusable
+    objects in the reference too, docs/basics.md:111)"""
+    key = (id(op), "rec")
+    if key in bld.cache:
+        rec = bld.cache[key].copy()
+        base_flags = int(rec["flags"]) & ~(F_BASE | F_PARTIALS | F_INJECT)
+        rec["flags"] = base_flags | flags
+        bld.records.append(rec)
+        return
+    _emit_form(bld, form, flags)
+    bld.cache[key] = bld.records[-1].copy()

@@ -1,0 +1,955 @@
+"""Host-side mirror of the reference's operator API (epgpy/operators.py:1-25, epgpy/core.py:80-83).
+
+Same constructors, attributes, shapes and error behaviour as the reference's operators, but an
+operator here is only a DESCRIPTION: it stores its parameters and knows how to emit compact
+coefficient blocks for the op-tape (`_form`, `_dform`).  Nothing is applied on the host -- the
+arithmetic of the reference's `_apply` bodies (opmatrix.py:199-221, opscalar.py:213-232,
+shift.py:271-294, diffusion.py:60-79, exchange.py:89-120) runs in the sm_100a kernels of
+csrc/ through lowering.py.
+
+Coefficient "forms" (see include/epgx.h for the device-side layout); every block is a float64 array
+`lead_shape + (entry,)` where lead_shape is the operator's own, un-broadcast, left-aligned shape:
+  ('tgen',  [a, w, B.re, B.im, U.re, U.im])                        RF pulse in rotated-Rx form
+  ('e',     [e1, r0], [e2], [cos, sin] | None)                     relaxation / precession / recovery
+  ('diag',  [aP.re, aP.im, aM.re, aM.im, aZ.re, aZ.im, a0.re, a0.im])   generic diagonal + affine
+  ('matrix',[18 reals], [6 reals] | None)                          generic 3x3 + affine
+"""
+
+import numpy as np
+
+from . import common
+from .common import DEG, asparam, expand_left, get_shape, isscalar, op_shape
+
+
+# --------------------------------------------------------------------------------------------- #
+# base classes (epgpy/operator.py)
+# --------------------------------------------------------------------------------------------- #
+
+
+class Operator:
+    """base operator (epgpy/operator.py:13-115)"""
+
+    def __init__(self, *, name=None, duration=None):
+        if duration is None:
+            duration = 0
+        elif np.any(np.asarray(duration) < 0):
+            raise ValueError("Cannot have duration < 0")
+        self.duration = duration
+        self.name = name if name else type(self).__name__
+
+    @property
+    def shape(self):
+        return (1,)
+
+    @property
+    def ndim(self):
+        return len(self.shape)
+
+    @property
+    def size(self):
+        return int(np.prod(self.shape))
+
+    @property
+    def nshift(self):
+        return 0
+
+    def __repr__(self):
+        return self.name
+
+    def __mul__(self, other):
+        return MultiOperator([self, other])
+
+    def __call__(self, sm, *, inplace=False):
+        """apply to a StateMatrix: one-operator tape on the engine (statematrix.StateMatrix.apply)"""
+        from .functions import apply_operators
+
+        return apply_operators([self], sm)
+
+    def copy(self, name=None, duration=None):
+        import copy as _copy
+
+        new = _copy.copy(self)
+        new.name = name or self.name
+        new.duration = duration or self.duration
+        return new
+
+
+class MultiOperator(Operator):
+    """an operator made of a sequence of operators (epgpy/operator.py:118-203)"""
+
+    def __init__(self, operators=None, *, name=None, duration=None):
+        self._nshift = 0
+        self._shape = (1,)
+        self.operators = []
+        self.duration = 0
+        operators = [] if not operators else list(operators)
+        for op in operators:
+            self.append(op)
+        if not name:
+            name = " | ".join(op.name for op in operators)
+        if duration is None:
+            duration = self.duration
+        super().__init__(name=name, duration=duration)
+
+    @property
+    def shape(self):
+        return self._shape
+
+    @property
+    def nshift(self):
+        return self._nshift
+
+    def __iter__(self):
+        return iter(self.operators)
+
+    def __len__(self):
+        return len(self.operators)
+
+    def __getitem__(self, i):
+        return self.operators[i]
+
+    def __mul__(self, other):
+        self.append(other)
+        return self
+
+    def append(self, op):
+        if not isinstance(op, Operator):
+            raise TypeError("Invalid operator: %s" % str(op))
+        shape = common.broadcast_shapes(self.shape, op.shape, append=True)
+        if isinstance(op, MultiOperator):
+            self.operators.extend(op.operators)
+        else:
+            self.operators.append(op)
+        self._shape = shape
+        self._nshift += op.nshift
+        self.duration = self.duration + op.duration
+
+
+class EmptyOperator(Operator):
+    """does nothing (epgpy/operator.py:248-252)"""
+
+
+NULL = EmptyOperator(name="NULL")
+
+
+class Wait(EmptyOperator):
+    """empty operator with a duration (epgpy/operator.py:259-265)"""
+
+    def __init__(self, duration, name=None):
+        super().__init__(duration=duration, name=name if name is not None else f"Wait({duration})")
+
+
+class Offset(EmptyOperator):
+    """empty operator with a possibly negative duration (epgpy/operator.py:268-274)"""
+
+    def __init__(self, duration, name=None):
+        super().__init__(duration=abs(duration), name=name if name is not None else f"Offset({duration})")
+        self.duration = duration
+
+
+class Spoiler(Operator):
+    """perfect spoiler: F+ = F- = 0 (epgpy/operator.py:281-286)"""
+
+
+SPOILER = Spoiler(name="Spoiler")
+
+
+class Reset(Operator):
+    """return to equilibrium, order 0 (epgpy/operator.py:297-304)"""
+
+
+RESET = Reset(name="Reset")
+
+
+class PD(Operator):
+    """set the proton density / equilibrium (epgpy/operator.py:315-341)"""
+
+    def __init__(self, pd, *, reset=True, name=None, **kwargs):
+        self.pd = asparam(pd)
+        self.reset = reset
+        if name is None:
+            name = common.repr_operator("PD", ["pd"], [self.pd], [".1f"])
+        super().__init__(name=name, **kwargs)
+
+    @property
+    def shape(self):
+        return getattr(self.pd, "shape", (1,)) or (1,)
+
+
+class System(Operator):
+    """system arrays of the Imaging probe (epgpy/operator.py:348-361): outside the hot path"""
+
+    def __init__(self, name=None, **properties):
+        super().__init__(name=name)
+        self.properties = properties
+
+
+# --------------------------------------------------------------------------------------------- #
+# differentiable operators (epgpy/diff.py:20-262, order 1)
+# --------------------------------------------------------------------------------------------- #
+
+
+def parse_order1(order1, parameters):
+    """normalise the `order1` keyword to {variable: {parameter: coefficient}} (epgpy/diff.py:153-195)"""
+    if isinstance(order1, str):
+        order1 = [order1]
+    if not order1:
+        return {}
+    if order1 is True:
+        order1 = {p: {p: 1} for p in sorted(parameters)}
+    elif isinstance(order1, (list, tuple, set)):
+        order1 = {p: {p: 1} for p in order1}
+    elif isinstance(order1, dict) and all(isinstance(v, str) for v in order1.values()):
+        order1 = {var: {order1[var]: 1} for var in order1}
+    elif isinstance(order1, dict) and all(isinstance(v, dict) for v in order1.values()):
+        order1 = {var: dict(order1[var]) for var in order1}
+    else:
+        raise ValueError(f"Invalid parameter 'order1' value: {order1}")
+    invalid = {p for var in order1 for p in set(order1[var]) - set(parameters)}
+    if invalid:
+        raise ValueError(f"Unknown parameter(s): {invalid}")
+    return order1
+
+
+class DiffOperator(Operator):
+    """operator with order-1 partial derivatives (epgpy/diff.py:20-139)
+
+    order1: False | True | parameter name(s) | {alias: parameter} | {variable: {parameter: coeff}}
+    The partial state matrices are propagated on the device in the same pass as the base state.
+    """
+
+    PARAMETERS_ORDER1 = set()
+
+    def __init__(self, *, order1=False, order2=False, name=None, duration=None):
+        super().__init__(name=name, duration=duration)
+        if order2:
+            raise NotImplementedError(
+                "second-order derivatives (order2 / Hessian, epgpy/diff.py:290-378) are not part of the B200 hot path yet"
+            )
+        self.order1 = parse_order1(order1, self.PARAMETERS_ORDER1)
+        self.order2 = {}
+
+    @property
+    def parameters_order1(self):
+        return {p for var in self.order1 for p in self.order1[var]}
+
+    # lowering interface
+    def _form(self):
+        raise NotImplementedError
+
+    def _dform(self, param):
+        raise NotImplementedError
+
+    # generic dense coefficients (for `@` and for the public .mat / .arr attributes)
+    def _dense(self):
+        """('mat', mat[...,3,3], mat0|None) or ('diag', arr[...,3], arr0|None)"""
+        raise NotImplementedError
+
+    def _ddense(self, param):
+        raise NotImplementedError
+
+
+def _combine(op1, op2, name=None, duration=None):
+    """`op1 @ op2`: one operator equal to op1 followed by op2 (epgpy/operator.py:206-241,
+    opmatrix.py:89-135, opscalar.py:101-147).  Derivatives are carried per VARIABLE with the chain-rule
+    coefficients folded in: d(M2 M1) = M2 dM1 + dM2 M1, affine terms included."""
+    if not isinstance(op1, DiffOperator) or not isinstance(op2, DiffOperator) or isinstance(op1, S) or isinstance(op2, S):
+        raise TypeError(f"Non-combinable operator: {op2 if isinstance(op1, DiffOperator) else op1}")
+    k1, c1, c01 = op1._dense()
+    k2, c2, c02 = op2._dense()
+    diag = k1 == "diag" and k2 == "diag"
+
+    def as_mat(kind, c):
+        if c is None or kind == "mat" or diag:
+            return c
+        return c[..., None] * np.eye(3)
+
+    tail = 1 if diag else 2
+
+    def mul(b, a):  # b after a
+        if a is None or b is None:
+            return None
+        a, b = expand_left(a, b, tail=tail)
+        return b * a if diag else b @ a
+
+    def add(a, b):
+        if a is None:
+            return b
+        if b is None:
+            return a
+        a, b = expand_left(a, b, tail=tail)
+        return a + b
+
+    m1, m01, m2, m02 = as_mat(k1, c1), as_mat(k1, c01), as_mat(k2, c2), as_mat(k2, c02)
+    mat = mul(m2, m1)
+    mat0 = add(mul(m2, m01), m02)
+
+    def scaled(c, coeff):
+        if c is None:
+            return None
+        coeff = np.asarray(coeff)
+        if coeff.ndim == 0:
+            return c * coeff
+        c, coeff = expand_left(c, coeff[(...,) + (None,) * tail], tail=tail)
+        return c * coeff
+
+    dvars = {}
+    for op, first in ((op1, True), (op2, False)):
+        for var, pc in op.order1.items():
+            for param, coeff in pc.items():
+                kd, d, d0 = op._ddense(param)
+                d, d0 = as_mat(kd, d), as_mat(kd, d0)
+                if first:  # M2 dM1, M2 dM01
+                    d, d0 = mul(m2, d), mul(m2, d0)
+                else:  # dM2 M1, dM2 M01 + dM02
+                    d, d0 = mul(d, m1), add(mul(d, m01), d0)
+                d, d0 = scaled(d, coeff), scaled(d0, coeff)
+                if var in dvars:
+                    dvars[var] = (add(dvars[var][0], d), add(dvars[var][1], d0))
+                else:
+                    dvars[var] = (d, d0)
+    if name is None:
+        name = f"{op1.name}|{op2.name}"
+    if duration is None:
+        duration = op1.duration + op2.duration
+    cls = ScalarOp if diag else MatrixOp
+    key = "darrs" if diag else "dmats"
+    return cls(mat, mat0, **{key: dvars}, order1={v: {v: 1} for v in dvars}, name=name, duration=duration, check=False)
+
+
+class CombinableOperator(DiffOperator):
+    def __matmul__(self, other):
+        return _combine(self, other)
+
+    def __rmatmul__(self, other):
+        return _combine(other, self)
+
+    def combine(self, other, *, right=False, name=None, duration=None):
+        return _combine(other, self, name, duration) if right else _combine(self, other, name, duration)
+
+
+def _cplx_block(*cols):
+    """stack complex / real columns into a float64 block lead + (entry,)"""
+    cols = np.broadcast_arrays(*cols)
+    parts = []
+    for c in cols:
+        if np.iscomplexobj(c):
+            parts += [c.real, c.imag]
+        else:
+            parts.append(np.asarray(c, dtype=float))
+    return np.stack(parts, axis=-1).astype(np.float64)
+
+
+class MatrixOp(CombinableOperator):
+    """generic state-wise 3x3 operator with affine term (epgpy/opmatrix.py:10-135)"""
+
+    def __init__(self, mat, mat0=None, *, dmats=None, d2mats=None, axes=None, check=True, **kwargs):
+        dmats = dmats or {}
+        self.PARAMETERS_ORDER1 = set(kwargs.pop("parameters_order1", None) or dmats)
+        if d2mats:
+            raise NotImplementedError("second-order derivative matrices are not supported")
+        super().__init__(**kwargs)
+        self.mat, self.mat0 = _matrix_setup(mat, mat0, check=check)
+        self.dmats = {p: _matrix_setup(*(d if isinstance(d, tuple) else (d, None)), check=check) for p, d in dmats.items()}
+        if axes is not None:
+            raise NotImplementedError("the `axes` keyword is not supported: give parameters their grid axes directly")
+
+    @property
+    def shape(self):
+        return self.mat.shape[:-2]
+
+    def _dense(self):
+        return "mat", self.mat, self.mat0
+
+    def _ddense(self, param):
+        return ("mat",) + tuple(self.dmats[param])
+
+    @staticmethod
+    def _matrix_form(mat, mat0):
+        blk = np.stack([mat.real, mat.imag], axis=-1).reshape(mat.shape[:-2] + (18,)).astype(np.float64)
+        blk0 = None
+        if mat0 is not None:
+            col = mat0[..., :, 2]
+            blk0 = np.stack([col.real, col.imag], axis=-1).reshape(col.shape[:-1] + (6,)).astype(np.float64)
+        return ("matrix", blk, blk0)
+
+    def _form(self):
+        return self._matrix_form(self.mat, self.mat0)
+
+    def _dform(self, param):
+        return self._matrix_form(*self.dmats[param])
+
+
+def _matrix_setup(mat, mat0=None, check=True):
+    """epgpy/opmatrix.py:140-170"""
+    mat = np.asarray(mat, dtype=complex)
+    if mat.ndim == 2:
+        mat = mat[None]
+    if mat.ndim < 3 or mat.shape[-2:] != (3, 3):
+        raise ValueError(f"Expected ...x3x3 array shape, found: {mat.shape}")
+    if check and not np.allclose(mat, mat[..., (1, 0, 2), :][..., (1, 0, 2)].conj()):
+        raise ValueError(f"Invalid matrix coefficients: {mat}")
+    if mat0 is not None:
+        mat0 = np.asarray(mat0, dtype=complex)
+        if mat0.ndim == 2:
+            mat0 = mat0[None]
+        if mat0.ndim < 3 or mat0.shape[-2:] != (3, 3):
+            raise ValueError(f"Expected ...x3x3 array shape, found: {mat0.shape}")
+        mat, mat0 = expand_left(mat, mat0, tail=2)
+        mat, mat0 = np.broadcast_arrays(mat, mat0)
+    return mat, mat0
+
+
+class ScalarOp(CombinableOperator):
+    """generic diagonal operator with affine term (epgpy/opscalar.py:11-147)"""
+
+    def __init__(self, arr, arr0=None, *, darrs=None, d2arrs=None, axes=None, check=True, **kwargs):
+        darrs = darrs or {}
+        self.PARAMETERS_ORDER1 = set(kwargs.pop("parameters_order1", None) or darrs)
+        if d2arrs:
+            raise NotImplementedError("second-order derivative arrays are not supported")
+        super().__init__(**kwargs)
+        self.arr, self.arr0 = _scalar_setup(arr, arr0, check=check)
+        self.darrs = {p: _scalar_setup(*(d if isinstance(d, tuple) else (d, None)), check=check) for p, d in darrs.items()}
+        if axes is not None:
+            raise NotImplementedError("the `axes` keyword is not supported: give parameters their grid axes directly")
+
+    @property
+    def shape(self):
+        return self.arr.shape[:-1]
+
+    def _dense(self):
+        return "diag", self.arr, self.arr0
+
+    def _ddense(self, param):
+        return ("diag",) + tuple(self.darrs[param])
+
+    @staticmethod
+    def _diag_form(arr, arr0):
+        a0 = np.zeros(arr.shape[:-1], dtype=complex) if arr0 is None else arr0[..., 2]
+        return ("diag", _cplx_block(arr[..., 0].astype(complex), arr[..., 1].astype(complex),
+                                    arr[..., 2].astype(complex), a0.astype(complex)), arr0 is not None)
+
+    def _form(self):
+        return self._diag_form(self.arr, self.arr0)
+
+    def _dform(self, param):
+        return self._diag_form(*self.darrs[param])
+
+
+def _scalar_setup(arr, arr0=None, check=True):
+    """epgpy/opscalar.py:161-192"""
+    arr = np.asarray(arr, dtype=complex)
+    if arr.ndim == 1:
+        arr = arr[None]
+    if arr.ndim < 2 or arr.shape[-1] != 3:
+        raise ValueError(f"Expected ...x3 array shape, found: {arr.shape}")
+    if check and not np.allclose(arr, arr[..., (1, 0, 2)].conj()):
+        raise ValueError(f"Invalid coefficients: {arr}")
+    if arr0 is not None:
+        arr0 = np.asarray(arr0, dtype=complex)
+        if arr0.ndim == 1:
+            arr0 = arr0[None]
+        arr, arr0 = expand_left(arr, arr0, tail=1)
+        arr, arr0 = np.broadcast_arrays(arr, arr0)
+    return arr, arr0
+
+
+# --------------------------------------------------------------------------------------------- #
+# T, Phi (epgpy/transition.py)
+# --------------------------------------------------------------------------------------------- #
+
+
+def _snap(x):
+    """remove the 1e-17 residue of cos/sin at multiples of 90 degrees"""
+    x = np.asarray(x, dtype=float).copy()
+    x[np.abs(x) < 4e-16] = 0.0
+    return x
+
+
+def _cis_deg(phi, mult=1):
+    p = DEG * np.asarray(phi, dtype=float) * mult
+    return _snap(np.cos(p)) + 1j * _snap(np.sin(p))
+
+
+class T(CombinableOperator):
+    """instantaneous RF pulse: T = Rz(phi) Rx(alpha) Rz(-phi), angles in degrees
+    (epgpy/transition.py:7-65, 114-151)"""
+
+    PARAMETERS_ORDER1 = {"alpha", "phi"}
+
+    def __init__(self, alpha, phi, *, axes=None, name=None, duration=None, **kwargs):
+        if axes is not None:
+            raise NotImplementedError("the `axes` keyword is not supported: give parameters their grid axes directly")
+        self.alpha, self.phi = asparam(alpha), asparam(phi)
+        if not name:
+            name = common.repr_operator("T", ["alpha", "phi"], [alpha, phi], [".1f", ".1f"])
+        super().__init__(name=name, duration=duration, **kwargs)
+        self._shape = op_shape(self.alpha, self.phi)
+
+    @property
+    def shape(self):
+        return self._shape
+
+    def _ap(self):
+        a, p = expand_left(np.asarray(self.alpha, dtype=float), np.asarray(self.phi, dtype=float))
+        return DEG * a, p
+
+    def _form(self):
+        # a = cos^2(alpha/2), w = cos(alpha), B = sin^2(alpha/2) e^{2 i phi}, U = -i sin(alpha) e^{i phi}
+        a, phi = self._ap()
+        B = np.sin(a / 2) ** 2 * _cis_deg(phi, 2)
+        U = -1j * np.sin(a) * _cis_deg(phi)
+        return ("tgen", _cplx_block(np.cos(a / 2) ** 2 + 0 * B.real, np.cos(a) + 0 * B.real, B, U))
+
+    def _dform(self, param):
+        a, phi = self._ap()
+        if param == "alpha":  # transition.py:172-186 (per degree)
+            B = 0.5 * np.sin(a) * _cis_deg(phi, 2) * DEG
+            U = -1j * np.cos(a) * _cis_deg(phi) * DEG
+            return ("tgen", _cplx_block(-0.5 * np.sin(a) * DEG + 0 * B.real, -np.sin(a) * DEG + 0 * B.real, B, U))
+        if param == "phi":  # transition.py:165-169, 189-196: dB = 2i B, dU = i U (per degree)
+            B = 2j * np.sin(a / 2) ** 2 * _cis_deg(phi, 2) * DEG
+            U = np.sin(a) * _cis_deg(phi) * DEG
+            return ("tgen", _cplx_block(0 * B.real, 0 * B.real, B, U))
+        raise ValueError(param)
+
+    @staticmethod
+    def _tgen_dense(blk):
+        a, w = blk[..., 0], blk[..., 1]
+        B, U = blk[..., 2] + 1j * blk[..., 3], blk[..., 4] + 1j * blk[..., 5]
+        m = np.zeros(blk.shape[:-1] + (3, 3), dtype=complex)
+        m[..., 0, 0], m[..., 0, 1], m[..., 0, 2] = a, B, U
+        m[..., 1, 0], m[..., 1, 1], m[..., 1, 2] = B.conj(), a, U.conj()
+        m[..., 2, 0], m[..., 2, 1], m[..., 2, 2] = -0.5 * U.conj(), -0.5 * U, w
+        return m
+
+    def _dense(self):
+        return "mat", self._tgen_dense(self._form()[1]), None
+
+    def _ddense(self, param):
+        return "mat", self._tgen_dense(self._dform(param)[1]), None
+
+    @property
+    def mat(self):
+        return self._dense()[1]
+
+    mat0 = None
+
+
+class Tx(T):
+    def __init__(self, alpha, **kwargs):
+        T.__init__(self, alpha, 0, **kwargs)
+
+
+class Ty(T):
+    def __init__(self, alpha, **kwargs):
+        T.__init__(self, alpha, 90, **kwargs)
+
+
+class Phi(CombinableOperator):
+    """phase offset Rz(phi) (epgpy/transition.py:79-108, 140-151)"""
+
+    PARAMETERS_ORDER1 = {"phi"}
+
+    def __init__(self, phi, *, axes=None, name=None, duration=0, **kwargs):
+        if axes is not None:
+            raise NotImplementedError("the `axes` keyword is not supported")
+        self.phi = asparam(phi)
+        if not name:
+            name = common.repr_operator("Phi", ["phi"], [phi], [".1f"])
+        super().__init__(name=name, duration=duration, **kwargs)
+
+    @property
+    def shape(self):
+        return op_shape(self.phi)
+
+    def _arrs(self, deriv=False):
+        z = np.atleast_1d(_cis_deg(self.phi))
+        if deriv:
+            return np.stack([1j * z * DEG, -1j * z.conj() * DEG, 0 * z], axis=-1)
+        return np.stack([z, z.conj(), 1 + 0 * z], axis=-1)
+
+    def _form(self):
+        return ScalarOp._diag_form(self._arrs(), None)
+
+    def _dform(self, param):
+        return ScalarOp._diag_form(self._arrs(True), None)
+
+    def _dense(self):
+        return "diag", self._arrs(), None
+
+    def _ddense(self, param):
+        return "diag", self._arrs(True), None
+
+    @property
+    def mat(self):
+        return self._arrs()[..., None] * np.eye(3)
+
+
+# --------------------------------------------------------------------------------------------- #
+# E, P, R (epgpy/evolution.py)
+# --------------------------------------------------------------------------------------------- #
+
+
+class _Evolution(CombinableOperator):
+    def _dense(self):
+        return ("diag",) + tuple(self._arrs())
+
+    def _ddense(self, param):
+        return ("diag",) + tuple(self._darrs(param))
+
+    def _dform(self, param):
+        return ScalarOp._diag_form(*self._darrs(param))
+
+    @property
+    def arr(self):
+        return self._arrs()[0]
+
+    @property
+    def arr0(self):
+        return self._arrs()[1]
+
+
+def _evolution_arrays(rT, rL, r0=None):
+    """arr = [conj e^{-rT}, e^{-rT}, e^{-rL}], arr0 = [0, 0, 1 - e^{-r0}] (epgpy/evolution.py:220-242)"""
+    args = [np.asarray(rT), np.asarray(rL)] + ([] if r0 is None else [np.asarray(r0)])
+    args = np.broadcast_arrays(*expand_left(*args))
+    shape = args[0].shape
+    arr = np.zeros(shape + (3,), dtype=complex)
+    arr[..., 1] = np.exp(-args[0])
+    arr[..., 0] = arr[..., 1].conj()
+    arr[..., 2] = np.exp(-args[1])
+    arr0 = None
+    if r0 is not None:
+        arr0 = np.zeros(shape + (3,), dtype=complex)
+        arr0[..., 2] = 1 - np.exp(-args[2])
+    return arr, arr0
+
+
+class E(_Evolution):
+    """relaxation, precession and recovery (epgpy/evolution.py:69-153, 251-256)
+    tau, T1, T2 in ms, g in kHz"""
+
+    PARAMETERS_ORDER1 = {"tau", "T1", "T2", "g"}
+
+    def __init__(self, tau, T1, T2, g=0, *, axes=None, name=None, duration=None, **kwargs):
+        if axes is not None:
+            raise NotImplementedError("the `axes` keyword is not supported")
+        self.tau, self.T1, self.T2, self.g = asparam(tau), asparam(T1), asparam(T2), asparam(g)
+        if not name:
+            name = common.repr_operator("E", ["tau", "T1", "T2", "g"], [tau, T1, T2, g], [".1f", ".1f", ".1f", ".3f"])
+        self._duration = duration
+        duration = self.tau if duration is True else duration
+        super().__init__(name=name, duration=duration, **kwargs)
+        self._shape = op_shape(self.tau, self.T1, self.T2, self.g)
+
+    @property
+    def shape(self):
+        return self._shape
+
+    def _params(self):
+        return expand_left(*[np.asarray(x, dtype=float) for x in (self.tau, self.T1, self.T2, self.g)])
+
+    def _form(self):
+        tau, T1, T2, g = self._params()
+        e1 = np.exp(-tau / T1)
+        blk0 = _cplx_block(e1, 1 - e1)
+        blk1 = _cplx_block(np.exp(-tau / T2))
+        blk2 = None
+        if np.any(g != 0):
+            ph = 2 * np.pi * g * tau
+            blk2 = _cplx_block(np.cos(ph), np.sin(ph))
+        return ("e", blk0, blk1, blk2, True)
+
+    def _arrs(self):
+        tau, T1, T2, g = self._params()
+        return _evolution_arrays(tau * (1 / T2 + 2j * np.pi * g), tau / T1, tau / T1)
+
+    def _darrs(self, param):
+        """first derivatives (epgpy/evolution.py:360-399)"""
+        tau, T1, T2, g = self._params()
+        rT, rL = tau * (1 / T2 + 2j * np.pi * g), tau / T1
+        if param == "tau":
+            arr, arr0 = _evolution_arrays(rT, rL, rL)
+            arr[..., 1] *= -rT / tau
+            arr[..., 0] = arr[..., 1].conj()
+            arr[..., 2] *= -1 / T1
+            arr0[..., 2] = -arr[..., 2]
+            return arr, arr0
+        if param == "T1":
+            arr, arr0 = _evolution_arrays(0 * rT, rL, rL)
+            arr[..., :2] = 0
+            arr[..., 2] *= tau / T1**2
+            arr0[..., 2] = -arr[..., 2]
+            return arr, arr0
+        if param == "T2":
+            arr, _ = _evolution_arrays(rT, 0 * rL)
+            arr[..., :2] *= (tau / T2**2)[..., None]
+            arr[..., 2] = 0
+            return arr, None
+        if param == "g":
+            arr, _ = _evolution_arrays(rT, 0 * rL)
+            arr[..., 1] *= -2j * np.pi * tau
+            arr[..., 0] = arr[..., 1].conj()
+            arr[..., 2] = 0
+            return arr, None
+        raise ValueError(param)
+
+
+class P(_Evolution):
+    """precession only (epgpy/evolution.py:156-213, 245-248)"""
+
+    PARAMETERS_ORDER1 = {"tau", "g"}
+
+    def __init__(self, tau, g, *, axes=None, name=None, duration=None, **kwargs):
+        if axes is not None:
+            raise NotImplementedError("the `axes` keyword is not supported")
+        self.tau, self.g = asparam(tau), asparam(g)
+        if not name:
+            name = common.repr_operator("P", ["tau", "g"], [tau, g], [".1f", ".3f"])
+        self._duration = duration
+        duration = self.tau if duration is True else duration
+        super().__init__(name=name, duration=duration, **kwargs)
+
+    @property
+    def shape(self):
+        return op_shape(self.tau, self.g)
+
+    def _params(self):
+        return expand_left(np.asarray(self.tau, dtype=float), np.asarray(self.g, dtype=float))
+
+    def _form(self):
+        tau, g = self._params()
+        ph = 2 * np.pi * g * tau
+        one = np.ones((1,) * ph.ndim)
+        return ("e", _cplx_block(one, 0 * one), _cplx_block(one), _cplx_block(np.cos(ph), np.sin(ph)), False)
+
+    def _arrs(self):
+        tau, g = self._params()
+        return _evolution_arrays(2j * np.pi * g * tau, 0 * tau * g)
+
+    def _darrs(self, param):
+        """epgpy/evolution.py:313-328"""
+        tau, g = self._params()
+        arr, _ = _evolution_arrays(2j * np.pi * g * tau, 0 * tau * g)
+        arr[..., 1] *= -2j * np.pi * (g if param == "tau" else tau)
+        arr[..., 0] = arr[..., 1].conj()
+        arr[..., 2] = 0
+        return arr, None
+
+
+class R(_Evolution):
+    """raw-rate evolution: F+- *= e^{-rT} (conj for F+), Z *= e^{-rL}, recovery 1 - e^{-r0}
+    (epgpy/evolution.py:9-66, 220-242)"""
+
+    PARAMETERS_ORDER1 = {"rT", "rL", "r0"}
+
+    def __init__(self, rT=0, rL=0, *, r0=None, axes=None, name=None, duration=None, **kwargs):
+        if axes is not None:
+            raise NotImplementedError("the `axes` keyword is not supported")
+        self.rT, self.rL, self.r0 = asparam(rT), asparam(rL), asparam(r0)
+        if not name:
+            name = common.repr_operator("R", ["rT", "rL", "r0"], [rT, rL, r0], [".1f", ".1f", ".1f"])
+        super().__init__(name=name, duration=duration, **kwargs)
+
+    @property
+    def shape(self):
+        return op_shape(self.rT, self.rL, self.r0)
+
+    def _arrs(self):
+        return _evolution_arrays(self.rT, self.rL, self.r0)
+
+    def _form(self):
+        return ScalarOp._diag_form(*self._arrs())
+
+    def _darrs(self, param):
+        """epgpy/evolution.py:263-280"""
+        rT, rL = np.asarray(self.rT), np.asarray(self.rL)
+        if param == "rT":
+            arr, _ = _evolution_arrays(rT, 0 * rL)
+            arr[..., 2] = 0
+            return -arr, None
+        if param == "rL":
+            arr, _ = _evolution_arrays(0 * rT, rL)
+            arr[..., :2] = 0
+            return -arr, None
+        if param == "r0":
+            arr, arr0 = _evolution_arrays(0 * rT, 0 * rL, 0 if self.r0 is None else self.r0)
+            arr[:] = 0
+            arr0[..., 2] -= 1
+            return arr, -arr0
+        raise ValueError(param)
+
+
+# --------------------------------------------------------------------------------------------- #
+# S (epgpy/shift.py), D (epgpy/diffusion.py)
+# --------------------------------------------------------------------------------------------- #
+
+
+class S(DiffOperator):
+    """configuration shift (epgpy/shift.py:14-101).
+
+    The device path implements the reference's `shift-1d` method: an integer k.  An integer VECTOR k
+    (the reference's `shift-nd`) is accepted when every vector shift of the sequence is an integer
+    multiple of one base vector: the occupied configurations are then collinear and the problem is
+    exactly the 1-d one.  Float shifts (`shift-merge` / `shift-prune`) are outside the hot path."""
+
+    def __init__(self, k, *, nmax=None, kgrid=None, prune=1e-8, name=None, duration=None):
+        if np.allclose(k, 0):
+            raise TypeError("Cannot have k == 0")
+        if isinstance(k, (int, np.integer)) and not isinstance(k, bool):
+            k = int(k)
+        else:
+            k = np.atleast_2d(k)
+            if k.shape[-1] not in (1, 2, 3, 4):
+                raise ValueError("k.shape[-1] must belong to [1, 2, 3, 4]")
+        self.k, self.nmax, self.prune, self.kgrid = k, nmax, prune, kgrid
+        if not name:
+            name = common.repr_operator("S", ["k"], [k], ["" if isinstance(k, int) else ".2f"])
+        super().__init__(name=name, duration=duration)
+
+    @property
+    def nshift(self):
+        if isscalar(self.k):
+            return abs(self.k)
+        return int(np.round(np.max(np.abs(self.k))))
+
+    @property
+    def shape(self):
+        return (1,) if isscalar(self.k) else self.k.shape[:-1]
+
+    @property
+    def kdim(self):
+        return 1 if isscalar(self.k) else self.k.shape[-1]
+
+
+class D(Operator):
+    """diffusion attenuation (epgpy/diffusion.py:14-79): tau in ms, D in mm^2/s (scalar or kdim x kdim),
+    k (rad/m per unit shift) the shift of the S operator that immediately precedes it, if any"""
+
+    def __init__(self, tau, D, k=None, *, method=None, name=None, duration=None):
+        tau, D, k = asparam(tau), asparam(D), asparam(k)
+        tau_shape, k_shape, D_shape = get_shape(tau), get_shape(k), get_shape(D)
+        if len(k_shape) == 1:
+            k_shape = (1,) + k_shape
+        if len(D_shape) == 1:
+            raise ValueError("D can only be a scalar or a 2d matrix")
+        if len(set(D_shape[-2:])) == 2:
+            raise ValueError("D must be a square 2d matrix")
+        if len(D_shape) and len(k_shape) and D_shape[-1] != k_shape[-1]:
+            raise ValueError("Incompatible D and k dimensions")
+        self._shape = common.broadcast_shapes(tau_shape, D_shape[:-2], k_shape[:-1], (1,))
+        self._kdim = k_shape[-1] if k_shape else 1
+        if name is None:
+            name = common.repr_operator("D", ["tau", "D", "k"], [tau, D, k], [".1f", "", ""])
+        self._duration = duration
+        if duration is True:
+            duration = tau
+        self.tau, self.D, self.k = tau, D, k
+        super().__init__(name=name, duration=duration)
+
+    @property
+    def shape(self):
+        return self._shape
+
+    @property
+    def kdim(self):
+        return self._kdim
+
+
+# --------------------------------------------------------------------------------------------- #
+# probes (epgpy/probe.py, epgpy/diff.py:384-416)
+# --------------------------------------------------------------------------------------------- #
+
+
+class Probe(EmptyOperator):
+    """base probe (epgpy/probe.py:7-79).  Only state-matrix attribute expressions that the engine can
+    read on the device ('F0', 'Z0') are accepted; arbitrary callables / eval expressions would need the
+    whole state matrix on the host and are not supported (no CPU path)."""
+
+    def __init__(self, obj, *args, post=None, **kwargs):
+        if isinstance(obj, str) and obj.strip() in ("F0", "Z0"):
+            self.attr = obj.strip()
+        else:
+            raise NotImplementedError(
+                f"Probe({obj!r}): only the 'F0' / 'Z0' attributes can be probed on the device; "
+                "use Adc(attr, phase=, weights=, reduce=) or Jacobian"
+            )
+        self.phase = self.reduce = self.weights = None
+        self._post = post
+        super().__init__()
+
+    def __call__(self, sm, **kwargs):
+        return sm
+
+    def post(self, obj):
+        return obj if not getattr(self, "_post", None) else self._post(obj)
+
+
+class Adc(Probe):
+    """read-out with phase compensation / weights / reduction (epgpy/probe.py:82-165)"""
+
+    SM_LOCALS = ["nstate", "ndim", "kdim", "states", "coords", "F", "F0", "F0t", "Z", "Z0", "k", "t", "t0"]
+
+    def __init__(self, attr="F0", *, phase=None, reduce=None, weights=None, name="ADC"):
+        if attr not in self.SM_LOCALS:
+            raise ValueError(f"Invalid StateMatrix attribute: {attr}")
+        self.attr = attr
+        if phase is not None:
+            phase = np.asarray(phase)
+            self.phasor = np.exp(1j * phase / 180 * np.pi)
+        self.phase = phase
+        if reduce is not None and reduce is not True and reduce:
+            reduce = (reduce,) if isinstance(reduce, int) else tuple(reduce)
+            if not all(isinstance(ax, int) for ax in reduce):
+                raise ValueError(f"Expected (tuple of) int, got: {reduce}")
+        self.reduce = reduce
+        if weights is not None:
+            weights = np.asarray(weights)
+            ndim = max(weights.ndim, 1)
+            if reduce is None:
+                self.reduce = tuple(range(ndim))
+            elif reduce is not True and reduce:
+                if not set(reduce) <= set(range(ndim)):
+                    raise ValueError(f"Invalid reduce dimension(s): {reduce}")
+        self.weights = weights
+        Operator.__init__(self, name=name)
+
+    def _post(self, obj):
+        """phase compensation, applied on the host AFTER reduction like the reference (probe.py:155-165)"""
+        arr = np.asarray(obj)
+        if self.phase is not None:
+            phasor = self.phasor
+            if phasor.size > 1 and phasor.ndim < arr.ndim:
+                phasor = np.expand_dims(phasor, tuple(range(phasor.ndim, arr.ndim)))
+            arr = arr * phasor
+        return arr
+
+
+ADC = Adc()
+
+
+class Jacobian(Probe):
+    """probe returning the order-1 derivatives of the signal, stacked on a last axis
+    (epgpy/diff.py:384-416); 'magnitude' inserts the signal itself"""
+
+    def __init__(self, variables, *, probe="F0"):
+        if probe not in ("F0", "Z0"):
+            raise NotImplementedError("Jacobian probes 'F0' or 'Z0' only")
+        self.probe = probe
+        self.variables = variables if isinstance(variables, list) else [variables]
+        self.phase = self.reduce = self.weights = None
+        self.duration = 0
+        self.name = f"Jacobian({probe})"
+
+    def __repr__(self):
+        return self.name
+
+
+class Hessian(Probe):
+    def __init__(self, *args, **kwargs):
+        raise NotImplementedError("Hessian probe (epgpy/diff.py:419-476): second-order derivatives are not on the B200 hot path yet")
+
+
+from .exchange import X  # noqa: E402  (needs Operator)

@@ -1,0 +1,234 @@
+/*
+ * epgx.h -- C ABI of libepgx.so: the B200 (sm_100a) execution engine behind the epgpy
+ * operator API.
+ *
+ * What this replaces in the reference (py-baudin/epgpy, all Python, no FFI of its own):
+ *   - the array-module seam         epgpy/common.py:21-74   (numpy|cupy dispatch)
+ *   - the per-operator loop         epgpy/functions.py:173-192 (simulate_simple)
+ *   - the per-operator "kernels"    epgpy/opmatrix.py:199-221 (T, MatrixOp), opscalar.py:213-232
+ *                                   (E, P, R, ScalarOp), shift.py:271-294 (S, shift-1d),
+ *                                   diffusion.py:60-79 (D), exchange.py:89-120 (X),
+ *                                   probe.py:63-66,138-165 (ADC), diff.py:264-288 (order-1 partials),
+ *                                   operator.py:281-341 (SPOILER, RESET, PD)
+ *   - the state container storage   epgpy/statematrix.py:388-422, 793-804
+ *
+ * Model.  The Python host lowers a flattened operator sequence into
+ *   (1) a COEFFICIENT TABLE : reals, one block per operator parameter group, kept in the group's
+ *                             own (un-broadcast) shape -- e.g. E(tau, T1[100,1,1], T2[1,100,1])
+ *                             stores 100 (e1, 1-e1) pairs and 100 e2 values,
+ *   (2) PATTERNS            : per-grid-axis strides in reals (0 = broadcast) that map an atom to its
+ *                             entry of a block -- the left-aligned broadcasting of
+ *                             epgpy/common.py:273-334 becomes integer strides,
+ *   (3) an OP TAPE          : one 32-byte record per operator application, referring to up to three
+ *                             coefficient blocks through (offset, pattern) pairs,
+ *   (4) SEGMENTS            : maximal runs of records that act on each configuration order
+ *                             independently (everything except S / RESET); a segment is ONE pass
+ *                             over the on-chip state, followed by at most one unit shift.
+ * One launch of the fused kernel runs the WHOLE tape for a slab of atoms.  The F+/F-/Z state of an
+ * atom (half storage, orders k >= 0) stays on chip for the whole sequence; only ADC samples go to
+ * HBM.  Order-1 partial states (diff.py) are further state sets of the same atom and are propagated
+ * in the same pass.
+ *
+ * Conventions: every entry point returns 0 on success, a negative epgx_status otherwise, and
+ * never throws.  epgx_last_error() returns a thread-local message.  The CALLER owns every
+ * buffer; device pointers typically come from torch tensors (tensor.data_ptr()).  Launches are
+ * asynchronous on the given CUDA stream (cudaStream_t passed as void*; NULL = default stream);
+ * the library never synchronises the device except in epgx_simulate_host and epgx_fma_peak.
+ * A plan is immutable after creation (except epgx_plan_set_variant) and may be used from several
+ * host threads / devices concurrently.
+ */
+#ifndef EPGX_H
+#define EPGX_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EPGX_VERSION 102 /* 0.1.2 */
+#define EPGX_MAX_DIMS 8
+#define EPGX_MAX_PATTERNS 64
+#define EPGX_MAX_POOLS 2
+
+typedef enum {
+  EPGX_OK = 0,
+  EPGX_ERR_INVALID = -1,     /* malformed tape / arguments */
+  EPGX_ERR_CAPACITY = -2,    /* the state of one atom does not fit the on-chip memory of an SM */
+  EPGX_ERR_CUDA = -3,        /* CUDA runtime error (message in epgx_last_error) */
+  EPGX_ERR_UNSUPPORTED = -4, /* valid request the engine does not implement */
+  EPGX_ERR_NO_DEVICE = -5
+} epgx_status;
+
+typedef enum { EPGX_F64 = 0, EPGX_F32 = 1 } epgx_dtype;
+
+/* ---- tape record codes.  "blk i: (...)" lists the reals of one entry of coefficient block i. */
+typedef enum {
+  EPGX_OP_NOP = 0,
+  /* RF pulse and its derivatives in rotated-Rx form (transition.py:114-196).  With a, w real and
+   * B, U complex:
+   *   F+' = a F+ + B F- + U Z ; F-' = conj(B) F+ + a F- + conj(U) Z ; Z' = -1/2 (conj(U) F+ + U F-) + w Z
+   * T = Rz(phi)Rx(alpha)Rz(-phi) has a = cos^2(alpha/2), B = sin^2(alpha/2) e^{2i phi},
+   * U = -i sin(alpha) e^{i phi}, w = cos(alpha); dT/dalpha and dT/dphi have the same shape.
+   *   T_GEN blk0: (a, w, B.re, B.im, U.re, U.im)
+   *   T_RE  blk0: (a, w, b, u)  B = b, U = u   (phi = +-90 deg)
+   *   T_IM  blk0: (a, w, b, u)  B = b, U = -i u (phi = 0 / 180 deg) */
+  EPGX_OP_T_GEN = 1,
+  EPGX_OP_T_RE = 2,
+  EPGX_OP_T_IM = 3,
+  /* relaxation (evolution.py:220-256): F+ *= e2 (c + i s), F- *= e2 (c - i s), Z *= e1,
+   * Z(0) += r0 * M0 (EPGX_FLAG_AFFINE).
+   *   blk0: (e1, r0)   blk1: (e2)   blk2: (c, s) = cis(2 pi g tau), only with EPGX_FLAG_G */
+  EPGX_OP_E = 4,
+  /* generic diagonal operator (opscalar.py:213-232):
+   *   blk0: (aP.re, aP.im, aM.re, aM.im, aZ.re, aZ.im, a0Z.re, a0Z.im); Z(0) += a0Z * M0 (AFFINE) */
+  EPGX_OP_DIAG = 5,
+  /* generic 3x3 operator (opmatrix.py:199-221): blk0: 9 complex row-major (18 reals),
+   *   blk1: mat0[:,2] (3 complex), only with EPGX_FLAG_AFFINE: state(0) += mat0[:,2] * M0 */
+  EPGX_OP_MATRIX = 6,
+  /* diffusion (diffusion.py:60-79): blk0: per-order rows (dT+[k], dT-[k], dL[k]), one entry =
+   *   3*(max_order+1) reals: F+(k) *= dT+[k], F-(k) *= dT-[k], Z(k) *= dL[k] */
+  EPGX_OP_D = 7,
+  /* exchange (exchange.py:89-120): blk0: N*N complex mT[dst][src] then N*N complex mL[dst][src];
+   *   s_c <- m_c (s_c - eq_c) + eq_c over the pool axis, m = (mT, conj mT, mL) */
+  EPGX_OP_X = 8,
+  EPGX_OP_SPOIL = 9, /* F+ = F- = 0 (operator.py:281-286) */
+  EPGX_OP_PD = 10,   /* blk0: (M0): set the equilibrium density (operator.py:315-341) */
+  /* read-out (probe.py:138-165): value = F+(0) or Z(0), times blk0: (re, im) if EPGX_FLAG_SCALE
+   *   (ADC phasor x weights).  aux = row of `signal` (EPGX_FLAG_BASE), aux1 = row of `jacobian`
+   *   (EPGX_FLAG_PARTIALS). */
+  EPGX_OP_ADC = 11,
+  EPGX_OP_COUNT = 12
+} epgx_opcode;
+
+enum {
+  EPGX_FLAG_BASE = 1 << 0,     /* apply to the base state                                      */
+  EPGX_FLAG_PARTIALS = 1 << 1, /* apply (without affine term) to the order-1 partial states    */
+  /* derivative injection (diff.py:279-286): partial[aux] += form(base), affine term included,
+   * where `form` is the record's code and `base` the current (pre-operator) base state */
+  EPGX_FLAG_INJECT = 1 << 2,
+  EPGX_FLAG_G = 1 << 3,      /* E: precession phasor present                  */
+  EPGX_FLAG_AFFINE = 1 << 4, /* E/DIAG/MATRIX: equilibrium term present       */
+  EPGX_FLAG_Z0 = 1 << 5,     /* ADC: read Z(0) instead of F+(0)               */
+  EPGX_FLAG_SCALE = 1 << 6   /* ADC: multiply by the complex factor in blk0   */
+};
+
+/* tape record, 32 bytes */
+typedef struct {
+  uint16_t code;
+  uint16_t flags;
+  int32_t aux;
+  uint32_t off[3]; /* offset (reals) of coefficient block i in the coefficient table */
+  uint8_t pat[3];  /* pattern of block i: entry offset = sum_axis idx[axis]*stride + pool*pool_stride */
+  uint8_t rsv;
+  int32_t aux1;
+  int32_t rsv1;
+} epgx_op;
+
+enum {
+  EPGX_SEG_RESET = 1 << 0 /* after the pass: state <- equilibrium, order <- 0 (operator.py:297-304) */
+};
+
+/* segment, 32 bytes: one pass over orders 0..nact applying records [first, first+count), then
+ * one unit shift (shift = -1, 0, +1; shift.py:86-101; S(k) lowers to |k| unit shifts), the highest
+ * order going from n_old to n_new = min(n_old + |shift|, cap) */
+typedef struct {
+  int32_t first;
+  int32_t count;
+  int32_t nact;  /* orders 0..nact are updated (-1: none; <= n_old, fewer when the top orders are unobservable) */
+  int32_t shift;
+  int32_t n_old;
+  int32_t n_new;
+  int32_t flags;
+  int32_t rsv;
+} epgx_segment;
+
+/* the lowered sequence (host memory, copied by epgx_plan_create) */
+typedef struct {
+  int32_t dtype;                /* epgx_dtype */
+  int32_t ndim;                 /* grid dimensions WITHOUT the pool axis, outermost first */
+  int64_t shape[EPGX_MAX_DIMS]; /* atoms = prod(shape); an atom = all pools of one grid point */
+  int32_t npool;                /* exchange compartments coupled by X (1 = none) */
+  int32_t npattern;
+  int32_t stride[EPGX_MAX_PATTERNS][EPGX_MAX_DIMS]; /* pattern strides, in reals */
+  int32_t pool_stride[EPGX_MAX_PATTERNS];
+  int64_t nop;
+  const epgx_op *ops;
+  int64_t nseg;
+  const epgx_segment *segs;
+  int64_t ncoef;
+  const double *coef; /* coefficient table (converted to float for EPGX_F32) */
+  /* initial state: block of (init_n+1) x (F+.re, F+.im, F-.re, F-.im, Z.re, Z.im) and block of (M0) */
+  uint32_t init_off;
+  uint32_t m0_off;
+  uint8_t init_pat;
+  uint8_t m0_pat;
+  uint8_t rsv0[2];
+  int32_t init_n;    /* highest order of the initial state */
+  int32_t nadc;      /* rows of `signal`   */
+  int32_t njac;      /* rows of `jacobian` */
+  int32_t nvar;      /* order-1 variables (0 = forward only) */
+  int32_t max_order; /* highest configuration order of the whole tape */
+  int32_t rsv[3];
+} epgx_tape;
+
+typedef struct epgx_plan epgx_plan;
+
+/* kernel configuration chosen for a plan (reported for DESIGN/bench/roofline accounting) */
+typedef struct {
+  int32_t kernel;         /* 0 = ring (state in shared memory), 1 = reg (state in registers) */
+  int32_t lanes_per_atom; /* G */
+  int32_t slots_per_lane; /* reg kernel: orders held per lane */
+  int32_t vars_per_pass;  /* partial states resident per atom */
+  int32_t var_tiles;      /* ceil(nvar / vars_per_pass): grid.y */
+  int32_t atoms_per_cta;
+  int32_t threads_per_cta;
+  int32_t smem_bytes;     /* dynamic shared memory per CTA */
+  int32_t ring;           /* ring-buffer length C = max_order + 1 */
+  int32_t rsv[3];
+  double flops_per_atom;   /* real flops one atom executes through the tape (half storage, base + partials) */
+  double updates_per_atom; /* state-updates: sum over T/E/D/X/S records of orders touched */
+} epgx_config;
+
+int epgx_version(void);
+int epgx_device_count(void);
+const char *epgx_last_error(void);
+
+/* validate + copy the tape, choose the kernel variant.  Host-only; no CUDA call. */
+int epgx_plan_create(const epgx_tape *tape, epgx_plan **plan);
+int epgx_plan_destroy(epgx_plan *plan);
+int epgx_plan_config(const epgx_plan *plan, epgx_config *cfg);
+/* force a kernel variant (tuning / tests): a 0 / negative argument keeps the automatic choice */
+int epgx_plan_set_variant(epgx_plan *plan, int kernel, int lanes_per_atom, int vars_per_pass,
+                          int atoms_per_cta);
+
+/* bytes of device workspace needed by epgx_plan_upload (tape + segments + coefficient table) */
+int epgx_plan_workspace_bytes(const epgx_plan *plan, int64_t *bytes);
+/* H2D copy of the tape, segments, patterns and coefficient table into `workspace` on `stream`.
+ * `workspace` (256-byte aligned) must stay alive while the plan is simulated from it. */
+int epgx_plan_upload(const epgx_plan *plan, void *workspace, void *stream);
+
+/* Run the whole tape for atoms [atom_begin, atom_begin+atom_count) of the enumeration.
+ *   signal    device, complex<real>[nadc][atom_count][npool]
+ *   jacobian  device, complex<real>[njac][nvar][atom_count][npool], or NULL when nvar == 0 */
+int epgx_simulate(const epgx_plan *plan, const void *workspace, int64_t atom_begin, int64_t atom_count,
+                  void *signal, void *jacobian, void *stream);
+
+/* Convenience end-to-end call on HOST buffers (allocates, copies H2D, runs, copies D2H, frees,
+ * synchronises): same layouts as epgx_simulate but host pointers. */
+int epgx_simulate_host(const epgx_plan *plan, int device, int64_t atom_begin, int64_t atom_count,
+                       void *signal, void *jacobian);
+
+/* sum over one axis of a complex array (Adc(reduce=), probe.py:148-153):
+ *   out[o][i] = sum_r in[o][r][i],  in: complex<real>[nouter][nred][ninner] (device) */
+int epgx_reduce(int dtype, const void *in, void *out, int64_t nouter, int64_t nred, int64_t ninner,
+                void *stream);
+
+/* dependent-FMA micro-benchmark: sustained FMA throughput of the CUDA cores in TFLOP/s
+ * (2 flops per FMA) for the roofline denominator; synchronises. */
+int epgx_fma_peak(int device, int dtype, double seconds, double *tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EPGX_H */

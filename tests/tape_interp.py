@@ -1,0 +1,191 @@
+"""Numpy interpreter of the op-tape (include/epgx.h) -- TEST INFRASTRUCTURE ONLY.
+
+Executes a `lowering.Lowered` with the semantics the CUDA kernels implement, vectorised over atoms,
+so that the host lowering (patterns, records, segments, order schedule, pruning) can be checked on a
+machine without a GPU against the oracle and the golden vectors.  It is never imported by the
+product package.
+"""
+
+import numpy as np
+
+from epgpy_b200 import lowering as L
+
+
+def run(low):
+    """-> signal [nadc, natoms, npool], jac [njac, nvar, natoms, npool] (complex128)"""
+    coef = low.coef
+    ashape, npool = low.atom_shape, low.npool
+    natoms = low.natoms
+    idx = np.stack(np.unravel_index(np.arange(natoms), ashape), axis=-1)  # [natoms, ndim]
+    poff = []
+    for strides, ps in low.patterns:
+        base = (idx[:, : len(strides)] * np.asarray(strides)[None, :]).sum(-1)
+        poff.append(base[:, None] + ps * np.arange(npool)[None, :])  # [natoms, npool]
+
+    def blk(off, pat, n, extra=0):
+        """[natoms, npool, n] reals of a block"""
+        o = off + poff[pat][..., None] + extra + np.arange(n)
+        return coef[o]
+
+    C = low.max_order + 1
+    nset = 1 + low.nvar
+    P = np.zeros((natoms, npool, nset, C), dtype=complex)
+    M = np.zeros_like(P)
+    Z = np.zeros_like(P)
+    ib = blk(low.init_ref[0], low.init_ref[1], 6 * (low.init_n + 1)).reshape(natoms, npool, low.init_n + 1, 6)
+    P[:, :, 0, : low.init_n + 1] = ib[..., 0] + 1j * ib[..., 1]
+    M[:, :, 0, : low.init_n + 1] = ib[..., 2] + 1j * ib[..., 3]
+    Z[:, :, 0, : low.init_n + 1] = ib[..., 4] + 1j * ib[..., 5]
+    m0 = blk(low.m0_ref[0], low.m0_ref[1], 1)[..., 0]  # [natoms, npool]
+    sig = np.zeros((low.nadc, natoms, npool), dtype=complex)
+    jac = np.zeros((low.njac, low.nvar, natoms, npool), dtype=complex)
+
+    def cplx(b, i):
+        return b[..., i] + 1j * b[..., i + 1]
+
+    for seg in low.segs:
+        na = int(seg["nact"]) + 1
+        for r in range(seg["first"], seg["first"] + seg["count"]):
+            rec = low.ops[r]
+            code, flags, aux, aux1 = int(rec["code"]), int(rec["flags"]), int(rec["aux"]), int(rec["aux1"])
+            off, pat = rec["off"], rec["pat"]
+            sets = []
+            if flags & L.F_INJECT:
+                sets = ["inject"]
+            else:
+                if flags & L.F_BASE:
+                    sets.append(0)
+                if flags & L.F_PARTIALS:
+                    sets += list(range(1, nset))
+            if na <= 0 and code != L.OP_PD:
+                continue
+            p, m, z = P[..., :na], M[..., :na], Z[..., :na]  # views [natoms, npool, nset, na]
+
+            def linear(fn, affine):
+                """fn(p, m, z) -> (p', m', z') on [natoms, npool, na]; affine: (ap, am, az) at k = 0"""
+                for s in sets:
+                    src = 0 if s == "inject" else s
+                    o = fn(p[:, :, src], m[:, :, src], z[:, :, src])
+                    o = [np.array(x) for x in o]
+                    if affine is not None and (s == "inject" or s == 0) and (flags & L.F_AFFINE):
+                        for x, a in zip(o, affine):
+                            x[..., 0] += a
+                    if s == "inject":
+                        p[:, :, aux + 1] += o[0]; m[:, :, aux + 1] += o[1]; z[:, :, aux + 1] += o[2]
+                    else:
+                        p[:, :, s], m[:, :, s], z[:, :, s] = o
+
+            if code in (L.OP_T_GEN, L.OP_T_RE, L.OP_T_IM):
+                if code == L.OP_T_GEN:
+                    b = blk(off[0], pat[0], 6)
+                    a, w, B, U = b[..., 0], b[..., 1], cplx(b, 2), cplx(b, 4)
+                else:
+                    b = blk(off[0], pat[0], 4)
+                    a, w, B = b[..., 0], b[..., 1], b[..., 2] + 0j
+                    U = b[..., 3] + 0j if code == L.OP_T_RE else -1j * b[..., 3]
+                a, w, B, U = (x[..., None] for x in (a, w, B, U))
+                linear(lambda p_, m_, z_: (a * p_ + B * m_ + U * z_, B.conj() * p_ + a * m_ + U.conj() * z_,
+                                           -0.5 * (U.conj() * p_ + U * m_) + w * z_), None)
+            elif code == L.OP_E:
+                b0 = blk(off[0], pat[0], 2)
+                e1, r0 = b0[..., 0, None], b0[..., 1]
+                e2 = blk(off[1], pat[1], 1)[..., 0, None]
+                f = e2 + 0j
+                if flags & L.F_G:
+                    b2 = blk(off[2], pat[2], 2)
+                    f = e2 * cplx(b2, 0)[..., None]
+                linear(lambda p_, m_, z_: (f * p_, f.conj() * m_, e1 * z_), (0, 0, r0 * m0))
+            elif code == L.OP_DIAG:
+                b = blk(off[0], pat[0], 8)
+                aP, aM, aZ, a0 = (cplx(b, i) for i in (0, 2, 4, 6))
+                linear(lambda p_, m_, z_: (aP[..., None] * p_, aM[..., None] * m_, aZ[..., None] * z_), (0, 0, a0 * m0))
+            elif code == L.OP_MATRIX:
+                b = blk(off[0], pat[0], 18)
+                mm = (b[..., 0::2] + 1j * b[..., 1::2]).reshape(b.shape[:-1] + (3, 3))[..., None]
+                aff = None
+                if flags & L.F_AFFINE:
+                    b1 = blk(off[1], pat[1], 6)
+                    aff = tuple(cplx(b1, i) * m0 for i in (0, 2, 4))
+                linear(lambda p_, m_, z_: tuple(mm[..., i, 0, :] * p_ + mm[..., i, 1, :] * m_ + mm[..., i, 2, :] * z_
+                                                for i in range(3)), aff)
+            elif code == L.OP_D:
+                b = blk(off[0], pat[0], 3 * C).reshape(natoms, npool, C, 3)[:, :, :na]
+                for s in sets:
+                    p[:, :, s] *= b[..., 0]; m[:, :, s] *= b[..., 1]; z[:, :, s] *= b[..., 2]
+            elif code == L.OP_X:
+                n2 = npool * npool * 2
+                b = coef[off[0] + poff[pat[0]][:, 0, None] + np.arange(2 * n2)]  # [natoms, 2*n2]
+                mt = (b[:, 0:n2:2] + 1j * b[:, 1:n2:2]).reshape(natoms, npool, npool)
+                ml = (b[:, n2::2] + 1j * b[:, n2 + 1::2]).reshape(natoms, npool, npool)
+                for s in sets:
+                    eq = np.zeros((natoms, npool, na), dtype=complex)
+                    if s == 0:
+                        eq[..., 0] = m0
+                    p[:, :, s] = np.einsum("aij,ajk->aik", mt, p[:, :, s])
+                    m[:, :, s] = np.einsum("aij,ajk->aik", mt.conj(), m[:, :, s])
+                    z[:, :, s] = np.einsum("aij,ajk->aik", ml, z[:, :, s] - eq) + eq
+            elif code == L.OP_SPOIL:
+                for s in sets:
+                    p[:, :, s] = 0; m[:, :, s] = 0
+            elif code == L.OP_PD:
+                m0 = blk(off[0], pat[0], 1)[..., 0]
+            elif code == L.OP_ADC:
+                f = 1.0
+                if flags & L.F_SCALE:
+                    f = cplx(blk(off[0], pat[0], 2), 0)
+                src = Z if flags & L.F_Z0 else P
+                if flags & L.F_BASE:
+                    sig[aux] = src[:, :, 0, 0] * f
+                if flags & L.F_PARTIALS:
+                    for v in range(low.nvar):
+                        jac[aux1, v] = src[:, :, 1 + v, 0] * f
+        n_old, n_new, sh = int(seg["n_old"]), int(seg["n_new"]), int(seg["shift"])
+        if seg["flags"] & L.SEG_RESET:
+            P[:] = 0; M[:] = 0; Z[:] = 0
+            Z[:, :, 0, 0] = m0
+        elif sh:
+            up, dn = (P, M) if sh > 0 else (M, P)
+            new0 = dn[..., 1].conj() if (n_old >= 1 and C > 1) else 0 * dn[..., 0]
+            up[..., 1:] = up[..., :-1].copy()
+            up[..., 0] = new0
+            dn[..., :-1] = dn[..., 1:].copy()
+            dn[..., -1] = 0
+            dn[..., n_old:] = 0
+            up[..., n_new + 1:] = 0
+    return sig, jac
+
+
+def simulate(epg_mod, sequence, **kw):
+    """like functions.simulate, but executed by this interpreter (host only)"""
+    from epgpy_b200 import functions
+
+    init = kw.pop("init", None)
+    probe = kw.pop("probe", None)
+    propagate = kw.pop("propagate_nondiff", False)
+    prune = kw.pop("prune_unobservable", True)
+    low = L.lower(sequence, init=init, probe=probe, options=kw, propagate_nondiff=propagate, prune_unobservable=prune)
+    sig, jac = run(low)
+
+    class _T:  # minimal stand-in for a device tensor
+        def __init__(self, a):
+            self.a = a
+
+        def cpu(self):
+            return self
+
+        def numpy(self):
+            return self.a
+
+        def __getitem__(self, i):
+            return _T(self.a[i])
+
+        def reshape(self, shape):
+            return _T(self.a.reshape(shape))
+
+    saved = functions.engine.device_reduce
+    functions.engine.device_reduce = lambda t, axis: _T(t.a.sum(axis=axis))
+    try:
+        values = functions._assemble(low, [(0, 0, low.natoms, _T(sig), _T(jac))])
+    finally:
+        functions.engine.device_reduce = saved
+    return values[0] if len(values) == 1 else values

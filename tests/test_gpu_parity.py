@@ -1,0 +1,144 @@
+"""Parity of the CUDA path (through the C ABI) with the reference's golden vectors and the oracle.
+Runs on the B200 box: pytest -m gpu"""
+
+import numpy as np
+import pytest
+
+import cases
+import oracle_api
+from util import RTOL32, RTOL64, product_namespace, rel_err, run_case
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def epg():
+    return product_namespace()
+
+
+@pytest.mark.parametrize("name", sorted(cases.CASES))
+def test_fp64_matches_reference(name, golden, epg):
+    ref = golden(name)
+    case = cases.CASES[name](epg)
+    sig, jac = run_case(epg.simulate, epg, case)
+    assert sig.dtype == np.complex128
+    assert rel_err(sig, ref["signal"]) < RTOL64
+    if "jacobian" in ref.files:
+        assert rel_err(jac, ref["jacobian"]) < RTOL64
+
+
+@pytest.mark.parametrize("name", sorted(cases.CASES))
+def test_fp32_matches_reference(name, golden, epg):
+    ref = golden(name)
+    case = cases.CASES[name](epg)
+    sig, jac = run_case(epg.simulate, epg, case, dtype="float32")
+    assert sig.dtype == np.complex64
+    assert rel_err(sig, ref["signal"]) < RTOL32
+    if "jacobian" in ref.files:
+        # derivative columns of very different magnitude share one array: compare column-wise
+        for i in range(jac.shape[-1]):
+            if np.abs(ref["jacobian"][..., i]).max() > 0:
+                assert rel_err(jac[..., i], ref["jacobian"][..., i]) < 5 * RTOL32
+
+
+def _run_variant(epg, case, dtype="f64", **variant):
+    from epgpy_b200 import engine, functions, lowering
+
+    opts = dict(case.get("options") or {})
+    init = epg.StateMatrix(density=case["density"]) if case.get("density") is not None else None
+    probe = [None, epg.Jacobian(case["jac"])] if case.get("jac") else None
+    low = lowering.lower(case["seq"], init=init, probe=probe, options=opts, dtype=dtype)
+    plan = engine.Plan(low)
+    plan.set_variant(**variant)
+    cfg = plan.config()
+    parts, _ = functions.run_lowered(low, plan=plan)
+    vals = functions._assemble(low, parts)
+    return vals, cfg
+
+
+@pytest.mark.parametrize("lanes,atoms", [(1, 1), (1, 32), (2, 3), (8, 16), (32, 2), (64, 1), (128, 2), (256, 1)])
+@pytest.mark.parametrize("name", ["fisp_unbounded", "fisp_bounded", "misc_ops", "spgr_exchange", "fisp_jac_global"])
+def test_kernel_variants(name, lanes, atoms, golden, epg):
+    """every lanes-per-atom / atoms-per-CTA mapping gives the same answer (ragged tails included)"""
+    ref = golden(name)
+    vals, cfg = _run_variant(epg, cases.CASES[name](epg), lanes_per_atom=lanes, atoms_per_cta=atoms)
+    assert cfg["lanes_per_atom"] == lanes
+    assert rel_err(vals[0], ref["signal"]) < RTOL64
+    if "jacobian" in ref.files:
+        assert rel_err(vals[1], ref["jacobian"]) < RTOL64
+
+
+@pytest.mark.parametrize("vars_per_pass", [1, 3])
+@pytest.mark.parametrize("name", ["fisp_jac_pulses", "jac_all_params", "mse_jac"])
+def test_variable_tiling(name, vars_per_pass, golden, epg):
+    ref = golden(name)
+    vals, cfg = _run_variant(epg, cases.CASES[name](epg), vars_per_pass=vars_per_pass)
+    assert cfg["vars_per_pass"] == vars_per_pass
+    assert rel_err(vals[0], ref["signal"]) < RTOL64 and rel_err(vals[1], ref["jacobian"]) < RTOL64
+
+
+def test_c_abi_host_call(golden, epg):
+    """epgx_simulate_host: plain pointers in, plain pointers out; atom sub-ranges"""
+    from epgpy_b200 import engine, lowering
+
+    ref = golden("fisp_bounded")["signal"]
+    low = lowering.lower(cases.fisp_bounded(epg)["seq"], options={"max_nstate": 10})
+    plan = engine.Plan(low)
+    out = np.zeros((low.nadc, low.natoms, 1), dtype=np.complex128)
+    plan.run_host(0, 0, low.natoms, out)
+    assert rel_err(out.reshape(ref.shape), ref) < RTOL64
+    # a ragged sub-range of atoms
+    part = np.zeros((low.nadc, 7, 1), dtype=np.complex128)
+    plan.run_host(0, 5, 7, part)
+    assert np.array_equal(part, out[:, 5:12])
+
+
+def test_partials_through_nondiff_ops_gpu(epg):
+    """D / X / SPOILER applied to the partial states (propagate_nondiff=True) vs the oracle"""
+    def seq(e):
+        T2 = np.array([40.0, 80.0])
+        out = [e.T(90, 90)]
+        for i in range(6):
+            out += [e.S(1), e.D(3.0, 1.5e-3, k=1), e.E(3, 900.0, T2), e.T(35, 10.0 * i, order1={"a": "alpha"}),
+                    e.SPOILER if i == 3 else e.NULL if hasattr(e, "NULL") else e.Wait(0), e.ADC]
+        return out
+
+    sig, jac = epg.simulate(seq(epg), probe=[None, epg.Jacobian(["a"])], kvalue=3000.0, propagate_nondiff=True)
+    rs, rj = oracle_api.O.simulate(seq(oracle_api.epg), jacobian=["a"], kvalue=3000.0, propagate_nondiff=True)
+    assert rel_err(sig, rs) < RTOL64 and rel_err(jac, rj) < RTOL64
+
+
+def test_larger_grid_vs_oracle(epg):
+    """FISP at a size the oracle still finishes in seconds: 12 x 10 x 8 atoms, 120 TRs, unbounded"""
+    case = cases.fisp(epg, 120, sizes=(12, 10, 8))
+    sig = np.asarray(epg.simulate(case["seq"]))
+    ref, _ = oracle_api.run(cases.fisp(oracle_api.epg, 120, sizes=(12, 10, 8)))
+    assert rel_err(sig, ref) < RTOL64
+    sig32 = np.asarray(epg.simulate(case["seq"], dtype="float32"))
+    assert rel_err(sig32, ref) < RTOL32
+
+
+def test_linearity_and_density_scaling(epg):
+    """size-independent properties at a large grid (50k atoms): the signal is linear in the proton
+    density, and PD(2) == 2 x PD(1); pruning of unobservable orders does not change any sample"""
+    from epgpy_b200 import engine, functions, lowering
+
+    T1 = np.linspace(300, 3000, 50)
+    T2 = np.linspace(20, 300, 40)[None, :]
+    B1 = np.linspace(0.7, 1.2, 25)[None, None, :]
+    fa, tr = cases._fisp_schedule(100)
+
+    def seq(pd):
+        s = [epg.PD(pd), epg.T(180, 0), epg.E(20, T1, T2)]
+        for i in range(100):
+            s += [epg.T(fa[i] * B1, 90), epg.E(3, T1, T2), epg.ADC, epg.E(tr[i] - 3, T1, T2), epg.S(1)]
+        return s
+
+    a = epg.simulate(seq(1.0), max_nstate=16)
+    b = epg.simulate(seq(2.5), max_nstate=16)
+    assert a.shape == (100, 50, 40, 25)
+    assert rel_err(b, 2.5 * a) < 1e-13
+    low = lowering.lower(seq(1.0), options={"max_nstate": 16}, prune_unobservable=False)
+    parts, _ = functions.run_lowered(low)
+    c = functions._assemble(low, parts)[0]
+    assert rel_err(c, a) < 1e-14

@@ -1,0 +1,128 @@
+"""Host logic without a GPU: the lowering (patterns, records, segments, order schedule, pruning) is
+executed by the numpy tape interpreter (tests/tape_interp.py) and compared with the golden vectors
+of the unmodified reference and with the oracle."""
+
+import numpy as np
+import pytest
+
+import cases
+import oracle_api
+import tape_interp
+from util import RTOL64, product_namespace, rel_err, run_case
+
+
+def interp_simulate(seq, **kw):
+    return tape_interp.simulate(None, seq, **kw)
+
+
+@pytest.mark.parametrize("name", sorted(cases.CASES))
+@pytest.mark.parametrize("prune", [True, False])
+def test_tape_matches_reference(name, prune, golden):
+    ref = golden(name)
+    epg = product_namespace()
+    case = cases.CASES[name](epg)
+    sig, jac = run_case(interp_simulate, epg, case, prune_unobservable=prune)
+    assert rel_err(sig, ref["signal"]) < RTOL64
+    if "jacobian" in ref.files:
+        assert rel_err(jac, ref["jacobian"]) < RTOL64
+
+
+def test_api_surface_and_shapes(golden):
+    epg = product_namespace()
+    for name, fn in cases.CASES.items():
+        case = fn(epg)
+        ref = golden(name)
+        assert tuple(ref["shape"]) == tuple(epg.getshape(case["seq"])), name
+        if "times" in ref.files:
+            assert np.allclose(np.asarray(epg.get_adc_times(case["seq"]), dtype=float), ref["times"]), name
+
+
+def test_errors_like_reference():
+    """error conventions of SURVEY 8b"""
+    epg = product_namespace()
+    with pytest.raises(ValueError):  # no probe (functions.py:108-111)
+        interp_simulate([epg.T(90, 90), epg.S(1)])
+    with pytest.raises(ValueError):  # non-operator (functions.py:367-368)
+        interp_simulate([epg.T(90, 90), "x", epg.ADC])
+    with pytest.raises(ValueError):  # incompatible shapes (common.py:301)
+        interp_simulate([epg.T([1, 2, 3], 90), epg.E(1, [1, 2], 3), epg.ADC])
+    with pytest.raises(TypeError):  # S(0) (shift.py:35-36)
+        epg.S(0)
+    with pytest.raises(ValueError):  # negative duration (operator.py:34-35)
+        epg.T(1, 2, duration=-1)
+    with pytest.raises(ValueError):  # unknown derivative parameter (diff.py:197-199)
+        epg.T(1, 2, order1="T2")
+    with pytest.raises(NotImplementedError):  # float shifts need shift-merge: outside the hot path
+        interp_simulate([epg.T(90, 90), epg.S([0.5, 0.1]), epg.ADC])
+    with pytest.raises(RuntimeError):  # X non-conserving khi (exchange.py:97-100)
+        kmat = epg.exchange_matrix(1e-2, densities=[0.5, 0.5])
+        interp_simulate([epg.T(30, 0), epg.X(5, kmat, T1=[1e3, 1e3], T2=[50, 10]), epg.Adc(reduce=0)],
+                        init=epg.StateMatrix(density=[0.8, 0.2]))
+
+
+def test_multioperator_and_nested_lists(golden):
+    """list vs `*`-chained MultiOperator (reference test/test_functions.py:6-37)"""
+    epg = product_namespace()
+    exc, rfc, rlx, sh = epg.T(90, 90), epg.T(150, 0), epg.E(5, 1000, [30, 50]), epg.S(1)
+    a = interp_simulate([exc] + [[sh, rlx, rfc, sh, rlx, epg.ADC]] * 4)
+    b = interp_simulate([exc] + [sh * rlx * rfc * sh * rlx * epg.ADC] * 4)
+    assert np.array_equal(a, b) and a.shape == (4, 2)
+
+
+def test_combined_operator_matches_sequential():
+    """`@` fusion vs sequential application, partials included (reference test/test_diff.py:471-512)"""
+    epg = product_namespace()
+    rlx = epg.E(1.0, 100.0, [10.0, 20.0], order1=["T2", "g"])
+    angles = [3.0, 7.0, 12.0, 20.0, 12.0, 7.0]
+    seq = [op for a in angles for op in (epg.T(a, 10.0, order1={"al": "alpha"}), rlx)] + [epg.ADC]
+    comb = seq[0]
+    for op in seq[1:-1]:
+        comb = comb @ op
+    jv = ["T2", "g", "al"]
+    s1, j1 = interp_simulate(seq, probe=[None, epg.Jacobian(jv)])
+    s2, j2 = interp_simulate([comb, epg.ADC], probe=[None, epg.Jacobian(jv)])
+    assert rel_err(s2, s1) < 1e-12 and rel_err(j2, j1) < 1e-12
+
+
+def test_init_forms():
+    """init as 3-vector, (2n+1)x3 array and StateMatrix (reference test/test_functions.py:79-107)"""
+    epg = product_namespace()
+    import oracle_api as oa
+    O = oa.O
+    init = np.array([[0.1 - 0.2j, 0, 0.05], [0.3j, -0.3j, 0.7], [0, 0.1 + 0.2j, 0.05]])
+    seq = lambda e: [e.S(1), e.E(5, 300.0, [30.0, 60.0]), e.T(60, 20), e.S(1), e.ADC, e.Adc("Z0")]  # noqa: E731
+    got = interp_simulate(seq(epg), init=init)
+    ref = O.simulate(seq(oa.epg), init=init)
+    assert rel_err(got, ref) < 1e-13
+    got = interp_simulate(seq(epg), init=[0.5j, -0.5j, 0.3])
+    ref = O.simulate(seq(oa.epg), init=[0.5j, -0.5j, 0.3])
+    assert rel_err(got, ref) < 1e-13
+    got = interp_simulate(seq(epg), init=epg.StateMatrix(init, density=[1.0, 2.0]))
+    ref = O.simulate(seq(oa.epg), init=init, density=[1.0, 2.0])
+    assert rel_err(got, ref) < 1e-13
+
+
+def test_partials_through_nondiff_ops():
+    """propagate_nondiff=True: D / X / SPOILER act on the partial states too (exact chain rule;
+    the reference skips them, SURVEY 8c caveat).  Oracle: same switch, checked vs finite differences."""
+    epg = product_namespace()
+    import oracle_api as oa
+
+    def seq(e, da=0.0):
+        T2 = np.array([40.0, 80.0])
+        out = [e.T(90, 90)]
+        for i in range(6):
+            kw = {"order1": {"a": "alpha"}} if da == 0.0 else {}
+            out += [e.S(1), e.D(3.0, 1.5e-3, k=1), e.E(3, 900.0, T2), e.T(35 + da, 10.0 * i, **kw), e.ADC]
+        return out
+
+    sig, jac = interp_simulate(seq(epg), probe=[None, epg.Jacobian(["a"])], kvalue=3000.0, propagate_nondiff=True)
+    rs, rj = oa.O.simulate(seq(oa.epg), jacobian=["a"], kvalue=3000.0, propagate_nondiff=True)
+    assert rel_err(sig, rs) < 1e-12 and rel_err(jac, rj) < 1e-12
+    h = 1e-5
+    fd = (oa.O.simulate(seq(oa.epg, h), kvalue=3000.0) - oa.O.simulate(seq(oa.epg, -h), kvalue=3000.0)) / (2 * h)
+    assert rel_err(jac[..., 0], fd) < 1e-6
+    # reference behaviour (partials skip D)
+    sig, jac0 = interp_simulate(seq(epg), probe=[None, epg.Jacobian(["a"])], kvalue=3000.0)
+    _, rj0 = oa.O.simulate(seq(oa.epg), jacobian=["a"], kvalue=3000.0)
+    assert rel_err(jac0, rj0) < 1e-12 and rel_err(jac0, jac) > 1e-5
