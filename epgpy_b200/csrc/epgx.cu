@@ -315,7 +315,14 @@ template <typename real> static int dispatch_ring(const epgx_plan *pl, const KPa
 
 extern "C" int epgx_simulate(const epgx_plan *pl, const void *ws, int64_t atom_begin, int64_t atom_count, void *signal,
                              void *jacobian, void *stream) {
+  return epgx_simulate_strided(pl, ws, atom_begin, atom_count, signal, atom_count, jacobian, atom_count, stream);
+}
+
+extern "C" int epgx_simulate_strided(const epgx_plan *pl, const void *ws, int64_t atom_begin, int64_t atom_count,
+                                     void *signal, int64_t signal_stride, void *jacobian, int64_t jacobian_stride,
+                                     void *stream) {
   if (!pl || !ws) return fail(EPGX_ERR_INVALID, "null argument");
+  if (signal_stride < atom_count || jacobian_stride < atom_count) return fail(EPGX_ERR_INVALID, "row stride < atom_count");
   if (atom_begin < 0 || atom_count < 0 || atom_begin + atom_count > pl->natoms)
     return fail(EPGX_ERR_INVALID, "atom range out of the grid");
   if (atom_count == 0) return EPGX_OK;
@@ -333,6 +340,8 @@ extern "C" int epgx_simulate(const epgx_plan *pl, const void *ws, int64_t atom_b
   kp.jac = jacobian;
   kp.atom_begin = atom_begin;
   kp.atom_count = atom_count;
+  kp.sig_stride = signal_stride;
+  kp.jac_stride = jacobian_stride;
   for (int d = 0; d < t.ndim; ++d) kp.shape[d] = (int)t.shape[d];
   kp.ndim = t.ndim;
   kp.npattern = t.npattern;
@@ -386,6 +395,14 @@ extern "C" int epgx_simulate_host(const epgx_plan *pl, int device, int64_t atom_
   cudaFree(dsig);
   cudaFree(djac);
   return rc;
+}
+
+extern "C" int epgx_copy2d_to_host(void *dst, int64_t dst_pitch, const void *src, int64_t src_pitch, int64_t width,
+                                   int64_t height, void *stream) {
+  if (!dst || !src) return fail(EPGX_ERR_INVALID, "null argument");
+  CUDA_TRY(cudaMemcpy2DAsync(dst, (size_t)dst_pitch, src, (size_t)src_pitch, (size_t)width, (size_t)height,
+                             cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  return EPGX_OK;
 }
 
 // ---- Adc(reduce=axis): out[o][i] = sum_r in[o][r][i]   (probe.py:148-153)

@@ -127,6 +127,7 @@ struct KParams {
   void *signal;
   void *jac;
   long long atom_begin, atom_count;
+  long long sig_stride, jac_stride; // atoms per output row (>= atom_count)
   int shape[EPGX_MAX_DIMS];
   int ndim, npattern, nseg;
   int G, A, C, nvar;

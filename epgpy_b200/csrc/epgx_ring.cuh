@@ -266,7 +266,7 @@ __global__ void __launch_bounds__(256) ring_kernel(const KParams p) {
                 const bool z0 = flags & EPGX_FLAG_Z0;
                 if (on_base && blockIdx.y == 0) {
                   const real xr = z0 ? st[0][q].zr : st[0][q].pr, xi = z0 ? st[0][q].zi : st[0][q].pi;
-                  sig[((long long)aux * p.atom_count + a_rel) * NP + q] = real2{xr * fr - xi * fi, xr * fi + xi * fr};
+                  sig[((long long)aux * p.sig_stride + a_rel) * NP + q] = real2{xr * fr - xi * fi, xr * fi + xi * fr};
                 }
                 if (on_part) {
 #pragma unroll
@@ -274,7 +274,7 @@ __global__ void __launch_bounds__(256) ring_kernel(const KParams p) {
                     const int v = v0 + s - 1;
                     if (v < p.nvar) {
                       const real xr = z0 ? st[s][q].zr : st[s][q].pr, xi = z0 ? st[s][q].zi : st[s][q].pi;
-                      jac[(((long long)aux1 * p.nvar + v) * p.atom_count + a_rel) * NP + q] =
+                      jac[(((long long)aux1 * p.nvar + v) * p.jac_stride + a_rel) * NP + q] =
                           real2{xr * fr - xi * fi, xr * fi + xi * fr};
                     }
                   }

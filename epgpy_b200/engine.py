@@ -53,7 +53,8 @@ _lock = threading.Lock()
 EXPORTS = [
     "epgx_version", "epgx_device_count", "epgx_last_error", "epgx_plan_create", "epgx_plan_destroy",
     "epgx_plan_config", "epgx_plan_set_variant", "epgx_plan_workspace_bytes", "epgx_plan_upload",
-    "epgx_simulate", "epgx_simulate_host", "epgx_reduce", "epgx_fma_peak",
+    "epgx_simulate", "epgx_simulate_strided", "epgx_copy2d_to_host", "epgx_simulate_host", "epgx_reduce",
+    "epgx_fma_peak",
 ]
 
 
@@ -79,6 +80,8 @@ def lib():
             L.epgx_plan_workspace_bytes.argtypes = [vp, ctypes.POINTER(i64)]
             L.epgx_plan_upload.argtypes = [vp, vp, vp]
             L.epgx_simulate.argtypes = [vp, vp, i64, i64, vp, vp, vp]
+            L.epgx_simulate_strided.argtypes = [vp, vp, i64, i64, vp, i64, vp, i64, vp]
+            L.epgx_copy2d_to_host.argtypes = [vp, i64, vp, i64, i64, i64, vp]
             L.epgx_simulate_host.argtypes = [vp, i32, i64, i64, vp, vp]
             L.epgx_reduce.argtypes = [i32, vp, vp, i64, i64, i64, vp]
             L.epgx_fma_peak.argtypes = [i32, i32, ctypes.c_double, ctypes.POINTER(ctypes.c_double)]
@@ -158,14 +161,16 @@ class Plan:
         return n.value
 
     # ---- device side
-    def upload(self, device):
-        """H2D of tape + coefficient table (cached per device); returns the workspace tensor"""
+    def upload(self, device, force=False):
+        """H2D of tape + coefficient table (cached per device unless `force`); returns the workspace tensor"""
         import torch
 
         dev = torch.device("cuda", device)
-        if device not in self._ws:
+        if device not in self._ws or force:
             with torch.cuda.device(dev):
-                ws = torch.empty(self.workspace_bytes(), dtype=torch.uint8, device=dev)
+                ws = self._ws.get(device)
+                if ws is None:
+                    ws = torch.empty(self.workspace_bytes(), dtype=torch.uint8, device=dev)
                 st = torch.cuda.current_stream(dev).cuda_stream
                 _check(lib().epgx_plan_upload(self._h, ws.data_ptr(), st))
             self._ws[device] = ws
@@ -193,6 +198,56 @@ class Plan:
                                        signal.data_ptr() if signal is not None and signal.numel() else None,
                                        jacobian.data_ptr() if jacobian is not None and jacobian.numel() else None, st))
         return signal, jacobian
+
+    def run_to_host(self, device, out_signal, atom_begin=0, atom_count=None, nchunk=8, out_jacobian=None,
+                    dev_signal=None, dev_jacobian=None):
+        """pipelined end-to-end run: H2D of the tape, then the atom range is cut in `nchunk` column ranges;
+        range i+1 is computed while range i is copied to the (pinned) host buffers with pitched D2H copies.
+        out_signal: host torch tensor / numpy array [nadc][atom_count][npool] complex (pinned for overlap).
+        Synchronises before returning."""
+        import torch
+
+        require_cuda()
+        low = self.low
+        if atom_count is None:
+            atom_count = low.natoms - atom_begin
+        dev = torch.device("cuda", device)
+        cdt = torch.complex128 if low.dtype == "f64" else torch.complex64
+        csz = 16 if low.dtype == "f64" else 8
+        L = lib()
+        with torch.cuda.device(dev):
+            ws = self.upload(device, force=True)
+            if dev_signal is None:
+                dev_signal = torch.empty((low.nadc, atom_count, low.npool), dtype=cdt, device=dev)
+            has_jac = bool(low.nvar and low.njac)
+            if has_jac and dev_jacobian is None:
+                dev_jacobian = torch.empty((low.njac * low.nvar, atom_count, low.npool), dtype=cdt, device=dev)
+            compute = torch.cuda.current_stream(dev)
+            copy = torch.cuda.Stream(dev)
+            per = -(-atom_count // max(1, nchunk))
+            hs = out_signal.data_ptr() if hasattr(out_signal, "data_ptr") else out_signal.ctypes.data
+            hj = None
+            if has_jac:
+                hj = out_jacobian.data_ptr() if hasattr(out_jacobian, "data_ptr") else out_jacobian.ctypes.data
+            pitch = atom_count * low.npool * csz
+            for b in range(0, atom_count, per):
+                c = min(per, atom_count - b)
+                colb = b * low.npool * csz
+                _check(L.epgx_simulate_strided(
+                    self._h, ws.data_ptr(), atom_begin + b, c, dev_signal.data_ptr() + colb, atom_count,
+                    (dev_jacobian.data_ptr() + colb) if has_jac else None, atom_count, compute.cuda_stream))
+                ev = torch.cuda.Event()
+                ev.record(compute)
+                copy.wait_event(ev)
+                if low.nadc:
+                    _check(L.epgx_copy2d_to_host(hs + colb, pitch, dev_signal.data_ptr() + colb, pitch, c * low.npool * csz,
+                                                 low.nadc, copy.cuda_stream))
+                if has_jac:
+                    _check(L.epgx_copy2d_to_host(hj + colb, pitch, dev_jacobian.data_ptr() + colb, pitch,
+                                                 c * low.npool * csz, low.njac * low.nvar, copy.cuda_stream))
+            copy.synchronize()
+            compute.synchronize()
+        return dev_signal, dev_jacobian
 
     def run_host(self, device, atom_begin, atom_count, signal, jacobian=None):
         """epgx_simulate_host: the plain C-ABI call on HOST numpy buffers (alloc + H2D + run + D2H)"""

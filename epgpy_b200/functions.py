@@ -121,7 +121,7 @@ def _assemble(low, parts, asarray=True):
                     keep = [g for g in order if g not in red]
                     arr = np.transpose(arr, np.argsort(keep)) if keep else arr.reshape(())[()]
                 if row.post is not None:
-                    arr = row.post(arr)
+                    arr = np.asarray(row.post(arr)).astype(cdt, copy=False)
                 values[ip].append(arr)
             else:
                 jrow, cols = row.jac
@@ -132,7 +132,7 @@ def _assemble(low, parts, asarray=True):
                     elif kind == "var":
                         out[..., ic] = to_grid(jac_host[jrow, vi])
                 if row.post is not None:
-                    out = row.post(out)
+                    out = np.asarray(row.post(out)).astype(cdt, copy=False)
                 values[ip].append(out)
     if asarray:
         return tuple(np.asarray(v) for v in values)

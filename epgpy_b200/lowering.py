@@ -511,6 +511,13 @@ def lower(sequence, *, init=None, probe=None, options=None, dtype="f64", propaga
             if np.any(r["code"] == OP_ADC):
                 reach = max(reach, 0)
             segs[i]["nact"] = min(int(s["n_old"]), reach)
+        # orders above the highest observable one need no storage either: clamp the order schedule
+        # like a max_nstate truncation would (what is cut off could never come back to k = 0 in time)
+        cap_eff = max(int(segs["nact"].max()) if len(segs) else 0, init_n, 0)
+        if cap_eff < max_order:
+            segs["n_old"] = np.minimum(segs["n_old"], cap_eff)
+            segs["n_new"] = np.minimum(segs["n_new"], cap_eff)
+            max_order = cap_eff
 
     low = Lowered()
     low.dtype = dtype

@@ -214,6 +214,19 @@ int epgx_plan_upload(const epgx_plan *plan, void *workspace, void *stream);
 int epgx_simulate(const epgx_plan *plan, const void *workspace, int64_t atom_begin, int64_t atom_count,
                   void *signal, void *jacobian, void *stream);
 
+/* Same, writing rows that are `signal_stride` / `jacobian_stride` atoms apart (>= atom_count), so that
+ * several launches over atom sub-ranges fill one [row][all atoms][npool] buffer:
+ *   signal[(row * signal_stride + a) * npool + pool], a = atom - atom_begin; pass the pointer of the
+ *   sub-range's first column. */
+int epgx_simulate_strided(const epgx_plan *plan, const void *workspace, int64_t atom_begin, int64_t atom_count,
+                          void *signal, int64_t signal_stride, void *jacobian, int64_t jacobian_stride,
+                          void *stream);
+
+/* asynchronous pitched device->host copy (cudaMemcpy2DAsync) of `height` rows of `width` bytes: brings a
+ * column range of the signal slab to (pinned) host memory while the next range is computed */
+int epgx_copy2d_to_host(void *dst, int64_t dst_pitch, const void *src, int64_t src_pitch, int64_t width,
+                        int64_t height, void *stream);
+
 /* Convenience end-to-end call on HOST buffers (allocates, copies H2D, runs, copies D2H, frees,
  * synchronises): same layouts as epgx_simulate but host pointers. */
 int epgx_simulate_host(const epgx_plan *plan, int device, int64_t atom_begin, int64_t atom_count,
