@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "epgx_common.cuh"
+#include "epgx_reg.cuh"
 #include "epgx_ring.cuh"
 
 using namespace epgx;
@@ -73,11 +74,50 @@ static double form_flops(int code, int flags, int npool) {
   }
 }
 
+static const int kRegSlots[5] = {1, 2, 4, 8, 16};
+
 static int choose_variant(epgx_plan *pl, int kernel, int lanes, int vars, int atoms) {
   const epgx_tape &t = pl->tape;
   epgx_config &c = pl->cfg;
   const int rsz = t.dtype == EPGX_F64 ? 8 : 4;
   const int C = t.max_order + 1;
+  const bool reg_ok = t.nvar == 0 && t.npool == 1;
+  if (kernel == 2 && !reg_ok)
+    return fail(EPGX_ERR_UNSUPPORTED, "the register kernel runs forward simulations of one pool only");
+  if (reg_ok && kernel != 1) {
+    // ---- register kernel: G lanes x NS slots >= C orders
+    const int ns_max = t.dtype == EPGX_F64 ? 8 : 16;
+    int G;
+    if (lanes > 0) {
+      G = pow2ceil(lanes);
+    } else {
+      G = pow2ceil((C + 7) / 8);
+      if (G > 32 && C <= 32 * ns_max) G = 32;
+    }
+    if (G > 256) G = 256;
+    int need = (C + G - 1) / G, NS = 0;
+    for (int o : kRegSlots)
+      if (o >= need && !NS) NS = o;
+    if (NS && (NS <= ns_max || lanes > 0 || kernel == 2)) {
+      int A = atoms > 0 ? atoms : (128 / G > 0 ? 128 / G : 1);
+      if (G > 32 && A > 15) A = 15; // named barriers 1..15
+      while (A * G > 256 && A > 1) --A;
+      if (A * G <= 256) {
+        const int W = G > 32 ? G / 32 : 1;
+        c.kernel = 1;
+        c.lanes_per_atom = G;
+        c.slots_per_lane = NS;
+        c.vars_per_pass = 0;
+        c.var_tiles = 1;
+        c.atoms_per_cta = A;
+        c.threads_per_cta = A * G;
+        c.smem_bytes = ((A * t.npattern + 3) & ~3) * 4 + (W > 1 ? 2 * A * W * 2 * NS * 2 * rsz : 0) + 32;
+        c.ring = C;
+        return EPGX_OK;
+      }
+    }
+    if (kernel == 2) return fail(EPGX_ERR_CAPACITY, "no register-kernel instance holds " + std::to_string(C) + " orders");
+  }
   int G = lanes > 0 ? pow2ceil(lanes) : pow2ceil((C + 3) / 4);
   if (G > 256) G = 256;
   int nvt = nvt_choice(t.nvar, vars);
@@ -97,7 +137,6 @@ static int choose_variant(epgx_plan *pl, int kernel, int lanes, int vars, int at
   while (A * G > 256) --A;
   if (A < 1) A = 1;
   c.kernel = 0;
-  (void)kernel;
   c.lanes_per_atom = G;
   c.slots_per_lane = 0;
   c.vars_per_pass = nvt;
@@ -304,6 +343,26 @@ static int launch_ring(const epgx_plan *pl, const KParams &kp, cudaStream_t st) 
   return EPGX_OK;
 }
 
+template <typename real, int NS> static int launch_reg(const epgx_plan *pl, const KParams &kp, cudaStream_t st) {
+  const epgx_config &c = pl->cfg;
+  auto kern = reg_kernel<real, NS>;
+  dim3 grid((unsigned)((kp.atom_count + c.atoms_per_cta - 1) / c.atoms_per_cta), 1);
+  kern<<<grid, c.threads_per_cta, c.smem_bytes, st>>>(kp);
+  CUDA_TRY(cudaGetLastError());
+  return EPGX_OK;
+}
+
+template <typename real> static int dispatch_reg(const epgx_plan *pl, const KParams &kp, cudaStream_t st) {
+  switch (pl->cfg.slots_per_lane) {
+  case 1: return launch_reg<real, 1>(pl, kp, st);
+  case 2: return launch_reg<real, 2>(pl, kp, st);
+  case 4: return launch_reg<real, 4>(pl, kp, st);
+  case 8: return launch_reg<real, 8>(pl, kp, st);
+  case 16: return launch_reg<real, 16>(pl, kp, st);
+  }
+  return fail(EPGX_ERR_UNSUPPORTED, "no register-kernel instance for slots_per_lane=" + std::to_string(pl->cfg.slots_per_lane));
+}
+
 template <typename real> static int dispatch_ring(const epgx_plan *pl, const KParams &kp, cudaStream_t st) {
   const int np = pl->tape.npool, nvt = pl->cfg.vars_per_pass;
 #define CASE(NP_, NVT_) \
@@ -356,6 +415,7 @@ extern "C" int epgx_simulate_strided(const epgx_plan *pl, const void *ws, int64_
   kp.m0_pat = t.m0_pat;
   kp.init_n = t.init_n;
   cudaStream_t st = (cudaStream_t)stream;
+  if (pl->cfg.kernel == 1) return t.dtype == EPGX_F64 ? dispatch_reg<double>(pl, kp, st) : dispatch_reg<float>(pl, kp, st);
   if (t.dtype == EPGX_F64) return dispatch_ring<double>(pl, kp, st);
   return dispatch_ring<float>(pl, kp, st);
 }

@@ -1,0 +1,263 @@
+// epgx_reg.cuh -- the fast forward kernel: the whole F+/F-/Z state of an atom lives in REGISTERS
+// for the entire sequence.
+//
+//  * G lanes (G = 1..32 inside a warp, or G = 32 W with W warps) own one atom; order k sits in slot
+//    k / G of lane k % G (cyclic layout), so the growing triangle of populated orders keeps all lanes
+//    busy and a pass touches only the slots s with s*G <= nact (warp-uniform predicate);
+//  * every record of a segment is decoded ONCE per lane and applied to up to NS orders with fully
+//    unrolled FMA code: coefficient loads and tape decode are amortised over the slots;
+//  * the unit shift S(+-1) (epgpy/shift.py:283-292) is a rotate-by-one-lane of the F+ registers
+//    (__shfl_sync) with the wrap-around lane moving to the next slot, the mirrored rotation of F-,
+//    and F+(0) <- conj(F-(1)) (symmetry of epgpy/statematrix.py:418-421); warps of a multi-warp atom
+//    exchange one boundary value per slot through shared memory;
+//  * shared memory holds nothing but the per-atom pattern offsets and those boundary values; HBM sees
+//    only the coefficient tables (L2-resident) and the ADC samples.
+// Forward simulation, one pool.  Partial derivatives and exchange run in the ring kernel.
+#pragma once
+#include "epgx_common.cuh"
+
+namespace epgx {
+
+template <typename real, int NS>
+__global__ void __launch_bounds__(256) reg_kernel(const KParams p) {
+  typedef typename vec2<real>::type real2;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+
+  const int G = p.G;
+  const int tid = threadIdx.x;
+  const int al = tid / G;
+  const int lane = tid - al * G;
+  const int lw = tid & 31;
+  const int W = G > 32 ? G >> 5 : 1;       // warps per atom
+  const int GW = G > 32 ? 32 : G;          // lanes of the atom inside this warp
+  const int wq = G > 32 ? lane >> 5 : 0;   // warp index inside the atom
+  const int gbase = lw & ~(GW - 1);
+  const int lq = lw - gbase;               // lane inside the warp-local group
+  const int srcUp = gbase | ((lq - 1) & (GW - 1));
+  const int srcDn = gbase | ((lq + 1) & (GW - 1));
+  const unsigned FULL = 0xffffffffu;
+  int lgG = 0;
+  while ((1 << lgG) < G) ++lgG;
+
+  const long long a_rel = (long long)blockIdx.x * p.A + al;
+  const bool valid = a_rel < p.atom_count;
+  const long long atom = p.atom_begin + (valid ? a_rel : p.atom_count - 1);
+  const real *__restrict__ coef = (const real *)p.coef;
+
+  // shared memory: pattern offsets [A][npattern] int, then (multi-warp atoms) boundary exchange
+  int *patoff = (int *)smem_raw + al * p.npattern;
+  real2 *xbuf = (real2 *)((int *)smem_raw + ((p.A * p.npattern + 3) & ~3)); // [2 parity][A][W][2 (P,M)][NS]
+  {
+    int idx[EPGX_MAX_DIMS];
+    long long r = atom;
+    for (int d = p.ndim - 1; d >= 0; --d) {
+      idx[d] = (int)(r % p.shape[d]);
+      r /= p.shape[d];
+    }
+    for (int q = lane; q < p.npattern; q += G) {
+      const int *st = p.pats + q * (EPGX_MAX_DIMS + 1);
+      int o = 0;
+      for (int d = 0; d < p.ndim; ++d) o += idx[d] * st[d];
+      patoff[q] = o;
+    }
+  }
+  __syncthreads();
+
+  real Pr[NS], Pi[NS], Mr[NS], Mi[NS], Zr[NS], Zi[NS];
+  real m0 = ldc(coef + p.m0_off + patoff[p.m0_pat]);
+  {
+    const real *ib = coef + p.init_off + patoff[p.init_pat];
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+      const int k = s * G + lane;
+      const bool in = k <= p.init_n;
+      Pr[s] = in ? ldc(ib + 6 * k) : real(0);
+      Pi[s] = in ? ldc(ib + 6 * k + 1) : real(0);
+      Mr[s] = in ? ldc(ib + 6 * k + 2) : real(0);
+      Mi[s] = in ? ldc(ib + 6 * k + 3) : real(0);
+      Zr[s] = in ? ldc(ib + 6 * k + 4) : real(0);
+      Zi[s] = in ? ldc(ib + 6 * k + 5) : real(0);
+    }
+  }
+
+  real2 *sig = (real2 *)p.signal;
+  int parity = 0;
+
+#define LOAD_TRI(s) Tri<real> t_ = {Pr[s], Pi[s], Mr[s], Mi[s], Zr[s], Zi[s]}
+#define STORE_TRI(s, o) { Pr[s] = o.pr; Pi[s] = o.pi; Mr[s] = o.mr; Mi[s] = o.mi; Zr[s] = o.zr; Zi[s] = o.zi; }
+#define FOR_SLOTS(EXPR)                                  \
+  _Pragma("unroll") for (int s = 0; s < NS; ++s) {       \
+    if (s < nslot) {                                     \
+      LOAD_TRI(s);                                       \
+      const Tri<real> o_ = EXPR;                         \
+      STORE_TRI(s, o_);                                  \
+    }                                                    \
+  }
+
+  for (int sg = 0; sg < p.nseg; ++sg) {
+    const int4 s0 = __ldg((const int4 *)(p.segs + sg));
+    const int4 s1 = __ldg((const int4 *)(p.segs + sg) + 1);
+    const int first = s0.x, count = s0.y, nact = s0.z, shift = s0.w;
+    const int n_old = s1.x, n_new = s1.y, sflags = s1.z;
+    const int nslot = nact < 0 ? 0 : (nact >> lgG) + 1; // slots with at least one order <= nact
+
+    for (int r = first; r < first + count; ++r) {
+      const int4 r0 = __ldg((const int4 *)(p.ops + r));
+      const int4 r1 = __ldg((const int4 *)(p.ops + r) + 1);
+      const int code = r0.x & 0xffff, flags = (r0.x >> 16) & 0xffff, aux = r0.y;
+      const unsigned off0 = (unsigned)r0.z, off1 = (unsigned)r0.w, off2 = (unsigned)r1.x;
+      const int pat0 = r1.y & 0xff, pat1 = (r1.y >> 8) & 0xff, pat2 = (r1.y >> 16) & 0xff;
+      const bool aff = (flags & EPGX_FLAG_AFFINE) && lane == 0 && nslot > 0;
+
+      switch (code) {
+      case EPGX_OP_T_GEN: {
+        const real *c = coef + off0 + patoff[pat0];
+        const real a = ldc(c), w = ldc(c + 1), Br = ldc(c + 2), Bi = ldc(c + 3), Ur = ldc(c + 4), Ui = ldc(c + 5);
+        FOR_SLOTS(form_t_gen(t_, a, w, Br, Bi, Ur, Ui))
+      } break;
+      case EPGX_OP_T_RE: {
+        const real *c = coef + off0 + patoff[pat0];
+        const real a = ldc(c), w = ldc(c + 1), b = ldc(c + 2), u = ldc(c + 3);
+        FOR_SLOTS(form_t_re(t_, a, w, b, u))
+      } break;
+      case EPGX_OP_T_IM: {
+        const real *c = coef + off0 + patoff[pat0];
+        const real a = ldc(c), w = ldc(c + 1), b = ldc(c + 2), u = ldc(c + 3);
+        FOR_SLOTS(form_t_im(t_, a, w, b, u))
+      } break;
+      case EPGX_OP_E: {
+        const real *c0 = coef + off0 + patoff[pat0];
+        const real e1 = ldc(c0), r0v = ldc(c0 + 1);
+        const real e2 = ldc(coef + off1 + patoff[pat1]);
+        if (flags & EPGX_FLAG_G) {
+          const real *c2 = coef + off2 + patoff[pat2];
+          const real er = e2 * ldc(c2), ei = e2 * ldc(c2 + 1);
+          FOR_SLOTS(form_e_g(t_, e1, er, ei))
+        } else {
+          FOR_SLOTS(form_e(t_, e1, e2))
+        }
+        if (aff) Zr[0] += r0v * m0;
+      } break;
+      case EPGX_OP_DIAG: {
+        const real *c = coef + off0 + patoff[pat0];
+        real d[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) d[i] = ldc(c + i);
+        FOR_SLOTS(form_diag(t_, d))
+        if (aff) { Zr[0] += d[6] * m0; Zi[0] += d[7] * m0; }
+      } break;
+      case EPGX_OP_MATRIX: {
+        const real *c = coef + off0 + patoff[pat0];
+        real m[18];
+#pragma unroll
+        for (int i = 0; i < 18; ++i) m[i] = ldc(c + i);
+        FOR_SLOTS(form_matrix(t_, m))
+        if (aff) {
+          const real *c1 = coef + off1 + patoff[pat1];
+          Pr[0] += ldc(c1) * m0; Pi[0] += ldc(c1 + 1) * m0; Mr[0] += ldc(c1 + 2) * m0;
+          Mi[0] += ldc(c1 + 3) * m0; Zr[0] += ldc(c1 + 4) * m0; Zi[0] += ldc(c1 + 5) * m0;
+        }
+      } break;
+      case EPGX_OP_D: {
+        const real *c = coef + off0 + patoff[pat0] + 3 * lane;
+#pragma unroll
+        for (int s = 0; s < NS; ++s)
+          if (s < nslot && s * G + lane <= nact) {
+            const real dp = ldc(c + 3 * s * G), dm = ldc(c + 3 * s * G + 1), dl = ldc(c + 3 * s * G + 2);
+            Pr[s] *= dp; Pi[s] *= dp; Mr[s] *= dm; Mi[s] *= dm; Zr[s] *= dl; Zi[s] *= dl;
+          }
+      } break;
+      case EPGX_OP_SPOIL:
+#pragma unroll
+        for (int s = 0; s < NS; ++s)
+          if (s < nslot) Pr[s] = Pi[s] = Mr[s] = Mi[s] = real(0);
+        break;
+      case EPGX_OP_PD:
+        m0 = ldc(coef + off0 + patoff[pat0]);
+        break;
+      case EPGX_OP_ADC:
+        if (lane == 0 && valid && (flags & EPGX_FLAG_BASE)) {
+          real fr = real(1), fi = real(0);
+          if (flags & EPGX_FLAG_SCALE) {
+            const real *c = coef + off0 + patoff[pat0];
+            fr = ldc(c); fi = ldc(c + 1);
+          }
+          const bool z0 = flags & EPGX_FLAG_Z0;
+          const real xr = z0 ? Zr[0] : Pr[0], xi = z0 ? Zi[0] : Pi[0];
+          sig[(long long)aux * p.sig_stride + a_rel] = real2{xr * fr - xi * fi, xr * fi + xi * fr};
+        }
+        break;
+      default:
+        break;
+      }
+    }
+
+    if (sflags & EPGX_SEG_RESET) {
+#pragma unroll
+      for (int s = 0; s < NS; ++s) Pr[s] = Pi[s] = Mr[s] = Mi[s] = Zr[s] = Zi[s] = real(0);
+      if (lane == 0) Zr[0] = m0;
+    } else if (shift != 0) {
+      const int nsl = (n_new >> lgG) + 1; // slots that hold an order <= n_new after the shift
+      const bool mask_top = sflags & EPGX_SEG_MASK_TOP;
+      // UR/UI: the component whose orders move up (F+ for shift > 0, F- for shift < 0); DR/DI: the other
+#define DO_SHIFT(UR, UI, DR, DI)                                                                          \
+  {                                                                                                        \
+    /* new order 0 of `up` = conj(old order 1 of `dn`): order 1 is lane 1 slot 0 (slot 1 if G == 1) */     \
+    real cr, ci;                                                                                           \
+    if (G == 1) { cr = NS > 1 ? DR[NS > 1 ? 1 : 0] : real(0); ci = NS > 1 ? DI[NS > 1 ? 1 : 0] : real(0); } \
+    else { cr = __shfl_sync(FULL, DR[0], gbase | 1); ci = __shfl_sync(FULL, DI[0], gbase | 1); }          \
+    if (n_old < 1) { cr = real(0); ci = real(0); }                                                         \
+    ci = -ci;                                                                                              \
+    real2 *xb = xbuf + (size_t)(parity * p.A + al) * W * 2 * NS;                                           \
+    if (W > 1) { /* boundary values of every warp of the atom: [warp][up | dn][slot] */                    \
+      if (lq == 31) { _Pragma("unroll") for (int s = 0; s < NS; ++s) xb[(wq * 2 + 0) * NS + s] = real2{UR[s], UI[s]}; } \
+      if (lq == 0) { _Pragma("unroll") for (int s = 0; s < NS; ++s) xb[(wq * 2 + 1) * NS + s] = real2{DR[s], DI[s]}; }  \
+      asm volatile("bar.sync %0, %1;" ::"r"(1 + al), "r"(G) : "memory");                                   \
+      parity ^= 1;                                                                                         \
+    }                                                                                                      \
+    /* up: rotate by one lane; the first lane takes the wrap-around value */                               \
+    _Pragma("unroll") for (int s = 0; s < NS; ++s) {                                                       \
+      if (s < nsl) {                                                                                       \
+        const real rr = __shfl_sync(FULL, UR[s], srcUp), ri = __shfl_sync(FULL, UI[s], srcUp);             \
+        real vr = rr, vi = ri;                                                                             \
+        if (lq == 0) {                                                                                     \
+          if (W == 1 || wq == 0) { vr = cr; vi = ci; }                                                     \
+          else { const real2 x = xb[((wq - 1) * 2 + 0) * NS + s]; vr = x.x; vi = x.y; }                    \
+        }                                                                                                  \
+        if (W == 1) { cr = rr; ci = ri; }                                                                  \
+        else if (lane == 0) { const real2 x = xb[((W - 1) * 2 + 0) * NS + s]; cr = x.x; ci = x.y; }        \
+        UR[s] = vr; UI[s] = vi;                                                                            \
+        if (mask_top && s * G + lane > n_new) { UR[s] = real(0); UI[s] = real(0); }                        \
+      }                                                                                                    \
+    }                                                                                                      \
+    /* dn: rotate the other way; the last lane takes the value of the NEXT slot (next warp) */             \
+    real nr = __shfl_sync(FULL, DR[0], srcDn), ni = __shfl_sync(FULL, DI[0], srcDn);                       \
+    _Pragma("unroll") for (int s = 0; s < NS; ++s) {                                                       \
+      if (s < nsl) {                                                                                       \
+        real xr = real(0), xi = real(0);                                                                   \
+        if (s + 1 < NS) {                                                                                  \
+          xr = __shfl_sync(FULL, DR[s + 1 < NS ? s + 1 : s], srcDn);                                       \
+          xi = __shfl_sync(FULL, DI[s + 1 < NS ? s + 1 : s], srcDn);                                       \
+        }                                                                                                  \
+        real vr = nr, vi = ni;                                                                             \
+        if (lq == GW - 1) {                                                                                \
+          if (W == 1) { vr = xr; vi = xi; }                                                                \
+          else if (wq < W - 1) { const real2 x = xb[((wq + 1) * 2 + 1) * NS + s]; vr = x.x; vi = x.y; }    \
+          else if (s + 1 < NS) { const real2 x = xb[(0 * 2 + 1) * NS + (s + 1 < NS ? s + 1 : s)]; vr = x.x; vi = x.y; } \
+          else { vr = real(0); vi = real(0); }                                                             \
+        }                                                                                                  \
+        DR[s] = vr; DI[s] = vi;                                                                            \
+        nr = xr; ni = xi;                                                                                  \
+      }                                                                                                    \
+    }                                                                                                      \
+  }
+      if (shift > 0) DO_SHIFT(Pr, Pi, Mr, Mi) else DO_SHIFT(Mr, Mi, Pr, Pi)
+#undef DO_SHIFT
+    }
+  }
+#undef FOR_SLOTS
+#undef LOAD_TRI
+#undef STORE_TRI
+}
+
+} // namespace epgx

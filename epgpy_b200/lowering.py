@@ -26,7 +26,7 @@ from .statematrix import StateMatrix
 # opcodes / flags (include/epgx.h)
 OP_NOP, OP_T_GEN, OP_T_RE, OP_T_IM, OP_E, OP_DIAG, OP_MATRIX, OP_D, OP_X, OP_SPOIL, OP_PD, OP_ADC = range(12)
 F_BASE, F_PARTIALS, F_INJECT, F_G, F_AFFINE, F_Z0, F_SCALE = (1 << i for i in range(7))
-SEG_RESET = 1
+SEG_RESET, SEG_MASK_TOP = 1, 2
 MAX_DIMS, MAX_PATTERNS, MAX_POOLS = 8, 64, 2
 
 OP_DTYPE = np.dtype([("code", "<u2"), ("flags", "<u2"), ("aux", "<i4"), ("off", "<u4", (3,)), ("pat", "u1", (3,)),
@@ -367,7 +367,7 @@ def lower(sequence, *, init=None, probe=None, options=None, dtype="f64", propaga
             cap = max_nstate or op.nmax or None
             for _ in range(abs(m)):
                 n_new = n + 1 if cap is None else min(n + 1, max(cap, 0))
-                close_segment(1 if m > 0 else -1, n, n_new)
+                close_segment(1 if m > 0 else -1, n, n_new, SEG_MASK_TOP if n_new == n else 0)
                 n = n_new
         elif isinstance(op, (X, D, Spoiler)):
             fl = F_BASE | (part_flag() if propagate_nondiff else 0)

@@ -126,7 +126,9 @@ typedef struct {
 } epgx_op;
 
 enum {
-  EPGX_SEG_RESET = 1 << 0 /* after the pass: state <- equilibrium, order <- 0 (operator.py:297-304) */
+  EPGX_SEG_RESET = 1 << 0, /* after the pass: state <- equilibrium, order <- 0 (operator.py:297-304) */
+  /* the shift truncates at max_nstate (n_new == n_old): what moves above n_new must read as zero */
+  EPGX_SEG_MASK_TOP = 1 << 1
 };
 
 /* segment, 32 bytes: one pass over orders 0..nact applying records [first, first+count), then
@@ -198,7 +200,8 @@ const char *epgx_last_error(void);
 int epgx_plan_create(const epgx_tape *tape, epgx_plan **plan);
 int epgx_plan_destroy(epgx_plan *plan);
 int epgx_plan_config(const epgx_plan *plan, epgx_config *cfg);
-/* force a kernel variant (tuning / tests): a 0 / negative argument keeps the automatic choice */
+/* force a kernel variant (tuning / tests): a 0 / negative argument keeps the automatic choice;
+ * kernel: 1 = ring (shared-memory state), 2 = reg (register state; forward, one pool only) */
 int epgx_plan_set_variant(epgx_plan *plan, int kernel, int lanes_per_atom, int vars_per_pass,
                           int atoms_per_cta);
 

@@ -58,14 +58,47 @@ def _run_variant(epg, case, dtype="f64", **variant):
 
 @pytest.mark.parametrize("lanes,atoms", [(1, 1), (1, 32), (2, 3), (8, 16), (32, 2), (64, 1), (128, 2), (256, 1)])
 @pytest.mark.parametrize("name", ["fisp_unbounded", "fisp_bounded", "misc_ops", "spgr_exchange", "fisp_jac_global"])
-def test_kernel_variants(name, lanes, atoms, golden, epg):
-    """every lanes-per-atom / atoms-per-CTA mapping gives the same answer (ragged tails included)"""
+def test_ring_kernel_variants(name, lanes, atoms, golden, epg):
+    """ring kernel: every lanes-per-atom / atoms-per-CTA mapping gives the same answer (ragged tails included)"""
     ref = golden(name)
-    vals, cfg = _run_variant(epg, cases.CASES[name](epg), lanes_per_atom=lanes, atoms_per_cta=atoms)
-    assert cfg["lanes_per_atom"] == lanes
+    vals, cfg = _run_variant(epg, cases.CASES[name](epg), kernel=1, lanes_per_atom=lanes, atoms_per_cta=atoms)
+    assert cfg["lanes_per_atom"] == lanes and cfg["kernel"] == 0
     assert rel_err(vals[0], ref["signal"]) < RTOL64
     if "jacobian" in ref.files:
         assert rel_err(vals[1], ref["jacobian"]) < RTOL64
+
+
+FORWARD = ["readme_mse", "mse_grid", "fisp_unbounded", "fisp_bounded", "bssfp_offres", "gre_diffusion",
+           "gre_diffusion_1d", "hyperecho", "misc_ops", "adc_reduce"]
+
+
+@pytest.mark.parametrize("dtype", ["f64", "f32"])
+@pytest.mark.parametrize("lanes,atoms", [(1, 5), (2, 3), (4, 32), (8, 16), (16, 1), (32, 2), (64, 1), (64, 3), (128, 2), (256, 1)])
+@pytest.mark.parametrize("name", FORWARD)
+def test_reg_kernel_variants(name, lanes, atoms, dtype, golden, epg):
+    """register kernel: sub-warp groups, one warp and several warps per atom, every slot count"""
+    ref = golden(name)
+    try:
+        vals, cfg = _run_variant(epg, cases.CASES[name](epg), dtype=dtype, kernel=2, lanes_per_atom=lanes, atoms_per_cta=atoms)
+    except MemoryError:
+        pytest.skip("more orders than lanes x slots of any instance")
+    assert cfg["kernel"] == 1 and cfg["lanes_per_atom"] == lanes
+    assert rel_err(vals[0], ref["signal"]) < (RTOL64 if dtype == "f64" else RTOL32)
+
+
+def test_reg_and_ring_agree_on_large_orders(epg):
+    """400-TR FISP (200 live orders): register kernel (1, 2, 4 warps per atom) vs ring kernel"""
+    case = cases.fisp(epg, 400, sizes=(3, 2, 2))
+    ring, _ = _run_variant(epg, case, kernel=1)
+    for lanes in (32, 64, 128):
+        reg, cfg = _run_variant(epg, case, kernel=2, lanes_per_atom=lanes)
+        assert cfg["kernel"] == 1
+        assert rel_err(reg[0], ring[0]) < 1e-12
+    bounded = cases.fisp(epg, 400, sizes=(3, 2, 2), max_nstate=37)
+    ring, _ = _run_variant(epg, bounded, kernel=1)
+    for lanes in (4, 8, 32):
+        reg, _ = _run_variant(epg, bounded, kernel=2, lanes_per_atom=lanes)
+        assert rel_err(reg[0], ring[0]) < 1e-12
 
 
 @pytest.mark.parametrize("vars_per_pass", [1, 3])
