@@ -65,6 +65,7 @@ static double form_flops(int code, int flags, int npool) {
   case EPGX_OP_T_GEN: return 56;
   case EPGX_OP_T_RE:
   case EPGX_OP_T_IM: return 28;
+  case EPGX_OP_FUSED: return 28;
   case EPGX_OP_E: return (flags & EPGX_FLAG_G) ? 14 : 6;
   case EPGX_OP_DIAG: return 18;
   case EPGX_OP_MATRIX: return 66;
@@ -172,6 +173,8 @@ static int entry_reals(int code, int blk, int flags, const epgx_tape &t) {
   case EPGX_OP_D: return blk == 0 ? 3 * (t.max_order + 1) : 0;
   case EPGX_OP_X: return blk == 0 ? 4 * t.npool * t.npool : 0;
   case EPGX_OP_PD: return blk == 0 ? 1 : 0;
+  case EPGX_OP_FUSED: return blk == 0 ? 4 : blk == 1 ? 2 : 1;
+  case EPGX_OP_CONT: return blk == 0 ? 2 : blk == 1 ? 1 : 0;
   case EPGX_OP_ADC: return (blk == 0 && (flags & EPGX_FLAG_SCALE)) ? 2 : 0;
   default: return 0;
   }
@@ -221,6 +224,8 @@ extern "C" int epgx_plan_create(const epgx_tape *t, epgx_plan **out) {
       if (n && !block_ok(o.off[b], o.pat[b], n))
         return fail(EPGX_ERR_INVALID, "coefficient block out of range in record " + std::to_string(i));
     }
+    if (o.code == EPGX_OP_FUSED && (i + 1 >= t->nop || t->ops[i + 1].code != EPGX_OP_CONT))
+      return fail(EPGX_ERR_INVALID, "FUSED record without its CONT record at " + std::to_string(i));
     if ((o.flags & EPGX_FLAG_INJECT) && (o.aux < 0 || o.aux >= t->nvar))
       return fail(EPGX_ERR_INVALID, "injection into unknown variable in record " + std::to_string(i));
     if (o.code == EPGX_OP_ADC) {
@@ -239,6 +244,8 @@ extern "C" int epgx_plan_create(const epgx_tape *t, epgx_plan **out) {
       return fail(EPGX_ERR_INVALID, "bad segment " + std::to_string(i));
     for (int r = s.first; r < s.first + s.count; ++r) {
       const epgx_op &o = t->ops[r];
+      if (o.code == EPGX_OP_FUSED && r + 1 >= s.first + s.count)
+        return fail(EPGX_ERR_INVALID, "FUSED record split from its CONT record in segment " + std::to_string(i));
       const double f = form_flops(o.code, o.flags, t->npool) * t->npool * (s.nact + 1.0);
       if (f == 0) continue;
       double sets = 0;

@@ -71,6 +71,56 @@ __device__ __forceinline__ Tri<real> form_t_im(const Tri<real> &s, real a, real 
   return o;
 }
 
+// fused E.T.E with real couplings (T_RE kind): five independent coefficients
+template <typename real>
+__device__ __forceinline__ Tri<real> form_t5_re(const Tri<real> &s, real a, real w, real b, real u, real h) {
+  Tri<real> o;
+  o.pr = a * s.pr + b * s.mr + u * s.zr;
+  o.pi = a * s.pi + b * s.mi + u * s.zi;
+  o.mr = a * s.mr + b * s.pr + u * s.zr;
+  o.mi = a * s.mi + b * s.pi + u * s.zi;
+  o.zr = w * s.zr + h * (s.pr + s.mr);
+  o.zi = w * s.zi + h * (s.pi + s.mi);
+  return o;
+}
+
+// fused E.T.E, T_IM kind (U = -i u): h = +1/2 e1' e2 u
+template <typename real>
+__device__ __forceinline__ Tri<real> form_t5_im(const Tri<real> &s, real a, real w, real b, real u, real h) {
+  Tri<real> o;
+  o.pr = a * s.pr + b * s.mr + u * s.zi;
+  o.pi = a * s.pi + b * s.mi - u * s.zr;
+  o.mr = a * s.mr + b * s.pr - u * s.zi;
+  o.mi = a * s.mi + b * s.pi + u * s.zr;
+  o.zr = w * s.zr + h * (s.pi - s.mi);
+  o.zi = w * s.zi - h * (s.pr - s.mr);
+  return o;
+}
+
+// coefficient assembly of a FUSED record (see include/epgx.h)
+template <typename real> struct Fused5 {
+  real a, w, b, u, h; // per-order coefficients
+  real fz, zz;        // affine terms at k = 0: F+-(0) += fz (RE) / -+ i fz (IM), Z(0) += zz
+};
+
+template <typename real>
+__device__ __forceinline__ Fused5<real> fuse5(real ta, real tw, real tb, real tu, bool pre, real e1a, real r0a, real e2a,
+                                              bool post, real e1b, real r0b, real e2b, bool im, real m0) {
+  if (!pre) { e1a = real(1); e2a = real(1); r0a = real(0); }
+  if (!post) { e1b = real(1); e2b = real(1); r0b = real(0); }
+  Fused5<real> f;
+  const real ff = e2b * e2a;
+  f.a = ff * ta;
+  f.b = ff * tb;
+  f.u = e2b * e1a * tu;
+  f.h = (im ? real(0.5) : real(-0.5)) * e1b * e2a * tu;
+  f.w = e1b * e1a * tw;
+  const real c1 = r0a * m0; // Z(0) offset of E_pre, pushed through T and E_post
+  f.fz = e2b * tu * c1;
+  f.zz = e1b * tw * c1 + r0b * m0;
+  return f;
+}
+
 // F+ *= (er + i ei), F- *= (er - i ei), Z *= e1     (er + i ei = e2 cis(2 pi g tau))
 template <typename real>
 __device__ __forceinline__ Tri<real> form_e_g(const Tri<real> &s, real e1, real er, real ei) {

@@ -36,6 +36,7 @@ __global__ void __launch_bounds__(256) reg_kernel(const KParams p) {
   const int srcUp = gbase | ((lq - 1) & (GW - 1));
   const int srcDn = gbase | ((lq + 1) & (GW - 1));
   const unsigned FULL = 0xffffffffu;
+  const bool is_first = lq == 0, is_last = lq == GW - 1;
   int lgG = 0;
   while ((1 << lgG) < G) ++lgG;
 
@@ -87,11 +88,10 @@ __global__ void __launch_bounds__(256) reg_kernel(const KParams p) {
 #define STORE_TRI(s, o) { Pr[s] = o.pr; Pi[s] = o.pi; Mr[s] = o.mr; Mi[s] = o.mi; Zr[s] = o.zr; Zi[s] = o.zi; }
 #define FOR_SLOTS(EXPR)                                  \
   _Pragma("unroll") for (int s = 0; s < NS; ++s) {       \
-    if (s < nslot) {                                     \
-      LOAD_TRI(s);                                       \
-      const Tri<real> o_ = EXPR;                         \
-      STORE_TRI(s, o_);                                  \
-    }                                                    \
+    if (s >= nslot) break;                               \
+    LOAD_TRI(s);                                         \
+    const Tri<real> o_ = EXPR;                           \
+    STORE_TRI(s, o_);                                    \
   }
 
   for (int sg = 0; sg < p.nseg; ++sg) {
@@ -159,13 +159,34 @@ __global__ void __launch_bounds__(256) reg_kernel(const KParams p) {
         }
       } break;
       case EPGX_OP_D: {
-        const real *c = coef + off0 + patoff[pat0] + 3 * lane;
+        // orders above nact inside the last active slot hold zeros / unobservable values: clamp the row
+        const real *c = coef + off0 + patoff[pat0];
 #pragma unroll
         for (int s = 0; s < NS; ++s)
-          if (s < nslot && s * G + lane <= nact) {
-            const real dp = ldc(c + 3 * s * G), dm = ldc(c + 3 * s * G + 1), dl = ldc(c + 3 * s * G + 2);
+          if (s < nslot) {
+            const int k = min(s * G + lane, p.C - 1);
+            const real dp = ldc(c + 3 * k), dm = ldc(c + 3 * k + 1), dl = ldc(c + 3 * k + 2);
             Pr[s] *= dp; Pi[s] *= dp; Mr[s] *= dm; Mi[s] *= dm; Zr[s] *= dl; Zi[s] *= dl;
           }
+      } break;
+      case EPGX_OP_FUSED: {
+        const int4 q0 = __ldg((const int4 *)(p.ops + r + 1));
+        const int4 q1 = __ldg((const int4 *)(p.ops + r + 1) + 1);
+        const real *ct = coef + off0 + patoff[pat0];
+        const real *ca = coef + off1 + patoff[pat1];
+        const real *cb = coef + (unsigned)q0.z + patoff[q1.y & 0xff];
+        const Fused5<real> f = fuse5<real>(ldc(ct), ldc(ct + 1), ldc(ct + 2), ldc(ct + 3), flags & EPGX_FLAG_PRE, ldc(ca),
+                                           ldc(ca + 1), ldc(coef + off2 + patoff[pat2]), flags & EPGX_FLAG_POST, ldc(cb),
+                                           ldc(cb + 1), ldc(coef + (unsigned)q0.w + patoff[(q1.y >> 8) & 0xff]),
+                                           flags & EPGX_FLAG_IM, m0);
+        if (flags & EPGX_FLAG_IM) {
+          FOR_SLOTS(form_t5_im(t_, f.a, f.w, f.b, f.u, f.h))
+          if (lane == 0 && nslot > 0) { Pi[0] -= f.fz; Mi[0] += f.fz; Zr[0] += f.zz; }
+        } else {
+          FOR_SLOTS(form_t5_re(t_, f.a, f.w, f.b, f.u, f.h))
+          if (lane == 0 && nslot > 0) { Pr[0] += f.fz; Mr[0] += f.fz; Zr[0] += f.zz; }
+        }
+        ++r; // the CONT record
       } break;
       case EPGX_OP_SPOIL:
 #pragma unroll
@@ -198,61 +219,82 @@ __global__ void __launch_bounds__(256) reg_kernel(const KParams p) {
       if (lane == 0) Zr[0] = m0;
     } else if (shift != 0) {
       const int nsl = (n_new >> lgG) + 1; // slots that hold an order <= n_new after the shift
-      const bool mask_top = sflags & EPGX_SEG_MASK_TOP;
-      // UR/UI: the component whose orders move up (F+ for shift > 0, F- for shift < 0); DR/DI: the other
-#define DO_SHIFT(UR, UI, DR, DI)                                                                          \
-  {                                                                                                        \
-    /* new order 0 of `up` = conj(old order 1 of `dn`): order 1 is lane 1 slot 0 (slot 1 if G == 1) */     \
-    real cr, ci;                                                                                           \
-    if (G == 1) { cr = NS > 1 ? DR[NS > 1 ? 1 : 0] : real(0); ci = NS > 1 ? DI[NS > 1 ? 1 : 0] : real(0); } \
-    else { cr = __shfl_sync(FULL, DR[0], gbase | 1); ci = __shfl_sync(FULL, DI[0], gbase | 1); }          \
-    if (n_old < 1) { cr = real(0); ci = real(0); }                                                         \
-    ci = -ci;                                                                                              \
-    real2 *xb = xbuf + (size_t)(parity * p.A + al) * W * 2 * NS;                                           \
-    if (W > 1) { /* boundary values of every warp of the atom: [warp][up | dn][slot] */                    \
-      if (lq == 31) { _Pragma("unroll") for (int s = 0; s < NS; ++s) xb[(wq * 2 + 0) * NS + s] = real2{UR[s], UI[s]}; } \
-      if (lq == 0) { _Pragma("unroll") for (int s = 0; s < NS; ++s) xb[(wq * 2 + 1) * NS + s] = real2{DR[s], DI[s]}; }  \
-      asm volatile("bar.sync %0, %1;" ::"r"(1 + al), "r"(G) : "memory");                                   \
-      parity ^= 1;                                                                                         \
-    }                                                                                                      \
-    /* up: rotate by one lane; the first lane takes the wrap-around value */                               \
-    _Pragma("unroll") for (int s = 0; s < NS; ++s) {                                                       \
-      if (s < nsl) {                                                                                       \
-        const real rr = __shfl_sync(FULL, UR[s], srcUp), ri = __shfl_sync(FULL, UI[s], srcUp);             \
-        real vr = rr, vi = ri;                                                                             \
-        if (lq == 0) {                                                                                     \
-          if (W == 1 || wq == 0) { vr = cr; vi = ci; }                                                     \
-          else { const real2 x = xb[((wq - 1) * 2 + 0) * NS + s]; vr = x.x; vi = x.y; }                    \
-        }                                                                                                  \
-        if (W == 1) { cr = rr; ci = ri; }                                                                  \
-        else if (lane == 0) { const real2 x = xb[((W - 1) * 2 + 0) * NS + s]; cr = x.x; ci = x.y; }        \
-        UR[s] = vr; UI[s] = vi;                                                                            \
-        if (mask_top && s * G + lane > n_new) { UR[s] = real(0); UI[s] = real(0); }                        \
-      }                                                                                                    \
-    }                                                                                                      \
-    /* dn: rotate the other way; the last lane takes the value of the NEXT slot (next warp) */             \
-    real nr = __shfl_sync(FULL, DR[0], srcDn), ni = __shfl_sync(FULL, DI[0], srcDn);                       \
-    _Pragma("unroll") for (int s = 0; s < NS; ++s) {                                                       \
-      if (s < nsl) {                                                                                       \
-        real xr = real(0), xi = real(0);                                                                   \
-        if (s + 1 < NS) {                                                                                  \
-          xr = __shfl_sync(FULL, DR[s + 1 < NS ? s + 1 : s], srcDn);                                       \
-          xi = __shfl_sync(FULL, DI[s + 1 < NS ? s + 1 : s], srcDn);                                       \
-        }                                                                                                  \
-        real vr = nr, vi = ni;                                                                             \
-        if (lq == GW - 1) {                                                                                \
-          if (W == 1) { vr = xr; vi = xi; }                                                                \
-          else if (wq < W - 1) { const real2 x = xb[((wq + 1) * 2 + 1) * NS + s]; vr = x.x; vi = x.y; }    \
-          else if (s + 1 < NS) { const real2 x = xb[(0 * 2 + 1) * NS + (s + 1 < NS ? s + 1 : s)]; vr = x.x; vi = x.y; } \
-          else { vr = real(0); vi = real(0); }                                                             \
-        }                                                                                                  \
-        DR[s] = vr; DI[s] = vi;                                                                            \
-        nr = xr; ni = xi;                                                                                  \
-      }                                                                                                    \
-    }                                                                                                      \
+      // UR/UI: the component whose orders move up (F+ for shift > 0, F- for shift < 0); DR/DI: the other.
+      // new order 0 of `up` = conj(old order 1 of `dn`): order 1 is lane 1 slot 0 (slot 1 if G == 1)
+#define SHIFT_HEAD(DR, DI)                                                                                  \
+    real cr, ci;                                                                                             \
+    if (G == 1) { cr = NS > 1 ? DR[NS > 1 ? 1 : 0] : real(0); ci = NS > 1 ? DI[NS > 1 ? 1 : 0] : real(0); }  \
+    else { cr = __shfl_sync(FULL, DR[0], gbase | 1); ci = __shfl_sync(FULL, DI[0], gbase | 1); }             \
+    if (n_old < 1) { cr = real(0); ci = real(0); }                                                           \
+    ci = -ci;
+      // one warp (or less) per atom: pure register / shuffle traffic
+#define SHIFT_W1(UR, UI, DR, DI)                                                                             \
+  {                                                                                                          \
+    SHIFT_HEAD(DR, DI)                                                                                       \
+    _Pragma("unroll") for (int s = 0; s < NS; ++s) {                                                         \
+      if (s >= nsl) break;                                                                                   \
+      const real rr = __shfl_sync(FULL, UR[s], srcUp), ri = __shfl_sync(FULL, UI[s], srcUp);                 \
+      UR[s] = is_first ? cr : rr;                                                                            \
+      UI[s] = is_first ? ci : ri;                                                                            \
+      cr = rr; ci = ri;                                                                                      \
+    }                                                                                                        \
+    real nr = __shfl_sync(FULL, DR[0], srcDn), ni = __shfl_sync(FULL, DI[0], srcDn);                         \
+    _Pragma("unroll") for (int s = 0; s < NS; ++s) {                                                         \
+      if (s >= nsl) break;                                                                                   \
+      real xr = real(0), xi = real(0);                                                                       \
+      if (s + 1 < NS) {                                                                                      \
+        xr = __shfl_sync(FULL, DR[s + 1 < NS ? s + 1 : s], srcDn);                                           \
+        xi = __shfl_sync(FULL, DI[s + 1 < NS ? s + 1 : s], srcDn);                                           \
+      }                                                                                                      \
+      DR[s] = is_last ? xr : nr;                                                                             \
+      DI[s] = is_last ? xi : ni;                                                                             \
+      nr = xr; ni = xi;                                                                                      \
+    }                                                                                                        \
   }
-      if (shift > 0) DO_SHIFT(Pr, Pi, Mr, Mi) else DO_SHIFT(Mr, Mi, Pr, Pi)
-#undef DO_SHIFT
+      // several warps per atom: the boundary lanes of each warp go through shared memory
+#define SHIFT_WN(UR, UI, DR, DI)                                                                             \
+  {                                                                                                          \
+    SHIFT_HEAD(DR, DI)                                                                                       \
+    real2 *xb = xbuf + (size_t)(parity * p.A + al) * W * 2 * NS; /* [warp][up | dn][slot] */                 \
+    if (lq == 31) { _Pragma("unroll") for (int s = 0; s < NS; ++s) xb[(wq * 2 + 0) * NS + s] = real2{UR[s], UI[s]}; } \
+    if (lq == 0) { _Pragma("unroll") for (int s = 0; s < NS; ++s) xb[(wq * 2 + 1) * NS + s] = real2{DR[s], DI[s]}; }  \
+    asm volatile("bar.sync %0, %1;" ::"r"(1 + al), "r"(G) : "memory");                                       \
+    parity ^= 1;                                                                                             \
+    _Pragma("unroll") for (int s = 0; s < NS; ++s) {                                                         \
+      if (s >= nsl) break;                                                                                   \
+      real vr = __shfl_sync(FULL, UR[s], srcUp), vi = __shfl_sync(FULL, UI[s], srcUp);                       \
+      if (lq == 0) {                                                                                         \
+        if (wq == 0) { vr = cr; vi = ci; const real2 x = xb[((W - 1) * 2 + 0) * NS + s]; cr = x.x; ci = x.y; } \
+        else { const real2 x = xb[((wq - 1) * 2 + 0) * NS + s]; vr = x.x; vi = x.y; }                        \
+      }                                                                                                      \
+      UR[s] = vr; UI[s] = vi;                                                                                \
+    }                                                                                                        \
+    _Pragma("unroll") for (int s = 0; s < NS; ++s) {                                                         \
+      if (s >= nsl) break;                                                                                   \
+      real vr = __shfl_sync(FULL, DR[s], srcDn), vi = __shfl_sync(FULL, DI[s], srcDn);                       \
+      if (lq == 31) {                                                                                        \
+        if (wq < W - 1) { const real2 x = xb[((wq + 1) * 2 + 1) * NS + s]; vr = x.x; vi = x.y; }             \
+        else if (s + 1 < NS) { const real2 x = xb[(0 * 2 + 1) * NS + (s + 1 < NS ? s + 1 : s)]; vr = x.x; vi = x.y; } \
+        else { vr = real(0); vi = real(0); }                                                                 \
+      }                                                                                                      \
+      DR[s] = vr; DI[s] = vi;                                                                                \
+    }                                                                                                        \
+  }
+      if (W == 1) {
+        if (shift > 0) SHIFT_W1(Pr, Pi, Mr, Mi) else SHIFT_W1(Mr, Mi, Pr, Pi)
+      } else {
+        if (shift > 0) SHIFT_WN(Pr, Pi, Mr, Mi) else SHIFT_WN(Mr, Mi, Pr, Pi)
+      }
+#undef SHIFT_HEAD
+#undef SHIFT_W1
+#undef SHIFT_WN
+      if (sflags & EPGX_SEG_MASK_TOP) { // truncation at max_nstate: what moved above n_new reads as zero
+#pragma unroll
+        for (int s = 0; s < NS; ++s)
+          if (s * G + lane > n_new) {
+            if (shift > 0) { Pr[s] = real(0); Pi[s] = real(0); } else { Mr[s] = real(0); Mi[s] = real(0); }
+          }
+      }
     }
   }
 #undef FOR_SLOTS

@@ -24,8 +24,9 @@ from .operators import (PD, Adc, D, DiffOperator, EmptyOperator, Jacobian, Multi
 from .statematrix import StateMatrix
 
 # opcodes / flags (include/epgx.h)
-OP_NOP, OP_T_GEN, OP_T_RE, OP_T_IM, OP_E, OP_DIAG, OP_MATRIX, OP_D, OP_X, OP_SPOIL, OP_PD, OP_ADC = range(12)
-F_BASE, F_PARTIALS, F_INJECT, F_G, F_AFFINE, F_Z0, F_SCALE = (1 << i for i in range(7))
+(OP_NOP, OP_T_GEN, OP_T_RE, OP_T_IM, OP_E, OP_DIAG, OP_MATRIX, OP_D, OP_X, OP_SPOIL, OP_PD, OP_ADC, OP_FUSED,
+ OP_CONT) = range(14)
+F_BASE, F_PARTIALS, F_INJECT, F_G, F_AFFINE, F_Z0, F_SCALE, F_PRE, F_POST, F_IM = (1 << i for i in range(10))
 SEG_RESET, SEG_MASK_TOP = 1, 2
 MAX_DIMS, MAX_PATTERNS, MAX_POOLS = 8, 64, 2
 
@@ -207,8 +208,56 @@ def _multiple(v, base):
     return m
 
 
+def fuse_records(recs, segs):
+    """peephole pass ("squeeze", a stub in the reference: epgpy/functions.py:350-352): runs of
+    [E] [T_RE | T_IM] [E] without precession or derivatives become one FUSED + CONT record pair, applied
+    in a single sweep over the orders.  An E that closes a segment acts identically on every order, so
+    it commutes with the unit shift and is moved to the head of the next segment when a T waits there."""
+
+    def pure_e(r):
+        return r["code"] == OP_E and (int(r["flags"]) & ~F_AFFINE) == F_BASE
+
+    def pulse(r):
+        return r["code"] in (OP_T_RE, OP_T_IM) and int(r["flags"]) == F_BASE
+
+    out, carry = [], []
+    for i in range(len(segs)):
+        seg = segs[i]
+        rs = carry + [recs[j] for j in range(seg["first"], seg["first"] + seg["count"])]
+        carry = []
+        if seg["shift"] != 0 and not (seg["flags"] & SEG_RESET) and i + 1 < len(segs) and segs[i + 1]["count"] > 0 \
+                and pulse(recs[segs[i + 1]["first"]]) and rs and pure_e(rs[-1]):
+            carry = [rs.pop()]
+        new, j = [], 0
+        while j < len(rs):
+            pre = None
+            if pure_e(rs[j]) and j + 1 < len(rs) and pulse(rs[j + 1]):
+                pre, j = rs[j], j + 1
+            if pulse(rs[j]) and (pre is not None or (j + 1 < len(rs) and pure_e(rs[j + 1]))):
+                t = rs[j]
+                post = rs[j + 1] if j + 1 < len(rs) and pure_e(rs[j + 1]) else None
+                f = np.zeros((), dtype=OP_DTYPE)
+                c = np.zeros((), dtype=OP_DTYPE)
+                f["code"], c["code"] = OP_FUSED, OP_CONT
+                f["flags"] = F_BASE | (F_IM if t["code"] == OP_T_IM else 0) | (F_PRE if pre is not None else 0) \
+                    | (F_POST if post is not None else 0)
+                f["off"][0], f["pat"][0] = t["off"][0], t["pat"][0]
+                if pre is not None:
+                    f["off"][1:3], f["pat"][1:3] = pre["off"][0:2], pre["pat"][0:2]
+                if post is not None:
+                    c["off"][0:2], c["pat"][0:2] = post["off"][0:2], post["pat"][0:2]
+                new += [f, c]
+                j += 2 if post is not None else 1
+            else:
+                new.append(rs[j])
+                j += 1
+        segs[i]["first"], segs[i]["count"] = len(out), len(new)
+        out += new
+    return (np.array(out, dtype=OP_DTYPE) if out else np.zeros(0, dtype=OP_DTYPE)), segs
+
+
 def lower(sequence, *, init=None, probe=None, options=None, dtype="f64", propagate_nondiff=False,
-          prune_unobservable=True):
+          prune_unobservable=True, fuse=True):
     """sequence -> Lowered"""
     options = dict(options or {})
     seq = flatten_sequence(sequence)
@@ -499,6 +548,8 @@ def lower(sequence, *, init=None, probe=None, options=None, dtype="f64", propaga
     # ---- prune orders that cannot reach k = 0 before the last read-out
     recs = np.array(bld.records, dtype=OP_DTYPE) if bld.records else np.zeros(0, dtype=OP_DTYPE)
     segs = np.array(segs, dtype=SEG_DTYPE)
+    if fuse and not nvar:
+        recs, segs = fuse_records(recs, segs)
     if prune_unobservable:
         reach = -1
         for i in range(len(segs) - 1, -1, -1):

@@ -98,7 +98,16 @@ typedef enum {
    *   (ADC phasor x weights).  aux = row of `signal` (EPGX_FLAG_BASE), aux1 = row of `jacobian`
    *   (EPGX_FLAG_PARTIALS). */
   EPGX_OP_ADC = 11,
-  EPGX_OP_COUNT = 12
+  /* fused E_pre -> T -> E_post (the host's peephole pass over [E, T_RE|T_IM, E] runs without precession;
+   * an E that closes a segment commutes with the shift and becomes the E_pre of the next segment).
+   * Two records: FUSED carries blk0: T (a, w, b, u), blk1: pre (e1, r0), blk2: pre (e2);
+   * the CONT record that follows carries blk0: post (e1, r0), blk1: post (e2).  Per atom the kernel
+   * assembles A = e2' e2 a, B = e2' e2 b, U = e2' e1 u, H = -+1/2 e1' e2 u, W = e1' e1 w and applies
+   *   F+' = A F+ + B F- + U' Z ; F-' = B F+ + A F- + conj(U') Z ; Z' = W Z + H (..)   (U' = U or -iU)
+   * to every order, then the affine terms of both E at k = 0. */
+  EPGX_OP_FUSED = 12,
+  EPGX_OP_CONT = 13,
+  EPGX_OP_COUNT = 14
 } epgx_opcode;
 
 enum {
@@ -110,7 +119,10 @@ enum {
   EPGX_FLAG_G = 1 << 3,      /* E: precession phasor present                  */
   EPGX_FLAG_AFFINE = 1 << 4, /* E/DIAG/MATRIX: equilibrium term present       */
   EPGX_FLAG_Z0 = 1 << 5,     /* ADC: read Z(0) instead of F+(0)               */
-  EPGX_FLAG_SCALE = 1 << 6   /* ADC: multiply by the complex factor in blk0   */
+  EPGX_FLAG_SCALE = 1 << 6,  /* ADC: multiply by the complex factor in blk0   */
+  EPGX_FLAG_PRE = 1 << 7,    /* FUSED: E_pre present                          */
+  EPGX_FLAG_POST = 1 << 8,   /* FUSED: E_post present (in the CONT record)    */
+  EPGX_FLAG_IM = 1 << 9      /* FUSED: T is of the T_IM kind (else T_RE)      */
 };
 
 /* tape record, 32 bytes */

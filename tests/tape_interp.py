@@ -43,10 +43,34 @@ def run(low):
     def cplx(b, i):
         return b[..., i] + 1j * b[..., i + 1]
 
+    def expand(records):
+        """FUSED + CONT -> the E / T / E records they stand for (independent check of the fusion)"""
+        out, it = [], iter(records)
+        for rec in it:
+            if int(rec["code"]) != L.OP_FUSED:
+                out.append(rec)
+                continue
+            cont = next(it)
+            fl = int(rec["flags"])
+            if fl & L.F_PRE:
+                e = np.zeros((), dtype=L.OP_DTYPE)
+                e["code"], e["flags"] = L.OP_E, L.F_BASE | L.F_AFFINE
+                e["off"][0:2], e["pat"][0:2] = rec["off"][1:3], rec["pat"][1:3]
+                out.append(e)
+            t = np.zeros((), dtype=L.OP_DTYPE)
+            t["code"], t["flags"] = (L.OP_T_IM if fl & L.F_IM else L.OP_T_RE), L.F_BASE
+            t["off"][0], t["pat"][0] = rec["off"][0], rec["pat"][0]
+            out.append(t)
+            if fl & L.F_POST:
+                e = np.zeros((), dtype=L.OP_DTYPE)
+                e["code"], e["flags"] = L.OP_E, L.F_BASE | L.F_AFFINE
+                e["off"][0:2], e["pat"][0:2] = cont["off"][0:2], cont["pat"][0:2]
+                out.append(e)
+        return out
+
     for seg in low.segs:
         na = int(seg["nact"]) + 1
-        for r in range(seg["first"], seg["first"] + seg["count"]):
-            rec = low.ops[r]
+        for rec in expand(low.ops[seg["first"]: seg["first"] + seg["count"]]):
             code, flags, aux, aux1 = int(rec["code"]), int(rec["flags"]), int(rec["aux"]), int(rec["aux1"])
             off, pat = rec["off"], rec["pat"]
             sets = []
