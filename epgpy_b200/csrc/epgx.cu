@@ -35,10 +35,11 @@ struct epgx_plan {
   std::vector<double> coef64;
   std::vector<float> coef32;
   std::vector<int> pats; // [npattern][MAX_DIMS+1]
+  std::vector<epgx_op> stream; // segments + records merged (register kernel)
   int64_t natoms;
   epgx_config cfg;
   // workspace layout (bytes)
-  int64_t off_ops, off_segs, off_pats, off_coef, ws_bytes;
+  int64_t off_ops, off_segs, off_pats, off_stream, off_coef, ws_bytes;
 };
 
 static const int kSmemLimit = 227 * 1024;
@@ -87,7 +88,7 @@ static int choose_variant(epgx_plan *pl, int kernel, int lanes, int vars, int at
     return fail(EPGX_ERR_UNSUPPORTED, "the register kernel runs forward simulations of one pool only");
   if (reg_ok && kernel != 1) {
     // ---- register kernel: G lanes x NS slots >= C orders
-    const int ns_max = t.dtype == EPGX_F64 ? 8 : 16;
+    const int ns_max = 16;
     int G;
     if (lanes > 0) {
       G = pow2ceil(lanes);
@@ -112,7 +113,7 @@ static int choose_variant(epgx_plan *pl, int kernel, int lanes, int vars, int at
         c.var_tiles = 1;
         c.atoms_per_cta = A;
         c.threads_per_cta = A * G;
-        c.smem_bytes = ((A * t.npattern + 3) & ~3) * 4 + (W > 1 ? 2 * A * W * 2 * NS * 2 * rsz : 0) + 32;
+        c.smem_bytes = 2 * epgx::TAPE_CHUNK * 32 + ((A * t.npattern + 3) & ~3) * 4 + (W > 1 ? 2 * A * W * 2 * NS * 2 * rsz : 0) + 32;
         c.ring = C;
         return EPGX_OK;
       }
@@ -272,6 +273,35 @@ extern "C" int epgx_plan_create(const epgx_tape *t, epgx_plan **out) {
     for (int d = 0; d < t->ndim; ++d) pl->pats[q * (EPGX_MAX_DIMS + 1) + d] = t->stride[q][d];
     pl->pats[q * (EPGX_MAX_DIMS + 1) + EPGX_MAX_DIMS] = t->pool_stride[q];
   }
+  {
+    // merged stream: [SEG(open seg 0)] recs_0 [SEG(close 0, open 1)] recs_1 ... [SEG(close last)]; a FUSED record
+    // is never the last one of a TAPE_CHUNK window (NOP padding)
+    auto seg_rec = [](int shift, int n_old, int n_new, int flags, int next_nact) {
+      epgx_op o;
+      memset(&o, 0, sizeof(o));
+      o.code = EPGX_OP_SEG;
+      o.aux = next_nact;
+      o.off[0] = (uint32_t)shift;
+      o.off[1] = (uint32_t)n_old;
+      o.off[2] = (uint32_t)n_new;
+      o.aux1 = flags;
+      return o;
+    };
+    std::vector<epgx_op> &st = pl->stream;
+    epgx_op nop;
+    memset(&nop, 0, sizeof(nop));
+    for (int64_t i = 0; i <= t->nseg; ++i) {
+      const epgx_segment *prev = i > 0 ? &t->segs[i - 1] : nullptr;
+      const int next_nact = i < t->nseg ? t->segs[i].nact : -1;
+      st.push_back(prev ? seg_rec(prev->shift, prev->n_old, prev->n_new, prev->flags, next_nact) : seg_rec(0, 0, 0, 0, next_nact));
+      if (i == t->nseg) break;
+      const epgx_segment &sg = t->segs[i];
+      for (int r = sg.first; r < sg.first + sg.count; ++r) {
+        if (t->ops[r].code == EPGX_OP_FUSED && (int)(st.size() % epgx::TAPE_CHUNK) == epgx::TAPE_CHUNK - 1) st.push_back(nop);
+        st.push_back(t->ops[r]);
+      }
+    }
+  }
   pl->tape.ops = pl->ops.data();
   pl->tape.segs = pl->segs.data();
   pl->tape.coef = nullptr;
@@ -290,7 +320,8 @@ extern "C" int epgx_plan_create(const epgx_tape *t, epgx_plan **out) {
   pl->off_ops = 0;
   pl->off_segs = align(pl->off_ops + (int64_t)sizeof(epgx_op) * (t->nop ? t->nop : 1));
   pl->off_pats = align(pl->off_segs + (int64_t)sizeof(epgx_segment) * (t->nseg ? t->nseg : 1));
-  pl->off_coef = align(pl->off_pats + (int64_t)pl->pats.size() * 4);
+  pl->off_stream = align(pl->off_pats + (int64_t)pl->pats.size() * 4);
+  pl->off_coef = align(pl->off_stream + (int64_t)sizeof(epgx_op) * pl->stream.size());
   pl->ws_bytes = align(pl->off_coef + t->ncoef * rsz);
   *out = pl;
   return EPGX_OK;
@@ -332,6 +363,7 @@ extern "C" int epgx_plan_upload(const epgx_plan *pl, void *ws, void *stream) {
   if (t.nseg)
     CUDA_TRY(cudaMemcpyAsync(w + pl->off_segs, pl->segs.data(), sizeof(epgx_segment) * t.nseg, cudaMemcpyHostToDevice, st));
   CUDA_TRY(cudaMemcpyAsync(w + pl->off_pats, pl->pats.data(), pl->pats.size() * 4, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(w + pl->off_stream, pl->stream.data(), sizeof(epgx_op) * pl->stream.size(), cudaMemcpyHostToDevice, st));
   if (t.dtype == EPGX_F64)
     CUDA_TRY(cudaMemcpyAsync(w + pl->off_coef, pl->coef64.data(), t.ncoef * 8, cudaMemcpyHostToDevice, st));
   else
@@ -401,6 +433,8 @@ extern "C" int epgx_simulate_strided(const epgx_plan *pl, const void *ws, int64_
   kp.ops = (const epgx_op *)(w + pl->off_ops);
   kp.segs = (const epgx_segment *)(w + pl->off_segs);
   kp.pats = (const int *)(w + pl->off_pats);
+  kp.stream = w + pl->off_stream;
+  kp.nstream = (int)pl->stream.size();
   kp.coef = w + pl->off_coef;
   kp.signal = signal;
   kp.jac = jacobian;

@@ -10,6 +10,10 @@
 
 #include "epgx.h"
 
+// internal record of the merged stream: ends a segment (unit shift / reset of the segment that just ran:
+// off[0] = shift, off[1] = n_old, off[2] = n_new, aux1 = segment flags) and opens the next one (aux = nact)
+#define EPGX_OP_SEG 64
+
 namespace epgx {
 
 template <typename real> struct vec2;
@@ -173,6 +177,8 @@ struct KParams {
   const epgx_op *ops;
   const epgx_segment *segs;
   const void *coef;
+  const void *stream; // reg kernel: segments and records merged in one record stream (EPGX_OP_SEG markers)
+  int nstream;
   const int *pats; // [npattern][EPGX_MAX_DIMS + 1]: axis strides then pool stride (reals)
   void *signal;
   void *jac;

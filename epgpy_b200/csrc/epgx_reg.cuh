@@ -14,9 +14,13 @@
 //    only the coefficient tables (L2-resident) and the ADC samples.
 // Forward simulation, one pool.  Partial derivatives and exchange run in the ring kernel.
 #pragma once
+#include <cuda_pipeline.h>
+
 #include "epgx_common.cuh"
 
 namespace epgx {
+
+constexpr int TAPE_CHUNK = 64; // records per shared-memory tape window
 
 template <typename real, int NS>
 __global__ void __launch_bounds__(256) reg_kernel(const KParams p) {
@@ -45,9 +49,11 @@ __global__ void __launch_bounds__(256) reg_kernel(const KParams p) {
   const long long atom = p.atom_begin + (valid ? a_rel : p.atom_count - 1);
   const real *__restrict__ coef = (const real *)p.coef;
 
-  // shared memory: pattern offsets [A][npattern] int, then (multi-warp atoms) boundary exchange
-  int *patoff = (int *)smem_raw + al * p.npattern;
-  real2 *xbuf = (real2 *)((int *)smem_raw + ((p.A * p.npattern + 3) & ~3)); // [2 parity][A][W][2 (P,M)][NS]
+  // shared memory: tape window [2][TAPE_CHUNK] records, pattern offsets [A][npattern] int, then
+  // (multi-warp atoms) boundary exchange [2 parity][A][W][2 (up, dn)][NS]
+  int4 *tbuf = (int4 *)smem_raw;
+  int *patoff = (int *)(tbuf + 2 * TAPE_CHUNK * 2) + al * p.npattern;
+  real2 *xbuf = (real2 *)((int *)(tbuf + 2 * TAPE_CHUNK * 2) + ((p.A * p.npattern + 3) & ~3));
   {
     int idx[EPGX_MAX_DIMS];
     long long r = atom;
@@ -94,16 +100,27 @@ __global__ void __launch_bounds__(256) reg_kernel(const KParams p) {
     STORE_TRI(s, o_);                                    \
   }
 
-  for (int sg = 0; sg < p.nseg; ++sg) {
-    const int4 s0 = __ldg((const int4 *)(p.segs + sg));
-    const int4 s1 = __ldg((const int4 *)(p.segs + sg) + 1);
-    const int first = s0.x, count = s0.y, nact = s0.z, shift = s0.w;
-    const int n_old = s1.x, n_new = s1.y, sflags = s1.z;
-    const int nslot = nact < 0 ? 0 : (nact >> lgG) + 1; // slots with at least one order <= nact
-
-    for (int r = first; r < first + count; ++r) {
-      const int4 r0 = __ldg((const int4 *)(p.ops + r));
-      const int4 r1 = __ldg((const int4 *)(p.ops + r) + 1);
+  // ---- the tape is streamed through shared memory in chunks of TAPE_CHUNK records (cp.async, double
+  // buffered): a record fetch is two broadcast LDS instead of two dependent global loads
+  const int4 *stream = (const int4 *)p.stream;
+  const int nthreads = blockDim.x;
+  for (int i = tid; i < 2 * TAPE_CHUNK && i < 2 * p.nstream; i += nthreads) __pipeline_memcpy_async(tbuf + i, stream + i, 16);
+  __pipeline_commit();
+  int nact = -1, nslot = 0;
+  for (int base = 0, chunk = 0; base < p.nstream; base += TAPE_CHUNK, ++chunk) {
+    __pipeline_wait_prior(0);
+    __syncthreads(); // chunk `chunk` has landed; every warp is done with the buffer about to be refilled
+    {
+      const int nb = base + TAPE_CHUNK;
+      int4 *dst = tbuf + ((chunk + 1) & 1) * 2 * TAPE_CHUNK;
+      for (int i = tid; i < 2 * TAPE_CHUNK && nb * 2 + i < 2 * p.nstream; i += nthreads)
+        __pipeline_memcpy_async(dst + i, stream + (size_t)nb * 2 + i, 16);
+      __pipeline_commit();
+    }
+    const int4 *tb = tbuf + (chunk & 1) * 2 * TAPE_CHUNK;
+    const int cnt = min(TAPE_CHUNK, p.nstream - base);
+    for (int r = 0; r < cnt; ++r) {
+      const int4 r0 = tb[2 * r], r1 = tb[2 * r + 1];
       const int code = r0.x & 0xffff, flags = (r0.x >> 16) & 0xffff, aux = r0.y;
       const unsigned off0 = (unsigned)r0.z, off1 = (unsigned)r0.w, off2 = (unsigned)r1.x;
       const int pat0 = r1.y & 0xff, pat1 = (r1.y >> 8) & 0xff, pat2 = (r1.y >> 16) & 0xff;
@@ -170,8 +187,7 @@ __global__ void __launch_bounds__(256) reg_kernel(const KParams p) {
           }
       } break;
       case EPGX_OP_FUSED: {
-        const int4 q0 = __ldg((const int4 *)(p.ops + r + 1));
-        const int4 q1 = __ldg((const int4 *)(p.ops + r + 1) + 1);
+        const int4 q0 = tb[2 * r + 2], q1 = tb[2 * r + 3]; // the CONT record (never split from FUSED)
         const real *ct = coef + off0 + patoff[pat0];
         const real *ca = coef + off1 + patoff[pat1];
         const real *cb = coef + (unsigned)q0.z + patoff[q1.y & 0xff];
@@ -208,16 +224,16 @@ __global__ void __launch_bounds__(256) reg_kernel(const KParams p) {
           sig[(long long)aux * p.sig_stride + a_rel] = real2{xr * fr - xi * fi, xr * fi + xi * fr};
         }
         break;
-      default:
-        break;
-      }
-    }
-
-    if (sflags & EPGX_SEG_RESET) {
+      case EPGX_OP_SEG: {
+        // end of a segment: unit shift / reset of the previous one, then the next pass's order count
+        const int shift = (int)off0, n_old = (int)off1, n_new = (int)off2, sflags = r1.z;
+        nact = aux;
+        nslot = nact < 0 ? 0 : (nact >> lgG) + 1; // slots with at least one order <= nact
+        if (sflags & EPGX_SEG_RESET) {
 #pragma unroll
-      for (int s = 0; s < NS; ++s) Pr[s] = Pi[s] = Mr[s] = Mi[s] = Zr[s] = Zi[s] = real(0);
-      if (lane == 0) Zr[0] = m0;
-    } else if (shift != 0) {
+          for (int s = 0; s < NS; ++s) Pr[s] = Pi[s] = Mr[s] = Mi[s] = Zr[s] = Zi[s] = real(0);
+          if (lane == 0) Zr[0] = m0;
+        } else if (shift != 0) {
       const int nsl = (n_new >> lgG) + 1; // slots that hold an order <= n_new after the shift
       // UR/UI: the component whose orders move up (F+ for shift > 0, F- for shift < 0); DR/DI: the other.
       // new order 0 of `up` = conj(old order 1 of `dn`): order 1 is lane 1 slot 0 (slot 1 if G == 1)
@@ -288,12 +304,17 @@ __global__ void __launch_bounds__(256) reg_kernel(const KParams p) {
 #undef SHIFT_HEAD
 #undef SHIFT_W1
 #undef SHIFT_WN
-      if (sflags & EPGX_SEG_MASK_TOP) { // truncation at max_nstate: what moved above n_new reads as zero
+          if (sflags & EPGX_SEG_MASK_TOP) { // truncation at max_nstate: what moved above n_new reads as zero
 #pragma unroll
-        for (int s = 0; s < NS; ++s)
-          if (s * G + lane > n_new) {
-            if (shift > 0) { Pr[s] = real(0); Pi[s] = real(0); } else { Mr[s] = real(0); Mi[s] = real(0); }
+            for (int s = 0; s < NS; ++s)
+              if (s * G + lane > n_new) {
+                if (shift > 0) { Pr[s] = real(0); Pi[s] = real(0); } else { Mr[s] = real(0); Mi[s] = real(0); }
+              }
           }
+        }
+      } break;
+      default:
+        break;
       }
     }
   }
