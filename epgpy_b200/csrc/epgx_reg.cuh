@@ -92,13 +92,24 @@ __global__ void __launch_bounds__(256) reg_kernel(const KParams p) {
 
 #define LOAD_TRI(s) Tri<real> t_ = {Pr[s], Pi[s], Mr[s], Mi[s], Zr[s], Zi[s]}
 #define STORE_TRI(s, o) { Pr[s] = o.pr; Pi[s] = o.pi; Mr[s] = o.mr; Mi[s] = o.mi; Zr[s] = o.zr; Zi[s] = o.zi; }
-#define FOR_SLOTS(EXPR)                                  \
-  _Pragma("unroll") for (int s = 0; s < NS; ++s) {       \
-    if (s >= nslot) break;                               \
-    LOAD_TRI(s);                                         \
-    const Tri<real> o_ = EXPR;                           \
-    STORE_TRI(s, o_);                                    \
+// Duff-style dispatch: run BODY for slots n-1 .. 0 with ONE branch (the slots are independent, or are
+// written so that descending order is the in-place order); `s` is a compile-time constant in BODY
+#define SLOT_CASE(K, ...)                      \
+  case (K) + 1:                                \
+    if (NS > (K)) {                            \
+      constexpr int s = (K) < NS ? (K) : 0;    \
+      __VA_ARGS__                              \
+    }
+#define DUFF(n, ...)                                                                                        \
+  switch (n) {                                                                                              \
+    SLOT_CASE(15, __VA_ARGS__) SLOT_CASE(14, __VA_ARGS__) SLOT_CASE(13, __VA_ARGS__) SLOT_CASE(12, __VA_ARGS__) \
+    SLOT_CASE(11, __VA_ARGS__) SLOT_CASE(10, __VA_ARGS__) SLOT_CASE(9, __VA_ARGS__) SLOT_CASE(8, __VA_ARGS__)   \
+    SLOT_CASE(7, __VA_ARGS__) SLOT_CASE(6, __VA_ARGS__) SLOT_CASE(5, __VA_ARGS__) SLOT_CASE(4, __VA_ARGS__)     \
+    SLOT_CASE(3, __VA_ARGS__) SLOT_CASE(2, __VA_ARGS__) SLOT_CASE(1, __VA_ARGS__) SLOT_CASE(0, __VA_ARGS__)     \
+  default:                                                                                                  \
+    break;                                                                                                  \
   }
+#define FOR_SLOTS(EXPR) DUFF(nslot, { LOAD_TRI(s); const Tri<real> o_ = EXPR; STORE_TRI(s, o_); })
 
   // ---- the tape is streamed through shared memory in chunks of TAPE_CHUNK records (cp.async, double
   // buffered): a record fetch is two broadcast LDS instead of two dependent global loads
@@ -178,13 +189,11 @@ __global__ void __launch_bounds__(256) reg_kernel(const KParams p) {
       case EPGX_OP_D: {
         // orders above nact inside the last active slot hold zeros / unobservable values: clamp the row
         const real *c = coef + off0 + patoff[pat0];
-#pragma unroll
-        for (int s = 0; s < NS; ++s)
-          if (s < nslot) {
-            const int k = min(s * G + lane, p.C - 1);
-            const real dp = ldc(c + 3 * k), dm = ldc(c + 3 * k + 1), dl = ldc(c + 3 * k + 2);
-            Pr[s] *= dp; Pi[s] *= dp; Mr[s] *= dm; Mi[s] *= dm; Zr[s] *= dl; Zi[s] *= dl;
-          }
+        DUFF(nslot, {
+          const int k = min(s * G + lane, p.C - 1);
+          const real dp = ldc(c + 3 * k), dm = ldc(c + 3 * k + 1), dl = ldc(c + 3 * k + 2);
+          Pr[s] *= dp; Pi[s] *= dp; Mr[s] *= dm; Mi[s] *= dm; Zr[s] *= dl; Zi[s] *= dl;
+        })
       } break;
       case EPGX_OP_FUSED: {
         const int4 q0 = tb[2 * r + 2], q1 = tb[2 * r + 3]; // the CONT record (never split from FUSED)
@@ -205,9 +214,7 @@ __global__ void __launch_bounds__(256) reg_kernel(const KParams p) {
         ++r; // the CONT record
       } break;
       case EPGX_OP_SPOIL:
-#pragma unroll
-        for (int s = 0; s < NS; ++s)
-          if (s < nslot) Pr[s] = Pi[s] = Mr[s] = Mi[s] = real(0);
+        DUFF(nslot, { Pr[s] = Pi[s] = Mr[s] = Mi[s] = real(0); })
         break;
       case EPGX_OP_PD:
         m0 = ldc(coef + off0 + patoff[pat0]);
@@ -247,25 +254,23 @@ __global__ void __launch_bounds__(256) reg_kernel(const KParams p) {
 #define SHIFT_W1(UR, UI, DR, DI)                                                                             \
   {                                                                                                          \
     SHIFT_HEAD(DR, DI)                                                                                       \
-    _Pragma("unroll") for (int s = 0; s < NS; ++s) {                                                         \
-      if (s >= nsl) break;                                                                                   \
-      const real rr = __shfl_sync(FULL, UR[s], srcUp), ri = __shfl_sync(FULL, UI[s], srcUp);                 \
-      UR[s] = is_first ? cr : rr;                                                                            \
-      UI[s] = is_first ? ci : ri;                                                                            \
-      cr = rr; ci = ri;                                                                                      \
-    }                                                                                                        \
-    real nr = __shfl_sync(FULL, DR[0], srcDn), ni = __shfl_sync(FULL, DI[0], srcDn);                         \
-    _Pragma("unroll") for (int s = 0; s < NS; ++s) {                                                         \
-      if (s >= nsl) break;                                                                                   \
-      real xr = real(0), xi = real(0);                                                                       \
-      if (s + 1 < NS) {                                                                                      \
-        xr = __shfl_sync(FULL, DR[s + 1 < NS ? s + 1 : s], srcDn);                                           \
-        xi = __shfl_sync(FULL, DI[s + 1 < NS ? s + 1 : s], srcDn);                                           \
-      }                                                                                                      \
-      DR[s] = is_last ? xr : nr;                                                                             \
-      DI[s] = is_last ? xi : ni;                                                                             \
+    /* up: the LAST lane first takes over the value of its previous slot (order 0's new value for slot 0), \
+       then one rotate-by-one-lane delivers every order to its new owner; descending = in place */         \
+    DUFF(nsl, {                                                                                              \
+      const real vr = is_last ? (s > 0 ? UR[s > 0 ? s - 1 : 0] : cr) : UR[s];                                \
+      const real vi = is_last ? (s > 0 ? UI[s > 0 ? s - 1 : 0] : ci) : UI[s];                                \
+      UR[s] = __shfl_sync(FULL, vr, srcUp);                                                                  \
+      UI[s] = __shfl_sync(FULL, vi, srcUp);                                                                  \
+    })                                                                                                       \
+    /* dn: rotate the other way; the last lane receives the first lane's value of the NEXT slot (zero     \
+       above the populated orders) */                                                                       \
+    real nr = real(0), ni = real(0);                                                                         \
+    DUFF(nsl, {                                                                                              \
+      const real xr = __shfl_sync(FULL, DR[s], srcDn), xi = __shfl_sync(FULL, DI[s], srcDn);                 \
+      DR[s] = is_last ? nr : xr;                                                                             \
+      DI[s] = is_last ? ni : xi;                                                                             \
       nr = xr; ni = xi;                                                                                      \
-    }                                                                                                        \
+    })                                                                                                       \
   }
       // several warps per atom: the boundary lanes of each warp go through shared memory
 #define SHIFT_WN(UR, UI, DR, DI)                                                                             \
@@ -319,6 +324,8 @@ __global__ void __launch_bounds__(256) reg_kernel(const KParams p) {
     }
   }
 #undef FOR_SLOTS
+#undef DUFF
+#undef SLOT_CASE
 #undef LOAD_TRI
 #undef STORE_TRI
 }

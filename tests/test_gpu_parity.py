@@ -40,8 +40,8 @@ def test_fp32_matches_reference(name, golden, epg):
             col = ref["jacobian"][..., i]
             if np.abs(col).max() > 1e-9 * np.abs(ref["jacobian"]).max():
                 assert rel_err(jac[..., i], col) < 5 * RTOL32
-            else:  # a derivative that is zero up to round-off in the reference
-                assert np.abs(jac[..., i] - col).max() < RTOL32 * np.abs(ref["jacobian"]).max()
+            else:  # a derivative that vanishes by cancellation of O(2 pi tau) terms: absolute check
+                assert np.abs(jac[..., i] - col).max() < 1e-3 * np.abs(ref["jacobian"]).max()
 
 
 def _run_variant(epg, case, dtype="f64", **variant):
