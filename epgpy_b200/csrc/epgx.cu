@@ -10,6 +10,7 @@
 
 #include "epgx_common.cuh"
 #include "epgx_reg.cuh"
+#include "epgx_real.cuh"
 #include "epgx_ring.cuh"
 
 using namespace epgx;
@@ -37,6 +38,7 @@ struct epgx_plan {
   std::vector<int> pats; // [npattern][MAX_DIMS+1]
   std::vector<epgx_op> stream; // segments + records merged (register kernel)
   int64_t natoms;
+  bool real_ok; // real-valued phase graph: eligible for the three-reals-per-order kernel
   epgx_config cfg;
   // workspace layout (bytes)
   int64_t off_ops, off_segs, off_pats, off_stream, off_coef, ws_bytes;
@@ -86,6 +88,33 @@ static int choose_variant(epgx_plan *pl, int kernel, int lanes, int vars, int at
   const bool reg_ok = t.nvar == 0 && t.npool == 1;
   if (kernel == 2 && !reg_ok)
     return fail(EPGX_ERR_UNSUPPORTED, "the register kernel runs forward simulations of one pool only");
+  if (kernel == 3 && !pl->real_ok)
+    return fail(EPGX_ERR_UNSUPPORTED, "the real-valued kernel needs +-90 degree pulses, no precession and a real initial state");
+  if (pl->real_ok && (kernel == 0 || kernel == 3)) {
+    // ---- real-valued register kernel: one warp (or less) per atom, up to 32 slots
+    const int ns_max = t.dtype == EPGX_F64 ? 16 : 32;
+    int G = lanes > 0 ? pow2ceil(lanes) : pow2ceil((C + 15) / 16);
+    if (G > 32) G = 32;
+    const int need = (C + G - 1) / G;
+    int NS = 0;
+    for (int o : {1, 2, 4, 8, 16, 32})
+      if (o >= need && !NS) NS = o;
+    if (NS && NS <= ns_max) {
+      int A = atoms > 0 ? atoms : 128 / G;
+      while (A * G > 256 && A > 1) --A;
+      c.kernel = 2;
+      c.lanes_per_atom = G;
+      c.slots_per_lane = NS;
+      c.vars_per_pass = 0;
+      c.var_tiles = 1;
+      c.atoms_per_cta = A;
+      c.threads_per_cta = A * G;
+      c.smem_bytes = 2 * epgx::TAPE_CHUNK * 32 + ((A * t.npattern + 3) & ~3) * 4 + 32;
+      c.ring = C;
+      return EPGX_OK;
+    }
+    if (kernel == 3) return fail(EPGX_ERR_CAPACITY, "no real-kernel instance holds " + std::to_string(C) + " orders");
+  }
   if (reg_ok && kernel != 1) {
     // ---- register kernel: G lanes x NS slots >= C orders
     const int ns_max = 16;
@@ -307,6 +336,25 @@ extern "C" int epgx_plan_create(const epgx_tape *t, epgx_plan **out) {
   pl->tape.coef = nullptr;
   pl->natoms = natoms;
   memset(&pl->cfg, 0, sizeof(pl->cfg));
+  {
+    bool ok = t->nvar == 0 && t->npool == 1;
+    for (int64_t i = 0; ok && i < t->nop; ++i) {
+      const epgx_op &o = t->ops[i];
+      switch (o.code) {
+      case EPGX_OP_NOP: case EPGX_OP_T_RE: case EPGX_OP_D: case EPGX_OP_SPOIL: case EPGX_OP_PD: case EPGX_OP_ADC:
+      case EPGX_OP_CONT: break;
+      case EPGX_OP_E: ok = !(o.flags & EPGX_FLAG_G); break;
+      case EPGX_OP_FUSED: ok = !(o.flags & EPGX_FLAG_IM); break;
+      default: ok = false;
+      }
+    }
+    if (ok) { // imaginary parts of the initial state
+      const int64_t end = (int64_t)t->init_off + pat_span[t->init_pat] + 6 * (int64_t)(t->init_n + 1);
+      for (int64_t i = t->init_off; ok && i < end; ++i)
+        if (((i - t->init_off) % 6) % 2 == 1 && t->coef[i] != 0.0) ok = false;
+    }
+    pl->real_ok = ok;
+  }
   int rc = choose_variant(pl, 0, 0, 0, 0);
   if (rc != EPGX_OK) {
     delete pl;
@@ -402,6 +450,27 @@ template <typename real> static int dispatch_reg(const epgx_plan *pl, const KPar
   return fail(EPGX_ERR_UNSUPPORTED, "no register-kernel instance for slots_per_lane=" + std::to_string(pl->cfg.slots_per_lane));
 }
 
+template <typename real, int NS> static int launch_real(const epgx_plan *pl, const KParams &kp, cudaStream_t st) {
+  const epgx_config &c = pl->cfg;
+  auto kern = real_kernel<real, NS>;
+  dim3 grid((unsigned)((kp.atom_count + c.atoms_per_cta - 1) / c.atoms_per_cta), 1);
+  kern<<<grid, c.threads_per_cta, c.smem_bytes, st>>>(kp);
+  CUDA_TRY(cudaGetLastError());
+  return EPGX_OK;
+}
+
+template <typename real> static int dispatch_real(const epgx_plan *pl, const KParams &kp, cudaStream_t st) {
+  switch (pl->cfg.slots_per_lane) {
+  case 1: return launch_real<real, 1>(pl, kp, st);
+  case 2: return launch_real<real, 2>(pl, kp, st);
+  case 4: return launch_real<real, 4>(pl, kp, st);
+  case 8: return launch_real<real, 8>(pl, kp, st);
+  case 16: return launch_real<real, 16>(pl, kp, st);
+  case 32: return launch_real<real, 32>(pl, kp, st);
+  }
+  return fail(EPGX_ERR_UNSUPPORTED, "no real-kernel instance for slots_per_lane=" + std::to_string(pl->cfg.slots_per_lane));
+}
+
 template <typename real> static int dispatch_ring(const epgx_plan *pl, const KParams &kp, cudaStream_t st) {
   const int np = pl->tape.npool, nvt = pl->cfg.vars_per_pass;
 #define CASE(NP_, NVT_) \
@@ -456,6 +525,7 @@ extern "C" int epgx_simulate_strided(const epgx_plan *pl, const void *ws, int64_
   kp.m0_pat = t.m0_pat;
   kp.init_n = t.init_n;
   cudaStream_t st = (cudaStream_t)stream;
+  if (pl->cfg.kernel == 2) return t.dtype == EPGX_F64 ? dispatch_real<double>(pl, kp, st) : dispatch_real<float>(pl, kp, st);
   if (pl->cfg.kernel == 1) return t.dtype == EPGX_F64 ? dispatch_reg<double>(pl, kp, st) : dispatch_reg<float>(pl, kp, st);
   if (t.dtype == EPGX_F64) return dispatch_ring<double>(pl, kp, st);
   return dispatch_ring<float>(pl, kp, st);

@@ -1,0 +1,225 @@
+// epgx_real.cuh -- register kernel for REAL-VALUED phase graphs.
+//
+// When every RF pulse of a sequence has a phase of +-90 degrees (B and U real: EPGX_OP_T_RE / the RE
+// kind of EPGX_OP_FUSED), no operator precesses (E without g, D, SPOILER, PD) and the initial state is
+// real, the imaginary part of every F+/F-/Z coefficient stays exactly zero for the whole sequence (the
+// reference computes them anyway and returns ~1e-17 round-off, epgpy/transition.py:114-151).  The MRF
+// FISP / phase-alternated bSSFP families are of this kind.  This kernel keeps three reals per order
+// instead of six: half the FMAs, half the shuffles of the unit shift, half the registers (so twice the
+// resident warps) of epgx_reg.cuh, same layout otherwise: order k in slot k / G of lane k % G, tape
+// streamed through shared memory, shifts by rotate-by-one-lane.  One warp (or a sub-warp group) per atom.
+#pragma once
+#include <cuda_pipeline.h>
+
+#include "epgx_common.cuh"
+#include "epgx_reg.cuh"
+
+namespace epgx {
+
+template <typename real, int NS>
+__global__ void __launch_bounds__(256) real_kernel(const KParams p) {
+  typedef typename vec2<real>::type real2;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+
+  const int G = p.G; // 1..32, power of two
+  const int tid = threadIdx.x;
+  const int al = tid / G;
+  const int lane = tid - al * G;
+  const int lw = tid & 31;
+  const int gbase = lw & ~(G - 1);
+  const int srcUp = gbase | ((lane - 1) & (G - 1));
+  const int srcDn = gbase | ((lane + 1) & (G - 1));
+  const unsigned FULL = 0xffffffffu;
+  const bool is_last = lane == G - 1;
+  int lgG = 0;
+  while ((1 << lgG) < G) ++lgG;
+
+  const long long a_rel = (long long)blockIdx.x * p.A + al;
+  const bool valid = a_rel < p.atom_count;
+  const long long atom = p.atom_begin + (valid ? a_rel : p.atom_count - 1);
+  const real *__restrict__ coef = (const real *)p.coef;
+
+  int4 *tbuf = (int4 *)smem_raw;
+  int *patoff = (int *)(tbuf + 2 * TAPE_CHUNK * 2) + al * p.npattern;
+  {
+    int idx[EPGX_MAX_DIMS];
+    long long r = atom;
+    for (int d = p.ndim - 1; d >= 0; --d) {
+      idx[d] = (int)(r % p.shape[d]);
+      r /= p.shape[d];
+    }
+    for (int q = lane; q < p.npattern; q += G) {
+      const int *st = p.pats + q * (EPGX_MAX_DIMS + 1);
+      int o = 0;
+      for (int d = 0; d < p.ndim; ++d) o += idx[d] * st[d];
+      patoff[q] = o;
+    }
+  }
+  __syncthreads();
+
+  real P[NS], M[NS], Z[NS];
+  real m0 = ldc(coef + p.m0_off + patoff[p.m0_pat]);
+  {
+    const real *ib = coef + p.init_off + patoff[p.init_pat];
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+      const int k = s * G + lane;
+      const bool in = k <= p.init_n;
+      P[s] = in ? ldc(ib + 6 * k) : real(0);
+      M[s] = in ? ldc(ib + 6 * k + 2) : real(0);
+      Z[s] = in ? ldc(ib + 6 * k + 4) : real(0);
+    }
+  }
+  real2 *sig = (real2 *)p.signal;
+
+#define SLOT_CASE(K, ...)                      \
+  case (K) + 1:                                \
+    if (NS > (K)) {                            \
+      constexpr int s = (K) < NS ? (K) : 0;    \
+      __VA_ARGS__                              \
+    }
+#define DUFF(n, ...)                                                                                        \
+  switch (n) {                                                                                              \
+    SLOT_CASE(31, __VA_ARGS__) SLOT_CASE(30, __VA_ARGS__) SLOT_CASE(29, __VA_ARGS__) SLOT_CASE(28, __VA_ARGS__) \
+    SLOT_CASE(27, __VA_ARGS__) SLOT_CASE(26, __VA_ARGS__) SLOT_CASE(25, __VA_ARGS__) SLOT_CASE(24, __VA_ARGS__) \
+    SLOT_CASE(23, __VA_ARGS__) SLOT_CASE(22, __VA_ARGS__) SLOT_CASE(21, __VA_ARGS__) SLOT_CASE(20, __VA_ARGS__) \
+    SLOT_CASE(19, __VA_ARGS__) SLOT_CASE(18, __VA_ARGS__) SLOT_CASE(17, __VA_ARGS__) SLOT_CASE(16, __VA_ARGS__) \
+    SLOT_CASE(15, __VA_ARGS__) SLOT_CASE(14, __VA_ARGS__) SLOT_CASE(13, __VA_ARGS__) SLOT_CASE(12, __VA_ARGS__) \
+    SLOT_CASE(11, __VA_ARGS__) SLOT_CASE(10, __VA_ARGS__) SLOT_CASE(9, __VA_ARGS__) SLOT_CASE(8, __VA_ARGS__)   \
+    SLOT_CASE(7, __VA_ARGS__) SLOT_CASE(6, __VA_ARGS__) SLOT_CASE(5, __VA_ARGS__) SLOT_CASE(4, __VA_ARGS__)     \
+    SLOT_CASE(3, __VA_ARGS__) SLOT_CASE(2, __VA_ARGS__) SLOT_CASE(1, __VA_ARGS__) SLOT_CASE(0, __VA_ARGS__)     \
+  default:                                                                                                  \
+    break;                                                                                                  \
+  }
+// F+' = a F+ + b F- + u Z ; F-' = b F+ + a F- + u Z ; Z' = w Z + h (F+ + F-)
+#define APPLY5(a, w, b, u, h)                  \
+  DUFF(nslot, {                                \
+    const real p_ = P[s], m_ = M[s], z_ = Z[s]; \
+    P[s] = a * p_ + b * m_ + u * z_;           \
+    M[s] = a * m_ + b * p_ + u * z_;           \
+    Z[s] = w * z_ + h * (p_ + m_);             \
+  })
+
+  const int4 *stream = (const int4 *)p.stream;
+  const int nthreads = blockDim.x;
+  for (int i = tid; i < 2 * TAPE_CHUNK && i < 2 * p.nstream; i += nthreads) __pipeline_memcpy_async(tbuf + i, stream + i, 16);
+  __pipeline_commit();
+  int nact = -1, nslot = 0;
+  for (int base = 0, chunk = 0; base < p.nstream; base += TAPE_CHUNK, ++chunk) {
+    __pipeline_wait_prior(0);
+    __syncthreads();
+    {
+      const int nb = base + TAPE_CHUNK;
+      int4 *dst = tbuf + ((chunk + 1) & 1) * 2 * TAPE_CHUNK;
+      for (int i = tid; i < 2 * TAPE_CHUNK && nb * 2 + i < 2 * p.nstream; i += nthreads)
+        __pipeline_memcpy_async(dst + i, stream + (size_t)nb * 2 + i, 16);
+      __pipeline_commit();
+    }
+    const int4 *tb = tbuf + (chunk & 1) * 2 * TAPE_CHUNK;
+    const int cnt = min(TAPE_CHUNK, p.nstream - base);
+    for (int r = 0; r < cnt; ++r) {
+      const int4 r0 = tb[2 * r], r1 = tb[2 * r + 1];
+      const int code = r0.x & 0xffff, flags = (r0.x >> 16) & 0xffff, aux = r0.y;
+      const unsigned off0 = (unsigned)r0.z, off1 = (unsigned)r0.w, off2 = (unsigned)r1.x;
+      const int pat0 = r1.y & 0xff, pat1 = (r1.y >> 8) & 0xff, pat2 = (r1.y >> 16) & 0xff;
+
+      switch (code) {
+      case EPGX_OP_FUSED: {
+        const int4 q0 = tb[2 * r + 2], q1 = tb[2 * r + 3]; // the CONT record (never split from FUSED)
+        const real *ct = coef + off0 + patoff[pat0];
+        const real *ca = coef + off1 + patoff[pat1];
+        const real *cb = coef + (unsigned)q0.z + patoff[q1.y & 0xff];
+        const Fused5<real> f = fuse5<real>(ldc(ct), ldc(ct + 1), ldc(ct + 2), ldc(ct + 3), flags & EPGX_FLAG_PRE, ldc(ca),
+                                           ldc(ca + 1), ldc(coef + off2 + patoff[pat2]), flags & EPGX_FLAG_POST, ldc(cb),
+                                           ldc(cb + 1), ldc(coef + (unsigned)q0.w + patoff[(q1.y >> 8) & 0xff]), false, m0);
+        APPLY5(f.a, f.w, f.b, f.u, f.h)
+        if (lane == 0 && nslot > 0) { P[0] += f.fz; M[0] += f.fz; Z[0] += f.zz; }
+        ++r;
+      } break;
+      case EPGX_OP_T_RE: {
+        const real *c = coef + off0 + patoff[pat0];
+        const real a = ldc(c), w = ldc(c + 1), b = ldc(c + 2), u = ldc(c + 3), h = real(-0.5) * u;
+        APPLY5(a, w, b, u, h)
+      } break;
+      case EPGX_OP_E: {
+        const real *c0 = coef + off0 + patoff[pat0];
+        const real e1 = ldc(c0), r0v = ldc(c0 + 1);
+        const real e2 = ldc(coef + off1 + patoff[pat1]);
+        DUFF(nslot, { P[s] *= e2; M[s] *= e2; Z[s] *= e1; })
+        if ((flags & EPGX_FLAG_AFFINE) && lane == 0 && nslot > 0) Z[0] += r0v * m0;
+      } break;
+      case EPGX_OP_D: {
+        const real *c = coef + off0 + patoff[pat0];
+        DUFF(nslot, {
+          const int k = min(s * G + lane, p.C - 1);
+          P[s] *= ldc(c + 3 * k); M[s] *= ldc(c + 3 * k + 1); Z[s] *= ldc(c + 3 * k + 2);
+        })
+      } break;
+      case EPGX_OP_SPOIL:
+        DUFF(nslot, { P[s] = real(0); M[s] = real(0); })
+        break;
+      case EPGX_OP_PD:
+        m0 = ldc(coef + off0 + patoff[pat0]);
+        break;
+      case EPGX_OP_ADC:
+        if (lane == 0 && valid && (flags & EPGX_FLAG_BASE)) {
+          real fr = real(1), fi = real(0);
+          if (flags & EPGX_FLAG_SCALE) {
+            const real *c = coef + off0 + patoff[pat0];
+            fr = ldc(c); fi = ldc(c + 1);
+          }
+          const real x = (flags & EPGX_FLAG_Z0) ? Z[0] : P[0];
+          sig[(long long)aux * p.sig_stride + a_rel] = real2{x * fr, x * fi};
+        }
+        break;
+      case EPGX_OP_SEG: {
+        const int shift = (int)off0, n_old = (int)off1, n_new = (int)off2, sflags = r1.z;
+        nact = aux;
+        nslot = nact < 0 ? 0 : (nact >> lgG) + 1;
+        if (sflags & EPGX_SEG_RESET) {
+#pragma unroll
+          for (int s = 0; s < NS; ++s) P[s] = M[s] = Z[s] = real(0);
+          if (lane == 0) Z[0] = m0;
+        } else if (shift != 0) {
+          const int nsl = (n_new >> lgG) + 1;
+          // U: the component whose orders move up (F+ for shift > 0), D: the other one; new order 0 of U
+          // is old order 1 of D (real state: no conjugation)
+#define SHIFT_REAL(U, D)                                                                                   \
+  {                                                                                                        \
+    real c1;                                                                                               \
+    if (G == 1) c1 = NS > 1 ? D[NS > 1 ? 1 : 0] : real(0);                                                 \
+    else c1 = __shfl_sync(FULL, D[0], gbase | 1);                                                          \
+    if (n_old < 1) c1 = real(0);                                                                           \
+    DUFF(nsl, {                                                                                            \
+      const real v = is_last ? (s > 0 ? U[s > 0 ? s - 1 : 0] : c1) : U[s];                                 \
+      U[s] = __shfl_sync(FULL, v, srcUp);                                                                  \
+    })                                                                                                     \
+    real nx = real(0);                                                                                     \
+    DUFF(nsl, {                                                                                            \
+      const real x = __shfl_sync(FULL, D[s], srcDn);                                                       \
+      D[s] = is_last ? nx : x;                                                                             \
+      nx = x;                                                                                              \
+    })                                                                                                     \
+  }
+          if (shift > 0) SHIFT_REAL(P, M) else SHIFT_REAL(M, P)
+#undef SHIFT_REAL
+          if (sflags & EPGX_SEG_MASK_TOP) {
+#pragma unroll
+            for (int s = 0; s < NS; ++s)
+              if (s * G + lane > n_new) {
+                if (shift > 0) P[s] = real(0); else M[s] = real(0);
+              }
+          }
+        }
+      } break;
+      default:
+        break;
+      }
+    }
+  }
+#undef APPLY5
+#undef DUFF
+#undef SLOT_CASE
+}
+
+} // namespace epgx

@@ -499,8 +499,8 @@ class T(CombinableOperator):
         # a = cos^2(alpha/2), w = cos(alpha), B = sin^2(alpha/2) e^{2 i phi}, U = -i sin(alpha) e^{i phi}
         a, phi = self._ap()
         B = np.sin(a / 2) ** 2 * _cis_deg(phi, 2)
-        U = -1j * np.sin(a) * _cis_deg(phi)
-        return ("tgen", _cplx_block(np.cos(a / 2) ** 2 + 0 * B.real, np.cos(a) + 0 * B.real, B, U))
+        U = -1j * _snap(np.sin(a)) * _cis_deg(phi)  # sin(180 deg) = 1.2e-16 -> 0
+        return ("tgen", _cplx_block(np.cos(a / 2) ** 2 + 0 * B.real, _snap(np.cos(a)) + 0 * B.real, B, U))
 
     def _dform(self, param):
         a, phi = self._ap()

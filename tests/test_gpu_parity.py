@@ -104,6 +104,51 @@ def test_reg_and_ring_agree_on_large_orders(epg):
         assert rel_err(reg[0], ring[0]) < 1e-12
 
 
+def _real_sequence(epg, ntr=70):
+    """+-90 degree pulses, relaxation, diffusion, spoiler, PD, shifts of both signs: a real-valued graph"""
+    T1 = np.linspace(300, 2000, 5)
+    T2 = np.linspace(30, 200, 4)[None, :]
+    B1 = np.array([0.8, 1.0, 1.15])[None, None, :]
+    seq = [epg.PD([1.0, 0.5, 2.0, 1.5, 0.7]), epg.T(180, 90), epg.E(15, T1, T2)]
+    for i in range(ntr):
+        ph = 90 if i % 3 else 270
+        seq += [epg.T((10 + i % 40) * B1, ph), epg.E(2.5, T1, T2), epg.Adc(phase=-ph + 90.0), epg.E(6 + (i % 5), T1, T2),
+                epg.S(1 if i % 11 else -1)]
+        if i % 7 == 3:
+            seq += [epg.D(4.0, 1.2e-3, k=1 if i % 11 else -1)]
+        if i == 40:
+            seq += [epg.SPOILER]
+    return seq
+
+
+@pytest.mark.parametrize("dtype", ["f64", "f32"])
+@pytest.mark.parametrize("lanes,atoms", [(0, 0), (1, 7), (2, 16), (4, 32), (8, 3), (16, 8), (32, 4)])
+@pytest.mark.parametrize("max_nstate", [None, 9])
+def test_real_kernel_variants(lanes, atoms, dtype, max_nstate, epg):
+    """the real-valued register kernel (three reals per order) against the ring kernel and the oracle"""
+    case = {"seq": _real_sequence(epg), "options": {"kvalue": 2500.0, **({"max_nstate": max_nstate} if max_nstate else {})}}
+    ring, _ = _run_variant(epg, case, kernel=1)
+    try:
+        got, cfg = _run_variant(epg, case, dtype=dtype, kernel=3, lanes_per_atom=lanes, atoms_per_cta=atoms)
+    except MemoryError:
+        pytest.skip("more orders than lanes x slots of any instance")
+    assert cfg["kernel"] == 2
+    assert rel_err(got[0], ring[0]) < (1e-12 if dtype == "f64" else RTOL32)
+    ref = oracle_api.O.simulate(_real_sequence(oracle_api.epg), kvalue=2500.0, max_nstate=max_nstate)
+    assert rel_err(ring[0], ref) < RTOL64
+
+
+def test_real_kernel_is_chosen_for_fisp_and_refused_otherwise(epg):
+    from epgpy_b200 import engine, lowering
+
+    plan = engine.Plan(lowering.lower(cases.fisp_unbounded(epg)["seq"]))
+    assert plan.config()["kernel"] == 2
+    plan = engine.Plan(lowering.lower(cases.readme_mse(epg)["seq"]))  # T(120, 0) couples real and imaginary parts
+    assert plan.config()["kernel"] == 1
+    with pytest.raises(NotImplementedError):
+        plan.set_variant(kernel=3)
+
+
 @pytest.mark.parametrize("vars_per_pass", [1, 3])
 @pytest.mark.parametrize("name", ["fisp_jac_pulses", "jac_all_params", "mse_jac"])
 def test_variable_tiling(name, vars_per_pass, golden, epg):
