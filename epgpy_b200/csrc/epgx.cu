@@ -38,6 +38,7 @@ struct epgx_plan {
   std::vector<int> pats; // [npattern][MAX_DIMS+1]
   std::vector<epgx_op> stream; // segments + records merged (register kernel)
   int64_t natoms;
+  double flops_cplx, flops_real, updates; // executed real flops per atom (complex / real-valued kernels)
   bool real_ok; // real-valued phase graph: eligible for the three-reals-per-order kernel
   epgx_config cfg;
   // workspace layout (bytes)
@@ -322,7 +323,25 @@ extern "C" int epgx_plan_create(const epgx_tape *t, epgx_plan **out) {
     for (int64_t i = 0; i <= t->nseg; ++i) {
       const epgx_segment *prev = i > 0 ? &t->segs[i - 1] : nullptr;
       const int next_nact = i < t->nseg ? t->segs[i].nact : -1;
-      st.push_back(prev ? seg_rec(prev->shift, prev->n_old, prev->n_new, prev->flags, next_nact) : seg_rec(0, 0, 0, 0, next_nact));
+      // a segment that is exactly [FUSED(RE), CONT, ADC(F0, unscaled)] merges with its closing SEG into one TR
+      bool merged = false;
+      if (prev && pl->real_ok && prev->count == 3 && prev->n_old < 65536 && prev->n_new < 65536) {
+        const epgx_op &f = t->ops[prev->first], &c = t->ops[prev->first + 1], &a = t->ops[prev->first + 2];
+        if (f.code == EPGX_OP_FUSED && a.code == EPGX_OP_ADC && a.flags == EPGX_FLAG_BASE && st.size() >= 3) {
+          epgx_op &sf = st[st.size() - 3], &sc = st[st.size() - 2];
+          if (sf.code == EPGX_OP_FUSED && sc.code == EPGX_OP_CONT) {
+            sf.code = EPGX_OP_TR;
+            sc.aux = a.aux;
+            sc.flags = (uint16_t)((prev->shift + 1) | (prev->flags << 2));
+            sc.off[2] = ((uint32_t)prev->n_old << 16) | (uint32_t)prev->n_new;
+            sc.aux1 = next_nact;
+            st.pop_back(); // the ADC record
+            merged = true;
+          }
+        }
+      }
+      if (!merged)
+        st.push_back(prev ? seg_rec(prev->shift, prev->n_old, prev->n_new, prev->flags, next_nact) : seg_rec(0, 0, 0, 0, next_nact));
       if (i == t->nseg) break;
       const epgx_segment &sg = t->segs[i];
       for (int r = sg.first; r < sg.first + sg.count; ++r) {
@@ -360,9 +379,11 @@ extern "C" int epgx_plan_create(const epgx_tape *t, epgx_plan **out) {
     delete pl;
     return rc;
   }
+  pl->flops_cplx = flops;
+  pl->flops_real = 0.5 * flops; // T_RE / FUSED / E / D on three reals per order
+  pl->updates = updates;
   pl->cfg.updates_per_atom = updates;
-  // the base state is recomputed by every variable tile
-  pl->cfg.flops_per_atom = flops;
+  pl->cfg.flops_per_atom = pl->cfg.kernel == 2 ? pl->flops_real : pl->flops_cplx;
   auto align = [](int64_t x) { return (x + 255) & ~(int64_t)255; };
   const int rsz = t->dtype == EPGX_F64 ? 8 : 4;
   pl->off_ops = 0;
@@ -388,10 +409,9 @@ extern "C" int epgx_plan_config(const epgx_plan *pl, epgx_config *cfg) {
 
 extern "C" int epgx_plan_set_variant(epgx_plan *pl, int kernel, int lanes, int vars, int atoms) {
   if (!pl) return fail(EPGX_ERR_INVALID, "null plan");
-  const double f = pl->cfg.flops_per_atom, u = pl->cfg.updates_per_atom;
   int rc = choose_variant(pl, kernel, lanes, vars, atoms);
-  pl->cfg.flops_per_atom = f;
-  pl->cfg.updates_per_atom = u;
+  pl->cfg.flops_per_atom = pl->cfg.kernel == 2 ? pl->flops_real : pl->flops_cplx;
+  pl->cfg.updates_per_atom = pl->updates;
   return rc;
 }
 

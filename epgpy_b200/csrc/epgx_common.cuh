@@ -13,6 +13,11 @@
 // internal record of the merged stream: ends a segment (unit shift / reset of the segment that just ran:
 // off[0] = shift, off[1] = n_old, off[2] = n_new, aux1 = segment flags) and opens the next one (aux = nact)
 #define EPGX_OP_SEG 64
+// internal: one whole TR = FUSED + plain ADC + the SEG that follows, merged by the stream builder when a
+// segment consists of exactly [FUSED, CONT, ADC(F0, no scale)].  First record as FUSED; second record:
+// off[0..1] / pat[0..1] post-E blocks, aux = ADC row, flags = (shift + 1) | segment flags << 2,
+// off[2] = n_old << 16 | n_new, aux1 = nact of the next segment
+#define EPGX_OP_TR 65
 
 namespace epgx {
 

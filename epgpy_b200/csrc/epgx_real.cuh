@@ -100,6 +100,48 @@ __global__ void __launch_bounds__(256) real_kernel(const KParams p) {
     Z[s] = w * z_ + h * (p_ + m_);             \
   })
 
+// close a segment (reset / unit shift) and open the next one (order count of the next pass)
+#define DO_SEG(SHIFT_, NOLD_, NNEW_, SFLAGS_, NEXT_)                                                       \
+  {                                                                                                        \
+    const int shift = (SHIFT_), n_old = (NOLD_), n_new = (NNEW_), sflags = (SFLAGS_);                      \
+    nact = (NEXT_);                                                                                        \
+    nslot = nact < 0 ? 0 : (nact >> lgG) + 1;                                                              \
+    if (sflags & EPGX_SEG_RESET) {                                                                         \
+      _Pragma("unroll") for (int s = 0; s < NS; ++s) P[s] = M[s] = Z[s] = real(0);                         \
+      if (lane == 0) Z[0] = m0;                                                                            \
+    } else if (shift != 0) {                                                                               \
+      const int nsl = (n_new >> lgG) + 1;                                                                  \
+      if (shift > 0) SHIFT_REAL(P, M) else SHIFT_REAL(M, P)                                                \
+      if (sflags & EPGX_SEG_MASK_TOP) {                                                                    \
+        _Pragma("unroll") for (int s = 0; s < NS; ++s)                                                     \
+          if (s * G + lane > n_new) {                                                                      \
+            if (shift > 0) P[s] = real(0); else M[s] = real(0);                                            \
+          }                                                                                                \
+      }                                                                                                    \
+    }                                                                                                      \
+  }
+// U: the component whose orders move up (F+ for shift > 0), D: the other one; new order 0 of U is old
+// order 1 of D (real state: no conjugation).  up: the LAST lane first takes over the value of its previous
+// slot, then one rotate-by-one-lane delivers every order to its new owner (descending = in place);
+// dn: rotate the other way, the last lane receives the first lane's value of the NEXT slot.
+#define SHIFT_REAL(U, D)                                                                                   \
+  {                                                                                                        \
+    real c1;                                                                                               \
+    if (G == 1) c1 = NS > 1 ? D[NS > 1 ? 1 : 0] : real(0);                                                 \
+    else c1 = __shfl_sync(FULL, D[0], gbase | 1);                                                          \
+    if (n_old < 1) c1 = real(0);                                                                           \
+    DUFF(nsl, {                                                                                            \
+      const real v = is_last ? (s > 0 ? U[s > 0 ? s - 1 : 0] : c1) : U[s];                                 \
+      U[s] = __shfl_sync(FULL, v, srcUp);                                                                  \
+    })                                                                                                     \
+    real nx = real(0);                                                                                     \
+    DUFF(nsl, {                                                                                            \
+      const real x = __shfl_sync(FULL, D[s], srcDn);                                                       \
+      D[s] = is_last ? nx : x;                                                                             \
+      nx = x;                                                                                              \
+    })                                                                                                     \
+  }
+
   const int4 *stream = (const int4 *)p.stream;
   const int nthreads = blockDim.x;
   for (int i = tid; i < 2 * TAPE_CHUNK && i < 2 * p.nstream; i += nthreads) __pipeline_memcpy_async(tbuf + i, stream + i, 16);
@@ -173,44 +215,23 @@ __global__ void __launch_bounds__(256) real_kernel(const KParams p) {
         }
         break;
       case EPGX_OP_SEG: {
-        const int shift = (int)off0, n_old = (int)off1, n_new = (int)off2, sflags = r1.z;
-        nact = aux;
-        nslot = nact < 0 ? 0 : (nact >> lgG) + 1;
-        if (sflags & EPGX_SEG_RESET) {
-#pragma unroll
-          for (int s = 0; s < NS; ++s) P[s] = M[s] = Z[s] = real(0);
-          if (lane == 0) Z[0] = m0;
-        } else if (shift != 0) {
-          const int nsl = (n_new >> lgG) + 1;
-          // U: the component whose orders move up (F+ for shift > 0), D: the other one; new order 0 of U
-          // is old order 1 of D (real state: no conjugation)
-#define SHIFT_REAL(U, D)                                                                                   \
-  {                                                                                                        \
-    real c1;                                                                                               \
-    if (G == 1) c1 = NS > 1 ? D[NS > 1 ? 1 : 0] : real(0);                                                 \
-    else c1 = __shfl_sync(FULL, D[0], gbase | 1);                                                          \
-    if (n_old < 1) c1 = real(0);                                                                           \
-    DUFF(nsl, {                                                                                            \
-      const real v = is_last ? (s > 0 ? U[s > 0 ? s - 1 : 0] : c1) : U[s];                                 \
-      U[s] = __shfl_sync(FULL, v, srcUp);                                                                  \
-    })                                                                                                     \
-    real nx = real(0);                                                                                     \
-    DUFF(nsl, {                                                                                            \
-      const real x = __shfl_sync(FULL, D[s], srcDn);                                                       \
-      D[s] = is_last ? nx : x;                                                                             \
-      nx = x;                                                                                              \
-    })                                                                                                     \
-  }
-          if (shift > 0) SHIFT_REAL(P, M) else SHIFT_REAL(M, P)
-#undef SHIFT_REAL
-          if (sflags & EPGX_SEG_MASK_TOP) {
-#pragma unroll
-            for (int s = 0; s < NS; ++s)
-              if (s * G + lane > n_new) {
-                if (shift > 0) P[s] = real(0); else M[s] = real(0);
-              }
-          }
-        }
+        DO_SEG((int)off0, (int)off1, (int)off2, r1.z, aux)
+      } break;
+      case EPGX_OP_TR: {
+        // one whole TR: FUSED (E.T.E) + plain ADC + the segment's unit shift, one decode (see epgx.cu)
+        const int4 q0 = tb[2 * r + 2], q1 = tb[2 * r + 3];
+        const real *ct = coef + off0 + patoff[pat0];
+        const real *ca = coef + off1 + patoff[pat1];
+        const real *cb = coef + (unsigned)q0.z + patoff[q1.y & 0xff];
+        const Fused5<real> f = fuse5<real>(ldc(ct), ldc(ct + 1), ldc(ct + 2), ldc(ct + 3), flags & EPGX_FLAG_PRE, ldc(ca),
+                                           ldc(ca + 1), ldc(coef + off2 + patoff[pat2]), flags & EPGX_FLAG_POST, ldc(cb),
+                                           ldc(cb + 1), ldc(coef + (unsigned)q0.w + patoff[(q1.y >> 8) & 0xff]), false, m0);
+        APPLY5(f.a, f.w, f.b, f.u, f.h)
+        if (lane == 0 && nslot > 0) { P[0] += f.fz; M[0] += f.fz; Z[0] += f.zz; }
+        if (lane == 0 && valid) sig[(long long)q0.y * p.sig_stride + a_rel] = real2{P[0], real(0)};
+        const int segw = (q0.x >> 16) & 0xffff; // (shift + 1) | segment flags << 2
+        DO_SEG((segw & 3) - 1, (int)((unsigned)q1.x >> 16), (int)((unsigned)q1.x & 0xffff), segw >> 2, q1.z)
+        ++r;
       } break;
       default:
         break;
@@ -218,6 +239,8 @@ __global__ void __launch_bounds__(256) real_kernel(const KParams p) {
     }
   }
 #undef APPLY5
+#undef DO_SEG
+#undef SHIFT_REAL
 #undef DUFF
 #undef SLOT_CASE
 }

@@ -111,6 +111,88 @@ __global__ void __launch_bounds__(256) reg_kernel(const KParams p) {
   }
 #define FOR_SLOTS(EXPR) DUFF(nslot, { LOAD_TRI(s); const Tri<real> o_ = EXPR; STORE_TRI(s, o_); })
 
+// segment close / open, shared by EPGX_OP_SEG and EPGX_OP_TR
+#define SHIFT_HEAD(DR, DI)                                                                                  \
+    real cr, ci;                                                                                             \
+    if (G == 1) { cr = NS > 1 ? DR[NS > 1 ? 1 : 0] : real(0); ci = NS > 1 ? DI[NS > 1 ? 1 : 0] : real(0); }  \
+    else { cr = __shfl_sync(FULL, DR[0], gbase | 1); ci = __shfl_sync(FULL, DI[0], gbase | 1); }             \
+    if (n_old < 1) { cr = real(0); ci = real(0); }                                                           \
+    ci = -ci;
+#define SHIFT_W1(UR, UI, DR, DI)                                                                             \
+  {                                                                                                          \
+    SHIFT_HEAD(DR, DI)                                                                                       \
+    /* up: the LAST lane first takes over the value of its previous slot (order 0's new value for slot 0), \
+       then one rotate-by-one-lane delivers every order to its new owner; descending = in place */         \
+    DUFF(nsl, {                                                                                              \
+      const real vr = is_last ? (s > 0 ? UR[s > 0 ? s - 1 : 0] : cr) : UR[s];                                \
+      const real vi = is_last ? (s > 0 ? UI[s > 0 ? s - 1 : 0] : ci) : UI[s];                                \
+      UR[s] = __shfl_sync(FULL, vr, srcUp);                                                                  \
+      UI[s] = __shfl_sync(FULL, vi, srcUp);                                                                  \
+    })                                                                                                       \
+    /* dn: rotate the other way; the last lane receives the first lane's value of the NEXT slot (zero     \
+       above the populated orders) */                                                                       \
+    real nr = real(0), ni = real(0);                                                                         \
+    DUFF(nsl, {                                                                                              \
+      const real xr = __shfl_sync(FULL, DR[s], srcDn), xi = __shfl_sync(FULL, DI[s], srcDn);                 \
+      DR[s] = is_last ? nr : xr;                                                                             \
+      DI[s] = is_last ? ni : xi;                                                                             \
+      nr = xr; ni = xi;                                                                                      \
+    })                                                                                                       \
+  }
+#define SHIFT_WN(UR, UI, DR, DI)                                                                             \
+  {                                                                                                          \
+    SHIFT_HEAD(DR, DI)                                                                                       \
+    real2 *xb = xbuf + (size_t)(parity * p.A + al) * W * 2 * NS; /* [warp][up | dn][slot] */                 \
+    if (lq == 31) { _Pragma("unroll") for (int s = 0; s < NS; ++s) xb[(wq * 2 + 0) * NS + s] = real2{UR[s], UI[s]}; } \
+    if (lq == 0) { _Pragma("unroll") for (int s = 0; s < NS; ++s) xb[(wq * 2 + 1) * NS + s] = real2{DR[s], DI[s]}; }  \
+    asm volatile("bar.sync %0, %1;" ::"r"(1 + al), "r"(G) : "memory");                                       \
+    parity ^= 1;                                                                                             \
+    _Pragma("unroll") for (int s = 0; s < NS; ++s) {                                                         \
+      if (s >= nsl) break;                                                                                   \
+      real vr = __shfl_sync(FULL, UR[s], srcUp), vi = __shfl_sync(FULL, UI[s], srcUp);                       \
+      if (lq == 0) {                                                                                         \
+        if (wq == 0) { vr = cr; vi = ci; const real2 x = xb[((W - 1) * 2 + 0) * NS + s]; cr = x.x; ci = x.y; } \
+        else { const real2 x = xb[((wq - 1) * 2 + 0) * NS + s]; vr = x.x; vi = x.y; }                        \
+      }                                                                                                      \
+      UR[s] = vr; UI[s] = vi;                                                                                \
+    }                                                                                                        \
+    _Pragma("unroll") for (int s = 0; s < NS; ++s) {                                                         \
+      if (s >= nsl) break;                                                                                   \
+      real vr = __shfl_sync(FULL, DR[s], srcDn), vi = __shfl_sync(FULL, DI[s], srcDn);                       \
+      if (lq == 31) {                                                                                        \
+        if (wq < W - 1) { const real2 x = xb[((wq + 1) * 2 + 1) * NS + s]; vr = x.x; vi = x.y; }             \
+        else if (s + 1 < NS) { const real2 x = xb[(0 * 2 + 1) * NS + (s + 1 < NS ? s + 1 : s)]; vr = x.x; vi = x.y; } \
+        else { vr = real(0); vi = real(0); }                                                                 \
+      }                                                                                                      \
+      DR[s] = vr; DI[s] = vi;                                                                                \
+    }                                                                                                        \
+  }
+#define DO_SEG(SHIFT_, NOLD_, NNEW_, SFLAGS_, NEXT_) \
+  { \
+    const int shift = (SHIFT_), n_old = (NOLD_), n_new = (NNEW_), sflags = (SFLAGS_); \
+    nact = (NEXT_); \
+    nslot = nact < 0 ? 0 : (nact >> lgG) + 1; \
+        if (sflags & EPGX_SEG_RESET) { \
+_Pragma("unroll") \
+          for (int s = 0; s < NS; ++s) Pr[s] = Pi[s] = Mr[s] = Mi[s] = Zr[s] = Zi[s] = real(0); \
+          if (lane == 0) Zr[0] = m0; \
+        } else if (shift != 0) { \
+      const int nsl = (n_new >> lgG) + 1; \
+      if (W == 1) { \
+        if (shift > 0) SHIFT_W1(Pr, Pi, Mr, Mi) else SHIFT_W1(Mr, Mi, Pr, Pi) \
+      } else { \
+        if (shift > 0) SHIFT_WN(Pr, Pi, Mr, Mi) else SHIFT_WN(Mr, Mi, Pr, Pi) \
+      } \
+          if (sflags & EPGX_SEG_MASK_TOP) { \
+_Pragma("unroll") \
+            for (int s = 0; s < NS; ++s) \
+              if (s * G + lane > n_new) { \
+                if (shift > 0) { Pr[s] = real(0); Pi[s] = real(0); } else { Mr[s] = real(0); Mi[s] = real(0); } \
+              } \
+          } \
+        } \
+  }
+
   // ---- the tape is streamed through shared memory in chunks of TAPE_CHUNK records (cp.async, double
   // buffered): a record fetch is two broadcast LDS instead of two dependent global loads
   const int4 *stream = (const int4 *)p.stream;
@@ -233,90 +315,23 @@ __global__ void __launch_bounds__(256) reg_kernel(const KParams p) {
         break;
       case EPGX_OP_SEG: {
         // end of a segment: unit shift / reset of the previous one, then the next pass's order count
-        const int shift = (int)off0, n_old = (int)off1, n_new = (int)off2, sflags = r1.z;
-        nact = aux;
-        nslot = nact < 0 ? 0 : (nact >> lgG) + 1; // slots with at least one order <= nact
-        if (sflags & EPGX_SEG_RESET) {
-#pragma unroll
-          for (int s = 0; s < NS; ++s) Pr[s] = Pi[s] = Mr[s] = Mi[s] = Zr[s] = Zi[s] = real(0);
-          if (lane == 0) Zr[0] = m0;
-        } else if (shift != 0) {
-      const int nsl = (n_new >> lgG) + 1; // slots that hold an order <= n_new after the shift
-      // UR/UI: the component whose orders move up (F+ for shift > 0, F- for shift < 0); DR/DI: the other.
-      // new order 0 of `up` = conj(old order 1 of `dn`): order 1 is lane 1 slot 0 (slot 1 if G == 1)
-#define SHIFT_HEAD(DR, DI)                                                                                  \
-    real cr, ci;                                                                                             \
-    if (G == 1) { cr = NS > 1 ? DR[NS > 1 ? 1 : 0] : real(0); ci = NS > 1 ? DI[NS > 1 ? 1 : 0] : real(0); }  \
-    else { cr = __shfl_sync(FULL, DR[0], gbase | 1); ci = __shfl_sync(FULL, DI[0], gbase | 1); }             \
-    if (n_old < 1) { cr = real(0); ci = real(0); }                                                           \
-    ci = -ci;
-      // one warp (or less) per atom: pure register / shuffle traffic
-#define SHIFT_W1(UR, UI, DR, DI)                                                                             \
-  {                                                                                                          \
-    SHIFT_HEAD(DR, DI)                                                                                       \
-    /* up: the LAST lane first takes over the value of its previous slot (order 0's new value for slot 0), \
-       then one rotate-by-one-lane delivers every order to its new owner; descending = in place */         \
-    DUFF(nsl, {                                                                                              \
-      const real vr = is_last ? (s > 0 ? UR[s > 0 ? s - 1 : 0] : cr) : UR[s];                                \
-      const real vi = is_last ? (s > 0 ? UI[s > 0 ? s - 1 : 0] : ci) : UI[s];                                \
-      UR[s] = __shfl_sync(FULL, vr, srcUp);                                                                  \
-      UI[s] = __shfl_sync(FULL, vi, srcUp);                                                                  \
-    })                                                                                                       \
-    /* dn: rotate the other way; the last lane receives the first lane's value of the NEXT slot (zero     \
-       above the populated orders) */                                                                       \
-    real nr = real(0), ni = real(0);                                                                         \
-    DUFF(nsl, {                                                                                              \
-      const real xr = __shfl_sync(FULL, DR[s], srcDn), xi = __shfl_sync(FULL, DI[s], srcDn);                 \
-      DR[s] = is_last ? nr : xr;                                                                             \
-      DI[s] = is_last ? ni : xi;                                                                             \
-      nr = xr; ni = xi;                                                                                      \
-    })                                                                                                       \
-  }
-      // several warps per atom: the boundary lanes of each warp go through shared memory
-#define SHIFT_WN(UR, UI, DR, DI)                                                                             \
-  {                                                                                                          \
-    SHIFT_HEAD(DR, DI)                                                                                       \
-    real2 *xb = xbuf + (size_t)(parity * p.A + al) * W * 2 * NS; /* [warp][up | dn][slot] */                 \
-    if (lq == 31) { _Pragma("unroll") for (int s = 0; s < NS; ++s) xb[(wq * 2 + 0) * NS + s] = real2{UR[s], UI[s]}; } \
-    if (lq == 0) { _Pragma("unroll") for (int s = 0; s < NS; ++s) xb[(wq * 2 + 1) * NS + s] = real2{DR[s], DI[s]}; }  \
-    asm volatile("bar.sync %0, %1;" ::"r"(1 + al), "r"(G) : "memory");                                       \
-    parity ^= 1;                                                                                             \
-    _Pragma("unroll") for (int s = 0; s < NS; ++s) {                                                         \
-      if (s >= nsl) break;                                                                                   \
-      real vr = __shfl_sync(FULL, UR[s], srcUp), vi = __shfl_sync(FULL, UI[s], srcUp);                       \
-      if (lq == 0) {                                                                                         \
-        if (wq == 0) { vr = cr; vi = ci; const real2 x = xb[((W - 1) * 2 + 0) * NS + s]; cr = x.x; ci = x.y; } \
-        else { const real2 x = xb[((wq - 1) * 2 + 0) * NS + s]; vr = x.x; vi = x.y; }                        \
-      }                                                                                                      \
-      UR[s] = vr; UI[s] = vi;                                                                                \
-    }                                                                                                        \
-    _Pragma("unroll") for (int s = 0; s < NS; ++s) {                                                         \
-      if (s >= nsl) break;                                                                                   \
-      real vr = __shfl_sync(FULL, DR[s], srcDn), vi = __shfl_sync(FULL, DI[s], srcDn);                       \
-      if (lq == 31) {                                                                                        \
-        if (wq < W - 1) { const real2 x = xb[((wq + 1) * 2 + 1) * NS + s]; vr = x.x; vi = x.y; }             \
-        else if (s + 1 < NS) { const real2 x = xb[(0 * 2 + 1) * NS + (s + 1 < NS ? s + 1 : s)]; vr = x.x; vi = x.y; } \
-        else { vr = real(0); vi = real(0); }                                                                 \
-      }                                                                                                      \
-      DR[s] = vr; DI[s] = vi;                                                                                \
-    }                                                                                                        \
-  }
-      if (W == 1) {
-        if (shift > 0) SHIFT_W1(Pr, Pi, Mr, Mi) else SHIFT_W1(Mr, Mi, Pr, Pi)
-      } else {
-        if (shift > 0) SHIFT_WN(Pr, Pi, Mr, Mi) else SHIFT_WN(Mr, Mi, Pr, Pi)
-      }
-#undef SHIFT_HEAD
-#undef SHIFT_W1
-#undef SHIFT_WN
-          if (sflags & EPGX_SEG_MASK_TOP) { // truncation at max_nstate: what moved above n_new reads as zero
-#pragma unroll
-            for (int s = 0; s < NS; ++s)
-              if (s * G + lane > n_new) {
-                if (shift > 0) { Pr[s] = real(0); Pi[s] = real(0); } else { Mr[s] = real(0); Mi[s] = real(0); }
-              }
-          }
-        }
+        DO_SEG((int)off0, (int)off1, (int)off2, r1.z, aux)
+      } break;
+      case EPGX_OP_TR: {
+        // one whole TR: FUSED (E.T.E, RE kind) + plain ADC + the segment's unit shift (see epgx.cu)
+        const int4 q0 = tb[2 * r + 2], q1 = tb[2 * r + 3];
+        const real *ct = coef + off0 + patoff[pat0];
+        const real *ca = coef + off1 + patoff[pat1];
+        const real *cb = coef + (unsigned)q0.z + patoff[q1.y & 0xff];
+        const Fused5<real> f = fuse5<real>(ldc(ct), ldc(ct + 1), ldc(ct + 2), ldc(ct + 3), flags & EPGX_FLAG_PRE, ldc(ca),
+                                           ldc(ca + 1), ldc(coef + off2 + patoff[pat2]), flags & EPGX_FLAG_POST, ldc(cb),
+                                           ldc(cb + 1), ldc(coef + (unsigned)q0.w + patoff[(q1.y >> 8) & 0xff]), false, m0);
+        FOR_SLOTS(form_t5_re(t_, f.a, f.w, f.b, f.u, f.h))
+        if (lane == 0 && nslot > 0) { Pr[0] += f.fz; Mr[0] += f.fz; Zr[0] += f.zz; }
+        if (lane == 0 && valid) sig[(long long)q0.y * p.sig_stride + a_rel] = real2{Pr[0], Pi[0]};
+        const int segw = (q0.x >> 16) & 0xffff; // (shift + 1) | segment flags << 2
+        DO_SEG((segw & 3) - 1, (int)((unsigned)q1.x >> 16), (int)((unsigned)q1.x & 0xffff), segw >> 2, q1.z)
+        ++r;
       } break;
       default:
         break;
@@ -324,6 +339,10 @@ __global__ void __launch_bounds__(256) reg_kernel(const KParams p) {
     }
   }
 #undef FOR_SLOTS
+#undef DO_SEG
+#undef SHIFT_HEAD
+#undef SHIFT_W1
+#undef SHIFT_WN
 #undef DUFF
 #undef SLOT_CASE
 #undef LOAD_TRI
