@@ -17,7 +17,7 @@
 namespace epgx {
 
 template <typename real, int NS>
-__global__ void __launch_bounds__(256) real_kernel(const KParams p) {
+__global__ void __launch_bounds__(256, (sizeof(real) * NS <= 64 ? 3 : 1)) real_kernel(const KParams p) {
   typedef typename vec2<real>::type real2;
   extern __shared__ __align__(16) unsigned char smem_raw[];
 
@@ -30,7 +30,7 @@ __global__ void __launch_bounds__(256) real_kernel(const KParams p) {
   const int srcUp = gbase | ((lane - 1) & (G - 1));
   const int srcDn = gbase | ((lane + 1) & (G - 1));
   const unsigned FULL = 0xffffffffu;
-  const bool is_last = lane == G - 1;
+  const bool is_last = lane == G - 1, is_first = lane == 0;
   int lgG = 0;
   while ((1 << lgG) < G) ++lgG;
 
@@ -123,7 +123,7 @@ __global__ void __launch_bounds__(256) real_kernel(const KParams p) {
 // U: the component whose orders move up (F+ for shift > 0), D: the other one; new order 0 of U is old
 // order 1 of D (real state: no conjugation).  up: the LAST lane first takes over the value of its previous
 // slot, then one rotate-by-one-lane delivers every order to its new owner (descending = in place);
-// dn: rotate the other way, the last lane receives the first lane's value of the NEXT slot.
+// dn: rotate the other way, the FIRST lane sends the value of its NEXT slot to the last lane.
 #define SHIFT_REAL(U, D)                                                                                   \
   {                                                                                                        \
     real c1;                                                                                               \
@@ -134,11 +134,11 @@ __global__ void __launch_bounds__(256) real_kernel(const KParams p) {
       const real v = is_last ? (s > 0 ? U[s > 0 ? s - 1 : 0] : c1) : U[s];                                 \
       U[s] = __shfl_sync(FULL, v, srcUp);                                                                  \
     })                                                                                                     \
-    real nx = real(0);                                                                                     \
+    real keep = real(0); /* old value of the slot above (zero above the populated orders) */               \
     DUFF(nsl, {                                                                                            \
-      const real x = __shfl_sync(FULL, D[s], srcDn);                                                       \
-      D[s] = is_last ? nx : x;                                                                             \
-      nx = x;                                                                                              \
+      const real cur = D[s];                                                                               \
+      D[s] = __shfl_sync(FULL, is_first ? keep : cur, srcDn);                                              \
+      keep = cur;                                                                                          \
     })                                                                                                     \
   }
 
