@@ -210,7 +210,7 @@ def main():
     import torch.distributed as dist
 
     import epgpy_b200
-    from epgpy_b200 import engine, epg, lowering
+    from epgpy_b200 import engine, epg, lowering, sharding
 
     engine.require_cuda()
     torch.cuda.set_device(local_rank)
@@ -237,8 +237,7 @@ def main():
         plan.set_variant(lanes_per_atom=args.lanes, atoms_per_cta=args.atoms_per_cta)
     cfg = plan.config()
     natoms = low.natoms
-    per = natoms // world
-    a0, cnt = rank * per, (per if rank < world - 1 else natoms - per * (world - 1))
+    a0, cnt = sharding.slab(natoms, rank, world)
 
     cdt = torch.complex128 if args.dtype == "f64" else torch.complex64
     csz = 16 if args.dtype == "f64" else 8
@@ -251,8 +250,8 @@ def main():
 
     def step():
         plan.run(dev, a0, cnt, signal=sig)
-        if gathered is not None:
-            dist.all_gather_into_tensor(gathered, sig)
+        if gathered is not None:  # the one collective of the path: final gather of the signal slabs (NCCL / NVLink)
+            dist.all_gather_into_tensor(torch.view_as_real(gathered).reshape(-1), torch.view_as_real(sig).reshape(-1))
 
     for _ in range(args.warmup):
         step()
@@ -275,7 +274,7 @@ def main():
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     total_ms = float(ms.item())
-    atoms_total = per * (world - 1) + (natoms - per * (world - 1))
+    atoms_total = natoms
     value = atoms_total * args.steps / (total_ms * 1e-3)
     launches = args.steps
 
@@ -310,6 +309,46 @@ def main():
             del host
         except Exception as ex:  # e.g. not enough pinnable host memory
             e2e = {"value": None, "unit": "atoms/s", "error": f"{type(ex).__name__}: {ex}"}
+
+    # ---- extra device-resident measurements (same grid): the other precision, and max_nstate = 32
+    extra = {}
+    if not args.no_extra:
+        def quick(dtype, mns):
+            lw = lowering.lower(seq, options=({} if mns is None else {"max_nstate": mns}), dtype=dtype)
+            pl = engine.Plan(lw)
+            c_ = pl.config()
+            out = torch.empty((lw.nadc, cnt, 1), dtype=torch.complex128 if dtype == "f64" else torch.complex64,
+                              device=f"cuda:{dev}")
+            pl.upload(dev)
+            for _ in range(2):
+                pl.run(dev, a0, cnt, signal=out)
+            barrier()
+            tot = 0.0
+            for _ in range(2):
+                flush.zero_()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                pl.run(dev, a0, cnt, signal=out)
+                e1.record()
+                torch.cuda.synchronize()
+                tot += e0.elapsed_time(e1)
+            t = torch.tensor([tot], dtype=torch.float64, device=f"cuda:{dev}")
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms_ = float(t.item()) / 2
+            del out
+            return {"value": natoms / (ms_ * 1e-3), "unit": "atoms/s", "ms_per_step": ms_, "kernel": c_,
+                    "state_updates_per_s": c_["updates_per_atom"] * natoms / (ms_ * 1e-3)}, c_["flops_per_atom"] * cnt / (ms_ * 1e-3) / 1e12
+
+        other = "f32" if args.dtype == "f64" else "f64"
+        del sig
+        torch.cuda.empty_cache()
+        extra[f"{other}_unbounded"], tf_other = quick(other, max_nstate)
+        extra[f"{args.dtype}_max_nstate32"], _ = quick(args.dtype, 32)
+        launches += 8
+        if rank == 0:
+            pk = engine.fma_peak(dev, other, 0.3)
+            extra[f"{other}_unbounded"]["roofline_frac"] = tf_other / pk if pk else None
 
     if rank == 0:
         # ---- roofline: CUDA-core FMA throughput (the bound of this path) + HBM for context
@@ -347,6 +386,7 @@ def main():
                        "state_updates_per_atom_executed": cfg["updates_per_atom"], "gather": bool(gathered is not None)},
             "state_updates_per_s": cfg["updates_per_atom"] * value,
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
+            "extra": extra,
         }
         print(json.dumps(line))
     if world > 1:

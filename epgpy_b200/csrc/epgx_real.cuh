@@ -17,7 +17,7 @@
 namespace epgx {
 
 template <typename real, int NS>
-__global__ void __launch_bounds__(256, (sizeof(real) * NS <= 64 ? 3 : 1)) real_kernel(const KParams p) {
+__global__ void __launch_bounds__(256, (sizeof(real) * NS <= 64 ? 3 : sizeof(real) * NS <= 128 ? 2 : 1)) real_kernel(const KParams p) {
   typedef typename vec2<real>::type real2;
   extern __shared__ __align__(16) unsigned char smem_raw[];
 
