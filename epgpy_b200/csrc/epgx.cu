@@ -350,6 +350,27 @@ extern "C" int epgx_plan_create(const epgx_tape *t, epgx_plan **out) {
       }
     }
   }
+  {
+    // TR records start at even stream positions (NOP padding) so that a tape window can hold TAPE_CHUNK / 2 of
+    // them; windows made only of plain TRs are flagged for the kernel's vectorised fast path
+    std::vector<epgx_op> al;
+    epgx_op nop;
+    memset(&nop, 0, sizeof(nop));
+    for (size_t i = 0; i < pl->stream.size(); ++i) {
+      const epgx_op &o = pl->stream[i];
+      if (o.code == EPGX_OP_TR && (al.size() & 1)) al.push_back(nop);
+      if (o.code == EPGX_OP_FUSED && (int)(al.size() % epgx::TAPE_CHUNK) == epgx::TAPE_CHUNK - 1) al.push_back(nop);
+      al.push_back(o);
+    }
+    pl->stream.swap(al);
+    std::vector<epgx_op> &st = pl->stream;
+    for (size_t b = 0; b + epgx::TAPE_CHUNK <= st.size(); b += epgx::TAPE_CHUNK) {
+      bool pure = true;
+      for (int j = 0; pure && j < epgx::TAPE_CHUNK; j += 2)
+        pure = st[b + j].code == EPGX_OP_TR && st[b + j + 1].flags == 2; // (shift + 1) | segflags << 2 == 2
+      if (pure) st[b].flags |= 0x8000;
+    }
+  }
   pl->tape.ops = pl->ops.data();
   pl->tape.segs = pl->segs.data();
   pl->tape.coef = nullptr;

@@ -18,6 +18,9 @@
 // off[0..1] / pat[0..1] post-E blocks, aux = ADC row, flags = (shift + 1) | segment flags << 2,
 // off[2] = n_old << 16 | n_new, aux1 = nact of the next segment
 #define EPGX_OP_TR 65
+// bit of the first word (flags bit 15) of the FIRST record of a tape window: the window consists of
+// TAPE_CHUNK / 2 EPGX_OP_TR record pairs with shift = +1 and no segment flags
+#define EPGX_CHUNK_PURE_TR 0x80000000
 
 namespace epgx {
 

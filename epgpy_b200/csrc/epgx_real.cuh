@@ -159,6 +159,39 @@ __global__ void __launch_bounds__(256, (sizeof(real) * NS <= 64 ? 3 : sizeof(rea
     }
     const int4 *tb = tbuf + (chunk & 1) * 2 * TAPE_CHUNK;
     const int cnt = min(TAPE_CHUNK, p.nstream - base);
+    if (G == 32 && (tb[0].x & EPGX_CHUNK_PURE_TR)) {
+      // ---- fast path: the window holds TAPE_CHUNK / 2 whole-TR records (shift +1, no flags).  Phase 1: lane j
+      // decodes TR j, gathers its coefficients and fuses them -- one vectorised pass for 32 TRs.  Phase 2: every
+      // TR broadcasts its coefficients from its lane; no global load and no decode on the per-TR path.
+      const int4 a0 = tb[4 * lw], a1 = tb[4 * lw + 1], b0 = tb[4 * lw + 2], b1 = tb[4 * lw + 3];
+      const int fl = (a0.x >> 16) & 0xffff;
+      const real *ct = coef + (unsigned)a0.z + patoff[a1.y & 0xff];
+      const real *ca = coef + (unsigned)a0.w + patoff[(a1.y >> 8) & 0xff];
+      const real *cb = coef + (unsigned)b0.z + patoff[b1.y & 0xff];
+      const Fused5<real> fv = fuse5<real>(ldc(ct), ldc(ct + 1), ldc(ct + 2), ldc(ct + 3), fl & EPGX_FLAG_PRE, ldc(ca),
+                                          ldc(ca + 1), ldc(coef + (unsigned)a1.x + patoff[(a1.y >> 16) & 0xff]),
+                                          fl & EPGX_FLAG_POST, ldc(cb), ldc(cb + 1),
+                                          ldc(coef + (unsigned)b0.w + patoff[(b1.y >> 8) & 0xff]), false, m0);
+      const int rowv = b0.y, nnewv = (int)((unsigned)b1.x & 0xffff), nextv = b1.z;
+#pragma unroll 1
+      for (int j = 0; j < TAPE_CHUNK / 2; ++j) {
+        const real fa = __shfl_sync(FULL, fv.a, j), fw = __shfl_sync(FULL, fv.w, j), fb = __shfl_sync(FULL, fv.b, j);
+        const real fu = __shfl_sync(FULL, fv.u, j), fh = __shfl_sync(FULL, fv.h, j);
+        const real ffz = __shfl_sync(FULL, fv.fz, j), fzz = __shfl_sync(FULL, fv.zz, j);
+        const int row = __shfl_sync(FULL, rowv, j), n_new = __shfl_sync(FULL, nnewv, j), nxt = __shfl_sync(FULL, nextv, j);
+        APPLY5(fa, fw, fb, fu, fh)
+        if (lane == 0 && nslot > 0) { P[0] += ffz; M[0] += ffz; Z[0] += fzz; }
+        if (lane == 0 && valid) sig[(long long)row * p.sig_stride + a_rel] = real2{P[0], real(0)};
+        {
+          const int n_old = 1; // orders above the populated ones are zero: no guard needed on this path
+          const int nsl = (n_new >> lgG) + 1;
+          SHIFT_REAL(P, M)
+        }
+        nact = nxt;
+        nslot = nact < 0 ? 0 : (nact >> lgG) + 1;
+      }
+      continue;
+    }
     for (int r = 0; r < cnt; ++r) {
       const int4 r0 = tb[2 * r], r1 = tb[2 * r + 1];
       const int code = r0.x & 0xffff, flags = (r0.x >> 16) & 0xffff, aux = r0.y;
