@@ -304,6 +304,25 @@ extern "C" int epgx_plan_create(const epgx_tape *t, epgx_plan **out) {
     pl->pats[q * (EPGX_MAX_DIMS + 1) + EPGX_MAX_DIMS] = t->pool_stride[q];
   }
   {
+    bool ok = t->nvar == 0 && t->npool == 1;
+    for (int64_t i = 0; ok && i < t->nop; ++i) {
+      const epgx_op &o = t->ops[i];
+      switch (o.code) {
+      case EPGX_OP_NOP: case EPGX_OP_T_RE: case EPGX_OP_D: case EPGX_OP_SPOIL: case EPGX_OP_PD: case EPGX_OP_ADC:
+      case EPGX_OP_CONT: break;
+      case EPGX_OP_E: ok = !(o.flags & EPGX_FLAG_G); break;
+      case EPGX_OP_FUSED: ok = !(o.flags & EPGX_FLAG_IM); break;
+      default: ok = false;
+      }
+    }
+    if (ok) { // imaginary parts of the initial state
+      const int64_t end = (int64_t)t->init_off + pat_span[t->init_pat] + 6 * (int64_t)(t->init_n + 1);
+      for (int64_t i = t->init_off; ok && i < end; ++i)
+        if (((i - t->init_off) % 6) % 2 == 1 && t->coef[i] != 0.0) ok = false;
+    }
+    pl->real_ok = ok;
+  }
+  {
     // merged stream: [SEG(open seg 0)] recs_0 [SEG(close 0, open 1)] recs_1 ... [SEG(close last)]; a FUSED record
     // is never the last one of a TAPE_CHUNK window (NOP padding)
     auto seg_rec = [](int shift, int n_old, int n_new, int flags, int next_nact) {
@@ -376,25 +395,6 @@ extern "C" int epgx_plan_create(const epgx_tape *t, epgx_plan **out) {
   pl->tape.coef = nullptr;
   pl->natoms = natoms;
   memset(&pl->cfg, 0, sizeof(pl->cfg));
-  {
-    bool ok = t->nvar == 0 && t->npool == 1;
-    for (int64_t i = 0; ok && i < t->nop; ++i) {
-      const epgx_op &o = t->ops[i];
-      switch (o.code) {
-      case EPGX_OP_NOP: case EPGX_OP_T_RE: case EPGX_OP_D: case EPGX_OP_SPOIL: case EPGX_OP_PD: case EPGX_OP_ADC:
-      case EPGX_OP_CONT: break;
-      case EPGX_OP_E: ok = !(o.flags & EPGX_FLAG_G); break;
-      case EPGX_OP_FUSED: ok = !(o.flags & EPGX_FLAG_IM); break;
-      default: ok = false;
-      }
-    }
-    if (ok) { // imaginary parts of the initial state
-      const int64_t end = (int64_t)t->init_off + pat_span[t->init_pat] + 6 * (int64_t)(t->init_n + 1);
-      for (int64_t i = t->init_off; ok && i < end; ++i)
-        if (((i - t->init_off) % 6) % 2 == 1 && t->coef[i] != 0.0) ok = false;
-    }
-    pl->real_ok = ok;
-  }
   int rc = choose_variant(pl, 0, 0, 0, 0);
   if (rc != EPGX_OK) {
     delete pl;
