@@ -16,6 +16,52 @@
 
 namespace epgx {
 
+// One tape window of TAPE_CHUNK / 2 whole-TR records (fused E.T.E, plain ADC, unit shift +1) for one atom
+// per warp, with a COMPILE-TIME number K of active slots: the per-TR body is a single basic block (no slot
+// dispatch), so the scheduler overlaps the coefficient broadcasts, the 9 K FMAs and the 4 K shuffles /
+// selects of the shift.  K is the largest slot count of the window; a slot above the populated orders
+// holds zeros, so over-covering by (at most) one slot changes nothing.
+template <typename real, int NS, int K>
+__device__ __forceinline__ void tr_window(real (&P)[NS], real (&M)[NS], real (&Z)[NS], const Fused5<real> &fv, int rowv,
+                                          bool lane0, bool valid, bool is_first, bool is_last, int srcUp, int srcDn,
+                                          typename vec2<real>::type *sig, long long sig_stride, long long a_rel) {
+  typedef typename vec2<real>::type real2;
+  const unsigned FULL = 0xffffffffu;
+  if constexpr (K <= NS) {
+#pragma unroll 1
+    for (int j = 0; j < TAPE_CHUNK / 2; ++j) {
+      const real a = __shfl_sync(FULL, fv.a, j), w = __shfl_sync(FULL, fv.w, j), b = __shfl_sync(FULL, fv.b, j);
+      const real u = __shfl_sync(FULL, fv.u, j), h = __shfl_sync(FULL, fv.h, j);
+      const real fz = __shfl_sync(FULL, fv.fz, j), zz = __shfl_sync(FULL, fv.zz, j);
+      const int row = __shfl_sync(FULL, rowv, j);
+#pragma unroll
+      for (int s = 0; s < K; ++s) {
+        const real p_ = P[s], m_ = M[s], z_ = Z[s];
+        P[s] = a * p_ + b * m_ + u * z_;
+        M[s] = a * m_ + b * p_ + u * z_;
+        Z[s] = w * z_ + h * (p_ + m_);
+      }
+      if (lane0) { P[0] += fz; M[0] += fz; Z[0] += zz; }
+      if (lane0 && valid) sig[(long long)row * sig_stride + a_rel] = real2{P[0], real(0)};
+      // unit shift +1: F+ up (last lane takes over its previous slot, then rotate), F- down (first lane sends its
+      // next slot), F+(0) <- F-(1)
+      const real c1 = __shfl_sync(FULL, M[0], 1);
+#pragma unroll
+      for (int s = K - 1; s >= 0; --s) {
+        const real v = is_last ? (s > 0 ? P[s > 0 ? s - 1 : 0] : c1) : P[s];
+        P[s] = __shfl_sync(FULL, v, srcUp);
+      }
+      real keep = real(0);
+#pragma unroll
+      for (int s = K - 1; s >= 0; --s) {
+        const real cur = M[s];
+        M[s] = __shfl_sync(FULL, is_first ? keep : cur, srcDn);
+        keep = cur;
+      }
+    }
+  }
+}
+
 template <typename real, int NS>
 __global__ void __launch_bounds__(256, (sizeof(real) * NS <= 64 ? 3 : sizeof(real) * NS <= 128 ? 2 : 1)) real_kernel(const KParams p) {
   typedef typename vec2<real>::type real2;
@@ -173,23 +219,18 @@ __global__ void __launch_bounds__(256, (sizeof(real) * NS <= 64 ? 3 : sizeof(rea
                                           fl & EPGX_FLAG_POST, ldc(cb), ldc(cb + 1),
                                           ldc(coef + (unsigned)b0.w + patoff[(b1.y >> 8) & 0xff]), false, m0);
       const int rowv = b0.y, nnewv = (int)((unsigned)b1.x & 0xffff), nextv = b1.z;
-#pragma unroll 1
-      for (int j = 0; j < TAPE_CHUNK / 2; ++j) {
-        const real fa = __shfl_sync(FULL, fv.a, j), fw = __shfl_sync(FULL, fv.w, j), fb = __shfl_sync(FULL, fv.b, j);
-        const real fu = __shfl_sync(FULL, fv.u, j), fh = __shfl_sync(FULL, fv.h, j);
-        const real ffz = __shfl_sync(FULL, fv.fz, j), fzz = __shfl_sync(FULL, fv.zz, j);
-        const int row = __shfl_sync(FULL, rowv, j), n_new = __shfl_sync(FULL, nnewv, j), nxt = __shfl_sync(FULL, nextv, j);
-        APPLY5(fa, fw, fb, fu, fh)
-        if (lane == 0 && nslot > 0) { P[0] += ffz; M[0] += ffz; Z[0] += fzz; }
-        if (lane == 0 && valid) sig[(long long)row * p.sig_stride + a_rel] = real2{P[0], real(0)};
-        {
-          const int n_old = 1; // orders above the populated ones are zero: no guard needed on this path
-          const int nsl = (n_new >> lgG) + 1;
-          SHIFT_REAL(P, M)
-        }
-        nact = nxt;
-        nslot = nact < 0 ? 0 : (nact >> lgG) + 1;
+      // largest slot count any TR of the window needs (apply: nact, shift: n_new)
+      int need = max(nnewv >> 5, nextv < 0 ? -1 : nextv >> 5) + 1;
+      need = max(__reduce_max_sync(FULL, need), nslot);
+#define TRW(K_) case K_: tr_window<real, NS, K_>(P, M, Z, fv, rowv, lane == 0, valid, is_first, is_last, srcUp, srcDn, sig, p.sig_stride, a_rel); break;
+      switch (need) {
+        TRW(1) TRW(2) TRW(3) TRW(4) TRW(5) TRW(6) TRW(7) TRW(8) TRW(9) TRW(10) TRW(11) TRW(12) TRW(13) TRW(14) TRW(15) TRW(16)
+        TRW(17) TRW(18) TRW(19) TRW(20) TRW(21) TRW(22) TRW(23) TRW(24) TRW(25) TRW(26) TRW(27) TRW(28) TRW(29) TRW(30) TRW(31) TRW(32)
+      default: break;
       }
+#undef TRW
+      nact = __shfl_sync(FULL, nextv, TAPE_CHUNK / 2 - 1);
+      nslot = nact < 0 ? 0 : (nact >> lgG) + 1;
       continue;
     }
     for (int r = 0; r < cnt; ++r) {
