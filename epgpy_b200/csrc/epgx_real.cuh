@@ -23,14 +23,13 @@ namespace epgx {
 // holds zeros, so over-covering by (at most) one slot changes nothing.
 template <typename real, int NS, int K>
 __device__ __forceinline__ void tr_window(real (&P)[NS], real (&M)[NS], real (&Z)[NS], const Fused5<real> &fv, int rowv,
-                                          int G, int gbase, bool lane0, bool valid, bool is_first, bool is_last, int srcUp,
-                                          int srcDn, typename vec2<real>::type *sig, long long sig_stride, long long a_rel) {
+                                          bool lane0, bool valid, bool is_first, bool is_last, int srcUp, int srcDn,
+                                          typename vec2<real>::type *sig, long long sig_stride, long long a_rel) {
   typedef typename vec2<real>::type real2;
   const unsigned FULL = 0xffffffffu;
   if constexpr (K <= NS) {
 #pragma unroll 1
-    for (int jj = 0; jj < G; ++jj) { // the G lanes of the atom hold the coefficients of G consecutive TRs
-      const int j = gbase + jj;
+    for (int j = 0; j < TAPE_CHUNK / 2; ++j) {
       const real a = __shfl_sync(FULL, fv.a, j), w = __shfl_sync(FULL, fv.w, j), b = __shfl_sync(FULL, fv.b, j);
       const real u = __shfl_sync(FULL, fv.u, j), h = __shfl_sync(FULL, fv.h, j);
       const real fz = __shfl_sync(FULL, fv.fz, j), zz = __shfl_sync(FULL, fv.zz, j);
@@ -46,7 +45,7 @@ __device__ __forceinline__ void tr_window(real (&P)[NS], real (&M)[NS], real (&Z
       if (lane0 && valid) sig[(long long)row * sig_stride + a_rel] = real2{P[0], real(0)};
       // unit shift +1: F+ up (last lane takes over its previous slot, then rotate), F- down (first lane sends its
       // next slot), F+(0) <- F-(1)
-      const real c1 = G > 1 ? __shfl_sync(FULL, M[0], gbase | 1) : (K > 1 ? M[K > 1 ? 1 : 0] : real(0));
+      const real c1 = __shfl_sync(FULL, M[0], 1);
 #pragma unroll
       for (int s = K - 1; s >= 0; --s) {
         const real v = is_last ? (s > 0 ? P[s > 0 ? s - 1 : 0] : c1) : P[s];
@@ -206,36 +205,32 @@ __global__ void __launch_bounds__(256, (sizeof(real) * NS <= 64 ? 3 : sizeof(rea
     }
     const int4 *tb = tbuf + (chunk & 1) * 2 * TAPE_CHUNK;
     const int cnt = min(TAPE_CHUNK, p.nstream - base);
-    if (tb[0].x & EPGX_CHUNK_PURE_TR) {
-      // ---- fast path: the window holds TAPE_CHUNK / 2 whole-TR records (shift +1, no flags).  Phase 1: lane l of
-      // the atom decodes TR w0 + l, gathers its coefficients and fuses them -- one vectorised pass for G TRs.
-      // Phase 2 (tr_window): every TR broadcasts its coefficients from its lane; no global load and no decode
-      // on the per-TR path.
-      for (int w0 = 0; w0 < TAPE_CHUNK / 2; w0 += G) {
-        const int jt = w0 + lane;
-        const int4 a0 = tb[4 * jt], a1 = tb[4 * jt + 1], b0 = tb[4 * jt + 2], b1 = tb[4 * jt + 3];
-        const int fl = (a0.x >> 16) & 0xffff;
-        const real *ct = coef + (unsigned)a0.z + patoff[a1.y & 0xff];
-        const real *ca = coef + (unsigned)a0.w + patoff[(a1.y >> 8) & 0xff];
-        const real *cb = coef + (unsigned)b0.z + patoff[b1.y & 0xff];
-        const Fused5<real> fv = fuse5<real>(ldc(ct), ldc(ct + 1), ldc(ct + 2), ldc(ct + 3), fl & EPGX_FLAG_PRE, ldc(ca),
-                                            ldc(ca + 1), ldc(coef + (unsigned)a1.x + patoff[(a1.y >> 16) & 0xff]),
-                                            fl & EPGX_FLAG_POST, ldc(cb), ldc(cb + 1),
-                                            ldc(coef + (unsigned)b0.w + patoff[(b1.y >> 8) & 0xff]), false, m0);
-        const int rowv = b0.y, nnewv = (int)((unsigned)b1.x & 0xffff), nextv = b1.z;
-        // largest slot count any TR of the window needs (apply: nact, shift: n_new)
-        int need = max(nnewv >> lgG, nextv < 0 ? -1 : nextv >> lgG) + 1;
-        need = max(__reduce_max_sync(FULL, need), nslot);
-#define TRW(K_) case K_: tr_window<real, NS, K_>(P, M, Z, fv, rowv, G, gbase, lane == 0, valid, is_first, is_last, srcUp, srcDn, sig, p.sig_stride, a_rel); break;
-        switch (need) {
-          TRW(1) TRW(2) TRW(3) TRW(4) TRW(5) TRW(6) TRW(7) TRW(8) TRW(9) TRW(10) TRW(11) TRW(12) TRW(13) TRW(14) TRW(15) TRW(16)
-          TRW(17) TRW(18) TRW(19) TRW(20) TRW(21) TRW(22) TRW(23) TRW(24) TRW(25) TRW(26) TRW(27) TRW(28) TRW(29) TRW(30) TRW(31) TRW(32)
-        default: break;
-        }
-#undef TRW
-        nact = __shfl_sync(FULL, nextv, gbase + G - 1);
-        nslot = nact < 0 ? 0 : (nact >> lgG) + 1;
+    if (G == 32 && (tb[0].x & EPGX_CHUNK_PURE_TR)) {
+      // ---- fast path: the window holds TAPE_CHUNK / 2 whole-TR records (shift +1, no flags).  Phase 1: lane j
+      // decodes TR j, gathers its coefficients and fuses them -- one vectorised pass for 32 TRs.  Phase 2: every
+      // TR broadcasts its coefficients from its lane; no global load and no decode on the per-TR path.
+      const int4 a0 = tb[4 * lw], a1 = tb[4 * lw + 1], b0 = tb[4 * lw + 2], b1 = tb[4 * lw + 3];
+      const int fl = (a0.x >> 16) & 0xffff;
+      const real *ct = coef + (unsigned)a0.z + patoff[a1.y & 0xff];
+      const real *ca = coef + (unsigned)a0.w + patoff[(a1.y >> 8) & 0xff];
+      const real *cb = coef + (unsigned)b0.z + patoff[b1.y & 0xff];
+      const Fused5<real> fv = fuse5<real>(ldc(ct), ldc(ct + 1), ldc(ct + 2), ldc(ct + 3), fl & EPGX_FLAG_PRE, ldc(ca),
+                                          ldc(ca + 1), ldc(coef + (unsigned)a1.x + patoff[(a1.y >> 16) & 0xff]),
+                                          fl & EPGX_FLAG_POST, ldc(cb), ldc(cb + 1),
+                                          ldc(coef + (unsigned)b0.w + patoff[(b1.y >> 8) & 0xff]), false, m0);
+      const int rowv = b0.y, nnewv = (int)((unsigned)b1.x & 0xffff), nextv = b1.z;
+      // largest slot count any TR of the window needs (apply: nact, shift: n_new)
+      int need = max(nnewv >> 5, nextv < 0 ? -1 : nextv >> 5) + 1;
+      need = max(__reduce_max_sync(FULL, need), nslot);
+#define TRW(K_) case K_: tr_window<real, NS, K_>(P, M, Z, fv, rowv, lane == 0, valid, is_first, is_last, srcUp, srcDn, sig, p.sig_stride, a_rel); break;
+      switch (need) {
+        TRW(1) TRW(2) TRW(3) TRW(4) TRW(5) TRW(6) TRW(7) TRW(8) TRW(9) TRW(10) TRW(11) TRW(12) TRW(13) TRW(14) TRW(15) TRW(16)
+        TRW(17) TRW(18) TRW(19) TRW(20) TRW(21) TRW(22) TRW(23) TRW(24) TRW(25) TRW(26) TRW(27) TRW(28) TRW(29) TRW(30) TRW(31) TRW(32)
+      default: break;
       }
+#undef TRW
+      nact = __shfl_sync(FULL, nextv, TAPE_CHUNK / 2 - 1);
+      nslot = nact < 0 ? 0 : (nact >> lgG) + 1;
       continue;
     }
     for (int r = 0; r < cnt; ++r) {
