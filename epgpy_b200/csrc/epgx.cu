@@ -11,6 +11,7 @@
 #include "epgx_common.cuh"
 #include "epgx_reg.cuh"
 #include "epgx_real.cuh"
+#include "epgx_realjac.cuh"
 #include "epgx_ring.cuh"
 
 using namespace epgx;
@@ -39,6 +40,7 @@ struct epgx_plan {
   std::vector<epgx_op> stream; // segments + records merged (register kernel)
   int64_t natoms;
   double flops_cplx, flops_real, updates; // executed real flops per atom (complex / real-valued kernels)
+  bool realjac_ok; // real-valued graph with real-valued derivative injections
   bool real_ok; // real-valued phase graph: eligible for the three-reals-per-order kernel
   epgx_config cfg;
   // workspace layout (bytes)
@@ -89,6 +91,37 @@ static int choose_variant(epgx_plan *pl, int kernel, int lanes, int vars, int at
   const bool reg_ok = t.nvar == 0 && t.npool == 1;
   if (kernel == 2 && !reg_ok)
     return fail(EPGX_ERR_UNSUPPORTED, "the register kernel runs forward simulations of one pool only");
+  if (kernel == 4 && !pl->realjac_ok)
+    return fail(EPGX_ERR_UNSUPPORTED, "the real-valued derivative kernel needs a real-valued tape with order-1 variables");
+  if (pl->realjac_ok && (kernel == 0 || kernel == 4)) {
+    // ---- real-valued register kernel with 3 resident partial states: G = 32 W lanes x NS slots >= C orders
+    const int ns_max = t.dtype == EPGX_F64 ? 4 : 8;
+    int G = lanes > 0 ? pow2ceil(lanes) : pow2ceil((C + ns_max - 1) / ns_max);
+    if (G > 256) G = 256;
+    const int need = (C + G - 1) / G;
+    int NS = 0;
+    for (int o : {1, 2, 4, 8})
+      if (o >= need && !NS) NS = o;
+    if (NS && (NS <= ns_max || lanes > 0)) {
+      const int W = G > 32 ? G / 32 : 1;
+      int A = atoms > 0 ? atoms : (128 / G > 0 ? 128 / G : 1);
+      if (W > 1 && A > 15) A = 15;
+      while (A * G > 256 && A > 1) --A;
+      if (A * G <= 256) {
+        c.kernel = 3;
+        c.lanes_per_atom = G;
+        c.slots_per_lane = NS;
+        c.vars_per_pass = 3;
+        c.var_tiles = (t.nvar + 2) / 3;
+        c.atoms_per_cta = A;
+        c.threads_per_cta = A * G;
+        c.smem_bytes = 2 * epgx::TAPE_CHUNK * 32 + ((A * t.npattern + 3) & ~3) * 4 + (W > 1 ? 2 * A * W * 4 * 2 * NS * rsz : 0) + 32;
+        c.ring = C;
+        return EPGX_OK;
+      }
+    }
+    if (kernel == 4) return fail(EPGX_ERR_CAPACITY, "no real-derivative-kernel instance holds " + std::to_string(C) + " orders");
+  }
   if (kernel == 3 && !pl->real_ok)
     return fail(EPGX_ERR_UNSUPPORTED, "the real-valued kernel needs +-90 degree pulses, no precession and a real initial state");
   if (pl->real_ok && (kernel == 0 || kernel == 3)) {
@@ -321,6 +354,27 @@ extern "C" int epgx_plan_create(const epgx_tape *t, epgx_plan **out) {
         if (((i - t->init_off) % 6) % 2 == 1 && t->coef[i] != 0.0) ok = false;
     }
     pl->real_ok = ok;
+    // the same with order-1 partial states: injections must be real as well
+    bool okj = t->nvar > 0 && t->npool == 1;
+    for (int64_t i = 0; okj && i < t->nop; ++i) {
+      const epgx_op &o = t->ops[i];
+      switch (o.code) {
+      case EPGX_OP_NOP: case EPGX_OP_T_RE: case EPGX_OP_D: case EPGX_OP_SPOIL: case EPGX_OP_PD: case EPGX_OP_ADC: break;
+      case EPGX_OP_E: okj = !(o.flags & EPGX_FLAG_G); break;
+      case EPGX_OP_DIAG: {
+        const int64_t end = (int64_t)o.off[0] + pat_span[o.pat[0]] + 8;
+        for (int64_t j = o.off[0]; okj && j < end; ++j)
+          if (((j - o.off[0]) % 8) % 2 == 1 && t->coef[j] != 0.0) okj = false;
+      } break;
+      default: okj = false;
+      }
+    }
+    if (okj) {
+      const int64_t end = (int64_t)t->init_off + pat_span[t->init_pat] + 6 * (int64_t)(t->init_n + 1);
+      for (int64_t i = t->init_off; okj && i < end; ++i)
+        if (((i - t->init_off) % 6) % 2 == 1 && t->coef[i] != 0.0) okj = false;
+    }
+    pl->realjac_ok = okj;
   }
   {
     // merged stream: [SEG(open seg 0)] recs_0 [SEG(close 0, open 1)] recs_1 ... [SEG(close last)]; a FUSED record
@@ -404,7 +458,7 @@ extern "C" int epgx_plan_create(const epgx_tape *t, epgx_plan **out) {
   pl->flops_real = 0.5 * flops; // T_RE / FUSED / E / D on three reals per order
   pl->updates = updates;
   pl->cfg.updates_per_atom = updates;
-  pl->cfg.flops_per_atom = pl->cfg.kernel == 2 ? pl->flops_real : pl->flops_cplx;
+  pl->cfg.flops_per_atom = pl->cfg.kernel >= 2 ? pl->flops_real : pl->flops_cplx;
   auto align = [](int64_t x) { return (x + 255) & ~(int64_t)255; };
   const int rsz = t->dtype == EPGX_F64 ? 8 : 4;
   pl->off_ops = 0;
@@ -431,7 +485,7 @@ extern "C" int epgx_plan_config(const epgx_plan *pl, epgx_config *cfg) {
 extern "C" int epgx_plan_set_variant(epgx_plan *pl, int kernel, int lanes, int vars, int atoms) {
   if (!pl) return fail(EPGX_ERR_INVALID, "null plan");
   int rc = choose_variant(pl, kernel, lanes, vars, atoms);
-  pl->cfg.flops_per_atom = pl->cfg.kernel == 2 ? pl->flops_real : pl->flops_cplx;
+  pl->cfg.flops_per_atom = pl->cfg.kernel >= 2 ? pl->flops_real : pl->flops_cplx;
   pl->cfg.updates_per_atom = pl->updates;
   return rc;
 }
@@ -512,6 +566,25 @@ template <typename real> static int dispatch_real(const epgx_plan *pl, const KPa
   return fail(EPGX_ERR_UNSUPPORTED, "no real-kernel instance for slots_per_lane=" + std::to_string(pl->cfg.slots_per_lane));
 }
 
+template <typename real, int NS> static int launch_realjac(const epgx_plan *pl, const KParams &kp, cudaStream_t st) {
+  const epgx_config &c = pl->cfg;
+  auto kern = realjac_kernel<real, NS, 3>;
+  dim3 grid((unsigned)((kp.atom_count + c.atoms_per_cta - 1) / c.atoms_per_cta), (unsigned)c.var_tiles);
+  kern<<<grid, c.threads_per_cta, c.smem_bytes, st>>>(kp);
+  CUDA_TRY(cudaGetLastError());
+  return EPGX_OK;
+}
+
+template <typename real> static int dispatch_realjac(const epgx_plan *pl, const KParams &kp, cudaStream_t st) {
+  switch (pl->cfg.slots_per_lane) {
+  case 1: return launch_realjac<real, 1>(pl, kp, st);
+  case 2: return launch_realjac<real, 2>(pl, kp, st);
+  case 4: return launch_realjac<real, 4>(pl, kp, st);
+  case 8: return launch_realjac<real, 8>(pl, kp, st);
+  }
+  return fail(EPGX_ERR_UNSUPPORTED, "no real-derivative-kernel instance for slots_per_lane=" + std::to_string(pl->cfg.slots_per_lane));
+}
+
 template <typename real> static int dispatch_ring(const epgx_plan *pl, const KParams &kp, cudaStream_t st) {
   const int np = pl->tape.npool, nvt = pl->cfg.vars_per_pass;
 #define CASE(NP_, NVT_) \
@@ -566,6 +639,7 @@ extern "C" int epgx_simulate_strided(const epgx_plan *pl, const void *ws, int64_
   kp.m0_pat = t.m0_pat;
   kp.init_n = t.init_n;
   cudaStream_t st = (cudaStream_t)stream;
+  if (pl->cfg.kernel == 3) return t.dtype == EPGX_F64 ? dispatch_realjac<double>(pl, kp, st) : dispatch_realjac<float>(pl, kp, st);
   if (pl->cfg.kernel == 2) return t.dtype == EPGX_F64 ? dispatch_real<double>(pl, kp, st) : dispatch_real<float>(pl, kp, st);
   if (pl->cfg.kernel == 1) return t.dtype == EPGX_F64 ? dispatch_reg<double>(pl, kp, st) : dispatch_reg<float>(pl, kp, st);
   if (t.dtype == EPGX_F64) return dispatch_ring<double>(pl, kp, st);

@@ -1,0 +1,305 @@
+// epgx_realjac.cuh -- register kernel for real-valued phase graphs WITH order-1 partial states.
+//
+// Same eligibility as epgx_real.cuh (+-90 degree pulses, no precession, real initial state) extended to
+// derivative tapes whose injection records are real too (dT/dalpha at phi = +-90, dE/dT1, dE/dT2, dE/dtau:
+// epgpy/transition.py:172-186, evolution.py:360-389).  An atom keeps 1 + NV state sets (base + NV partial
+// states, epgpy/diff.py:264-288) of three reals per order in registers, spread over G = 32 W lanes
+// (W warps; order k in slot k / G of lane k % G) so that four sets of 500 orders fit: the 1000-TR FISP
+// dictionary with its (B1, T1, T2) Jacobian runs with W = 4, NS = 4.  Variables beyond NV are tiled over
+// blockIdx.y (the base state is recomputed per tile).  Warps of one atom exchange the two boundary values
+// of every slot through shared memory at each unit shift (double-buffered, one named barrier).
+#pragma once
+#include <cuda_pipeline.h>
+
+#include "epgx_common.cuh"
+#include "epgx_reg.cuh"
+
+namespace epgx {
+
+template <typename real, int NS, int NV>
+__global__ void __launch_bounds__(256) realjac_kernel(const KParams p) {
+  typedef typename vec2<real>::type real2;
+  constexpr int SETS = 1 + NV;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+
+  const int G = p.G;
+  const int tid = threadIdx.x;
+  const int al = tid / G;
+  const int lane = tid - al * G;
+  const int lw = tid & 31;
+  const int W = G > 32 ? G >> 5 : 1;
+  const int GW = G > 32 ? 32 : G;
+  const int wq = G > 32 ? lane >> 5 : 0;
+  const int gbase = lw & ~(GW - 1);
+  const int lq = lw - gbase;
+  const int srcUp = gbase | ((lq - 1) & (GW - 1));
+  const int srcDn = gbase | ((lq + 1) & (GW - 1));
+  const unsigned FULL = 0xffffffffu;
+  const bool is_first = lq == 0, is_last = lq == GW - 1;
+  int lgG = 0;
+  while ((1 << lgG) < G) ++lgG;
+
+  const long long a_rel = (long long)blockIdx.x * p.A + al;
+  const bool valid = a_rel < p.atom_count;
+  const long long atom = p.atom_begin + (valid ? a_rel : p.atom_count - 1);
+  const int v0 = blockIdx.y * NV;
+  const real *__restrict__ coef = (const real *)p.coef;
+
+  // shared memory: tape window, pattern offsets [A][npattern], boundary exchange [2][A][W][SETS][2][NS]
+  int4 *tbuf = (int4 *)smem_raw;
+  int *patoff = (int *)(tbuf + 2 * TAPE_CHUNK * 2) + al * p.npattern;
+  real *xbuf = (real *)((int *)(tbuf + 2 * TAPE_CHUNK * 2) + ((p.A * p.npattern + 3) & ~3));
+  {
+    int idx[EPGX_MAX_DIMS];
+    long long r = atom;
+    for (int d = p.ndim - 1; d >= 0; --d) {
+      idx[d] = (int)(r % p.shape[d]);
+      r /= p.shape[d];
+    }
+    for (int q = lane; q < p.npattern; q += G) {
+      const int *st = p.pats + q * (EPGX_MAX_DIMS + 1);
+      int o = 0;
+      for (int d = 0; d < p.ndim; ++d) o += idx[d] * st[d];
+      patoff[q] = o;
+    }
+  }
+  __syncthreads();
+
+  real P[SETS][NS], M[SETS][NS], Z[SETS][NS];
+  real m0 = ldc(coef + p.m0_off + patoff[p.m0_pat]);
+  {
+    const real *ib = coef + p.init_off + patoff[p.init_pat];
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+      const int k = s * G + lane;
+      const bool in = k <= p.init_n;
+      P[0][s] = in ? ldc(ib + 6 * k) : real(0);
+      M[0][s] = in ? ldc(ib + 6 * k + 2) : real(0);
+      Z[0][s] = in ? ldc(ib + 6 * k + 4) : real(0);
+#pragma unroll
+      for (int q = 1; q < SETS; ++q) P[q][s] = M[q][s] = Z[q][s] = real(0);
+    }
+  }
+  real2 *sig = (real2 *)p.signal;
+  real2 *jac = (real2 *)p.jac;
+  int parity = 0;
+
+  const int4 *stream = (const int4 *)p.stream;
+  const int nthreads = blockDim.x;
+  for (int i = tid; i < 2 * TAPE_CHUNK && i < 2 * p.nstream; i += nthreads) __pipeline_memcpy_async(tbuf + i, stream + i, 16);
+  __pipeline_commit();
+  int nact = -1, nslot = 0;
+  for (int base = 0, chunk = 0; base < p.nstream; base += TAPE_CHUNK, ++chunk) {
+    __pipeline_wait_prior(0);
+    __syncthreads();
+    {
+      const int nb = base + TAPE_CHUNK;
+      int4 *dst = tbuf + ((chunk + 1) & 1) * 2 * TAPE_CHUNK;
+      for (int i = tid; i < 2 * TAPE_CHUNK && nb * 2 + i < 2 * p.nstream; i += nthreads)
+        __pipeline_memcpy_async(dst + i, stream + (size_t)nb * 2 + i, 16);
+      __pipeline_commit();
+    }
+    const int4 *tb = tbuf + (chunk & 1) * 2 * TAPE_CHUNK;
+    const int cnt = min(TAPE_CHUNK, p.nstream - base);
+    for (int r = 0; r < cnt; ++r) {
+      const int4 r0 = tb[2 * r], r1 = tb[2 * r + 1];
+      const int code = r0.x & 0xffff, flags = (r0.x >> 16) & 0xffff, aux = r0.y;
+      const unsigned off0 = (unsigned)r0.z, off1 = (unsigned)r0.w, off2 = (unsigned)r1.x;
+      const int pat0 = r1.y & 0xff, pat1 = (r1.y >> 8) & 0xff;
+      const bool on_base = flags & EPGX_FLAG_BASE, on_part = flags & EPGX_FLAG_PARTIALS;
+      const bool inject = flags & EPGX_FLAG_INJECT;
+      const int iset = aux - v0 + 1; // target set of an injection
+      const bool aff0 = (flags & EPGX_FLAG_AFFINE) && lane == 0 && nslot > 0;
+      (void)off2;
+
+      // F+' = a F+ + b F- + u Z ; F-' = b F+ + a F- + u Z ; Z' = w Z + h (F+ + F-)     (T_RE kind)
+#define LIN5(a, w, b, u, h)                                                                 \
+  {                                                                                         \
+    if (inject) {                                                                           \
+      if (iset >= 1 && iset < SETS) {                                                       \
+        _Pragma("unroll") for (int s = 0; s < NS; ++s) if (s < nslot) {                     \
+          const real p_ = P[0][s], m_ = M[0][s], z_ = Z[0][s];                              \
+          const real np_ = a * p_ + b * m_ + u * z_, nm_ = a * m_ + b * p_ + u * z_;        \
+          const real nz_ = w * z_ + h * (p_ + m_);                                          \
+          _Pragma("unroll") for (int q = 1; q < SETS; ++q) if (q == iset) {                 \
+            P[q][s] += np_; M[q][s] += nm_; Z[q][s] += nz_;                                 \
+          }                                                                                 \
+        }                                                                                   \
+      }                                                                                     \
+    } else {                                                                                \
+      _Pragma("unroll") for (int q = 0; q < SETS; ++q) if (q == 0 ? on_base : on_part) {    \
+        _Pragma("unroll") for (int s = 0; s < NS; ++s) if (s < nslot) {                     \
+          const real p_ = P[q][s], m_ = M[q][s], z_ = Z[q][s];                              \
+          P[q][s] = a * p_ + b * m_ + u * z_;                                               \
+          M[q][s] = a * m_ + b * p_ + u * z_;                                               \
+          Z[q][s] = w * z_ + h * (p_ + m_);                                                 \
+        }                                                                                   \
+      }                                                                                     \
+    }                                                                                       \
+  }
+      // F+- *= dp / dm, Z *= dz, Z(0) += z0 (affine, base and injections only)
+#define DIAG3(dp, dm, dz, z0)                                                               \
+  {                                                                                         \
+    if (inject) {                                                                           \
+      if (iset >= 1 && iset < SETS) {                                                       \
+        _Pragma("unroll") for (int q = 1; q < SETS; ++q) if (q == iset) {                   \
+          _Pragma("unroll") for (int s = 0; s < NS; ++s) if (s < nslot) {                   \
+            P[q][s] += dp * P[0][s]; M[q][s] += dm * M[0][s]; Z[q][s] += dz * Z[0][s];      \
+          }                                                                                 \
+          if (aff0) Z[q][0] += z0;                                                          \
+        }                                                                                   \
+      }                                                                                     \
+    } else {                                                                                \
+      _Pragma("unroll") for (int q = 0; q < SETS; ++q) if (q == 0 ? on_base : on_part) {    \
+        _Pragma("unroll") for (int s = 0; s < NS; ++s) if (s < nslot) {                     \
+          P[q][s] *= dp; M[q][s] *= dm; Z[q][s] *= dz;                                      \
+        }                                                                                   \
+        if (q == 0 && aff0) Z[0][0] += z0;                                                  \
+      }                                                                                     \
+    }                                                                                       \
+  }
+
+      switch (code) {
+      case EPGX_OP_T_RE: {
+        const real *c = coef + off0 + patoff[pat0];
+        const real a = ldc(c), w = ldc(c + 1), b = ldc(c + 2), u = ldc(c + 3), h = real(-0.5) * u;
+        LIN5(a, w, b, u, h)
+      } break;
+      case EPGX_OP_E: {
+        const real *c0 = coef + off0 + patoff[pat0];
+        const real e1 = ldc(c0), z0 = ldc(c0 + 1) * m0;
+        const real e2 = ldc(coef + off1 + patoff[pat1]);
+        DIAG3(e2, e2, e1, z0)
+      } break;
+      case EPGX_OP_DIAG: { // real entries only (checked by the host): (aP, 0, aM, 0, aZ, 0, a0, 0)
+        const real *c = coef + off0 + patoff[pat0];
+        const real dp = ldc(c), dm = ldc(c + 2), dz = ldc(c + 4), z0 = ldc(c + 6) * m0;
+        DIAG3(dp, dm, dz, z0)
+      } break;
+      case EPGX_OP_D: {
+        const real *c = coef + off0 + patoff[pat0];
+#pragma unroll
+        for (int s = 0; s < NS; ++s)
+          if (s < nslot) {
+            const int k = min(s * G + lane, p.C - 1);
+            const real dp = ldc(c + 3 * k), dm = ldc(c + 3 * k + 1), dl = ldc(c + 3 * k + 2);
+#pragma unroll
+            for (int q = 0; q < SETS; ++q)
+              if (q == 0 ? on_base : on_part) { P[q][s] *= dp; M[q][s] *= dm; Z[q][s] *= dl; }
+          }
+      } break;
+      case EPGX_OP_SPOIL:
+#pragma unroll
+        for (int q = 0; q < SETS; ++q)
+          if (q == 0 ? on_base : on_part) {
+#pragma unroll
+            for (int s = 0; s < NS; ++s)
+              if (s < nslot) { P[q][s] = real(0); M[q][s] = real(0); }
+          }
+        break;
+      case EPGX_OP_PD:
+        m0 = ldc(coef + off0 + patoff[pat0]);
+        break;
+      case EPGX_OP_ADC:
+        if (lane == 0 && valid) {
+          real fr = real(1), fi = real(0);
+          if (flags & EPGX_FLAG_SCALE) {
+            const real *c = coef + off0 + patoff[pat0];
+            fr = ldc(c); fi = ldc(c + 1);
+          }
+          const bool z0 = flags & EPGX_FLAG_Z0;
+          if (on_base && blockIdx.y == 0) {
+            const real x = z0 ? Z[0][0] : P[0][0];
+            sig[(long long)aux * p.sig_stride + a_rel] = real2{x * fr, x * fi};
+          }
+          if (on_part) {
+#pragma unroll
+            for (int q = 1; q < SETS; ++q) {
+              const int v = v0 + q - 1;
+              if (v < p.nvar) {
+                const real x = z0 ? Z[q][0] : P[q][0];
+                jac[((long long)r1.z * p.nvar + v) * p.jac_stride + a_rel] = real2{x * fr, x * fi};
+              }
+            }
+          }
+        }
+        break;
+      case EPGX_OP_SEG: {
+        const int shift = (int)off0, n_old = (int)off1, n_new = (int)off2, sflags = r1.z;
+        nact = aux;
+        nslot = nact < 0 ? 0 : (nact >> lgG) + 1;
+        if (sflags & EPGX_SEG_RESET) {
+#pragma unroll
+          for (int q = 0; q < SETS; ++q)
+#pragma unroll
+            for (int s = 0; s < NS; ++s) P[q][s] = M[q][s] = Z[q][s] = real(0);
+          if (lane == 0) Z[0][0] = m0;
+        } else if (shift != 0) {
+          const int nsl = (n_new >> lgG) + 1;
+          // U moves up (F+ for shift > 0), D moves down; new order 0 of U = old order 1 of D (real state)
+#define SHIFT_SETS(U, D)                                                                                     \
+  {                                                                                                          \
+    real *xb = xbuf + (size_t)(parity * p.A + al) * W * SETS * 2 * NS; /* [warp][set][up | dn][slot] */      \
+    if (W > 1) {                                                                                             \
+      _Pragma("unroll") for (int q = 0; q < SETS; ++q) {                                                     \
+        if (lq == 31) { _Pragma("unroll") for (int s = 0; s < NS; ++s) xb[((wq * SETS + q) * 2 + 0) * NS + s] = U[q][s]; } \
+        if (lq == 0) { _Pragma("unroll") for (int s = 0; s < NS; ++s) xb[((wq * SETS + q) * 2 + 1) * NS + s] = D[q][s]; }  \
+      }                                                                                                      \
+      asm volatile("bar.sync %0, %1;" ::"r"(1 + al), "r"(G) : "memory");                                     \
+      parity ^= 1;                                                                                           \
+    }                                                                                                        \
+    _Pragma("unroll") for (int q = 0; q < SETS; ++q) {                                                       \
+      real c1;                                                                                               \
+      if (G == 1) c1 = NS > 1 ? D[q][NS > 1 ? 1 : 0] : real(0);                                              \
+      else c1 = __shfl_sync(FULL, D[q][0], gbase | 1); /* only lane 0 of the atom (warp 0) uses it */        \
+      if (n_old < 1) c1 = real(0);                                                                           \
+      /* up, descending (in place): the last lane of a warp hands over the value of its previous slot */    \
+      _Pragma("unroll") for (int s = NS - 1; s >= 0; --s) if (s < nsl) {                                     \
+        real v = U[q][s];                                                                                    \
+        if (W == 1) { if (is_last) v = s > 0 ? U[q][s > 0 ? s - 1 : 0] : c1; }                               \
+        v = __shfl_sync(FULL, v, srcUp);                                                                     \
+        if (W > 1 && is_first) {                                                                             \
+          if (wq > 0) v = xb[(((wq - 1) * SETS + q) * 2 + 0) * NS + s];                                      \
+          else v = s > 0 ? xb[(((W - 1) * SETS + q) * 2 + 0) * NS + (s > 0 ? s - 1 : 0)] : c1;               \
+        }                                                                                                    \
+        U[q][s] = v;                                                                                         \
+      }                                                                                                      \
+      /* down, ascending reads of the old next slot are kept in `keep` while descending */                   \
+      real keep = real(0);                                                                                   \
+      _Pragma("unroll") for (int s = NS - 1; s >= 0; --s) if (s < nsl) {                                     \
+        const real cur = D[q][s];                                                                            \
+        real v = cur;                                                                                        \
+        if (W == 1) { if (is_first) v = keep; }                                                              \
+        v = __shfl_sync(FULL, v, srcDn);                                                                     \
+        if (W > 1 && is_last) {                                                                              \
+          if (wq < W - 1) v = xb[(((wq + 1) * SETS + q) * 2 + 1) * NS + s];                                  \
+          else v = s + 1 < NS ? xb[((0 * SETS + q) * 2 + 1) * NS + (s + 1 < NS ? s + 1 : s)] : real(0);      \
+        }                                                                                                    \
+        D[q][s] = v;                                                                                         \
+        keep = cur;                                                                                          \
+      }                                                                                                      \
+    }                                                                                                        \
+  }
+          if (shift > 0) SHIFT_SETS(P, M) else SHIFT_SETS(M, P)
+#undef SHIFT_SETS
+          if (sflags & EPGX_SEG_MASK_TOP) {
+#pragma unroll
+            for (int q = 0; q < SETS; ++q)
+#pragma unroll
+              for (int s = 0; s < NS; ++s)
+                if (s * G + lane > n_new) {
+                  if (shift > 0) P[q][s] = real(0); else M[q][s] = real(0);
+                }
+          }
+        }
+      } break;
+      default:
+        break;
+      }
+#undef LIN5
+#undef DIAG3
+    }
+  }
+}
+
+} // namespace epgx

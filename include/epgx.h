@@ -191,7 +191,8 @@ typedef struct epgx_plan epgx_plan;
 /* kernel configuration chosen for a plan (reported for DESIGN/bench/roofline accounting) */
 typedef struct {
   int32_t kernel;         /* 0 = ring (state in shared memory), 1 = reg (state in registers), 2 = real (registers,
-                             real-valued phase graphs: three reals per order) */
+                             real-valued phase graphs: three reals per order), 3 = realjac (the same with
+                             order-1 partial states) */
   int32_t lanes_per_atom; /* G */
   int32_t slots_per_lane; /* reg kernel: orders held per lane */
   int32_t vars_per_pass;  /* partial states resident per atom */
@@ -215,7 +216,7 @@ int epgx_plan_destroy(epgx_plan *plan);
 int epgx_plan_config(const epgx_plan *plan, epgx_config *cfg);
 /* force a kernel variant (tuning / tests): a 0 / negative argument keeps the automatic choice;
  * kernel: 1 = ring (shared-memory state), 2 = reg (register state; forward, one pool only),
- * 3 = real (register state, real-valued phase graphs only) */
+ * 3 = real (register state, real-valued phase graphs only), 4 = realjac (real-valued with partials) */
 int epgx_plan_set_variant(epgx_plan *plan, int kernel, int lanes_per_atom, int vars_per_pass,
                           int atoms_per_cta);
 

@@ -138,6 +138,73 @@ def test_real_kernel_variants(lanes, atoms, dtype, max_nstate, epg):
     assert rel_err(ring[0], ref) < RTOL64
 
 
+def _real_jac_sequence(epg, ntr=50):
+    """real-valued graph with derivatives w.r.t. B1 (per-atom coefficient), T1, T2 and one pulse angle"""
+    T1 = np.linspace(300, 2000, 4)
+    T2 = np.linspace(30, 200, 3)[None, :]
+    B1 = np.array([0.8, 1.0, 1.15])[None, None, :]
+    o1 = ["T1", "T2"]
+    seq = [epg.T(180, 90), epg.E(15, T1, T2, order1=o1)]
+    for i in range(ntr):
+        ph = 90 if i % 3 else 270
+        fa = 10.0 + i % 40
+        od = {"B1": {"alpha": fa}}
+        if i == 7:
+            od["a7"] = {"alpha": B1}
+        seq += [epg.T(fa * B1, ph, order1=od), epg.E(2.5, T1, T2, order1=o1), epg.Adc(phase=-ph + 90.0),
+                epg.E(6 + (i % 5), T1, T2, order1={"T1": {"T1": 1}, "T2": {"T2": 1}, "tau": {"tau": 0.5}}), epg.S(1 if i % 11 else -1)]
+        if i % 7 == 3:
+            seq += [epg.D(4.0, 1.2e-3, k=1 if i % 11 else -1)]
+        if i == 30:
+            seq += [epg.SPOILER]
+    return seq
+
+
+@pytest.mark.parametrize("dtype", ["f64", "f32"])
+@pytest.mark.parametrize("lanes,atoms", [(0, 0), (1, 5), (2, 16), (8, 3), (32, 4), (64, 1), (64, 3), (128, 2), (256, 1)])
+@pytest.mark.parametrize("max_nstate", [None, 9])
+def test_realjac_kernel_variants(lanes, atoms, dtype, max_nstate, epg):
+    """real-valued register kernel with resident partial states (sub-warp, one warp, several warps per atom)
+    against the ring kernel and the oracle, D / SPOILER propagated to the partials"""
+    variables = ["B1", "T1", "T2", "tau", "a7"]  # 5 variables -> two tiles of three
+    case = {"seq": _real_jac_sequence(epg), "jac": variables,
+            "options": {"kvalue": 2500.0, **({"max_nstate": max_nstate} if max_nstate else {})}}
+    from epgpy_b200 import engine, functions, lowering
+
+    def run(kernel, dt, **variant):
+        low = lowering.lower(case["seq"], probe=[None, epg.Jacobian(variables)], options=dict(case["options"]), dtype=dt,
+                             propagate_nondiff=True)
+        plan = engine.Plan(low)
+        plan.set_variant(kernel=kernel, **variant)
+        parts, _ = functions.run_lowered(low, plan=plan)
+        return functions._assemble(low, parts), plan.config()
+
+    ring, _ = run(1, "f64")
+    try:
+        got, cfg = run(4, dtype, lanes_per_atom=lanes, atoms_per_cta=atoms)
+    except MemoryError:
+        pytest.skip("more orders than lanes x slots of any instance")
+    assert cfg["kernel"] == 3 and cfg["var_tiles"] == 2
+    tol = 1e-12 if dtype == "f64" else RTOL32
+    assert rel_err(got[0], ring[0]) < tol
+    for i in range(len(variables)):
+        assert rel_err(got[1][..., i], ring[1][..., i]) < (tol if dtype == "f64" else 5 * RTOL32)
+    rs, rj = oracle_api.O.simulate(_real_jac_sequence(oracle_api.epg), jacobian=variables, kvalue=2500.0,
+                                   max_nstate=max_nstate, propagate_nondiff=True)
+    assert rel_err(ring[0], rs) < RTOL64 and rel_err(ring[1], rj) < RTOL64
+
+
+def test_realjac_kernel_is_chosen_for_the_fisp_jacobian(golden, epg):
+    from epgpy_b200 import engine, lowering
+
+    case = cases.fisp_jac_global(epg)
+    low = lowering.lower(case["seq"], probe=[None, epg.Jacobian(case["jac"])])
+    assert engine.Plan(low).config()["kernel"] == 3
+    case = cases.mse_jac(epg)  # T(150, 0): complex couplings -> ring kernel
+    low = lowering.lower(case["seq"], probe=[None, epg.Jacobian(case["jac"])])
+    assert engine.Plan(low).config()["kernel"] == 0
+
+
 def test_real_kernel_is_chosen_for_fisp_and_refused_otherwise(epg):
     from epgpy_b200 import engine, lowering
 
