@@ -220,8 +220,8 @@ def test_real_kernel_is_chosen_for_fisp_and_refused_otherwise(epg):
 @pytest.mark.parametrize("name", ["fisp_jac_pulses", "jac_all_params", "mse_jac"])
 def test_variable_tiling(name, vars_per_pass, golden, epg):
     ref = golden(name)
-    vals, cfg = _run_variant(epg, cases.CASES[name](epg), vars_per_pass=vars_per_pass)
-    assert cfg["vars_per_pass"] == vars_per_pass
+    vals, cfg = _run_variant(epg, cases.CASES[name](epg), kernel=1, vars_per_pass=vars_per_pass)
+    assert cfg["vars_per_pass"] == vars_per_pass and cfg["kernel"] == 0
     assert rel_err(vals[0], ref["signal"]) < RTOL64 and rel_err(vals[1], ref["jacobian"]) < RTOL64
 
 
