@@ -16,6 +16,132 @@
 
 namespace epgx {
 
+// ---- slot-count-specialised bodies (K active slots, compile time): straight-line code, no per-slot predicate
+
+// F+' = a F+ + b F- + u Z ; F-' = b F+ + a F- + u Z ; Z' = w Z + h (F+ + F-)
+template <typename real, int NS, int SETS, int K>
+__device__ __forceinline__ void rj_lin5(real (&P)[SETS][NS], real (&M)[SETS][NS], real (&Z)[SETS][NS], real a, real w, real b,
+                                        real u, real h, bool on_base, bool on_part, bool inject, int iset) {
+  if constexpr (K <= NS) {
+    if (inject) {
+#pragma unroll
+      for (int q = 1; q < SETS; ++q)
+        if (q == iset) { // uniform branch: one target set
+#pragma unroll
+          for (int s = 0; s < K; ++s) {
+            const real p_ = P[0][s], m_ = M[0][s], z_ = Z[0][s];
+            P[q][s] += a * p_ + b * m_ + u * z_;
+            M[q][s] += a * m_ + b * p_ + u * z_;
+            Z[q][s] += w * z_ + h * (p_ + m_);
+          }
+        }
+    } else {
+#pragma unroll
+      for (int q = 0; q < SETS; ++q)
+        if (q == 0 ? on_base : on_part) {
+#pragma unroll
+          for (int s = 0; s < K; ++s) {
+            const real p_ = P[q][s], m_ = M[q][s], z_ = Z[q][s];
+            P[q][s] = a * p_ + b * m_ + u * z_;
+            M[q][s] = a * m_ + b * p_ + u * z_;
+            Z[q][s] = w * z_ + h * (p_ + m_);
+          }
+        }
+    }
+  }
+}
+
+// F+- *= dp / dm, Z *= dz (the affine term is added by the caller)
+template <typename real, int NS, int SETS, int K>
+__device__ __forceinline__ void rj_diag3(real (&P)[SETS][NS], real (&M)[SETS][NS], real (&Z)[SETS][NS], real dp, real dm,
+                                         real dz, bool on_base, bool on_part, bool inject, int iset) {
+  if constexpr (K <= NS) {
+    if (inject) {
+#pragma unroll
+      for (int q = 1; q < SETS; ++q)
+        if (q == iset) {
+#pragma unroll
+          for (int s = 0; s < K; ++s) { P[q][s] += dp * P[0][s]; M[q][s] += dm * M[0][s]; Z[q][s] += dz * Z[0][s]; }
+        }
+    } else {
+#pragma unroll
+      for (int q = 0; q < SETS; ++q)
+        if (q == 0 ? on_base : on_part) {
+#pragma unroll
+          for (int s = 0; s < K; ++s) { P[q][s] *= dp; M[q][s] *= dm; Z[q][s] *= dz; }
+        }
+    }
+  }
+}
+
+#define RJ_DISPATCH(n, FN, ...)                                        \
+  switch (n) {                                                         \
+  case 1: FN<real, NS, SETS, 1>(__VA_ARGS__); break;                   \
+  case 2: FN<real, NS, SETS, 2>(__VA_ARGS__); break;                   \
+  case 3: FN<real, NS, SETS, 3>(__VA_ARGS__); break;                   \
+  case 4: FN<real, NS, SETS, 4>(__VA_ARGS__); break;                   \
+  case 5: FN<real, NS, SETS, 5>(__VA_ARGS__); break;                   \
+  case 6: FN<real, NS, SETS, 6>(__VA_ARGS__); break;                   \
+  case 7: FN<real, NS, SETS, 7>(__VA_ARGS__); break;                   \
+  case 8: FN<real, NS, SETS, 8>(__VA_ARGS__); break;                   \
+  default: break;                                                      \
+  }
+
+// unit shift of all state sets, K slots: U moves up, D moves down, new order 0 of U = old order 1 of D
+template <typename real, int NS, int SETS, int K>
+__device__ __forceinline__ void rj_shift(real (&U)[SETS][NS], real (&D)[SETS][NS], int G, int W, int wq, int lq, int gbase,
+                                         int srcUp, int srcDn, bool is_first, bool is_last, bool has1, real *xb, int barrier_id) {
+  const unsigned FULL = 0xffffffffu;
+  if constexpr (K <= NS) {
+    if (W > 1) { // boundary values of every warp of the atom: [warp][set][up | dn][slot]
+#pragma unroll
+      for (int q = 0; q < SETS; ++q) {
+        if (lq == 31) {
+#pragma unroll
+          for (int s = 0; s < K; ++s) xb[((wq * SETS + q) * 2 + 0) * NS + s] = U[q][s];
+        }
+        if (lq == 0) {
+#pragma unroll
+          for (int s = 0; s < K; ++s) xb[((wq * SETS + q) * 2 + 1) * NS + s] = D[q][s];
+        }
+      }
+      asm volatile("bar.sync %0, %1;" ::"r"(barrier_id), "r"(G) : "memory");
+    }
+#pragma unroll
+    for (int q = 0; q < SETS; ++q) {
+      real c1;
+      if (G == 1) c1 = K > 1 ? D[q][K > 1 ? 1 : 0] : real(0);
+      else c1 = __shfl_sync(FULL, D[q][0], gbase | 1); // used by lane 0 of the atom only (warp 0)
+      if (!has1) c1 = real(0);
+#pragma unroll
+      for (int s = K - 1; s >= 0; --s) { // descending = in place
+        real v = U[q][s];
+        if (W == 1) { if (is_last) v = s > 0 ? U[q][s > 0 ? s - 1 : 0] : c1; }
+        v = __shfl_sync(FULL, v, srcUp);
+        if (W > 1 && is_first) {
+          if (wq > 0) v = xb[(((wq - 1) * SETS + q) * 2 + 0) * NS + s];
+          else v = s > 0 ? xb[(((W - 1) * SETS + q) * 2 + 0) * NS + (s > 0 ? s - 1 : 0)] : c1;
+        }
+        U[q][s] = v;
+      }
+      real keep = real(0);
+#pragma unroll
+      for (int s = K - 1; s >= 0; --s) {
+        const real cur = D[q][s];
+        real v = cur;
+        if (W == 1) { if (is_first) v = keep; }
+        v = __shfl_sync(FULL, v, srcDn);
+        if (W > 1 && is_last) {
+          if (wq < W - 1) v = xb[(((wq + 1) * SETS + q) * 2 + 1) * NS + s];
+          else v = s + 1 < K ? xb[((0 * SETS + q) * 2 + 1) * NS + (s + 1 < K ? s + 1 : s)] : real(0);
+        }
+        D[q][s] = v;
+        keep = cur;
+      }
+    }
+  }
+}
+
 template <typename real, int NS, int NV>
 __global__ void __launch_bounds__(256) realjac_kernel(const KParams p) {
   typedef typename vec2<real>::type real2;
@@ -112,51 +238,15 @@ __global__ void __launch_bounds__(256) realjac_kernel(const KParams p) {
       const bool aff0 = (flags & EPGX_FLAG_AFFINE) && lane == 0 && nslot > 0;
       (void)off2;
 
-      // F+' = a F+ + b F- + u Z ; F-' = b F+ + a F- + u Z ; Z' = w Z + h (F+ + F-)     (T_RE kind)
-#define LIN5(a, w, b, u, h)                                                                 \
-  {                                                                                         \
-    if (inject) {                                                                           \
-      if (iset >= 1 && iset < SETS) {                                                       \
-        _Pragma("unroll") for (int s = 0; s < NS; ++s) if (s < nslot) {                     \
-          const real p_ = P[0][s], m_ = M[0][s], z_ = Z[0][s];                              \
-          const real np_ = a * p_ + b * m_ + u * z_, nm_ = a * m_ + b * p_ + u * z_;        \
-          const real nz_ = w * z_ + h * (p_ + m_);                                          \
-          _Pragma("unroll") for (int q = 1; q < SETS; ++q) if (q == iset) {                 \
-            P[q][s] += np_; M[q][s] += nm_; Z[q][s] += nz_;                                 \
-          }                                                                                 \
-        }                                                                                   \
-      }                                                                                     \
-    } else {                                                                                \
-      _Pragma("unroll") for (int q = 0; q < SETS; ++q) if (q == 0 ? on_base : on_part) {    \
-        _Pragma("unroll") for (int s = 0; s < NS; ++s) if (s < nslot) {                     \
-          const real p_ = P[q][s], m_ = M[q][s], z_ = Z[q][s];                              \
-          P[q][s] = a * p_ + b * m_ + u * z_;                                               \
-          M[q][s] = a * m_ + b * p_ + u * z_;                                               \
-          Z[q][s] = w * z_ + h * (p_ + m_);                                                 \
-        }                                                                                   \
-      }                                                                                     \
-    }                                                                                       \
-  }
-      // F+- *= dp / dm, Z *= dz, Z(0) += z0 (affine, base and injections only)
-#define DIAG3(dp, dm, dz, z0)                                                               \
-  {                                                                                         \
-    if (inject) {                                                                           \
-      if (iset >= 1 && iset < SETS) {                                                       \
-        _Pragma("unroll") for (int q = 1; q < SETS; ++q) if (q == iset) {                   \
-          _Pragma("unroll") for (int s = 0; s < NS; ++s) if (s < nslot) {                   \
-            P[q][s] += dp * P[0][s]; M[q][s] += dm * M[0][s]; Z[q][s] += dz * Z[0][s];      \
-          }                                                                                 \
-          if (aff0) Z[q][0] += z0;                                                          \
-        }                                                                                   \
-      }                                                                                     \
-    } else {                                                                                \
-      _Pragma("unroll") for (int q = 0; q < SETS; ++q) if (q == 0 ? on_base : on_part) {    \
-        _Pragma("unroll") for (int s = 0; s < NS; ++s) if (s < nslot) {                     \
-          P[q][s] *= dp; M[q][s] *= dm; Z[q][s] *= dz;                                      \
-        }                                                                                   \
-        if (q == 0 && aff0) Z[0][0] += z0;                                                  \
-      }                                                                                     \
-    }                                                                                       \
+#define LIN5(a, w, b, u, h) RJ_DISPATCH(nslot, rj_lin5, P, M, Z, a, w, b, u, h, on_base, on_part, inject, iset)
+#define DIAG3(dp, dm, dz, z0)                                                                  \
+  {                                                                                            \
+    RJ_DISPATCH(nslot, rj_diag3, P, M, Z, dp, dm, dz, on_base, on_part, inject, iset)          \
+    if (aff0) {                                                                                \
+      if (inject) {                                                                            \
+        _Pragma("unroll") for (int q = 1; q < SETS; ++q) if (q == iset) Z[q][0] += z0;         \
+      } else if (on_base) Z[0][0] += z0;                                                       \
+    }                                                                                          \
   }
 
       switch (code) {
@@ -236,52 +326,10 @@ __global__ void __launch_bounds__(256) realjac_kernel(const KParams p) {
           if (lane == 0) Z[0][0] = m0;
         } else if (shift != 0) {
           const int nsl = (n_new >> lgG) + 1;
-          // U moves up (F+ for shift > 0), D moves down; new order 0 of U = old order 1 of D (real state)
-#define SHIFT_SETS(U, D)                                                                                     \
-  {                                                                                                          \
-    real *xb = xbuf + (size_t)(parity * p.A + al) * W * SETS * 2 * NS; /* [warp][set][up | dn][slot] */      \
-    if (W > 1) {                                                                                             \
-      _Pragma("unroll") for (int q = 0; q < SETS; ++q) {                                                     \
-        if (lq == 31) { _Pragma("unroll") for (int s = 0; s < NS; ++s) xb[((wq * SETS + q) * 2 + 0) * NS + s] = U[q][s]; } \
-        if (lq == 0) { _Pragma("unroll") for (int s = 0; s < NS; ++s) xb[((wq * SETS + q) * 2 + 1) * NS + s] = D[q][s]; }  \
-      }                                                                                                      \
-      asm volatile("bar.sync %0, %1;" ::"r"(1 + al), "r"(G) : "memory");                                     \
-      parity ^= 1;                                                                                           \
-    }                                                                                                        \
-    _Pragma("unroll") for (int q = 0; q < SETS; ++q) {                                                       \
-      real c1;                                                                                               \
-      if (G == 1) c1 = NS > 1 ? D[q][NS > 1 ? 1 : 0] : real(0);                                              \
-      else c1 = __shfl_sync(FULL, D[q][0], gbase | 1); /* only lane 0 of the atom (warp 0) uses it */        \
-      if (n_old < 1) c1 = real(0);                                                                           \
-      /* up, descending (in place): the last lane of a warp hands over the value of its previous slot */    \
-      _Pragma("unroll") for (int s = NS - 1; s >= 0; --s) if (s < nsl) {                                     \
-        real v = U[q][s];                                                                                    \
-        if (W == 1) { if (is_last) v = s > 0 ? U[q][s > 0 ? s - 1 : 0] : c1; }                               \
-        v = __shfl_sync(FULL, v, srcUp);                                                                     \
-        if (W > 1 && is_first) {                                                                             \
-          if (wq > 0) v = xb[(((wq - 1) * SETS + q) * 2 + 0) * NS + s];                                      \
-          else v = s > 0 ? xb[(((W - 1) * SETS + q) * 2 + 0) * NS + (s > 0 ? s - 1 : 0)] : c1;               \
-        }                                                                                                    \
-        U[q][s] = v;                                                                                         \
-      }                                                                                                      \
-      /* down, ascending reads of the old next slot are kept in `keep` while descending */                   \
-      real keep = real(0);                                                                                   \
-      _Pragma("unroll") for (int s = NS - 1; s >= 0; --s) if (s < nsl) {                                     \
-        const real cur = D[q][s];                                                                            \
-        real v = cur;                                                                                        \
-        if (W == 1) { if (is_first) v = keep; }                                                              \
-        v = __shfl_sync(FULL, v, srcDn);                                                                     \
-        if (W > 1 && is_last) {                                                                              \
-          if (wq < W - 1) v = xb[(((wq + 1) * SETS + q) * 2 + 1) * NS + s];                                  \
-          else v = s + 1 < NS ? xb[((0 * SETS + q) * 2 + 1) * NS + (s + 1 < NS ? s + 1 : s)] : real(0);      \
-        }                                                                                                    \
-        D[q][s] = v;                                                                                         \
-        keep = cur;                                                                                          \
-      }                                                                                                      \
-    }                                                                                                        \
-  }
-          if (shift > 0) SHIFT_SETS(P, M) else SHIFT_SETS(M, P)
-#undef SHIFT_SETS
+          real *xb = xbuf + (size_t)(parity * p.A + al) * W * SETS * 2 * NS;
+          if (shift > 0) { RJ_DISPATCH(nsl, rj_shift, P, M, G, W, wq, lq, gbase, srcUp, srcDn, is_first, is_last, n_old >= 1, xb, 1 + al) }
+          else { RJ_DISPATCH(nsl, rj_shift, M, P, G, W, wq, lq, gbase, srcUp, srcDn, is_first, is_last, n_old >= 1, xb, 1 + al) }
+          if (W > 1) parity ^= 1;
           if (sflags & EPGX_SEG_MASK_TOP) {
 #pragma unroll
             for (int q = 0; q < SETS; ++q)
