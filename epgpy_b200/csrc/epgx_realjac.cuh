@@ -227,38 +227,16 @@ __global__ void __launch_bounds__(256) realjac_kernel(const KParams p) {
     }
     const int4 *tb = tbuf + (chunk & 1) * 2 * TAPE_CHUNK;
     const int cnt = min(TAPE_CHUNK, p.nstream - base);
-    // ---- record windows with VECTORISED DECODE: the GW lanes of the atom (in this warp) each decode one of the
-    // next GW records and gather its coefficients in one pass (phase 1); the records are then executed in order,
-    // each broadcasting its fields / coefficients from its lane (phase 2).  Decode, address arithmetic and the
-    // latency of the coefficient loads leave the serial per-record path.
-    for (int h = 0; h < cnt; h += GW) {
-      const int nrec = min(GW, cnt - h);
-      int4 v0r = make_int4(0, 0, 0, 0), v1r = make_int4(0, 0, 0, 0);
-      real c0 = real(0), c1 = real(0), c2 = real(0), c3 = real(0);
-      if (lq < nrec) {
-        v0r = tb[2 * (h + lq)];
-        v1r = tb[2 * (h + lq) + 1];
-        const int code_ = v0r.x & 0xffff, flags_ = (v0r.x >> 16) & 0xffff;
-        const real *cb0 = coef + (unsigned)v0r.z + patoff[v1r.y & 0xff];
-        switch (code_) {
-        case EPGX_OP_T_RE: c0 = ldc(cb0); c1 = ldc(cb0 + 1); c2 = ldc(cb0 + 2); c3 = ldc(cb0 + 3); break;
-        case EPGX_OP_E: c0 = ldc(cb0); c1 = ldc(cb0 + 1); c2 = ldc(coef + (unsigned)v0r.w + patoff[(v1r.y >> 8) & 0xff]); break;
-        case EPGX_OP_DIAG: c0 = ldc(cb0); c1 = ldc(cb0 + 2); c2 = ldc(cb0 + 4); c3 = ldc(cb0 + 6); break;
-        case EPGX_OP_PD: c0 = ldc(cb0); break;
-        case EPGX_OP_ADC: c0 = real(1); if (flags_ & EPGX_FLAG_SCALE) { c0 = ldc(cb0); c1 = ldc(cb0 + 1); } break;
-        case EPGX_OP_D: v0r.z = (int)((unsigned)v0r.z + (unsigned)patoff[v1r.y & 0xff]); break; // table base of the atom
-        default: break;
-        }
-      }
-    for (int jr = 0; jr < nrec; ++jr) {
-      const int src = gbase + jr;
-      const int w0 = __shfl_sync(FULL, v0r.x, src), aux = __shfl_sync(FULL, v0r.y, src);
-      const int code = w0 & 0xffff, flags = (w0 >> 16) & 0xffff;
+    for (int r = 0; r < cnt; ++r) {
+      const int4 r0 = tb[2 * r], r1 = tb[2 * r + 1];
+      const int code = r0.x & 0xffff, flags = (r0.x >> 16) & 0xffff, aux = r0.y;
+      const unsigned off0 = (unsigned)r0.z, off1 = (unsigned)r0.w, off2 = (unsigned)r1.x;
+      const int pat0 = r1.y & 0xff, pat1 = (r1.y >> 8) & 0xff;
       const bool on_base = flags & EPGX_FLAG_BASE, on_part = flags & EPGX_FLAG_PARTIALS;
       const bool inject = flags & EPGX_FLAG_INJECT;
       const int iset = aux - v0 + 1; // target set of an injection
       const bool aff0 = (flags & EPGX_FLAG_AFFINE) && lane == 0 && nslot > 0;
-#define BC(x) __shfl_sync(FULL, x, src)
+      (void)off2;
 
 #define LIN5(a, w, b, u, h) RJ_DISPATCH(nslot, rj_lin5, P, M, Z, a, w, b, u, h, on_base, on_part, inject, iset)
 #define DIAG3(dp, dm, dz, z0)                                                                  \
@@ -273,19 +251,23 @@ __global__ void __launch_bounds__(256) realjac_kernel(const KParams p) {
 
       switch (code) {
       case EPGX_OP_T_RE: {
-        const real a = BC(c0), w = BC(c1), b = BC(c2), u = BC(c3), h = real(-0.5) * u;
+        const real *c = coef + off0 + patoff[pat0];
+        const real a = ldc(c), w = ldc(c + 1), b = ldc(c + 2), u = ldc(c + 3), h = real(-0.5) * u;
         LIN5(a, w, b, u, h)
       } break;
       case EPGX_OP_E: {
-        const real e1 = BC(c0), z0 = BC(c1) * m0, e2 = BC(c2);
+        const real *c0 = coef + off0 + patoff[pat0];
+        const real e1 = ldc(c0), z0 = ldc(c0 + 1) * m0;
+        const real e2 = ldc(coef + off1 + patoff[pat1]);
         DIAG3(e2, e2, e1, z0)
       } break;
       case EPGX_OP_DIAG: { // real entries only (checked by the host): (aP, 0, aM, 0, aZ, 0, a0, 0)
-        const real dp = BC(c0), dm = BC(c1), dz = BC(c2), z0 = BC(c3) * m0;
+        const real *c = coef + off0 + patoff[pat0];
+        const real dp = ldc(c), dm = ldc(c + 2), dz = ldc(c + 4), z0 = ldc(c + 6) * m0;
         DIAG3(dp, dm, dz, z0)
       } break;
       case EPGX_OP_D: {
-        const real *c = coef + (unsigned)BC(v0r.z);
+        const real *c = coef + off0 + patoff[pat0];
 #pragma unroll
         for (int s = 0; s < NS; ++s)
           if (s < nslot) {
@@ -306,12 +288,15 @@ __global__ void __launch_bounds__(256) realjac_kernel(const KParams p) {
           }
         break;
       case EPGX_OP_PD:
-        m0 = BC(c0);
+        m0 = ldc(coef + off0 + patoff[pat0]);
         break;
-      case EPGX_OP_ADC: {
-        const real fr = BC(c0), fi = BC(c1);
-        const int jrow = BC(v1r.z);
+      case EPGX_OP_ADC:
         if (lane == 0 && valid) {
+          real fr = real(1), fi = real(0);
+          if (flags & EPGX_FLAG_SCALE) {
+            const real *c = coef + off0 + patoff[pat0];
+            fr = ldc(c); fi = ldc(c + 1);
+          }
           const bool z0 = flags & EPGX_FLAG_Z0;
           if (on_base && blockIdx.y == 0) {
             const real x = z0 ? Z[0][0] : P[0][0];
@@ -323,14 +308,14 @@ __global__ void __launch_bounds__(256) realjac_kernel(const KParams p) {
               const int v = v0 + q - 1;
               if (v < p.nvar) {
                 const real x = z0 ? Z[q][0] : P[q][0];
-                jac[((long long)jrow * p.nvar + v) * p.jac_stride + a_rel] = real2{x * fr, x * fi};
+                jac[((long long)r1.z * p.nvar + v) * p.jac_stride + a_rel] = real2{x * fr, x * fi};
               }
             }
           }
         }
-      } break;
+        break;
       case EPGX_OP_SEG: {
-        const int shift = BC(v0r.z), n_old = BC(v0r.w), n_new = BC(v1r.x), sflags = BC(v1r.z);
+        const int shift = (int)off0, n_old = (int)off1, n_new = (int)off2, sflags = r1.z;
         nact = aux;
         nslot = nact < 0 ? 0 : (nact >> lgG) + 1;
         if (sflags & EPGX_SEG_RESET) {
@@ -361,8 +346,6 @@ __global__ void __launch_bounds__(256) realjac_kernel(const KParams p) {
       }
 #undef LIN5
 #undef DIAG3
-#undef BC
-    }
     }
   }
 }
