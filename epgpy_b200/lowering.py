@@ -257,7 +257,7 @@ def fuse_records(recs, segs):
 
 
 def lower(sequence, *, init=None, probe=None, options=None, dtype="f64", propagate_nondiff=False,
-          prune_unobservable=True, fuse=True):
+          prune_unobservable=True, fuse=True, pre_inject=True):
     """sequence -> Lowered"""
     options = dict(options or {})
     seq = flatten_sequence(sequence)
@@ -465,12 +465,21 @@ def lower(sequence, *, init=None, probe=None, options=None, dtype="f64", propaga
             if not inj:
                 _emit_or_reuse(bld, op, form, F_BASE | part_flag())
             else:
-                if alive:
-                    _emit_or_reuse(bld, op, form, F_PARTIALS)
-                for vi, param, coeff in inj:
-                    _emit_form(bld, _scaled_form(op._dform(param), coeff), F_INJECT, aux=vi)
-                alive = True
-                _emit_or_reuse(bld, op, form, F_BASE)
+                gens = [op._gform(param) for _, param, _ in inj] if pre_inject else [None]
+                if all(g is not None for g in gens):
+                    # pre-injection: x_v += c Op^-1 dOp x_0, then ONE record applies Op to every state set:
+                    # Op (x_v + c Op^-1 dOp x_0) = Op x_v + c dOp x_0, the update of diff.py:264-288
+                    for (vi, param, coeff), g in zip(inj, gens):
+                        _emit_form(bld, _scaled_form(g, coeff), F_INJECT, aux=vi)
+                    alive = True
+                    _emit_or_reuse(bld, op, form, F_BASE | F_PARTIALS)
+                else:
+                    if alive:
+                        _emit_or_reuse(bld, op, form, F_PARTIALS)
+                    for vi, param, coeff in inj:
+                        _emit_form(bld, _scaled_form(op._dform(param), coeff), F_INJECT, aux=vi)
+                    alive = True
+                    _emit_or_reuse(bld, op, form, F_BASE)
         elif isinstance(op, Probe):
             pass
         elif isinstance(op, (EmptyOperator, ops_mod.System)):

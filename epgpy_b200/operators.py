@@ -240,6 +240,10 @@ class DiffOperator(Operator):
     def _dform(self, param):
         raise NotImplementedError
 
+    def _gform(self, param):
+        """Op^-1 dOp/dparam as a coefficient form when it has a closed form (pre-injection), else None"""
+        return None
+
     # generic dense coefficients (for `@` and for the public .mat / .arr attributes)
     def _dense(self):
         """('mat', mat[...,3,3], mat0|None) or ('diag', arr[...,3], arr0|None)"""
@@ -514,6 +518,17 @@ class T(CombinableOperator):
             return ("tgen", _cplx_block(0 * B.real, 0 * B.real, B, U))
         raise ValueError(param)
 
+    def _gform(self, param):
+        """generator N = T^-1 dT/dparam, when it has a closed form: dT/dalpha = T . Rz(phi) Rx'(0) Rz(-phi), so a
+        derivative injection can be done BEFORE the pulse (x_v += c N x_0) and the pulse then applied to all
+        state sets at once: T(x_v + c N x_0) = T x_v + c dT x_0 (epgpy/diff.py:264-288 restated)."""
+        if param != "alpha":
+            return None
+        _, phi = self._ap()
+        U = -1j * _cis_deg(phi) * DEG
+        zero = 0 * U.real
+        return ("tgen", _cplx_block(zero, zero, zero + 0j, U))
+
     @staticmethod
     def _tgen_dense(blk):
         a, w = blk[..., 0], blk[..., 1]
@@ -666,6 +681,24 @@ class E(_Evolution):
         tau, T1, T2, g = self._params()
         return _evolution_arrays(tau * (1 / T2 + 2j * np.pi * g), tau / T1, tau / T1)
 
+    def _gform(self, param):
+        """E^-1 dE/dparam (diagonal; evolution.py:360-399 divided by the operator itself): the recovery term
+        makes Z'_v = e1 (Z_v + r (Z_0 - M0)), hence the affine part -r M0"""
+        tau, T1, T2, g = self._params()
+        zero = 0 * (tau + T1 + T2 + g)
+        if param == "tau":
+            rM = -(1 / T2 + 2j * np.pi * g) + zero
+            return _diag_gen(rM.conj(), rM, -1 / T1 + zero, True)
+        if param == "T1":
+            return _diag_gen(zero, zero, tau / T1**2 + zero, True)
+        if param == "T2":
+            r = tau / T2**2 + zero
+            return _diag_gen(r, r, zero, False)
+        if param == "g":
+            rM = -2j * np.pi * tau + zero
+            return _diag_gen(rM.conj(), rM, zero, False)
+        return None
+
     def _darrs(self, param):
         """first derivatives (epgpy/evolution.py:360-399)"""
         tau, T1, T2, g = self._params()
@@ -695,6 +728,13 @@ class E(_Evolution):
             arr[..., 2] = 0
             return arr, None
         raise ValueError(param)
+
+
+def _diag_gen(rP, rM, rZ, affine):
+    """pre-injection form of a diagonal operator: x_v += diag(rP, rM, rZ) x_0 (- rZ M0 at Z(0) if affine)"""
+    rP, rM, rZ = np.broadcast_arrays(np.asarray(rP, dtype=complex), np.asarray(rM, dtype=complex), np.asarray(rZ, dtype=complex))
+    a0 = -rZ if affine else 0 * rZ
+    return ("diag", _cplx_block(rP, rM, rZ, a0), bool(affine))
 
 
 class P(_Evolution):
@@ -728,6 +768,11 @@ class P(_Evolution):
     def _arrs(self):
         tau, g = self._params()
         return _evolution_arrays(2j * np.pi * g * tau, 0 * tau * g)
+
+    def _gform(self, param):
+        tau, g = self._params()
+        rM = -2j * np.pi * (g if param == "tau" else tau) + 0 * (tau + g)
+        return _diag_gen(rM.conj(), rM, 0 * rM, False)
 
     def _darrs(self, param):
         """epgpy/evolution.py:313-328"""

@@ -187,7 +187,9 @@ def simulate(epg_mod, sequence, **kw):
     probe = kw.pop("probe", None)
     propagate = kw.pop("propagate_nondiff", False)
     prune = kw.pop("prune_unobservable", True)
-    low = L.lower(sequence, init=init, probe=probe, options=kw, propagate_nondiff=propagate, prune_unobservable=prune)
+    extra = {k: kw.pop(k) for k in ("fuse", "pre_inject") if k in kw}
+    low = L.lower(sequence, init=init, probe=probe, options=kw, propagate_nondiff=propagate, prune_unobservable=prune,
+                  **extra)
     sig, jac = run(low)
 
     class _T:  # minimal stand-in for a device tensor

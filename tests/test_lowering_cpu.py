@@ -27,6 +27,18 @@ def test_tape_matches_reference(name, prune, golden):
         assert rel_err(jac, ref["jacobian"]) < RTOL64
 
 
+@pytest.mark.parametrize("name", ["fisp_jac_global", "fisp_jac_pulses", "mse_jac", "jac_all_params", "fisp_bounded", "mse_grid"])
+@pytest.mark.parametrize("fuse,pre_inject", [(False, False), (True, False), (False, True)])
+def test_tape_transformations_are_exact(name, fuse, pre_inject, golden):
+    """record fusion and derivative pre-injection are algebraic rewrites of the tape: same answers"""
+    ref = golden(name)
+    epg = product_namespace()
+    sig, jac = run_case(interp_simulate, epg, cases.CASES[name](epg), fuse=fuse, pre_inject=pre_inject)
+    assert rel_err(sig, ref["signal"]) < RTOL64
+    if "jacobian" in ref.files:
+        assert rel_err(jac, ref["jacobian"]) < RTOL64
+
+
 def test_api_surface_and_shapes(golden):
     epg = product_namespace()
     for name, fn in cases.CASES.items():
