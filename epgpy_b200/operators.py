@@ -685,18 +685,19 @@ class E(_Evolution):
         """E^-1 dE/dparam (diagonal; evolution.py:360-399 divided by the operator itself): the recovery term
         makes Z'_v = e1 (Z_v + r (Z_0 - M0)), hence the affine part -r M0"""
         tau, T1, T2, g = self._params()
-        zero = 0 * (tau + T1 + T2 + g)
+        # every block keeps the smallest broadcast shape of the parameters it really depends on
         if param == "tau":
-            rM = -(1 / T2 + 2j * np.pi * g) + zero
-            return _diag_gen(rM.conj(), rM, -1 / T1 + zero, True)
+            rM = -(1 / T2 + 2j * np.pi * g) + 0 * tau
+            return _diag_gen(rM.conj(), rM, -1 / T1 + 0 * tau, True)
         if param == "T1":
-            return _diag_gen(zero, zero, tau / T1**2 + zero, True)
+            r = tau / T1**2
+            return _diag_gen(0 * r, 0 * r, r, True)
         if param == "T2":
-            r = tau / T2**2 + zero
-            return _diag_gen(r, r, zero, False)
+            r = tau / T2**2
+            return _diag_gen(r, r, 0 * r, False)
         if param == "g":
-            rM = -2j * np.pi * tau + zero
-            return _diag_gen(rM.conj(), rM, zero, False)
+            rM = -2j * np.pi * tau + 0 * g
+            return _diag_gen(rM.conj(), rM, 0 * rM, False)
         return None
 
     def _darrs(self, param):
