@@ -346,6 +346,28 @@ def main():
         extra[f"{other}_unbounded"], tf_other = quick(other, max_nstate)
         extra[f"{args.dtype}_max_nstate32"], _ = quick(args.dtype, 32)
         launches += 8
+        # the (B1, T1, T2) Jacobian of the same dictionary on a 50 x 50 x 50 sub-grid
+        try:
+            Tj1, Tj2, Bj1 = T1[::2], T2[::2], B1[: grid[2] * world: 2 * world] if world > 1 else B1[::2]
+            seqj = fisp_sequence(epg, Tj1, Tj2, Bj1, args.ntr, jac=True)
+            lwj = lowering.lower(seqj, probe=[None, epg.Jacobian(["B1", "T1", "T2"])], options=opts, dtype=args.dtype)
+            plj = engine.Plan(lwj)
+            plj.upload(dev)
+            sj, jj = plj.run(dev)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            plj.run(dev, signal=sj, jacobian=jj)
+            e1.record()
+            torch.cuda.synchronize()
+            ms_ = e0.elapsed_time(e1)
+            extra[f"{args.dtype}_jacobian_B1_T1_T2"] = {
+                "value": lwj.natoms / (ms_ * 1e-3), "unit": "atoms/s (each with signal + 3 derivatives), one GPU", "ms_per_step": ms_,
+                "atoms": lwj.natoms, "kernel": plj.config()}
+            launches += 2
+            del sj, jj, plj
+        except Exception as ex:
+            extra["jacobian_error"] = f"{type(ex).__name__}: {ex}"
         if rank == 0:
             pk = engine.fma_peak(dev, other, 0.3)
             extra[f"{other}_unbounded"]["roofline_frac"] = tf_other / pk if pk else None

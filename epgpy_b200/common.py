@@ -99,3 +99,24 @@ def repr_operator(cls, names, values, fmts=None):
     fmts = fmts or [""] * len(names)
     args = [f"{n}={repr_value(v, f)}" if n else repr_value(v, f) for n, v, f in zip(names, values, fmts) if v is not None]
     return f"{cls}({', '.join(args)})"
+
+
+def set_axes(params, axes):
+    """`axes=` keyword of the reference's operators (epgpy/common.py:336-347, opmatrix.py:148-150): move the
+    (left-aligned, mutually broadcast) parameter axes of an operator to the given grid axes.
+    `axes` is an int (first axis) or a tuple of ints (one per parameter axis)."""
+    arrs = [None if p is None or isscalar(p) else np.asarray(p) for p in params]
+    ndim = max([a.ndim for a in arrs if a is not None] + [0])
+    if ndim == 0:
+        return list(params)
+    if isinstance(axes, (int, np.integer)):
+        axes = tuple(range(int(axes), int(axes) + ndim))
+    elif not isinstance(axes, tuple) or not all(isinstance(ax, (int, np.integer)) for ax in axes):
+        raise ValueError(f"Invalid axes: {axes}")
+    if len(axes) != ndim:
+        raise ValueError(f"Invalid axes: {axes} for {ndim} parameter axes")
+    newdims = tuple(i for i in range(max(axes)) if i not in axes)
+    out = []
+    for p, a in zip(params, arrs):
+        out.append(p if a is None else np.expand_dims(left(a, ndim), newdims))
+    return out

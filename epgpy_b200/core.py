@@ -6,6 +6,7 @@ for the EPG operator-chain hot path.
 """
 
 from .statematrix import StateMatrix
+from .utils import Axes, get_wavenumber
 from .operators import (
     Operator, MultiOperator, EmptyOperator, Spoiler, Wait, Offset, Reset, PD, System,
     DiffOperator, MatrixOp, ScalarOp,

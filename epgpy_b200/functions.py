@@ -95,16 +95,22 @@ def _assemble(low, parts, asarray=True):
 
     sig_host = jac_host = sig_dev = None
     if low.nadc:
-        sig_host = np.empty((low.nadc, low.natoms, npool), dtype=cdt)
-        for d, b, c, sig, jac in parts:
-            sig_host[:, b:b + c] = sig.cpu().numpy()
+        if len(parts) == 1:
+            sig_host = parts[0][3].cpu().numpy()
+        else:
+            sig_host = np.empty((low.nadc, low.natoms, npool), dtype=cdt)
+            for d, b, c, sig, jac in parts:
+                sig_host[:, b:b + c] = sig.cpu().numpy()
         # reduction of rows on the device (probe.py:148-153)
         if any(r.kind == "sig" and r.reduce is not None for rows in low.rows for r in rows):
             sig_dev = parts[0][3] if len(parts) == 1 else torch.cat([p[3].to(parts[0][3].device) for p in parts], dim=1)
     if low.nvar and low.njac:
-        jac_host = np.empty((low.njac, low.nvar, low.natoms, npool), dtype=cdt)
-        for d, b, c, sig, jac in parts:
-            jac_host[:, :, b:b + c] = jac.cpu().numpy()
+        if len(parts) == 1:
+            jac_host = parts[0][4].cpu().numpy()
+        else:
+            jac_host = np.empty((low.njac, low.nvar, low.natoms, npool), dtype=cdt)
+            for d, b, c, sig, jac in parts:
+                jac_host[:, :, b:b + c] = jac.cpu().numpy()
 
     values = [[] for _ in range(low.nprobe)]
     for rows in low.rows:
@@ -123,6 +129,9 @@ def _assemble(low, parts, asarray=True):
                 if row.post is not None:
                     arr = np.asarray(row.post(arr)).astype(cdt, copy=False)
                 values[ip].append(arr)
+            elif row.kind == "expr":
+                val = row.jac._eval(to_grid(sig_host[row.index]), to_grid(sig_host[row.index + 1]))
+                values[ip].append(row.post(val) if row.post is not None else val)
             else:
                 jrow, cols = row.jac
                 out = np.zeros(grid + (len(cols),), dtype=cdt)

@@ -518,6 +518,12 @@ def lower(sequence, *, init=None, probe=None, options=None, dtype="f64", propaga
                     if fl & (F_BASE | F_PARTIALS):
                         bld.record(OP_ADC, fl, blocks, aux=max(srow, 0), aux1=max(jrow, 0))
                     rows.append(Row("jac", srow, post=custom_post, jac=(jrow, cols)))
+                elif getattr(eff, "expr", None) is not None:
+                    # eval expression over F0 / Z0: read both on the device, evaluate on the host copy
+                    bld.record(OP_ADC, F_BASE, [], aux=nadc)
+                    bld.record(OP_ADC, F_BASE | F_Z0, [], aux=nadc + 1)
+                    rows.append(Row("expr", nadc, post=(op._post if isinstance(op, Adc) else custom_post), jac=eff))
+                    nadc += 2
                 else:
                     attr = eff.attr
                     if attr not in ("F0", "Z0"):

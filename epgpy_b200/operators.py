@@ -483,9 +483,9 @@ class T(CombinableOperator):
     PARAMETERS_ORDER1 = {"alpha", "phi"}
 
     def __init__(self, alpha, phi, *, axes=None, name=None, duration=None, **kwargs):
-        if axes is not None:
-            raise NotImplementedError("the `axes` keyword is not supported: give parameters their grid axes directly")
         self.alpha, self.phi = asparam(alpha), asparam(phi)
+        if axes is not None:
+            self.alpha, self.phi = common.set_axes([self.alpha, self.phi], axes)
         if not name:
             name = common.repr_operator("T", ["alpha", "phi"], [alpha, phi], [".1f", ".1f"])
         super().__init__(name=name, duration=duration, **kwargs)
@@ -568,9 +568,9 @@ class Phi(CombinableOperator):
     PARAMETERS_ORDER1 = {"phi"}
 
     def __init__(self, phi, *, axes=None, name=None, duration=0, **kwargs):
-        if axes is not None:
-            raise NotImplementedError("the `axes` keyword is not supported")
         self.phi = asparam(phi)
+        if axes is not None:
+            (self.phi,) = common.set_axes([self.phi], axes)
         if not name:
             name = common.repr_operator("Phi", ["phi"], [phi], [".1f"])
         super().__init__(name=name, duration=duration, **kwargs)
@@ -649,9 +649,9 @@ class E(_Evolution):
     PARAMETERS_ORDER1 = {"tau", "T1", "T2", "g"}
 
     def __init__(self, tau, T1, T2, g=0, *, axes=None, name=None, duration=None, **kwargs):
-        if axes is not None:
-            raise NotImplementedError("the `axes` keyword is not supported")
         self.tau, self.T1, self.T2, self.g = asparam(tau), asparam(T1), asparam(T2), asparam(g)
+        if axes is not None:
+            self.tau, self.T1, self.T2, self.g = common.set_axes([self.tau, self.T1, self.T2, self.g], axes)
         if not name:
             name = common.repr_operator("E", ["tau", "T1", "T2", "g"], [tau, T1, T2, g], [".1f", ".1f", ".1f", ".3f"])
         self._duration = duration
@@ -744,9 +744,9 @@ class P(_Evolution):
     PARAMETERS_ORDER1 = {"tau", "g"}
 
     def __init__(self, tau, g, *, axes=None, name=None, duration=None, **kwargs):
-        if axes is not None:
-            raise NotImplementedError("the `axes` keyword is not supported")
         self.tau, self.g = asparam(tau), asparam(g)
+        if axes is not None:
+            self.tau, self.g = common.set_axes([self.tau, self.g], axes)
         if not name:
             name = common.repr_operator("P", ["tau", "g"], [tau, g], [".1f", ".3f"])
         self._duration = duration
@@ -792,9 +792,9 @@ class R(_Evolution):
     PARAMETERS_ORDER1 = {"rT", "rL", "r0"}
 
     def __init__(self, rT=0, rL=0, *, r0=None, axes=None, name=None, duration=None, **kwargs):
-        if axes is not None:
-            raise NotImplementedError("the `axes` keyword is not supported")
         self.rT, self.rL, self.r0 = asparam(rT), asparam(rL), asparam(r0)
+        if axes is not None:
+            self.rT, self.rL, self.r0 = common.set_axes([self.rT, self.rL, self.r0], axes)
         if not name:
             name = common.repr_operator("R", ["rT", "rL", "r0"], [rT, rL, r0], [".1f", ".1f", ".1f"])
         super().__init__(name=name, duration=duration, **kwargs)
@@ -910,27 +910,45 @@ class D(Operator):
 
 
 class Probe(EmptyOperator):
-    """base probe (epgpy/probe.py:7-79).  Only state-matrix attribute expressions that the engine can
-    read on the device ('F0', 'Z0') are accepted; arbitrary callables / eval expressions would need the
+    """base probe (epgpy/probe.py:7-79).  `obj` is a state-matrix attribute ('F0', 'Z0') or an eval expression over
+    them, e.g. "abs(F0)" or "(real(F0), imag(F0))" (numpy names allowed, as in the reference): F0 and Z0 are read
+    on the device and the expression is evaluated on the host copy, like the reference's `acquire`
+    (probe.py:57-66).  Callables and expressions over other attributes (states, F, Z, k, ...) would need the
     whole state matrix on the host and are not supported (no CPU path)."""
 
+    DEVICE_ATTRS = ("F0", "Z0")
+
     def __init__(self, obj, *args, post=None, **kwargs):
-        if isinstance(obj, str) and obj.strip() in ("F0", "Z0"):
+        self.attr = self.expr = None
+        if isinstance(obj, str) and obj.strip() in self.DEVICE_ATTRS:
             self.attr = obj.strip()
+        elif isinstance(obj, str):
+            names = set(compile(obj, "<probe>", "eval").co_names)
+            other = {n for n in names if n in Adc.SM_LOCALS and n not in self.DEVICE_ATTRS}
+            if other:
+                raise NotImplementedError(
+                    f"Probe({obj!r}): state-matrix attributes {sorted(other)} are not available on the device path "
+                    "(only F0 and Z0 are read back)")
+            self.expr = obj
         else:
-            raise NotImplementedError(
-                f"Probe({obj!r}): only the 'F0' / 'Z0' attributes can be probed on the device; "
-                "use Adc(attr, phase=, weights=, reduce=) or Jacobian"
-            )
+            raise NotImplementedError("callable probes need the whole state matrix on the host; use Adc / Jacobian "
+                                      "or an expression over F0 / Z0")
+        self._kwargs = kwargs
         self.phase = self.reduce = self.weights = None
         self._post = post
         super().__init__()
+        self.name = f"Probe('{obj}')"
 
     def __call__(self, sm, **kwargs):
         return sm
 
     def post(self, obj):
         return obj if not getattr(self, "_post", None) else self._post(obj)
+
+    def _eval(self, F0, Z0):
+        env = {"F0": F0, "Z0": Z0}
+        env.update(self._kwargs)
+        return eval(self.expr, vars(np), env)
 
 
 class Adc(Probe):

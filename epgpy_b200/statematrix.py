@@ -130,10 +130,6 @@ class StateMatrix:
         n = self.nstate
         return np.arange(-n, n + 1, dtype=float)[:, None] * self.kvalue
 
-    @property
-    def norm(self):
-        return np.sqrt(np.sum(np.abs(self._states) ** 2, axis=(-2, -1)) / 2 + np.abs(self.Z0) ** 2 / 2)
-
     def copy(self):
         new = object.__new__(StateMatrix)
         new._states = self._states.copy()

