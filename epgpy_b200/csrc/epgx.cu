@@ -127,7 +127,7 @@ static int choose_variant(epgx_plan *pl, int kernel, int lanes, int vars, int at
   if (pl->real_ok && (kernel == 0 || kernel == 3)) {
     // ---- real-valued register kernel: one warp (or less) per atom, up to 32 slots
     const int ns_max = t.dtype == EPGX_F64 ? 16 : 32;
-    int G = lanes > 0 ? pow2ceil(lanes) : pow2ceil((C + 15) / 16);
+    int G = lanes > 0 ? pow2ceil(lanes) : pow2ceil((C + 7) / 8); // about 8 orders per lane; small graphs pack several atoms per warp
     if (G > 32) G = 32;
     const int need = (C + G - 1) / G;
     int NS = 0;
