@@ -408,7 +408,9 @@ def main():
             "dtype": args.dtype, "data": "synthetic",
             "config": {"workload": workload, "atoms_per_gpu": cnt, "atoms_total": atoms_total, "ntr": args.ntr,
                        "l2": "256 MB buffer written between timed iterations (L2 flush)", "kernel": cfg,
-                       "state_updates_per_atom_executed": cfg["updates_per_atom"], "gather": bool(gathered is not None)},
+                       "state_updates_per_atom_executed": cfg["updates_per_atom"], "gather": bool(gathered is not None),
+                       # what the reference (full storage, no pruning, no fusion) performs for the same output
+                       "state_updates_per_atom_reference": 4002002 if (args.ntr == NTR and max_nstate is None) else None},
             "state_updates_per_s": cfg["updates_per_atom"] * value,
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
             "extra": extra,
