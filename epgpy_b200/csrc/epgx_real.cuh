@@ -14,6 +14,10 @@
 #include "epgx_common.cuh"
 #include "epgx_reg.cuh"
 
+#ifndef EPGX_MINB_128
+#define EPGX_MINB_128 2
+#endif
+
 namespace epgx {
 
 // One tape window of TAPE_CHUNK / 2 whole-TR records (fused E.T.E, plain ADC, unit shift +1) for one atom
@@ -28,12 +32,27 @@ __device__ __forceinline__ void tr_window(real (&P)[NS], real (&M)[NS], real (&Z
   typedef typename vec2<real>::type real2;
   const unsigned FULL = 0xffffffffu;
   if constexpr (K <= NS) {
+#ifdef EPGX_PIPELINE_BCAST
+    // software pipeline: the coefficients of TR j + 1 are broadcast while TR j computes
+    real a = __shfl_sync(FULL, fv.a, 0), w = __shfl_sync(FULL, fv.w, 0), b = __shfl_sync(FULL, fv.b, 0);
+    real u = __shfl_sync(FULL, fv.u, 0), h = __shfl_sync(FULL, fv.h, 0);
+    real fz = __shfl_sync(FULL, fv.fz, 0), zz = __shfl_sync(FULL, fv.zz, 0);
+    int row = __shfl_sync(FULL, rowv, 0);
+#pragma unroll 1
+    for (int j = 0; j < TAPE_CHUNK / 2; ++j) {
+      const int jn = (j + 1) & (TAPE_CHUNK / 2 - 1);
+      const real na = __shfl_sync(FULL, fv.a, jn), nw = __shfl_sync(FULL, fv.w, jn), nb = __shfl_sync(FULL, fv.b, jn);
+      const real nu = __shfl_sync(FULL, fv.u, jn), nh = __shfl_sync(FULL, fv.h, jn);
+      const real nfz = __shfl_sync(FULL, fv.fz, jn), nzz = __shfl_sync(FULL, fv.zz, jn);
+      const int nrow = __shfl_sync(FULL, rowv, jn);
+#else
 #pragma unroll 1
     for (int j = 0; j < TAPE_CHUNK / 2; ++j) {
       const real a = __shfl_sync(FULL, fv.a, j), w = __shfl_sync(FULL, fv.w, j), b = __shfl_sync(FULL, fv.b, j);
       const real u = __shfl_sync(FULL, fv.u, j), h = __shfl_sync(FULL, fv.h, j);
       const real fz = __shfl_sync(FULL, fv.fz, j), zz = __shfl_sync(FULL, fv.zz, j);
       const int row = __shfl_sync(FULL, rowv, j);
+#endif
 #pragma unroll
       for (int s = 0; s < K; ++s) {
         const real p_ = P[s], m_ = M[s], z_ = Z[s];
@@ -58,12 +77,15 @@ __device__ __forceinline__ void tr_window(real (&P)[NS], real (&M)[NS], real (&Z
         M[s] = __shfl_sync(FULL, is_first ? keep : cur, srcDn);
         keep = cur;
       }
+#ifdef EPGX_PIPELINE_BCAST
+      a = na; w = nw; b = nb; u = nu; h = nh; fz = nfz; zz = nzz; row = nrow;
+#endif
     }
   }
 }
 
 template <typename real, int NS>
-__global__ void __launch_bounds__(256, (sizeof(real) * NS <= 64 ? 3 : sizeof(real) * NS <= 128 ? 2 : 1)) real_kernel(const KParams p) {
+__global__ void __launch_bounds__(256, (sizeof(real) * NS <= 64 ? 3 : sizeof(real) * NS <= 128 ? EPGX_MINB_128 : 1)) real_kernel(const KParams p) {
   typedef typename vec2<real>::type real2;
   extern __shared__ __align__(16) unsigned char smem_raw[];
 

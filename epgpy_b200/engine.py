@@ -12,7 +12,7 @@ import threading
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libepgx.so")
+LIB_PATH = os.environ.get("EPGX_LIB") or os.path.join(_HERE, "libepgx.so")  # EPGX_LIB: experimental builds
 
 MAX_DIMS, MAX_PATTERNS = 8, 64
 

