@@ -60,3 +60,43 @@ def test_identity_is_preserved(ref):
     seq = [ref.core.T(90, 90), [ref.core.S(1), e, ref.core.T(150, 0), ref.core.S(1), e, ref.core.ADC]]
     out = compat.from_reference(seq)
     assert out[1][1] is out[1][4] and type(out[1][1]).__name__ == "E"
+
+
+def test_reference_sequence_layer_runs_unchanged_on_the_engine_path(ref, monkeypatch):
+    """the reference's symbolic `Sequence` layer (signal / jacobian / crlb) only calls
+    `functions.simulate`; with that one call routed through `compat.from_reference` + the lowering, it runs
+    unchanged (reference test/test_sequence.py:6-61 restated)."""
+    import epgpy_b200
+    from epgpy_b200 import compat
+    from epgpy.sequence import Sequence, Variable, operators
+
+    T2, B1 = Variable("T2"), Variable("B1")
+    necho = 5
+    exc, rfc = operators.T(90, 90), operators.T(180 * B1, 0)
+    spl, rlx, adc = operators.S(1, duration=5), operators.E(5, 1400, T2), operators.ADC
+    seq = Sequence([exc] + [spl, rlx, rfc, spl, rlx, adc] * necho)
+
+    want_sig = seq.signal(T2=30, B1=0.8)
+    want = seq.jacobian(["T2", "B1"], T2=[30, 40, 50], B1=0.8)
+    want_crlb = seq.crlb(["T2", "B1"])(T2=30, B1=0.8)
+
+    calls = []
+
+    def routed(sequence, **kw):
+        calls.append(len(sequence))
+        probe = kw.pop("probe", None)
+        if probe is not None:
+            probe = [compat.from_reference(p) if p is not None else None for p in (probe if isinstance(probe, (list, tuple)) else [probe])]
+        kw.pop("asarray", None)
+        return tape_interp.simulate(None, compat.from_reference(sequence), probe=probe, **kw)
+
+    import epgpy.sequence as refseq
+
+    monkeypatch.setattr(refseq._functions, "simulate", routed)
+    got_sig = seq.signal(T2=30, B1=0.8)
+    got = seq.jacobian(["T2", "B1"], T2=[30, 40, 50], B1=0.8)
+    got_crlb = seq.crlb(["T2", "B1"])(T2=30, B1=0.8)
+    assert calls, "the sequence layer did not go through the routed simulate"
+    assert rel_err(got_sig, want_sig) < RTOL64
+    assert rel_err(got[0], want[0]) < RTOL64 and rel_err(got[1], want[1]) < RTOL64
+    assert np.allclose(got_crlb, want_crlb, rtol=1e-8)
