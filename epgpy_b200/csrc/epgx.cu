@@ -71,7 +71,7 @@ static double form_flops(int code, int flags, int npool) {
   case EPGX_OP_T_GEN: return 56;
   case EPGX_OP_T_RE:
   case EPGX_OP_T_IM: return 28;
-  case EPGX_OP_FUSED: return 28;
+  case EPGX_OP_FUSED: return 56; // applied in the general (a, w, B, U, H) form by the complex kernels
   case EPGX_OP_E: return (flags & EPGX_FLAG_G) ? 14 : 6;
   case EPGX_OP_DIAG: return 18;
   case EPGX_OP_MATRIX: return 66;
@@ -82,6 +82,18 @@ static double form_flops(int code, int flags, int npool) {
 }
 
 static const int kRegSlots[5] = {1, 2, 4, 8, 16};
+
+// flops per order in the real-valued kernels (three reals per order)
+static double form_flops_real(int code) {
+  switch (code) {
+  case EPGX_OP_T_RE:
+  case EPGX_OP_FUSED: return 14;
+  case EPGX_OP_E:
+  case EPGX_OP_D:
+  case EPGX_OP_DIAG: return 3;
+  default: return 0;
+  }
+}
 
 static int choose_variant(epgx_plan *pl, int kernel, int lanes, int vars, int atoms) {
   const epgx_tape &t = pl->tape;
@@ -237,7 +249,7 @@ static int entry_reals(int code, int blk, int flags, const epgx_tape &t) {
   case EPGX_OP_D: return blk == 0 ? 3 * (t.max_order + 1) : 0;
   case EPGX_OP_X: return blk == 0 ? 4 * t.npool * t.npool : 0;
   case EPGX_OP_PD: return blk == 0 ? 1 : 0;
-  case EPGX_OP_FUSED: return blk == 0 ? 4 : blk == 1 ? 2 : 1;
+  case EPGX_OP_FUSED: return blk == 0 ? ((flags & EPGX_FLAG_GEN) ? 6 : 4) : blk == 1 ? 2 : 1;
   case EPGX_OP_CONT: return blk == 0 ? 2 : blk == 1 ? 1 : 0;
   case EPGX_OP_ADC: return (blk == 0 && (flags & EPGX_FLAG_SCALE)) ? 2 : 0;
   default: return 0;
@@ -299,7 +311,7 @@ extern "C" int epgx_plan_create(const epgx_tape *t, epgx_plan **out) {
         return fail(EPGX_ERR_INVALID, "jacobian row out of range in record " + std::to_string(i));
     }
   }
-  double flops = 0, updates = 0;
+  double flops = 0, flops_r = 0, updates = 0;
   for (int64_t i = 0; i < t->nseg; ++i) {
     const epgx_segment &s = t->segs[i];
     if (s.first < 0 || s.count < 0 || (int64_t)s.first + s.count > t->nop || s.nact < -1 || s.nact > t->max_order ||
@@ -316,6 +328,7 @@ extern "C" int epgx_plan_create(const epgx_tape *t, epgx_plan **out) {
       if (o.flags & EPGX_FLAG_INJECT) sets = 1;
       else sets = ((o.flags & EPGX_FLAG_BASE) ? 1 : 0) + ((o.flags & EPGX_FLAG_PARTIALS) ? t->nvar : 0);
       flops += f * sets;
+      flops_r += form_flops_real(o.code) * t->npool * (s.nact + 1.0) * sets;
       if (!(o.flags & EPGX_FLAG_INJECT) && (o.flags & EPGX_FLAG_BASE)) updates += s.nact + 1.0;
     }
     if (s.shift) updates += s.n_new + 1.0;
@@ -455,7 +468,7 @@ extern "C" int epgx_plan_create(const epgx_tape *t, epgx_plan **out) {
     return rc;
   }
   pl->flops_cplx = flops;
-  pl->flops_real = 0.5 * flops; // T_RE / FUSED / E / D on three reals per order
+  pl->flops_real = flops_r;
   pl->updates = updates;
   pl->cfg.updates_per_atom = updates;
   pl->cfg.flops_per_atom = pl->cfg.kernel >= 2 ? pl->flops_real : pl->flops_cplx;

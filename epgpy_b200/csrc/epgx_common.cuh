@@ -24,6 +24,8 @@
 
 namespace epgx {
 
+template <typename real> __device__ __forceinline__ real ldc(const real *p) { return __ldg(p); }
+
 template <typename real> struct vec2;
 template <> struct vec2<float> { typedef float2 type; };
 template <> struct vec2<double> { typedef double2 type; };
@@ -133,6 +135,56 @@ __device__ __forceinline__ Fused5<real> fuse5(real ta, real tw, real tb, real tu
   return f;
 }
 
+// fused E.T.E for ANY pulse kind: a, w real; B, U, H complex; H = -1/2 e1' e2 U
+//   F+' = a F+ + B F- + U Z ; F-' = conj(B) F+ + a F- + conj(U) Z ; Z' = w Z + conj(H) F+ + H F-
+template <typename real> struct Fused8 {
+  real a, w, Br, Bi, Ur, Ui, Hr, Hi;
+  real fzr, fzi, zz; // affine terms at k = 0: F+(0) += fz, F-(0) += conj(fz), Z(0) += zz
+};
+
+template <typename real>
+__device__ __forceinline__ Tri<real> form_t8(const Tri<real> &s, const Fused8<real> &f) {
+  Tri<real> o;
+  o.pr = f.a * s.pr + f.Br * s.mr - f.Bi * s.mi + f.Ur * s.zr - f.Ui * s.zi;
+  o.pi = f.a * s.pi + f.Br * s.mi + f.Bi * s.mr + f.Ur * s.zi + f.Ui * s.zr;
+  o.mr = f.a * s.mr + f.Br * s.pr + f.Bi * s.pi + f.Ur * s.zr + f.Ui * s.zi;
+  o.mi = f.a * s.mi + f.Br * s.pi - f.Bi * s.pr + f.Ur * s.zi - f.Ui * s.zr;
+  o.zr = f.w * s.zr + f.Hr * s.pr + f.Hi * s.pi + f.Hr * s.mr - f.Hi * s.mi;
+  o.zi = f.w * s.zi + f.Hr * s.pi - f.Hi * s.pr + f.Hr * s.mi + f.Hi * s.mr;
+  return o;
+}
+
+// T block (a, w, B, U) with real diagonal E_pre = (e2a, e2a, e1a; r0a) and E_post = (e2b, e2b, e1b; r0b)
+template <typename real>
+__device__ __forceinline__ Fused8<real> fuse8(real ta, real tw, real tBr, real tBi, real tUr, real tUi, bool pre, real e1a,
+                                              real r0a, real e2a, bool post, real e1b, real r0b, real e2b, real m0) {
+  if (!pre) { e1a = real(1); e2a = real(1); r0a = real(0); }
+  if (!post) { e1b = real(1); e2b = real(1); r0b = real(0); }
+  Fused8<real> f;
+  const real ff = e2b * e2a, fu = e2b * e1a, fh = real(-0.5) * e1b * e2a;
+  f.a = ff * ta;
+  f.Br = ff * tBr; f.Bi = ff * tBi;
+  f.Ur = fu * tUr; f.Ui = fu * tUi;
+  f.Hr = fh * tUr; f.Hi = fh * tUi;
+  f.w = e1b * e1a * tw;
+  const real c1 = r0a * m0; // Z(0) offset of E_pre, pushed through T and E_post
+  f.fzr = e2b * tUr * c1; f.fzi = e2b * tUi * c1;
+  f.zz = e1b * tw * c1 + r0b * m0;
+  return f;
+}
+
+// decode the T block of a FUSED record of any kind into (a, w, B, U)
+template <typename real>
+__device__ __forceinline__ void fused_pulse(const real *ct, int flags, real &a, real &w, real &Br, real &Bi, real &Ur, real &Ui) {
+  a = ldc(ct); w = ldc(ct + 1);
+  if (flags & EPGX_FLAG_GEN) { Br = ldc(ct + 2); Bi = ldc(ct + 3); Ur = ldc(ct + 4); Ui = ldc(ct + 5); }
+  else {
+    Br = ldc(ct + 2); Bi = real(0);
+    const real u = ldc(ct + 3);
+    if (flags & EPGX_FLAG_IM) { Ur = real(0); Ui = -u; } else { Ur = u; Ui = real(0); }
+  }
+}
+
 // F+ *= (er + i ei), F- *= (er - i ei), Z *= e1     (er + i ei = e2 cis(2 pi g tau))
 template <typename real>
 __device__ __forceinline__ Tri<real> form_e_g(const Tri<real> &s, real e1, real er, real ei) {
@@ -198,7 +250,5 @@ struct KParams {
   unsigned init_off, m0_off;
   int init_pat, m0_pat, init_n;
 };
-
-template <typename real> __device__ __forceinline__ real ldc(const real *p) { return __ldg(p); }
 
 } // namespace epgx

@@ -279,20 +279,15 @@ _Pragma("unroll") \
       } break;
       case EPGX_OP_FUSED: {
         const int4 q0 = tb[2 * r + 2], q1 = tb[2 * r + 3]; // the CONT record (never split from FUSED)
-        const real *ct = coef + off0 + patoff[pat0];
         const real *ca = coef + off1 + patoff[pat1];
         const real *cb = coef + (unsigned)q0.z + patoff[q1.y & 0xff];
-        const Fused5<real> f = fuse5<real>(ldc(ct), ldc(ct + 1), ldc(ct + 2), ldc(ct + 3), flags & EPGX_FLAG_PRE, ldc(ca),
-                                           ldc(ca + 1), ldc(coef + off2 + patoff[pat2]), flags & EPGX_FLAG_POST, ldc(cb),
-                                           ldc(cb + 1), ldc(coef + (unsigned)q0.w + patoff[(q1.y >> 8) & 0xff]),
-                                           flags & EPGX_FLAG_IM, m0);
-        if (flags & EPGX_FLAG_IM) {
-          FOR_SLOTS(form_t5_im(t_, f.a, f.w, f.b, f.u, f.h))
-          if (lane == 0 && nslot > 0) { Pi[0] -= f.fz; Mi[0] += f.fz; Zr[0] += f.zz; }
-        } else {
-          FOR_SLOTS(form_t5_re(t_, f.a, f.w, f.b, f.u, f.h))
-          if (lane == 0 && nslot > 0) { Pr[0] += f.fz; Mr[0] += f.fz; Zr[0] += f.zz; }
-        }
+        real ta, tw, tBr, tBi, tUr, tUi;
+        fused_pulse<real>(coef + off0 + patoff[pat0], flags, ta, tw, tBr, tBi, tUr, tUi);
+        const Fused8<real> f = fuse8<real>(ta, tw, tBr, tBi, tUr, tUi, flags & EPGX_FLAG_PRE, ldc(ca), ldc(ca + 1),
+                                           ldc(coef + off2 + patoff[pat2]), flags & EPGX_FLAG_POST, ldc(cb), ldc(cb + 1),
+                                           ldc(coef + (unsigned)q0.w + patoff[(q1.y >> 8) & 0xff]), m0);
+        FOR_SLOTS(form_t8(t_, f))
+        if (lane == 0 && nslot > 0) { Pr[0] += f.fzr; Pi[0] += f.fzi; Mr[0] += f.fzr; Mi[0] -= f.fzi; Zr[0] += f.zz; }
         ++r; // the CONT record
       } break;
       case EPGX_OP_SPOIL:

@@ -248,21 +248,20 @@ __global__ void __launch_bounds__(256) ring_kernel(const KParams p) {
             const int4 q1 = __ldg((const int4 *)(p.ops + r + 1) + 1);
 #pragma unroll
             for (int q = 0; q < NP; ++q) {
-              const real *ct = coef + off0 + POFF(pat0, q);
               const real *ca = coef + off1 + POFF(pat1, q);
               const real *cb = coef + (unsigned)q0.z + POFF(q1.y & 0xff, q);
-              const Fused5<real> f =
-                  fuse5<real>(ldc(ct), ldc(ct + 1), ldc(ct + 2), ldc(ct + 3), flags & EPGX_FLAG_PRE, ldc(ca), ldc(ca + 1),
+              real ta, tw, tBr, tBi, tUr, tUi;
+              fused_pulse<real>(coef + off0 + POFF(pat0, q), flags, ta, tw, tBr, tBi, tUr, tUi);
+              const Fused8<real> f =
+                  fuse8<real>(ta, tw, tBr, tBi, tUr, tUi, flags & EPGX_FLAG_PRE, ldc(ca), ldc(ca + 1),
                               ldc(coef + off2 + POFF(pat2, q)), flags & EPGX_FLAG_POST, ldc(cb), ldc(cb + 1),
-                              ldc(coef + (unsigned)q0.w + POFF((q1.y >> 8) & 0xff, q)), flags & EPGX_FLAG_IM, m0[q]);
+                              ldc(coef + (unsigned)q0.w + POFF((q1.y >> 8) & 0xff, q)), m0[q]);
               if (on_base) {
                 const Tri<real> s_ = st[0][q];
-                if (flags & EPGX_FLAG_IM) {
-                  st[0][q] = form_t5_im(s_, f.a, f.w, f.b, f.u, f.h);
-                  if (k == 0) { st[0][q].pi -= f.fz; st[0][q].mi += f.fz; st[0][q].zr += f.zz; }
-                } else {
-                  st[0][q] = form_t5_re(s_, f.a, f.w, f.b, f.u, f.h);
-                  if (k == 0) { st[0][q].pr += f.fz; st[0][q].mr += f.fz; st[0][q].zr += f.zz; }
+                st[0][q] = form_t8(s_, f);
+                if (k == 0) {
+                  st[0][q].pr += f.fzr; st[0][q].pi += f.fzi; st[0][q].mr += f.fzr; st[0][q].mi -= f.fzi;
+                  st[0][q].zr += f.zz;
                 }
               }
             }

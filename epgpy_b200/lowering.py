@@ -26,7 +26,7 @@ from .statematrix import StateMatrix
 # opcodes / flags (include/epgx.h)
 (OP_NOP, OP_T_GEN, OP_T_RE, OP_T_IM, OP_E, OP_DIAG, OP_MATRIX, OP_D, OP_X, OP_SPOIL, OP_PD, OP_ADC, OP_FUSED,
  OP_CONT) = range(14)
-F_BASE, F_PARTIALS, F_INJECT, F_G, F_AFFINE, F_Z0, F_SCALE, F_PRE, F_POST, F_IM = (1 << i for i in range(10))
+F_BASE, F_PARTIALS, F_INJECT, F_G, F_AFFINE, F_Z0, F_SCALE, F_PRE, F_POST, F_IM, F_GEN = (1 << i for i in range(11))
 SEG_RESET, SEG_MASK_TOP = 1, 2
 MAX_DIMS, MAX_PATTERNS, MAX_POOLS = 8, 64, 2
 
@@ -218,16 +218,28 @@ def fuse_records(recs, segs):
         return r["code"] == OP_E and (int(r["flags"]) & ~F_AFFINE) == F_BASE
 
     def pulse(r):
-        return r["code"] in (OP_T_RE, OP_T_IM) and int(r["flags"]) == F_BASE
+        return r["code"] in (OP_T_RE, OP_T_IM, OP_T_GEN) and int(r["flags"]) == F_BASE
+
+    def diffusion(r):
+        return r["code"] == OP_D and int(r["flags"]) == F_BASE
 
     out, carry = [], []
     for i in range(len(segs)):
         seg = segs[i]
-        rs = carry + [recs[j] for j in range(seg["first"], seg["first"] + seg["count"])]
+        rs = [recs[j] for j in range(seg["first"], seg["first"] + seg["count"])]
+        if carry:  # a diagonal E commutes with the (diagonal) D records that open the segment: put it next to the pulse
+            nd = 0
+            while nd < len(rs) and diffusion(rs[nd]):
+                nd += 1
+            rs = rs[:nd] + carry + rs[nd:]
         carry = []
-        if seg["shift"] != 0 and not (seg["flags"] & SEG_RESET) and i + 1 < len(segs) and segs[i + 1]["count"] > 0 \
-                and pulse(recs[segs[i + 1]["first"]]) and rs and pure_e(rs[-1]):
-            carry = [rs.pop()]
+        if seg["shift"] != 0 and not (seg["flags"] & SEG_RESET) and i + 1 < len(segs) and rs and pure_e(rs[-1]):
+            nxt = [recs[j] for j in range(segs[i + 1]["first"], segs[i + 1]["first"] + segs[i + 1]["count"])]
+            nd = 0
+            while nd < len(nxt) and diffusion(nxt[nd]):
+                nd += 1
+            if nd < len(nxt) and pulse(nxt[nd]):
+                carry = [rs.pop()]
         new, j = [], 0
         while j < len(rs):
             pre = None
@@ -239,8 +251,8 @@ def fuse_records(recs, segs):
                 f = np.zeros((), dtype=OP_DTYPE)
                 c = np.zeros((), dtype=OP_DTYPE)
                 f["code"], c["code"] = OP_FUSED, OP_CONT
-                f["flags"] = F_BASE | (F_IM if t["code"] == OP_T_IM else 0) | (F_PRE if pre is not None else 0) \
-                    | (F_POST if post is not None else 0)
+                f["flags"] = F_BASE | (F_IM if t["code"] == OP_T_IM else 0) | (F_GEN if t["code"] == OP_T_GEN else 0) \
+                    | (F_PRE if pre is not None else 0) | (F_POST if post is not None else 0)
                 f["off"][0], f["pat"][0] = t["off"][0], t["pat"][0]
                 if pre is not None:
                     f["off"][1:3], f["pat"][1:3] = pre["off"][0:2], pre["pat"][0:2]

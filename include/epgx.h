@@ -100,7 +100,8 @@ typedef enum {
   EPGX_OP_ADC = 11,
   /* fused E_pre -> T -> E_post (the host's peephole pass over [E, T_RE|T_IM, E] runs without precession;
    * an E that closes a segment commutes with the shift and becomes the E_pre of the next segment).
-   * Two records: FUSED carries blk0: T (a, w, b, u), blk1: pre (e1, r0), blk2: pre (e2);
+   * Two records: FUSED carries blk0: T (a, w, b, u) -- or the six reals of T_GEN with EPGX_FLAG_GEN --, blk1: pre
+ * (e1, r0), blk2: pre (e2);
    * the CONT record that follows carries blk0: post (e1, r0), blk1: post (e2).  Per atom the kernel
    * assembles A = e2' e2 a, B = e2' e2 b, U = e2' e1 u, H = -+1/2 e1' e2 u, W = e1' e1 w and applies
    *   F+' = A F+ + B F- + U' Z ; F-' = B F+ + A F- + conj(U') Z ; Z' = W Z + H (..)   (U' = U or -iU)
@@ -122,7 +123,8 @@ enum {
   EPGX_FLAG_SCALE = 1 << 6,  /* ADC: multiply by the complex factor in blk0   */
   EPGX_FLAG_PRE = 1 << 7,    /* FUSED: E_pre present                          */
   EPGX_FLAG_POST = 1 << 8,   /* FUSED: E_post present (in the CONT record)    */
-  EPGX_FLAG_IM = 1 << 9      /* FUSED: T is of the T_IM kind (else T_RE)      */
+  EPGX_FLAG_IM = 1 << 9,     /* FUSED: T is of the T_IM kind (else T_RE)      */
+  EPGX_FLAG_GEN = 1 << 10    /* FUSED: T is of the T_GEN kind: blk0 = (a, w, B.re, B.im, U.re, U.im) */
 };
 
 /* tape record, 32 bytes */

@@ -58,7 +58,7 @@ def run(low):
                 e["off"][0:2], e["pat"][0:2] = rec["off"][1:3], rec["pat"][1:3]
                 out.append(e)
             t = np.zeros((), dtype=L.OP_DTYPE)
-            t["code"], t["flags"] = (L.OP_T_IM if fl & L.F_IM else L.OP_T_RE), L.F_BASE
+            t["code"], t["flags"] = (L.OP_T_GEN if fl & L.F_GEN else L.OP_T_IM if fl & L.F_IM else L.OP_T_RE), L.F_BASE
             t["off"][0], t["pat"][0] = rec["off"][0], rec["pat"][0]
             out.append(t)
             if fl & L.F_POST:
