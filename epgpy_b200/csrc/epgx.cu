@@ -188,7 +188,8 @@ static int choose_variant(epgx_plan *pl, int kernel, int lanes, int vars, int at
         c.var_tiles = 1;
         c.atoms_per_cta = A;
         c.threads_per_cta = A * G;
-        c.smem_bytes = 2 * epgx::TAPE_CHUNK * 32 + ((A * t.npattern + 3) & ~3) * 4 + (W > 1 ? 2 * A * W * 2 * NS * 2 * rsz : 0) + 32;
+        c.smem_bytes = 2 * epgx::TAPE_CHUNK * 32 + ((A * t.npattern + 3) & ~3) * 4 + (W > 1 ? 2 * A * W * 2 * NS * 2 * rsz : 0) +
+                       ((A * G + 31) / 32) * epgx::TRC_PER_WINDOW * (epgx::TRC_REALS * rsz + 16) + 64;
         c.ring = C;
         return EPGX_OK;
       }
@@ -390,8 +391,13 @@ extern "C" int epgx_plan_create(const epgx_tape *t, epgx_plan **out) {
     pl->realjac_ok = okj;
   }
   {
-    // merged stream: [SEG(open seg 0)] recs_0 [SEG(close 0, open 1)] recs_1 ... [SEG(close last)]; a FUSED record
-    // is never the last one of a TAPE_CHUNK window (NOP padding)
+    // merged stream: [SEG(open seg 0)] seg_0 seg_1 ... where every segment is emitted as
+    //   its records + SEG(close it, open the next)                                   (general form)
+    //   TR  = [FUSED(RE) as TR, CONT']                 when it is exactly [FUSED, ADC(plain)] in a real-valued plan
+    //   TRC = [FUSED(any) as TRC, CONT', CONT2]        when it is [D?] [FUSED] [ADC(F0, optional scale)] otherwise
+    // (unit shift +-1 or none, any segment flags; the closing information rides in CONT').  TR pairs start at
+    // even positions and TRC triples at multiples of 3 inside a TAPE_CHUNK window (NOP padding); a FUSED record is
+    // never the last of a window.  Windows made only of plain TR / TRC records are flagged for the fast paths.
     auto seg_rec = [](int shift, int n_old, int n_new, int flags, int next_nact) {
       epgx_op o;
       memset(&o, 0, sizeof(o));
@@ -406,55 +412,58 @@ extern "C" int epgx_plan_create(const epgx_tape *t, epgx_plan **out) {
     std::vector<epgx_op> &st = pl->stream;
     epgx_op nop;
     memset(&nop, 0, sizeof(nop));
-    for (int64_t i = 0; i <= t->nseg; ++i) {
-      const epgx_segment *prev = i > 0 ? &t->segs[i - 1] : nullptr;
-      const int next_nact = i < t->nseg ? t->segs[i].nact : -1;
-      // a segment that is exactly [FUSED(RE), CONT, ADC(F0, unscaled)] merges with its closing SEG into one TR
-      bool merged = false;
-      if (prev && pl->real_ok && prev->count == 3 && prev->n_old < 65536 && prev->n_new < 65536) {
-        const epgx_op &f = t->ops[prev->first], &c = t->ops[prev->first + 1], &a = t->ops[prev->first + 2];
-        if (f.code == EPGX_OP_FUSED && a.code == EPGX_OP_ADC && a.flags == EPGX_FLAG_BASE && st.size() >= 3) {
-          epgx_op &sf = st[st.size() - 3], &sc = st[st.size() - 2];
-          if (sf.code == EPGX_OP_FUSED && sc.code == EPGX_OP_CONT) {
-            sf.code = EPGX_OP_TR;
-            sc.aux = a.aux;
-            sc.flags = (uint16_t)((prev->shift + 1) | (prev->flags << 2));
-            sc.off[2] = ((uint32_t)prev->n_old << 16) | (uint32_t)prev->n_new;
-            sc.aux1 = next_nact;
-            st.pop_back(); // the ADC record
-            merged = true;
-          }
-        }
-      }
-      if (!merged)
-        st.push_back(prev ? seg_rec(prev->shift, prev->n_old, prev->n_new, prev->flags, next_nact) : seg_rec(0, 0, 0, 0, next_nact));
-      if (i == t->nseg) break;
+    const int CH = epgx::TAPE_CHUNK;
+    st.push_back(seg_rec(0, 0, 0, 0, t->nseg ? t->segs[0].nact : -1));
+    for (int64_t i = 0; i < t->nseg; ++i) {
       const epgx_segment &sg = t->segs[i];
-      for (int r = sg.first; r < sg.first + sg.count; ++r) {
-        if (t->ops[r].code == EPGX_OP_FUSED && (int)(st.size() % epgx::TAPE_CHUNK) == epgx::TAPE_CHUNK - 1) st.push_back(nop);
-        st.push_back(t->ops[r]);
+      const epgx_op *rs = t->ops + sg.first;
+      const int next_nact = i + 1 < t->nseg ? t->segs[i + 1].nact : -1;
+      const bool small = sg.n_old < 65536 && sg.n_new < 65536;
+      auto close_into = [&](epgx_op &c) { // closing information of the segment in a CONT' record
+        c.flags = (uint16_t)((sg.shift + 1) | (sg.flags << 2));
+        c.off[2] = ((uint32_t)sg.n_old << 16) | (uint32_t)sg.n_new;
+        c.aux1 = next_nact;
+      };
+      if (pl->real_ok && small && sg.count == 3 && rs[0].code == EPGX_OP_FUSED && rs[2].code == EPGX_OP_ADC &&
+          rs[2].flags == EPGX_FLAG_BASE) {
+        if (st.size() & 1) st.push_back(nop);
+        epgx_op f = rs[0], c = rs[1];
+        f.code = EPGX_OP_TR;
+        c.aux = rs[2].aux;
+        close_into(c);
+        st.push_back(f);
+        st.push_back(c);
+        continue;
       }
+      const int nd = (sg.count >= 1 && rs[0].code == EPGX_OP_D && rs[0].flags == EPGX_FLAG_BASE) ? 1 : 0;
+      if (!pl->real_ok && t->nvar == 0 && t->npool == 1 && small && sg.count == nd + 3 && rs[nd].code == EPGX_OP_FUSED &&
+          rs[nd + 2].code == EPGX_OP_ADC && (rs[nd + 2].flags & ~EPGX_FLAG_SCALE) == EPGX_FLAG_BASE) {
+        while ((st.size() % CH) % 3 != 0 || (int)(st.size() % CH) == CH - 1) st.push_back(nop);
+        epgx_op f = rs[nd], c = rs[nd + 1], c2 = nop;
+        f.code = EPGX_OP_TRC;
+        c.aux = rs[nd + 2].aux;
+        close_into(c);
+        c2.code = EPGX_OP_CONT;
+        if (rs[nd + 2].flags & EPGX_FLAG_SCALE) { c2.flags |= 1; c2.off[0] = rs[nd + 2].off[0]; c2.pat[0] = rs[nd + 2].pat[0]; }
+        if (nd) { c2.flags |= 2; c2.off[1] = rs[0].off[0]; c2.pat[1] = rs[0].pat[0]; }
+        st.push_back(f);
+        st.push_back(c);
+        st.push_back(c2);
+        continue;
+      }
+      for (int r = 0; r < sg.count; ++r) {
+        if (rs[r].code == EPGX_OP_FUSED && (int)(st.size() % CH) == CH - 1) st.push_back(nop);
+        st.push_back(rs[r]);
+      }
+      st.push_back(seg_rec(sg.shift, sg.n_old, sg.n_new, sg.flags, next_nact));
     }
-  }
-  {
-    // TR records start at even stream positions (NOP padding) so that a tape window can hold TAPE_CHUNK / 2 of
-    // them; windows made only of plain TRs are flagged for the kernel's vectorised fast path
-    std::vector<epgx_op> al;
-    epgx_op nop;
-    memset(&nop, 0, sizeof(nop));
-    for (size_t i = 0; i < pl->stream.size(); ++i) {
-      const epgx_op &o = pl->stream[i];
-      if (o.code == EPGX_OP_TR && (al.size() & 1)) al.push_back(nop);
-      if (o.code == EPGX_OP_FUSED && (int)(al.size() % epgx::TAPE_CHUNK) == epgx::TAPE_CHUNK - 1) al.push_back(nop);
-      al.push_back(o);
-    }
-    pl->stream.swap(al);
-    std::vector<epgx_op> &st = pl->stream;
-    for (size_t b = 0; b + epgx::TAPE_CHUNK <= st.size(); b += epgx::TAPE_CHUNK) {
+    for (size_t b0 = 0; b0 + CH <= st.size(); b0 += CH) {
       bool pure = true;
-      for (int j = 0; pure && j < epgx::TAPE_CHUNK; j += 2)
-        pure = st[b + j].code == EPGX_OP_TR && st[b + j + 1].flags == 2; // (shift + 1) | segflags << 2 == 2
-      if (pure) st[b].flags |= 0x8000;
+      for (int j = 0; pure && j < CH; j += 2) pure = st[b0 + j].code == EPGX_OP_TR && st[b0 + j + 1].flags == 2;
+      if (pure) st[b0].flags |= 0x8000;
+      bool purec = st[b0 + CH - 1].code == EPGX_OP_NOP;
+      for (int j = 0; purec && j + 3 <= CH - 1; j += 3) purec = st[b0 + j].code == EPGX_OP_TRC && st[b0 + j + 1].flags == 2;
+      if (purec) st[b0].flags |= 0x4000;
     }
   }
   pl->tape.ops = pl->ops.data();

@@ -21,6 +21,11 @@
 // bit of the first word (flags bit 15) of the FIRST record of a tape window: the window consists of
 // TAPE_CHUNK / 2 EPGX_OP_TR record pairs with shift = +1 and no segment flags
 #define EPGX_CHUNK_PURE_TR 0x80000000
+// complex counterpart: [D?] [FUSED (any pulse kind)] [ADC(F0, optional scale)] + the segment's close, in three
+// records: FUSED as TRC; CONT' as for TR; CONT2: flags bit 0 = ADC scale in off[0] / pat[0], bit 1 = D table in
+// off[1] / pat[1].  A window of TAPE_CHUNK records holds (TAPE_CHUNK - 1) / 3 of them (flags bit 14).
+#define EPGX_OP_TRC 66
+#define EPGX_CHUNK_PURE_TRC 0x40000000
 
 namespace epgx {
 

@@ -22,8 +22,70 @@ namespace epgx {
 
 constexpr int TAPE_CHUNK = 64; // records per shared-memory tape window
 
+constexpr int TRC_PER_WINDOW = (TAPE_CHUNK - 1) / 3; // whole-TR triples per tape window
+constexpr int TRC_REALS = 14;                        // staged coefficients per TR (13 used)
+
+// One tape window of whole-TR triples ([D] . fused E.T.E of any pulse kind . ADC with optional phase . unit shift
+// +1) for one atom per warp, K active slots at compile time: the complex counterpart of tr_window in
+// epgx_real.cuh.  The per-TR coefficients were decoded, gathered and fused by the lanes in parallel and staged in
+// shared memory (cw / ci); each TR reads them back with broadcast loads.
+template <typename real, int NS, int K>
+__device__ __forceinline__ void trc_window(real (&Pr)[NS], real (&Pi)[NS], real (&Mr)[NS], real (&Mi)[NS], real (&Zr)[NS],
+                                           real (&Zi)[NS], const real *cw, const int *ci, int ntr, const real *coef, int C,
+                                           int lane, bool valid, bool is_first, bool is_last, int srcUp, int srcDn,
+                                           typename vec2<real>::type *sig, long long sig_stride, long long a_rel) {
+  typedef typename vec2<real>::type real2;
+  const unsigned FULL = 0xffffffffu;
+  if constexpr (K <= NS) {
+#pragma unroll 1
+    for (int j = 0; j < ntr; ++j) {
+      const real *c = cw + j * TRC_REALS;
+      Fused8<real> f;
+      f.a = c[0]; f.w = c[1]; f.Br = c[2]; f.Bi = c[3]; f.Ur = c[4]; f.Ui = c[5]; f.Hr = c[6]; f.Hi = c[7];
+      f.fzr = c[8]; f.fzi = c[9]; f.zz = c[10];
+      const real fr = c[11], fi = c[12];
+      const int row = ci[4 * j], dbase = ci[4 * j + 1];
+      if (dbase >= 0) { // diffusion attenuation of the order held by each slot
+#pragma unroll
+        for (int s = 0; s < K; ++s) {
+          const real *d = coef + dbase + 3 * min(s * 32 + lane, C - 1);
+          const real dp = ldc(d), dm = ldc(d + 1), dl = ldc(d + 2);
+          Pr[s] *= dp; Pi[s] *= dp; Mr[s] *= dm; Mi[s] *= dm; Zr[s] *= dl; Zi[s] *= dl;
+        }
+      }
+#pragma unroll
+      for (int s = 0; s < K; ++s) {
+        const Tri<real> t_ = {Pr[s], Pi[s], Mr[s], Mi[s], Zr[s], Zi[s]};
+        const Tri<real> o_ = form_t8(t_, f);
+        Pr[s] = o_.pr; Pi[s] = o_.pi; Mr[s] = o_.mr; Mi[s] = o_.mi; Zr[s] = o_.zr; Zi[s] = o_.zi;
+      }
+      if (lane == 0) {
+        Pr[0] += f.fzr; Pi[0] += f.fzi; Mr[0] += f.fzr; Mi[0] -= f.fzi; Zr[0] += f.zz;
+        if (valid) sig[(long long)row * sig_stride + a_rel] = real2{Pr[0] * fr - Pi[0] * fi, Pr[0] * fi + Pi[0] * fr};
+      }
+      // unit shift +1: F+(k) <- F+(k-1), F+(0) <- conj F-(1), F-(k) <- F-(k+1)
+      const real c1r = __shfl_sync(FULL, Mr[0], 1), c1i = -__shfl_sync(FULL, Mi[0], 1);
+#pragma unroll
+      for (int s = K - 1; s >= 0; --s) {
+        const real vr = is_last ? (s > 0 ? Pr[s > 0 ? s - 1 : 0] : c1r) : Pr[s];
+        const real vi = is_last ? (s > 0 ? Pi[s > 0 ? s - 1 : 0] : c1i) : Pi[s];
+        Pr[s] = __shfl_sync(FULL, vr, srcUp);
+        Pi[s] = __shfl_sync(FULL, vi, srcUp);
+      }
+      real kr = real(0), ki = real(0);
+#pragma unroll
+      for (int s = K - 1; s >= 0; --s) {
+        const real cr_ = Mr[s], ci_ = Mi[s];
+        Mr[s] = __shfl_sync(FULL, is_first ? kr : cr_, srcDn);
+        Mi[s] = __shfl_sync(FULL, is_first ? ki : ci_, srcDn);
+        kr = cr_; ki = ci_;
+      }
+    }
+  }
+}
+
 template <typename real, int NS>
-__global__ void __launch_bounds__(256) reg_kernel(const KParams p) {
+__global__ void __launch_bounds__(256, (6 * NS * sizeof(real) <= 384 ? 2 : 1)) reg_kernel(const KParams p) {
   typedef typename vec2<real>::type real2;
   extern __shared__ __align__(16) unsigned char smem_raw[];
 
@@ -54,6 +116,10 @@ __global__ void __launch_bounds__(256) reg_kernel(const KParams p) {
   int4 *tbuf = (int4 *)smem_raw;
   int *patoff = (int *)(tbuf + 2 * TAPE_CHUNK * 2) + al * p.npattern;
   real2 *xbuf = (real2 *)((int *)(tbuf + 2 * TAPE_CHUNK * 2) + ((p.A * p.npattern + 3) & ~3));
+  // staged whole-TR coefficients of this warp (one atom per warp only): [TRC_PER_WINDOW][TRC_REALS] reals + [..][4] ints
+  real *cwbuf = (real *)(xbuf + (G > 32 ? (size_t)2 * p.A * W * 2 * NS : 0)) + (size_t)(tid >> 5) * TRC_PER_WINDOW * TRC_REALS;
+  int *cibuf = (int *)((real *)(xbuf + (G > 32 ? (size_t)2 * p.A * W * 2 * NS : 0)) + (size_t)(blockDim.x >> 5) * TRC_PER_WINDOW * TRC_REALS) +
+               (size_t)(tid >> 5) * TRC_PER_WINDOW * 4;
   {
     int idx[EPGX_MAX_DIMS];
     long long r = atom;
@@ -212,6 +278,45 @@ _Pragma("unroll") \
     }
     const int4 *tb = tbuf + (chunk & 1) * 2 * TAPE_CHUNK;
     const int cnt = min(TAPE_CHUNK, p.nstream - base);
+    if (G == 32 && (tb[0].x & EPGX_CHUNK_PURE_TRC)) {
+      // ---- fast path: the window holds TRC_PER_WINDOW whole-TR triples.  Phase 1: lane j decodes TR j, gathers and
+      // fuses its coefficients and stages them in shared memory; phase 2 (trc_window) runs the TRs in order.
+      int need = 0;
+      if (lw < TRC_PER_WINDOW) {
+        const int4 a0 = tb[6 * lw], a1 = tb[6 * lw + 1], b0 = tb[6 * lw + 2], b1 = tb[6 * lw + 3];
+        const int4 c0 = tb[6 * lw + 4], c1 = tb[6 * lw + 5];
+        const int fl = (a0.x >> 16) & 0xffff, f2 = (c0.x >> 16) & 0xffff;
+        const real *ca = coef + (unsigned)a0.w + patoff[(a1.y >> 8) & 0xff];
+        const real *cb = coef + (unsigned)b0.z + patoff[b1.y & 0xff];
+        real ta, tw, tBr, tBi, tUr, tUi;
+        fused_pulse<real>(coef + (unsigned)a0.z + patoff[a1.y & 0xff], fl, ta, tw, tBr, tBi, tUr, tUi);
+        const Fused8<real> f = fuse8<real>(ta, tw, tBr, tBi, tUr, tUi, fl & EPGX_FLAG_PRE, ldc(ca), ldc(ca + 1),
+                                           ldc(coef + (unsigned)a1.x + patoff[(a1.y >> 16) & 0xff]), fl & EPGX_FLAG_POST,
+                                           ldc(cb), ldc(cb + 1), ldc(coef + (unsigned)b0.w + patoff[(b1.y >> 8) & 0xff]), m0);
+        real fr = real(1), fi = real(0);
+        if (f2 & 1) { const real *cs = coef + (unsigned)c0.z + patoff[c1.y & 0xff]; fr = ldc(cs); fi = ldc(cs + 1); }
+        real *c = cwbuf + lw * TRC_REALS;
+        c[0] = f.a; c[1] = f.w; c[2] = f.Br; c[3] = f.Bi; c[4] = f.Ur; c[5] = f.Ui; c[6] = f.Hr; c[7] = f.Hi;
+        c[8] = f.fzr; c[9] = f.fzi; c[10] = f.zz; c[11] = fr; c[12] = fi;
+        cibuf[4 * lw] = b0.y;                                                                  // ADC row
+        cibuf[4 * lw + 1] = (f2 & 2) ? (int)((unsigned)c0.w + (unsigned)patoff[(c1.y >> 8) & 0xff]) : -1; // D table
+        const int nnew = (int)((unsigned)b1.x & 0xffff), nxt = b1.z;
+        need = max(nnew >> 5, nxt < 0 ? -1 : nxt >> 5) + 1;
+        if (lw == TRC_PER_WINDOW - 1) cibuf[4 * lw + 2] = nxt;
+      }
+      need = max(__reduce_max_sync(FULL, need), nslot);
+      __syncwarp();
+#define TRCW(K_) case K_: trc_window<real, NS, K_>(Pr, Pi, Mr, Mi, Zr, Zi, cwbuf, cibuf, TRC_PER_WINDOW, coef, p.C, lane, valid, is_first, is_last, srcUp, srcDn, sig, p.sig_stride, a_rel); break;
+      switch (need) {
+        TRCW(1) TRCW(2) TRCW(3) TRCW(4) TRCW(5) TRCW(6) TRCW(7) TRCW(8) TRCW(9) TRCW(10) TRCW(11) TRCW(12) TRCW(13) TRCW(14) TRCW(15) TRCW(16)
+      default: break;
+      }
+#undef TRCW
+      nact = cibuf[4 * (TRC_PER_WINDOW - 1) + 2];
+      nslot = nact < 0 ? 0 : (nact >> lgG) + 1;
+      __syncwarp();
+      continue;
+    }
     for (int r = 0; r < cnt; ++r) {
       const int4 r0 = tb[2 * r], r1 = tb[2 * r + 1];
       const int code = r0.x & 0xffff, flags = (r0.x >> 16) & 0xffff, aux = r0.y;
@@ -311,6 +416,36 @@ _Pragma("unroll") \
       case EPGX_OP_SEG: {
         // end of a segment: unit shift / reset of the previous one, then the next pass's order count
         DO_SEG((int)off0, (int)off1, (int)off2, r1.z, aux)
+      } break;
+      case EPGX_OP_TRC: {
+        // [D] . FUSED . ADC(optional scale) . segment close, in three records (see epgx_common.cuh)
+        const int4 q0 = tb[2 * r + 2], q1 = tb[2 * r + 3], w0 = tb[2 * r + 4], w1 = tb[2 * r + 5];
+        const int f2 = (w0.x >> 16) & 0xffff;
+        if (f2 & 2) {
+          const real *c = coef + (unsigned)w0.w + patoff[(w1.y >> 8) & 0xff];
+          DUFF(nslot, {
+            const int k = min(s * G + lane, p.C - 1);
+            const real dp = ldc(c + 3 * k), dm = ldc(c + 3 * k + 1), dl = ldc(c + 3 * k + 2);
+            Pr[s] *= dp; Pi[s] *= dp; Mr[s] *= dm; Mi[s] *= dm; Zr[s] *= dl; Zi[s] *= dl;
+          })
+        }
+        const real *ca = coef + off1 + patoff[pat1];
+        const real *cb = coef + (unsigned)q0.z + patoff[q1.y & 0xff];
+        real ta, tw, tBr, tBi, tUr, tUi;
+        fused_pulse<real>(coef + off0 + patoff[pat0], flags, ta, tw, tBr, tBi, tUr, tUi);
+        const Fused8<real> f = fuse8<real>(ta, tw, tBr, tBi, tUr, tUi, flags & EPGX_FLAG_PRE, ldc(ca), ldc(ca + 1),
+                                           ldc(coef + off2 + patoff[pat2]), flags & EPGX_FLAG_POST, ldc(cb), ldc(cb + 1),
+                                           ldc(coef + (unsigned)q0.w + patoff[(q1.y >> 8) & 0xff]), m0);
+        FOR_SLOTS(form_t8(t_, f))
+        if (lane == 0 && nslot > 0) { Pr[0] += f.fzr; Pi[0] += f.fzi; Mr[0] += f.fzr; Mi[0] -= f.fzi; Zr[0] += f.zz; }
+        if (lane == 0 && valid) {
+          real fr = real(1), fi = real(0);
+          if (f2 & 1) { const real *cs = coef + (unsigned)w0.z + patoff[w1.y & 0xff]; fr = ldc(cs); fi = ldc(cs + 1); }
+          sig[(long long)q0.y * p.sig_stride + a_rel] = real2{Pr[0] * fr - Pi[0] * fi, Pr[0] * fi + Pi[0] * fr};
+        }
+        const int segw = (q0.x >> 16) & 0xffff; // (shift + 1) | segment flags << 2
+        DO_SEG((segw & 3) - 1, (int)((unsigned)q1.x >> 16), (int)((unsigned)q1.x & 0xffff), segw >> 2, q1.z)
+        r += 2;
       } break;
       case EPGX_OP_TR: {
         // one whole TR: FUSED (E.T.E, RE kind) + plain ADC + the segment's unit shift (see epgx.cu)
