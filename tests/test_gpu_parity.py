@@ -216,6 +216,31 @@ def test_real_kernel_is_chosen_for_fisp_and_refused_otherwise(epg):
         plan.set_variant(kernel=3)
 
 
+@pytest.mark.parametrize("dtype", ["f64", "f32"])
+@pytest.mark.parametrize("diffusion,phase,spoil", [(True, True, 117.0), (False, True, 50.0), (True, False, 0.0), (False, False, 90.0)])
+def test_complex_whole_tr_windows(diffusion, phase, spoil, dtype, epg):
+    """200-TR gradient-echo trains ([D] . E.T.E . ADC(phase) . S): several pure whole-TR windows of the complex
+    register kernel, against the ring kernel (FP64) and the oracle"""
+    def build(e, ntr=200):
+        T1 = np.array([600.0, 1200.0, 1500.0])
+        T2 = np.array([[40.0, 80.0]])
+        seq = []
+        for n in range(ntr):
+            ph = spoil * n * (n + 1) / 2
+            seq += [e.T(12 + n % 30, ph), e.E(2, T1, T2), e.Adc(phase=-ph) if phase else e.ADC, e.E(7, T1, T2), e.S(1)]
+            if diffusion:
+                seq += [e.D(9.0, 1.5e-3, k=1)]
+        return seq
+
+    case = {"seq": build(epg), "options": {"kvalue": 800.0}}
+    ring, _ = _run_variant(epg, case, kernel=1)
+    got, cfg = _run_variant(epg, case, dtype=dtype, kernel=2, lanes_per_atom=32)
+    assert cfg["kernel"] == 1
+    assert rel_err(got[0], ring[0]) < (1e-12 if dtype == "f64" else RTOL32)
+    ref = oracle_api.O.simulate(build(oracle_api.epg), kvalue=800.0)
+    assert rel_err(ring[0], ref) < RTOL64
+
+
 @pytest.mark.parametrize("vars_per_pass", [1, 3])
 @pytest.mark.parametrize("name", ["fisp_jac_pulses", "jac_all_params", "mse_jac"])
 def test_variable_tiling(name, vars_per_pass, golden, epg):
