@@ -399,7 +399,7 @@ def main():
         }
         cpu = None
         if not args.no_cpu and world == 1:
-            v, atoms, wall, side = cpu_reference(args.ntr, max_nstate, 1, args.cpu_atoms, grid)
+            v, atoms, wall, side = cpu_reference(args.ntr, max_nstate, 1, 216, grid)  # 6^3 atoms: 10-20 s on one core
             cpu = {"value": v, "unit": "atoms/s", "cores": 1, "kind": "port",
                    "sample": f"{side}^3 = {atoms} atoms of the bench grid, same {args.ntr}-TR sequence, {wall:.1f} s, numpy oracle port"}
         line = {

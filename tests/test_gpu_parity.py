@@ -315,3 +315,18 @@ def test_linearity_and_density_scaling(epg):
     parts, _ = functions.run_lowered(low)
     c = functions._assemble(low, parts)[0]
     assert rel_err(c, a) < 1e-14
+
+
+def test_simulate_over_several_devices_of_one_process(golden, epg):
+    """simulate(device=[0, 1]): contiguous atom slabs on two devices of one process, no inter-device traffic"""
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    ref = golden("mse_grid")["signal"]
+    sig = epg.simulate(cases.mse_grid(epg)["seq"], device=[0, 1])
+    assert rel_err(sig, ref) < RTOL64
+    case = cases.fisp_jac_global(epg)
+    sig, jac = epg.simulate(case["seq"], probe=[None, epg.Jacobian(case["jac"])], device=[1, 0])
+    assert rel_err(sig, golden("fisp_jac_global")["signal"]) < RTOL64
+    assert rel_err(jac, golden("fisp_jac_global")["jacobian"]) < RTOL64
