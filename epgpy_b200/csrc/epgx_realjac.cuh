@@ -227,35 +227,11 @@ __global__ void __launch_bounds__(256) realjac_kernel(const KParams p) {
     }
     const int4 *tb = tbuf + (chunk & 1) * 2 * TAPE_CHUNK;
     const int cnt = min(TAPE_CHUNK, p.nstream - base);
-    // software pipeline: the header and the (up to four) coefficients of record r + 1 are fetched while record r
-    // computes, so the LDS -> LDS -> LDG chain of a record is off the critical path
-    int4 nr0 = tb[0], nr1 = tb[1];
-    real nc0 = real(0), nc1 = real(0), nc2 = real(0), nc3 = real(0);
-#define RJ_FETCH(R0, R1)                                                                                  \
-    {                                                                                                      \
-      const real *cb0_ = coef + (unsigned)(R0).z + patoff[(R1).y & 0xff];                                  \
-      switch ((R0).x & 0xffff) {                                                                           \
-      case EPGX_OP_T_RE: nc0 = ldc(cb0_); nc1 = ldc(cb0_ + 1); nc2 = ldc(cb0_ + 2); nc3 = ldc(cb0_ + 3); break; \
-      case EPGX_OP_E: nc0 = ldc(cb0_); nc1 = ldc(cb0_ + 1); nc2 = ldc(coef + (unsigned)(R0).w + patoff[((R1).y >> 8) & 0xff]); break; \
-      case EPGX_OP_DIAG: nc0 = ldc(cb0_); nc1 = ldc(cb0_ + 2); nc2 = ldc(cb0_ + 4); nc3 = ldc(cb0_ + 6); break; \
-      case EPGX_OP_PD: nc0 = ldc(cb0_); break;                                                             \
-      case EPGX_OP_ADC: nc0 = real(1); nc1 = real(0);                                                      \
-        if (((R0).x >> 16) & EPGX_FLAG_SCALE) { nc0 = ldc(cb0_); nc1 = ldc(cb0_ + 1); } break;             \
-      default: break;                                                                                      \
-      }                                                                                                    \
-    }
-    RJ_FETCH(nr0, nr1)
     for (int r = 0; r < cnt; ++r) {
-      const int4 r0 = nr0, r1 = nr1;
-      const real c0 = nc0, c1 = nc1, c2 = nc2, c3 = nc3;
-      if (r + 1 < cnt) {
-        nr0 = tb[2 * r + 2]; nr1 = tb[2 * r + 3];
-        RJ_FETCH(nr0, nr1)
-      }
+      const int4 r0 = tb[2 * r], r1 = tb[2 * r + 1];
       const int code = r0.x & 0xffff, flags = (r0.x >> 16) & 0xffff, aux = r0.y;
       const unsigned off0 = (unsigned)r0.z, off1 = (unsigned)r0.w, off2 = (unsigned)r1.x;
       const int pat0 = r1.y & 0xff, pat1 = (r1.y >> 8) & 0xff;
-      (void)off1; (void)pat1; (void)c3;
       const bool on_base = flags & EPGX_FLAG_BASE, on_part = flags & EPGX_FLAG_PARTIALS;
       const bool inject = flags & EPGX_FLAG_INJECT;
       const int iset = aux - v0 + 1; // target set of an injection
@@ -275,15 +251,19 @@ __global__ void __launch_bounds__(256) realjac_kernel(const KParams p) {
 
       switch (code) {
       case EPGX_OP_T_RE: {
-        const real a = c0, w = c1, b = c2, u = c3, h = real(-0.5) * u;
+        const real *c = coef + off0 + patoff[pat0];
+        const real a = ldc(c), w = ldc(c + 1), b = ldc(c + 2), u = ldc(c + 3), h = real(-0.5) * u;
         LIN5(a, w, b, u, h)
       } break;
       case EPGX_OP_E: {
-        const real e1 = c0, z0 = c1 * m0, e2 = c2;
+        const real *c0 = coef + off0 + patoff[pat0];
+        const real e1 = ldc(c0), z0 = ldc(c0 + 1) * m0;
+        const real e2 = ldc(coef + off1 + patoff[pat1]);
         DIAG3(e2, e2, e1, z0)
       } break;
       case EPGX_OP_DIAG: { // real entries only (checked by the host): (aP, 0, aM, 0, aZ, 0, a0, 0)
-        const real dp = c0, dm = c1, dz = c2, z0 = c3 * m0;
+        const real *c = coef + off0 + patoff[pat0];
+        const real dp = ldc(c), dm = ldc(c + 2), dz = ldc(c + 4), z0 = ldc(c + 6) * m0;
         DIAG3(dp, dm, dz, z0)
       } break;
       case EPGX_OP_D: {
@@ -308,11 +288,15 @@ __global__ void __launch_bounds__(256) realjac_kernel(const KParams p) {
           }
         break;
       case EPGX_OP_PD:
-        m0 = c0;
+        m0 = ldc(coef + off0 + patoff[pat0]);
         break;
       case EPGX_OP_ADC:
         if (lane == 0 && valid) {
-          const real fr = c0, fi = c1;
+          real fr = real(1), fi = real(0);
+          if (flags & EPGX_FLAG_SCALE) {
+            const real *c = coef + off0 + patoff[pat0];
+            fr = ldc(c); fi = ldc(c + 1);
+          }
           const bool z0 = flags & EPGX_FLAG_Z0;
           if (on_base && blockIdx.y == 0) {
             const real x = z0 ? Z[0][0] : P[0][0];
@@ -363,7 +347,6 @@ __global__ void __launch_bounds__(256) realjac_kernel(const KParams p) {
 #undef LIN5
 #undef DIAG3
     }
-#undef RJ_FETCH
   }
 }
 
