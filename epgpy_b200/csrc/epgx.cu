@@ -9,10 +9,7 @@
 #include <vector>
 
 #include "epgx_common.cuh"
-#include "epgx_reg.cuh"
-#include "epgx_real.cuh"
-#include "epgx_realjac.cuh"
-#include "epgx_ring.cuh"
+#include "epgx_launch.h"
 
 using namespace epgx;
 
@@ -127,7 +124,7 @@ static int choose_variant(epgx_plan *pl, int kernel, int lanes, int vars, int at
         c.var_tiles = (t.nvar + 2) / 3;
         c.atoms_per_cta = A;
         c.threads_per_cta = A * G;
-        c.smem_bytes = 2 * epgx::TAPE_CHUNK * 32 + ((A * t.npattern + 3) & ~3) * 4 + (W > 1 ? 2 * A * W * 4 * 2 * NS * rsz : 0) + 32;
+        c.smem_bytes = 2 * epgx::kTapeChunk * 32 + ((A * t.npattern + 3) & ~3) * 4 + (W > 1 ? 2 * A * W * 4 * 2 * NS * rsz : 0) + 32;
         c.ring = C;
         return EPGX_OK;
       }
@@ -155,7 +152,7 @@ static int choose_variant(epgx_plan *pl, int kernel, int lanes, int vars, int at
       c.var_tiles = 1;
       c.atoms_per_cta = A;
       c.threads_per_cta = A * G;
-      c.smem_bytes = 2 * epgx::TAPE_CHUNK * 32 + ((A * t.npattern + 3) & ~3) * 4 + 32;
+      c.smem_bytes = 2 * epgx::kTapeChunk * 32 + ((A * t.npattern + 3) & ~3) * 4 + 32;
       c.ring = C;
       return EPGX_OK;
     }
@@ -188,8 +185,8 @@ static int choose_variant(epgx_plan *pl, int kernel, int lanes, int vars, int at
         c.var_tiles = 1;
         c.atoms_per_cta = A;
         c.threads_per_cta = A * G;
-        c.smem_bytes = 2 * epgx::TAPE_CHUNK * 32 + ((A * t.npattern + 3) & ~3) * 4 + (W > 1 ? 2 * A * W * 2 * NS * 2 * rsz : 0) +
-                       ((A * G + 31) / 32) * epgx::TRC_PER_WINDOW * (epgx::TRC_REALS * rsz + 16) + 64;
+        c.smem_bytes = 2 * epgx::kTapeChunk * 32 + ((A * t.npattern + 3) & ~3) * 4 + (W > 1 ? 2 * A * W * 2 * NS * 2 * rsz : 0) +
+                       ((A * G + 31) / 32) * epgx::kTrcPerWindow * (epgx::kTrcReals * rsz + 16) + 64;
         c.ring = C;
         return EPGX_OK;
       }
@@ -412,7 +409,7 @@ extern "C" int epgx_plan_create(const epgx_tape *t, epgx_plan **out) {
     std::vector<epgx_op> &st = pl->stream;
     epgx_op nop;
     memset(&nop, 0, sizeof(nop));
-    const int CH = epgx::TAPE_CHUNK;
+    const int CH = epgx::kTapeChunk;
     st.push_back(seg_rec(0, 0, 0, 0, t->nseg ? t->segs[0].nact : -1));
     for (int64_t i = 0; i < t->nseg; ++i) {
       const epgx_segment &sg = t->segs[i];
@@ -536,84 +533,27 @@ extern "C" int epgx_plan_upload(const epgx_plan *pl, void *ws, void *stream) {
   return EPGX_OK;
 }
 
-template <typename real, int NP, int NVT>
-static int launch_ring(const epgx_plan *pl, const KParams &kp, cudaStream_t st) {
+static int dispatch(const epgx_plan *pl, const KParams &kp, cudaStream_t st) {
   const epgx_config &c = pl->cfg;
-  auto kern = ring_kernel<real, NP, NVT>;
-  CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, c.smem_bytes));
+  const bool f64 = pl->tape.dtype == EPGX_F64;
   dim3 grid((unsigned)((kp.atom_count + c.atoms_per_cta - 1) / c.atoms_per_cta), (unsigned)c.var_tiles);
-  kern<<<grid, c.threads_per_cta, c.smem_bytes, st>>>(kp);
-  CUDA_TRY(cudaGetLastError());
-  return EPGX_OK;
-}
-
-template <typename real, int NS> static int launch_reg(const epgx_plan *pl, const KParams &kp, cudaStream_t st) {
-  const epgx_config &c = pl->cfg;
-  auto kern = reg_kernel<real, NS>;
-  dim3 grid((unsigned)((kp.atom_count + c.atoms_per_cta - 1) / c.atoms_per_cta), 1);
-  kern<<<grid, c.threads_per_cta, c.smem_bytes, st>>>(kp);
-  CUDA_TRY(cudaGetLastError());
-  return EPGX_OK;
-}
-
-template <typename real> static int dispatch_reg(const epgx_plan *pl, const KParams &kp, cudaStream_t st) {
-  switch (pl->cfg.slots_per_lane) {
-  case 1: return launch_reg<real, 1>(pl, kp, st);
-  case 2: return launch_reg<real, 2>(pl, kp, st);
-  case 4: return launch_reg<real, 4>(pl, kp, st);
-  case 8: return launch_reg<real, 8>(pl, kp, st);
-  case 16: return launch_reg<real, 16>(pl, kp, st);
+  cudaError_t e;
+  switch (c.kernel) {
+  case 3: e = f64 ? launch_realjac<double>(c.slots_per_lane, kp, grid, c.threads_per_cta, c.smem_bytes, st)
+                  : launch_realjac<float>(c.slots_per_lane, kp, grid, c.threads_per_cta, c.smem_bytes, st); break;
+  case 2: e = f64 ? launch_real<double>(c.slots_per_lane, kp, grid, c.threads_per_cta, c.smem_bytes, st)
+                  : launch_real<float>(c.slots_per_lane, kp, grid, c.threads_per_cta, c.smem_bytes, st); break;
+  case 1: e = f64 ? launch_reg<double>(c.slots_per_lane, kp, grid, c.threads_per_cta, c.smem_bytes, st)
+                  : launch_reg<float>(c.slots_per_lane, kp, grid, c.threads_per_cta, c.smem_bytes, st); break;
+  default: e = f64 ? launch_ring<double>(pl->tape.npool, c.vars_per_pass, kp, grid, c.threads_per_cta, c.smem_bytes, st)
+                   : launch_ring<float>(pl->tape.npool, c.vars_per_pass, kp, grid, c.threads_per_cta, c.smem_bytes, st);
   }
-  return fail(EPGX_ERR_UNSUPPORTED, "no register-kernel instance for slots_per_lane=" + std::to_string(pl->cfg.slots_per_lane));
-}
-
-template <typename real, int NS> static int launch_real(const epgx_plan *pl, const KParams &kp, cudaStream_t st) {
-  const epgx_config &c = pl->cfg;
-  auto kern = real_kernel<real, NS>;
-  dim3 grid((unsigned)((kp.atom_count + c.atoms_per_cta - 1) / c.atoms_per_cta), 1);
-  kern<<<grid, c.threads_per_cta, c.smem_bytes, st>>>(kp);
-  CUDA_TRY(cudaGetLastError());
+  if (e == cudaErrorInvalidValue)
+    return fail(EPGX_ERR_UNSUPPORTED, "no kernel instance for kernel=" + std::to_string(c.kernel) + " slots=" +
+                                          std::to_string(c.slots_per_lane) + " npool=" + std::to_string(pl->tape.npool) +
+                                          " vars_per_pass=" + std::to_string(c.vars_per_pass));
+  if (e != cudaSuccess) return fail(EPGX_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(e));
   return EPGX_OK;
-}
-
-template <typename real> static int dispatch_real(const epgx_plan *pl, const KParams &kp, cudaStream_t st) {
-  switch (pl->cfg.slots_per_lane) {
-  case 1: return launch_real<real, 1>(pl, kp, st);
-  case 2: return launch_real<real, 2>(pl, kp, st);
-  case 4: return launch_real<real, 4>(pl, kp, st);
-  case 8: return launch_real<real, 8>(pl, kp, st);
-  case 16: return launch_real<real, 16>(pl, kp, st);
-  case 32: return launch_real<real, 32>(pl, kp, st);
-  }
-  return fail(EPGX_ERR_UNSUPPORTED, "no real-kernel instance for slots_per_lane=" + std::to_string(pl->cfg.slots_per_lane));
-}
-
-template <typename real, int NS> static int launch_realjac(const epgx_plan *pl, const KParams &kp, cudaStream_t st) {
-  const epgx_config &c = pl->cfg;
-  auto kern = realjac_kernel<real, NS, 3>;
-  dim3 grid((unsigned)((kp.atom_count + c.atoms_per_cta - 1) / c.atoms_per_cta), (unsigned)c.var_tiles);
-  kern<<<grid, c.threads_per_cta, c.smem_bytes, st>>>(kp);
-  CUDA_TRY(cudaGetLastError());
-  return EPGX_OK;
-}
-
-template <typename real> static int dispatch_realjac(const epgx_plan *pl, const KParams &kp, cudaStream_t st) {
-  switch (pl->cfg.slots_per_lane) {
-  case 1: return launch_realjac<real, 1>(pl, kp, st);
-  case 2: return launch_realjac<real, 2>(pl, kp, st);
-  case 4: return launch_realjac<real, 4>(pl, kp, st);
-  case 8: return launch_realjac<real, 8>(pl, kp, st);
-  }
-  return fail(EPGX_ERR_UNSUPPORTED, "no real-derivative-kernel instance for slots_per_lane=" + std::to_string(pl->cfg.slots_per_lane));
-}
-
-template <typename real> static int dispatch_ring(const epgx_plan *pl, const KParams &kp, cudaStream_t st) {
-  const int np = pl->tape.npool, nvt = pl->cfg.vars_per_pass;
-#define CASE(NP_, NVT_) \
-  if (np == NP_ && nvt == NVT_) return launch_ring<real, NP_, NVT_>(pl, kp, st);
-  CASE(1, 0) CASE(1, 1) CASE(1, 3) CASE(2, 0) CASE(2, 1) CASE(2, 3)
-#undef CASE
-  return fail(EPGX_ERR_UNSUPPORTED, "no kernel instance for npool=" + std::to_string(np) + " vars_per_pass=" + std::to_string(nvt));
 }
 
 extern "C" int epgx_simulate(const epgx_plan *pl, const void *ws, int64_t atom_begin, int64_t atom_count, void *signal,
@@ -661,11 +601,7 @@ extern "C" int epgx_simulate_strided(const epgx_plan *pl, const void *ws, int64_
   kp.m0_pat = t.m0_pat;
   kp.init_n = t.init_n;
   cudaStream_t st = (cudaStream_t)stream;
-  if (pl->cfg.kernel == 3) return t.dtype == EPGX_F64 ? dispatch_realjac<double>(pl, kp, st) : dispatch_realjac<float>(pl, kp, st);
-  if (pl->cfg.kernel == 2) return t.dtype == EPGX_F64 ? dispatch_real<double>(pl, kp, st) : dispatch_real<float>(pl, kp, st);
-  if (pl->cfg.kernel == 1) return t.dtype == EPGX_F64 ? dispatch_reg<double>(pl, kp, st) : dispatch_reg<float>(pl, kp, st);
-  if (t.dtype == EPGX_F64) return dispatch_ring<double>(pl, kp, st);
-  return dispatch_ring<float>(pl, kp, st);
+  return dispatch(pl, kp, st);
 }
 
 extern "C" int epgx_simulate_host(const epgx_plan *pl, int device, int64_t atom_begin, int64_t atom_count, void *signal,

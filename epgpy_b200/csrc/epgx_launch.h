@@ -1,0 +1,16 @@
+// epgx_launch.h -- internal: kernel launchers, one translation unit per kernel family and precision so that the
+// library builds in parallel.  Each returns cudaErrorInvalidValue when no instance matches the keys.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "epgx_common.cuh"
+
+namespace epgx {
+template <typename real> cudaError_t launch_ring(int npool, int nvt, const KParams &kp, dim3 grid, int threads, int smem, cudaStream_t st);
+template <typename real> cudaError_t launch_reg(int slots, const KParams &kp, dim3 grid, int threads, int smem, cudaStream_t st);
+template <typename real> cudaError_t launch_real(int slots, const KParams &kp, dim3 grid, int threads, int smem, cudaStream_t st);
+template <typename real> cudaError_t launch_realjac(int slots, const KParams &kp, dim3 grid, int threads, int smem, cudaStream_t st);
+constexpr int kTapeChunk = 64;      // == TAPE_CHUNK of epgx_reg.cuh (checked there)
+constexpr int kTrcPerWindow = 21;   // == TRC_PER_WINDOW
+constexpr int kTrcReals = 14;       // == TRC_REALS
+} // namespace epgx
