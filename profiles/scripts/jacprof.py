@@ -1,5 +1,5 @@
 import sys, os
-sys.path.insert(0,'/root/repo'); sys.path.insert(0,'/root/repo/tests')
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))); sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import torch, bench_configs as bc
 from epgpy_b200 import engine, epg, lowering
 seq, opts, jac = bc.cfg_fisp(epg, (30,30,30), 1000, jac=True)
