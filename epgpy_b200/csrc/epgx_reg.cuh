@@ -85,7 +85,7 @@ __device__ __forceinline__ void trc_window(real (&Pr)[NS], real (&Pi)[NS], real 
 }
 
 template <typename real, int NS>
-__global__ void __launch_bounds__(256, (6 * NS * sizeof(real) <= 384 ? 2 : 1)) reg_kernel(const KParams p) {
+__global__ void __launch_bounds__(256, (6 * NS * sizeof(real) <= 192 ? 2 : 1)) reg_kernel(const KParams p) {
   typedef typename vec2<real>::type real2;
   extern __shared__ __align__(16) unsigned char smem_raw[];
 
