@@ -115,7 +115,9 @@ static int choose_variant(epgx_plan *pl, int kernel, int lanes, int vars, int at
       const int W = G > 32 ? G / 32 : 1;
       int A = atoms > 0 ? atoms : (128 / G > 0 ? 128 / G : 1);
       if (W > 1 && A > 15) A = 15;
+      if (A > 16 && atoms <= 0) A = 16; // per-atom TRJ coefficient windows in shared memory
       while (A * G > 256 && A > 1) --A;
+      while (A > 1 && A * epgx::kTrjPerWindow * epgx::kTrjReals * rsz > 32 * 1024) --A;
       if (A * G <= 256) {
         c.kernel = 3;
         c.lanes_per_atom = G;
@@ -124,7 +126,8 @@ static int choose_variant(epgx_plan *pl, int kernel, int lanes, int vars, int at
         c.var_tiles = (t.nvar + 2) / 3;
         c.atoms_per_cta = A;
         c.threads_per_cta = A * G;
-        c.smem_bytes = 2 * epgx::kTapeChunk * 32 + ((A * t.npattern + 3) & ~3) * 4 + (W > 1 ? 2 * A * W * 4 * 2 * NS * rsz : 0) + 32;
+        c.smem_bytes = 2 * epgx::kTapeChunk * 32 + ((A * t.npattern + 3) & ~3) * 4 + (W > 1 ? 2 * A * W * 4 * 2 * NS * rsz : 0) +
+                       A * epgx::kTrjPerWindow * epgx::kTrjReals * rsz + 32;
         c.ring = C;
         return EPGX_OK;
       }
@@ -411,9 +414,39 @@ extern "C" int epgx_plan_create(const epgx_tape *t, epgx_plan **out) {
     memset(&nop, 0, sizeof(nop));
     const int CH = epgx::kTapeChunk;
     st.push_back(seg_rec(0, 0, 0, 0, t->nseg ? t->segs[0].nact : -1));
+    // records of every segment (copied: derivative tapes are regrouped below)
+    std::vector<std::vector<epgx_op>> segrecs(t->nseg);
+    for (int64_t i = 0; i < t->nseg; ++i) segrecs[i].assign(t->ops + t->segs[i].first, t->ops + t->segs[i].first + t->segs[i].count);
+    const bool trj_ok = pl->realjac_ok && t->nvar <= 3;
+    const int kAll = EPGX_FLAG_BASE | EPGX_FLAG_PARTIALS;
+    auto is_inj = [&](const epgx_op &o, int code) {
+      if (o.code != code || !(o.flags & EPGX_FLAG_INJECT) || o.aux < 0 || o.aux >= 3) return false;
+      if (code == EPGX_OP_DIAG) { // the fused form needs the same factor on F+ and F-
+        const int64_t end = (int64_t)o.off[0] + pat_span[o.pat[0]] + 8;
+        for (int64_t j = o.off[0]; j < end; j += 8)
+          if (t->coef[j] != t->coef[j + 2]) return false;
+      }
+      return true;
+    };
+    auto is_e = [&](const epgx_op &o) { return o.code == EPGX_OP_E && (o.flags & (kAll | EPGX_FLAG_INJECT | EPGX_FLAG_G)) == kAll; };
+    if (trj_ok) {
+      // a trailing [INJECT(DIAG)* E] group acts identically on every order: it commutes with the unit shift and
+      // becomes the head of the next segment (the derivative counterpart of the E_pre hop of fuse_records)
+      for (int64_t i = 0; i + 1 < t->nseg; ++i) {
+        const epgx_segment &sg = t->segs[i];
+        std::vector<epgx_op> &rs = segrecs[i];
+        if (sg.shift == 0 || (sg.flags & EPGX_SEG_RESET) || rs.empty() || !is_e(rs.back()) || segrecs[i + 1].empty()) continue;
+        size_t b = rs.size() - 1;
+        while (b > 0 && is_inj(rs[b - 1], EPGX_OP_DIAG)) --b;
+        if (b == 0) continue; // keep at least one record (the ADC) in the segment
+        segrecs[i + 1].insert(segrecs[i + 1].begin(), rs.begin() + b, rs.end());
+        rs.erase(rs.begin() + b, rs.end());
+      }
+    }
     for (int64_t i = 0; i < t->nseg; ++i) {
-      const epgx_segment &sg = t->segs[i];
-      const epgx_op *rs = t->ops + sg.first;
+      epgx_segment sg = t->segs[i];
+      sg.count = (int)segrecs[i].size();
+      const epgx_op *rs = segrecs[i].data();
       const int next_nact = i + 1 < t->nseg ? t->segs[i + 1].nact : -1;
       const bool small = sg.n_old < 65536 && sg.n_new < 65536;
       auto close_into = [&](epgx_op &c) { // closing information of the segment in a CONT' record
@@ -448,6 +481,49 @@ extern "C" int epgx_plan_create(const epgx_tape *t, epgx_plan **out) {
         st.push_back(c2);
         continue;
       }
+      if (trj_ok && small) {
+        // [INJ(DIAG)*] [E]? [INJ(T_RE)*] T_RE [INJ(DIAG)*] [E]? ADC  ->  one TRJ group of five records
+        int pg[3] = {-1, -1, -1}, tg[3] = {-1, -1, -1}, qg[3] = {-1, -1, -1}, epre = -1, epost = -1, tt = -1, adc = -1, q = 0;
+        bool ok = true;
+        for (; q < sg.count && is_inj(rs[q], EPGX_OP_DIAG); ++q) { ok = ok && pg[rs[q].aux] < 0; pg[rs[q].aux] = q; }
+        if (q < sg.count && is_e(rs[q])) epre = q++;
+        else ok = ok && pg[0] < 0 && pg[1] < 0 && pg[2] < 0;
+        for (; q < sg.count && is_inj(rs[q], EPGX_OP_T_RE); ++q) { ok = ok && tg[rs[q].aux] < 0; tg[rs[q].aux] = q; }
+        if (q < sg.count && rs[q].code == EPGX_OP_T_RE && (rs[q].flags & (kAll | EPGX_FLAG_INJECT)) == kAll) tt = q++;
+        else ok = false;
+        for (; ok && q < sg.count && is_inj(rs[q], EPGX_OP_DIAG); ++q) { ok = ok && qg[rs[q].aux] < 0; qg[rs[q].aux] = q; }
+        if (ok && q < sg.count && is_e(rs[q])) epost = q++;
+        else ok = ok && qg[0] < 0 && qg[1] < 0 && qg[2] < 0;
+        // read-out of F0: one record for the signal row (BASE) and / or one for the Jacobian row (PARTIALS)
+        int jrow = -1;
+        while (ok && q < sg.count && rs[q].code == EPGX_OP_ADC && (rs[q].flags & kAll) && !(rs[q].flags & ~kAll)) {
+          if (rs[q].flags & EPGX_FLAG_BASE) { ok = adc < 0; adc = q; }
+          if (rs[q].flags & EPGX_FLAG_PARTIALS) { ok = ok && jrow < 0; jrow = rs[q].aux1; }
+          ++q;
+        }
+        if (ok && adc >= 0 && q == sg.count) {
+          while ((st.size() % CH) % 5 != 0 || (int)(st.size() % CH) > CH - 5) st.push_back(nop);
+          epgx_op g[5];
+          for (auto &o : g) o = nop;
+          g[0].code = EPGX_OP_TRJ;
+          g[0].flags = (uint16_t)((epre >= 0 ? EPGX_FLAG_PRE : 0) | (epost >= 0 ? EPGX_FLAG_POST : 0) |
+                                  (jrow >= 0 ? EPGX_FLAG_PARTIALS : 0));
+          g[0].off[0] = rs[tt].off[0]; g[0].pat[0] = rs[tt].pat[0];
+          if (epre >= 0) { g[0].off[1] = rs[epre].off[0]; g[0].pat[1] = rs[epre].pat[0]; g[0].off[2] = rs[epre].off[1]; g[0].pat[2] = rs[epre].pat[1]; }
+          for (int k = 1; k < 5; ++k) g[k].code = EPGX_OP_CONT;
+          if (epost >= 0) { g[1].off[0] = rs[epost].off[0]; g[1].pat[0] = rs[epost].pat[0]; g[1].off[1] = rs[epost].off[1]; g[1].pat[1] = rs[epost].pat[1]; }
+          g[1].aux = rs[adc].aux;
+          close_into(g[1]);
+          g[1].rsv1 = jrow; // Jacobian row
+          for (int v = 0; v < 3; ++v) {
+            if (pg[v] >= 0) { g[2].flags |= 1 << v; g[2].off[v] = rs[pg[v]].off[0]; g[2].pat[v] = rs[pg[v]].pat[0]; }
+            if (tg[v] >= 0) { g[3].flags |= 1 << v; g[3].off[v] = rs[tg[v]].off[0]; g[3].pat[v] = rs[tg[v]].pat[0]; }
+            if (qg[v] >= 0) { g[4].flags |= 1 << v; g[4].off[v] = rs[qg[v]].off[0]; g[4].pat[v] = rs[qg[v]].pat[0]; }
+          }
+          for (auto &o : g) st.push_back(o);
+          continue;
+        }
+      }
       for (int r = 0; r < sg.count; ++r) {
         if (rs[r].code == EPGX_OP_FUSED && (int)(st.size() % CH) == CH - 1) st.push_back(nop);
         st.push_back(rs[r]);
@@ -461,6 +537,11 @@ extern "C" int epgx_plan_create(const epgx_tape *t, epgx_plan **out) {
       bool purec = st[b0 + CH - 1].code == EPGX_OP_NOP;
       for (int j = 0; purec && j + 3 <= CH - 1; j += 3) purec = st[b0 + j].code == EPGX_OP_TRC && st[b0 + j + 1].flags == 2;
       if (purec) st[b0].flags |= 0x4000;
+    }
+    for (size_t b0 = 0; b0 < st.size(); b0 += CH) { // windows holding TRJ groups: coefficient assembly pass
+      bool anyj = false;
+      for (size_t j = b0; !anyj && j < st.size() && j < b0 + CH; j += 5) anyj = st[j].code == EPGX_OP_TRJ;
+      if (anyj) st[b0].flags |= 0x2000;
     }
   }
   pl->tape.ops = pl->ops.data();
@@ -507,6 +588,13 @@ extern "C" int epgx_plan_set_variant(epgx_plan *pl, int kernel, int lanes, int v
   pl->cfg.flops_per_atom = pl->cfg.kernel >= 2 ? pl->flops_real : pl->flops_cplx;
   pl->cfg.updates_per_atom = pl->updates;
   return rc;
+}
+
+extern "C" int epgx_plan_stream(const epgx_plan *pl, const epgx_op **records, int64_t *count) {
+  if (!pl || !records || !count) return fail(EPGX_ERR_INVALID, "null argument");
+  *records = pl->stream.data();
+  *count = (int64_t)pl->stream.size();
+  return EPGX_OK;
 }
 
 extern "C" int epgx_plan_workspace_bytes(const epgx_plan *pl, int64_t *bytes) {

@@ -25,6 +25,14 @@
 // records: FUSED as TRC; CONT' as for TR; CONT2: flags bit 0 = ADC scale in off[0] / pat[0], bit 1 = D table in
 // off[1] / pat[1].  A window of TAPE_CHUNK records holds (TAPE_CHUNK - 1) / 3 of them (flags bit 14).
 #define EPGX_OP_TRC 66
+// derivative counterpart (real-valued tapes, <= 3 variables): [INJ(DIAG)*] [E] [INJ(T_RE)*] T_RE [INJ(DIAG)*] [E] ADC
+// + the segment's close, in five records: TRJ (T block, E_pre blocks; flags PRE / POST / PARTIALS),
+// CONT' (E_post blocks, ADC signal row, close), then three CONT records with the blocks of the pre-E, pulse and
+// post-E injections of variables 0..2 (off[v] / pat[v], presence in flags bits 0..2); the Jacobian row rides in rsv1
+// of CONT'.  Groups start at multiples of five records inside a window (<= 12 per window); flags bit 13 of the
+// first record of a window says that it holds at least one of them.
+#define EPGX_OP_TRJ 67
+#define EPGX_CHUNK_ANY_TRJ 0x20000000
 #define EPGX_CHUNK_PURE_TRC 0x40000000
 
 namespace epgx {

@@ -13,4 +13,6 @@ template <typename real> cudaError_t launch_realjac(int slots, const KParams &kp
 constexpr int kTapeChunk = 64;      // == TAPE_CHUNK of epgx_reg.cuh (checked there)
 constexpr int kTrcPerWindow = 21;   // == TRC_PER_WINDOW
 constexpr int kTrcReals = 14;       // == TRC_REALS
+constexpr int kTrjPerWindow = 12;   // == TRJ_PER_WINDOW of epgx_realjac.cuh
+constexpr int kTrjReals = 32;       // == TRJ_REALS: (1 + 3) state sets x 8
 } // namespace epgx

@@ -142,6 +142,109 @@ __device__ __forceinline__ void rj_shift(real (&U)[SETS][NS], real (&D)[SETS][NS
   }
 }
 
+// ---- whole-TR groups of derivative tapes (EPGX_OP_TRJ, see epgx_common.cuh)
+//
+// Every operator of such a TR lies in the five-coefficient class L(a, w, b, u, h):
+//   F+' = a F+ + b F- + u Z ; F-' = b F+ + a F- + u Z ; Z' = w Z + h (F+ + F-)
+// (closed under products; E and the DIAG injections are its diagonal members), so the whole TR collapses to
+//   x' = F x + c_0 ,  y_v' = F y_v + J_v x + c_v          (x base state, y_v partial states, c at k = 0 only)
+// with F = E_post T E_pre and J_v = F P_v + E_post T G_v E_pre + E_post Q_v T E_pre, where P_v / G_v / Q_v are the
+// pre-E, pulse and post-E injection generators of variable v (epgpy/diff.py:264-288 in pre-injected form).
+// The 4 x 7 coefficients of a group (a, w, b, u, h, f, z per state set; f, z per unit M0) are assembled once per
+// tape window by one lane per (group, set) and kept in shared memory; the per-TR path is then straight-line FMAs.
+constexpr int TRJ_PER_WINDOW = 12;
+constexpr int TRJ_REALS = 32;
+static_assert(TRJ_PER_WINDOW == kTrjPerWindow && TRJ_REALS == kTrjReals && TRJ_PER_WINDOW * 5 <= TAPE_CHUNK, "TRJ window layout");
+
+template <typename real>
+__device__ __forceinline__ void trj_assemble(const int4 *g, int part, const real *__restrict__ coef, const int *patoff, real *out) {
+  const int4 a0 = g[0], a1 = g[1], b0 = g[2], b1 = g[3];
+  const int flags = (a0.x >> 16) & 0xffff;
+  const real *ct = coef + (unsigned)a0.z + patoff[a1.y & 0xff];
+  const real ta = ldc(ct), tw = ldc(ct + 1), tb = ldc(ct + 2), tu = ldc(ct + 3), th = real(-0.5) * tu;
+  real al1 = real(1), al2 = real(1), ra = real(0), be1 = real(1), be2 = real(1), rb = real(0);
+  if (flags & EPGX_FLAG_PRE) {
+    const real *c = coef + (unsigned)a0.w + patoff[(a1.y >> 8) & 0xff];
+    al1 = ldc(c); ra = ldc(c + 1);
+    al2 = ldc(coef + (unsigned)a1.x + patoff[(a1.y >> 16) & 0xff]);
+  }
+  if (flags & EPGX_FLAG_POST) {
+    const real *c = coef + (unsigned)b0.z + patoff[b1.y & 0xff];
+    be1 = ldc(c); rb = ldc(c + 1);
+    be2 = ldc(coef + (unsigned)b0.w + patoff[(b1.y >> 8) & 0xff]);
+  }
+  const real Fa = be2 * al2 * ta, Fb = be2 * al2 * tb, Fu = be2 * al1 * tu, Fh = be1 * al2 * th, Fw = be1 * al1 * tw;
+  if (part == 0) {
+    out[0] = Fa; out[1] = Fw; out[2] = Fb; out[3] = Fu; out[4] = Fh;
+    out[5] = be2 * tu * ra;
+    out[6] = be1 * tw * ra + rb;
+    out[7] = real(0);
+    return;
+  }
+  const int v = part - 1;
+  // block v of an injection record (two int4): off[v] / pat[v], presence in flags bit v
+  auto blk = [&](const int4 lo, const int4 hi) -> const real * {
+    const unsigned off = v == 0 ? (unsigned)lo.z : v == 1 ? (unsigned)lo.w : (unsigned)hi.x;
+    return coef + off + patoff[(hi.y >> (8 * v)) & 0xff];
+  };
+  real pp = real(0), pz = real(0), p0 = real(0), ga = real(0), gw = real(0), gb = real(0), gu = real(0), qq = real(0),
+       qz = real(0), q0 = real(0);
+  if ((g[4].x >> (16 + v)) & 1) {
+    const real *c = blk(g[4], g[5]);
+    pp = ldc(c); pz = ldc(c + 4); p0 = ldc(c + 6);
+  }
+  if ((g[6].x >> (16 + v)) & 1) {
+    const real *c = blk(g[6], g[7]);
+    ga = ldc(c); gw = ldc(c + 1); gb = ldc(c + 2); gu = ldc(c + 3);
+  }
+  if ((g[8].x >> (16 + v)) & 1) {
+    const real *c = blk(g[8], g[9]);
+    qq = ldc(c); qz = ldc(c + 4); q0 = ldc(c + 6);
+  }
+  const real gh = real(-0.5) * gu;
+  // T G_v
+  const real A = ta * ga + tb * gb + tu * gh, B = ta * gb + tb * ga + tu * gh, U = (ta + tb) * gu + tu * gw;
+  const real H = th * (ga + gb) + tw * gh, W = real(2) * th * gu + tw * gw;
+  out[0] = Fa * (pp + qq) + be2 * al2 * A;
+  out[1] = Fw * (pz + qz) + be1 * al1 * W;
+  out[2] = Fb * (pp + qq) + be2 * al2 * B;
+  out[3] = Fu * (pz + qq) + be2 * al1 * U;
+  out[4] = Fh * (pp + qz) + be1 * al2 * H;
+  out[5] = Fu * p0 + be2 * (U + qq * tu) * ra;
+  out[6] = Fw * p0 + be1 * ((W + qz * tw) * ra + q0);
+  out[7] = real(0);
+}
+
+// the per-TR arithmetic, K slots: 9 + 18 (SETS - 1) operations per order
+template <typename real, int NS, int SETS, int K>
+__device__ __forceinline__ void rj_trj(real (&P)[SETS][NS], real (&M)[SETS][NS], real (&Z)[SETS][NS], const real *cf) {
+  typedef typename vec2<real>::type real2;
+  if constexpr (K <= NS) {
+    const real2 f0 = ((const real2 *)cf)[0], f1 = ((const real2 *)cf)[1], f2 = ((const real2 *)cf)[2];
+    const real a = f0.x, w = f0.y, b = f1.x, u = f1.y, h = f2.x;
+#pragma unroll
+    for (int q = 1; q < SETS; ++q) {
+      const real2 j0 = ((const real2 *)cf)[4 * q], j1 = ((const real2 *)cf)[4 * q + 1], j2 = ((const real2 *)cf)[4 * q + 2];
+      const real ja = j0.x, jw = j0.y, jb = j1.x, ju = j1.y, jh = j2.x;
+#pragma unroll
+      for (int s = 0; s < K; ++s) {
+        const real xp = P[0][s], xm = M[0][s], xz = Z[0][s];
+        const real p_ = P[q][s], m_ = M[q][s], z_ = Z[q][s];
+        P[q][s] = a * p_ + b * m_ + u * z_ + ja * xp + jb * xm + ju * xz;
+        M[q][s] = a * m_ + b * p_ + u * z_ + ja * xm + jb * xp + ju * xz;
+        Z[q][s] = w * z_ + h * (p_ + m_) + jw * xz + jh * (xp + xm);
+      }
+    }
+#pragma unroll
+    for (int s = 0; s < K; ++s) {
+      const real p_ = P[0][s], m_ = M[0][s], z_ = Z[0][s];
+      P[0][s] = a * p_ + b * m_ + u * z_;
+      M[0][s] = a * m_ + b * p_ + u * z_;
+      Z[0][s] = w * z_ + h * (p_ + m_);
+    }
+  }
+}
+
 template <typename real, int NS, int NV>
 __global__ void __launch_bounds__(256) realjac_kernel(const KParams p) {
   typedef typename vec2<real>::type real2;
@@ -171,10 +274,12 @@ __global__ void __launch_bounds__(256) realjac_kernel(const KParams p) {
   const int v0 = blockIdx.y * NV;
   const real *__restrict__ coef = (const real *)p.coef;
 
-  // shared memory: tape window, pattern offsets [A][npattern], boundary exchange [2][A][W][SETS][2][NS]
+  // shared memory: tape window, pattern offsets [A][npattern], boundary exchange [2][A][W][SETS][2][NS],
+  // TRJ coefficients [A][TRJ_PER_WINDOW][SETS][8]
   int4 *tbuf = (int4 *)smem_raw;
   int *patoff = (int *)(tbuf + 2 * TAPE_CHUNK * 2) + al * p.npattern;
   real *xbuf = (real *)((int *)(tbuf + 2 * TAPE_CHUNK * 2) + ((p.A * p.npattern + 3) & ~3));
+  real *trjc = xbuf + (W > 1 ? (size_t)2 * p.A * W * SETS * 2 * NS : 0) + (size_t)al * TRJ_PER_WINDOW * TRJ_REALS;
   {
     int idx[EPGX_MAX_DIMS];
     long long r = atom;
@@ -227,6 +332,14 @@ __global__ void __launch_bounds__(256) realjac_kernel(const KParams p) {
     }
     const int4 *tb = tbuf + (chunk & 1) * 2 * TAPE_CHUNK;
     const int cnt = min(TAPE_CHUNK, p.nstream - base);
+    if (tb[0].x & EPGX_CHUNK_ANY_TRJ) { // block-uniform: coefficient assembly of the window's TRJ groups
+      for (int item = lane; item < TRJ_PER_WINDOW * SETS; item += G) {
+        const int j = item / SETS, part = item - j * SETS;
+        if (5 * j + 5 <= cnt && (tb[10 * j].x & 0xffff) == EPGX_OP_TRJ)
+          trj_assemble<real>(tb + 10 * j, part, coef, patoff, trjc + (j * SETS + part) * 8);
+      }
+      __syncthreads();
+    }
     for (int r = 0; r < cnt; ++r) {
       const int4 r0 = tb[2 * r], r1 = tb[2 * r + 1];
       const int code = r0.x & 0xffff, flags = (r0.x >> 16) & 0xffff, aux = r0.y;
@@ -247,6 +360,31 @@ __global__ void __launch_bounds__(256) realjac_kernel(const KParams p) {
         _Pragma("unroll") for (int q = 1; q < SETS; ++q) if (q == iset) Z[q][0] += z0;         \
       } else if (on_base) Z[0][0] += z0;                                                       \
     }                                                                                          \
+  }
+
+#define DO_SEG(SHIFT, NOLD, NNEW, SFLAGS, NEXT_NACT)                                                                  \
+  {                                                                                                                    \
+    const int shift = (SHIFT), n_old = (NOLD), n_new = (NNEW), sflags = (SFLAGS);                                      \
+    nact = (NEXT_NACT);                                                                                                \
+    nslot = nact < 0 ? 0 : (nact >> lgG) + 1;                                                                          \
+    if (sflags & EPGX_SEG_RESET) {                                                                                     \
+      _Pragma("unroll") for (int q = 0; q < SETS; ++q)                                                                 \
+        _Pragma("unroll") for (int s = 0; s < NS; ++s) P[q][s] = M[q][s] = Z[q][s] = real(0);                          \
+      if (lane == 0) Z[0][0] = m0;                                                                                     \
+    } else if (shift != 0) {                                                                                           \
+      const int nsl = (n_new >> lgG) + 1;                                                                              \
+      real *xb = xbuf + (size_t)(parity * p.A + al) * W * SETS * 2 * NS;                                               \
+      if (shift > 0) { RJ_DISPATCH(nsl, rj_shift, P, M, G, W, wq, lq, gbase, srcUp, srcDn, is_first, is_last, n_old >= 1, xb, 1 + al) } \
+      else { RJ_DISPATCH(nsl, rj_shift, M, P, G, W, wq, lq, gbase, srcUp, srcDn, is_first, is_last, n_old >= 1, xb, 1 + al) } \
+      if (W > 1) parity ^= 1;                                                                                          \
+      if (sflags & EPGX_SEG_MASK_TOP) {                                                                                \
+        _Pragma("unroll") for (int q = 0; q < SETS; ++q)                                                               \
+          _Pragma("unroll") for (int s = 0; s < NS; ++s)                                                               \
+            if (s * G + lane > n_new) {                                                                                \
+              if (shift > 0) P[q][s] = real(0); else M[q][s] = real(0);                                                \
+            }                                                                                                          \
+      }                                                                                                                \
+    }                                                                                                                  \
   }
 
       switch (code) {
@@ -314,38 +452,40 @@ __global__ void __launch_bounds__(256) realjac_kernel(const KParams p) {
           }
         }
         break;
-      case EPGX_OP_SEG: {
-        const int shift = (int)off0, n_old = (int)off1, n_new = (int)off2, sflags = r1.z;
-        nact = aux;
-        nslot = nact < 0 ? 0 : (nact >> lgG) + 1;
-        if (sflags & EPGX_SEG_RESET) {
+      case EPGX_OP_SEG:
+        DO_SEG((int)off0, (int)off1, (int)off2, r1.z, aux)
+        break;
+      case EPGX_OP_TRJ: { // one whole TR with its injections, ADC and the segment's close (coefficients: trjc)
+        const real *cf = trjc + (r / 5) * (SETS * 8);
+        RJ_DISPATCH(nslot, rj_trj, P, M, Z, cf)
+        if (lane == 0 && nslot > 0) {
 #pragma unroll
-          for (int q = 0; q < SETS; ++q)
-#pragma unroll
-            for (int s = 0; s < NS; ++s) P[q][s] = M[q][s] = Z[q][s] = real(0);
-          if (lane == 0) Z[0][0] = m0;
-        } else if (shift != 0) {
-          const int nsl = (n_new >> lgG) + 1;
-          real *xb = xbuf + (size_t)(parity * p.A + al) * W * SETS * 2 * NS;
-          if (shift > 0) { RJ_DISPATCH(nsl, rj_shift, P, M, G, W, wq, lq, gbase, srcUp, srcDn, is_first, is_last, n_old >= 1, xb, 1 + al) }
-          else { RJ_DISPATCH(nsl, rj_shift, M, P, G, W, wq, lq, gbase, srcUp, srcDn, is_first, is_last, n_old >= 1, xb, 1 + al) }
-          if (W > 1) parity ^= 1;
-          if (sflags & EPGX_SEG_MASK_TOP) {
-#pragma unroll
-            for (int q = 0; q < SETS; ++q)
-#pragma unroll
-              for (int s = 0; s < NS; ++s)
-                if (s * G + lane > n_new) {
-                  if (shift > 0) P[q][s] = real(0); else M[q][s] = real(0);
-                }
+          for (int q = 0; q < SETS; ++q) {
+            const real f = cf[8 * q + 5] * m0;
+            P[q][0] += f; M[q][0] += f; Z[q][0] += cf[8 * q + 6] * m0;
           }
         }
+        const int4 q0 = tb[2 * r + 2], q1 = tb[2 * r + 3];
+        if (lane == 0 && valid) {
+          if (blockIdx.y == 0) sig[(long long)q0.y * p.sig_stride + a_rel] = real2{P[0][0], real(0)};
+          if (on_part) {
+#pragma unroll
+            for (int q = 1; q < SETS; ++q) {
+              const int v = v0 + q - 1;
+              if (v < p.nvar) jac[((long long)q1.w * p.nvar + v) * p.jac_stride + a_rel] = real2{P[q][0], real(0)};
+            }
+          }
+        }
+        const int segw = (q0.x >> 16) & 0xffff; // (shift + 1) | segment flags << 2
+        DO_SEG((segw & 3) - 1, (int)((unsigned)q1.x >> 16), (int)((unsigned)q1.x & 0xffff), segw >> 2, q1.z)
+        r += 4;
       } break;
       default:
         break;
       }
 #undef LIN5
 #undef DIAG3
+#undef DO_SEG
     }
   }
 }

@@ -52,7 +52,7 @@ _lock = threading.Lock()
 
 EXPORTS = [
     "epgx_version", "epgx_device_count", "epgx_last_error", "epgx_plan_create", "epgx_plan_destroy",
-    "epgx_plan_config", "epgx_plan_set_variant", "epgx_plan_workspace_bytes", "epgx_plan_upload",
+    "epgx_plan_config", "epgx_plan_stream", "epgx_plan_set_variant", "epgx_plan_workspace_bytes", "epgx_plan_upload",
     "epgx_simulate", "epgx_simulate_strided", "epgx_copy2d_to_host", "epgx_simulate_host", "epgx_reduce",
     "epgx_fma_peak",
 ]
@@ -76,6 +76,7 @@ def lib():
             L.epgx_plan_create.argtypes = [ctypes.POINTER(_Tape), ctypes.POINTER(vp)]
             L.epgx_plan_destroy.argtypes = [vp]
             L.epgx_plan_config.argtypes = [vp, ctypes.POINTER(Config)]
+            L.epgx_plan_stream.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(i64)]
             L.epgx_plan_set_variant.argtypes = [vp, i32, i32, i32, i32]
             L.epgx_plan_workspace_bytes.argtypes = [vp, ctypes.POINTER(i64)]
             L.epgx_plan_upload.argtypes = [vp, vp, vp]
@@ -151,6 +152,16 @@ class Plan:
         c = Config()
         _check(lib().epgx_plan_config(self._h, ctypes.byref(c)))
         return c.asdict()
+
+    def stream(self):
+        """diagnostic: the merged record stream of the register kernels as a structured array (a copy)"""
+        ptr, n = ctypes.c_void_p(), ctypes.c_int64()
+        _check(lib().epgx_plan_stream(self._h, ctypes.byref(ptr), ctypes.byref(n)))
+        from .lowering import OP_DTYPE
+        if not n.value:
+            return np.zeros(0, dtype=OP_DTYPE)
+        buf = (ctypes.c_char * (n.value * OP_DTYPE.itemsize)).from_address(ptr.value)
+        return np.frombuffer(buf, dtype=OP_DTYPE).copy()
 
     def set_variant(self, kernel=0, lanes_per_atom=0, vars_per_pass=0, atoms_per_cta=0):
         _check(lib().epgx_plan_set_variant(self._h, kernel, lanes_per_atom, vars_per_pass, atoms_per_cta))

@@ -222,6 +222,10 @@ int epgx_plan_config(const epgx_plan *plan, epgx_config *cfg);
 int epgx_plan_set_variant(epgx_plan *plan, int kernel, int lanes_per_atom, int vars_per_pass,
                           int atoms_per_cta);
 
+/* diagnostic: the merged record stream the register kernels execute (segment markers and whole-TR groups
+ * included; internal codes >= 64 are described in csrc/epgx_common.cuh).  `*records` points into the plan. */
+int epgx_plan_stream(const epgx_plan *plan, const epgx_op **records, int64_t *count);
+
 /* bytes of device workspace needed by epgx_plan_upload (tape + segments + coefficient table) */
 int epgx_plan_workspace_bytes(const epgx_plan *plan, int64_t *bytes);
 /* H2D copy of the tape, segments, patterns and coefficient table into `workspace` on `stream`.

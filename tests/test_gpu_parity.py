@@ -194,6 +194,64 @@ def test_realjac_kernel_variants(lanes, atoms, dtype, max_nstate, epg):
     assert rel_err(ring[0], rs) < RTOL64 and rel_err(ring[1], rj) < RTOL64
 
 
+def _trj_sequence(epg, variables, ntr=70):
+    """FISP-like train whose TRs collapse to whole-TR derivative groups (EPGX_OP_TRJ), with a few TRs that do not
+    (phase-compensated ADC, diffusion, spoiler, negative shift, a proton-density change in between)"""
+    T1 = np.linspace(300, 2000, 4)
+    T2 = np.linspace(30, 200, 3)[None, :]
+    B1 = np.array([0.8, 1.0, 1.15])[None, None, :]
+    o1 = {v: {v: 1} for v in ("T1", "T2") if v in variables}
+    o2 = dict(o1, **({"tau": {"tau": 0.5}} if "tau" in variables else {}))
+    seq = [epg.T(180, 90), epg.E(15, T1, T2, order1=o1)]
+    for i in range(ntr):
+        ph = 90 if i % 3 else 270
+        fa = 10.0 + i % 40
+        od = {"B1": {"alpha": fa}} if "B1" in variables else {}
+        adc = epg.Adc(phase=40.0) if i == 17 else epg.ADC
+        seq += [epg.T(fa * B1, ph, order1=od), epg.E(2.5, T1, T2, order1=o1), adc, epg.E(6 + (i % 5), T1, T2, order1=o2),
+                epg.S(-1 if i == 29 else 1)]
+        if i == 23:
+            seq += [epg.D(4.0, 1.2e-3, k=1)]
+        if i == 37:
+            seq += [epg.PD(0.7)]
+        if i == 44:
+            seq += [epg.SPOILER]
+    return seq
+
+
+@pytest.mark.parametrize("dtype", ["f64", "f32"])
+@pytest.mark.parametrize("lanes,atoms", [(0, 0), (2, 16), (8, 3), (32, 4), (64, 3), (128, 2), (256, 1)])
+@pytest.mark.parametrize("variables,max_nstate", [(["B1", "T1", "T2"], None), (["B1", "T1", "T2"], 9), (["T2", "B1"], None),
+                                                  (["tau", "T1"], None), (["B1"], 20)])
+def test_realjac_whole_tr_groups(lanes, atoms, dtype, variables, max_nstate, epg):
+    """derivative tapes of at most three variables: TRs of the form [inj] E [inj] T [inj] E ADC + shift run as fused
+    five-coefficient groups in the real-valued derivative kernel; against the ring kernel and the oracle"""
+    from epgpy_b200 import engine, functions, lowering
+    options = {"kvalue": 2500.0, **({"max_nstate": max_nstate} if max_nstate else {})}
+
+    def run(kernel, dt, **variant):
+        low = lowering.lower(_trj_sequence(epg, variables), probe=[None, epg.Jacobian(variables)], options=dict(options), dtype=dt,
+                             propagate_nondiff=True)
+        plan = engine.Plan(low)
+        plan.set_variant(kernel=kernel, **variant)
+        parts, _ = functions.run_lowered(low, plan=plan)
+        return functions._assemble(low, parts), plan.config()
+
+    ring, _ = run(1, "f64")
+    try:
+        got, cfg = run(4, dtype, lanes_per_atom=lanes, atoms_per_cta=atoms)
+    except MemoryError:
+        pytest.skip("more orders than lanes x slots of any instance")
+    assert cfg["kernel"] == 3 and cfg["var_tiles"] == 1
+    tol = 1e-11 if dtype == "f64" else RTOL32
+    assert rel_err(got[0], ring[0]) < tol
+    for i in range(len(variables)):
+        assert rel_err(got[1][..., i], ring[1][..., i]) < (tol if dtype == "f64" else 5 * RTOL32)
+    rs, rj = oracle_api.O.simulate(_trj_sequence(oracle_api.epg, variables), jacobian=variables, kvalue=2500.0,
+                                   max_nstate=max_nstate, propagate_nondiff=True)
+    assert rel_err(ring[0], rs) < RTOL64 and rel_err(ring[1], rj) < RTOL64
+
+
 def test_realjac_kernel_is_chosen_for_the_fisp_jacobian(golden, epg):
     from epgpy_b200 import engine, lowering
 
