@@ -126,7 +126,7 @@ static int choose_variant(epgx_plan *pl, int kernel, int lanes, int vars, int at
         c.var_tiles = (t.nvar + 2) / 3;
         c.atoms_per_cta = A;
         c.threads_per_cta = A * G;
-        c.smem_bytes = 2 * epgx::kTapeChunk * 32 + ((A * t.npattern + 3) & ~3) * 4 + (W > 1 ? 2 * A * W * 4 * 2 * NS * rsz : 0) +
+        c.smem_bytes = 2 * epgx::kTapeChunk * 32 + ((A * t.npattern + 3) & ~3) * 4 + (W > 1 ? 2 * A * W * 4 * 2 * (NS + 2) * rsz : 0) +
                        A * epgx::kTrjPerWindow * epgx::kTrjReals * rsz + 32;
         c.ring = C;
         return EPGX_OK;

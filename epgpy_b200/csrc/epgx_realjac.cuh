@@ -87,58 +87,95 @@ __device__ __forceinline__ void rj_diag3(real (&P)[SETS][NS], real (&M)[SETS][NS
   default: break;                                                      \
   }
 
-// unit shift of all state sets, K slots: U moves up, D moves down, new order 0 of U = old order 1 of D
+// unit shift of all state sets, K slots, one warp or less per atom (G <= 32 lanes): U moves up, D moves down, the new
+// order 0 of U is the old order 1 of D
 template <typename real, int NS, int SETS, int K>
-__device__ __forceinline__ void rj_shift(real (&U)[SETS][NS], real (&D)[SETS][NS], int G, int W, int wq, int lq, int gbase,
-                                         int srcUp, int srcDn, bool is_first, bool is_last, bool has1, real *xb, int barrier_id) {
+__device__ __forceinline__ void rj_shift(real (&U)[SETS][NS], real (&D)[SETS][NS], int G, int gbase, int srcUp, int srcDn,
+                                         bool is_first, bool is_last, bool has1) {
   const unsigned FULL = 0xffffffffu;
   if constexpr (K <= NS) {
-    if (W > 1) { // boundary values of every warp of the atom: [warp][set][up | dn][slot]
-#pragma unroll
-      for (int q = 0; q < SETS; ++q) {
-        if (lq == 31) {
-#pragma unroll
-          for (int s = 0; s < K; ++s) xb[((wq * SETS + q) * 2 + 0) * NS + s] = U[q][s];
-        }
-        if (lq == 0) {
-#pragma unroll
-          for (int s = 0; s < K; ++s) xb[((wq * SETS + q) * 2 + 1) * NS + s] = D[q][s];
-        }
-      }
-      asm volatile("bar.sync %0, %1;" ::"r"(barrier_id), "r"(G) : "memory");
-    }
 #pragma unroll
     for (int q = 0; q < SETS; ++q) {
       real c1;
       if (G == 1) c1 = K > 1 ? D[q][K > 1 ? 1 : 0] : real(0);
-      else c1 = __shfl_sync(FULL, D[q][0], gbase | 1); // used by lane 0 of the atom only (warp 0)
+      else c1 = __shfl_sync(FULL, D[q][0], gbase | 1); // used by lane 0 of the atom only
       if (!has1) c1 = real(0);
 #pragma unroll
       for (int s = K - 1; s >= 0; --s) { // descending = in place
         real v = U[q][s];
-        if (W == 1) { if (is_last) v = s > 0 ? U[q][s > 0 ? s - 1 : 0] : c1; }
-        v = __shfl_sync(FULL, v, srcUp);
-        if (W > 1 && is_first) {
-          if (wq > 0) v = xb[(((wq - 1) * SETS + q) * 2 + 0) * NS + s];
-          else v = s > 0 ? xb[(((W - 1) * SETS + q) * 2 + 0) * NS + (s > 0 ? s - 1 : 0)] : c1;
-        }
-        U[q][s] = v;
+        if (is_last) v = s > 0 ? U[q][s > 0 ? s - 1 : 0] : c1;
+        U[q][s] = __shfl_sync(FULL, v, srcUp);
       }
       real keep = real(0);
 #pragma unroll
       for (int s = K - 1; s >= 0; --s) {
         const real cur = D[q][s];
-        real v = cur;
-        if (W == 1) { if (is_first) v = keep; }
-        v = __shfl_sync(FULL, v, srcDn);
-        if (W > 1 && is_last) {
-          if (wq < W - 1) v = xb[(((wq + 1) * SETS + q) * 2 + 1) * NS + s];
-          else v = s + 1 < K ? xb[((0 * SETS + q) * 2 + 1) * NS + (s + 1 < K ? s + 1 : s)] : real(0);
-        }
-        D[q][s] = v;
+        D[q][s] = __shfl_sync(FULL, is_first ? keep : cur, srcDn);
         keep = cur;
       }
     }
+  }
+}
+
+// predicated shared-memory access by 32-bit shared address (no branch, no address re-materialisation)
+__device__ __forceinline__ void lds_if(double &v, unsigned addr, bool pred) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %2, 0;\n\t@p ld.shared.f64 %0, [%1];\n\t}" : "+d"(v) : "r"(addr), "r"((unsigned)pred));
+}
+__device__ __forceinline__ void lds_if(float &v, unsigned addr, bool pred) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %2, 0;\n\t@p ld.shared.f32 %0, [%1];\n\t}" : "+f"(v) : "r"(addr), "r"((unsigned)pred));
+}
+__device__ __forceinline__ void sts_if(unsigned addr, double v, bool pred) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %2, 0;\n\t@p st.shared.f64 [%0], %1;\n\t}" ::"r"(addr), "d"(v), "r"((unsigned)pred) : "memory");
+}
+__device__ __forceinline__ void sts_if(unsigned addr, float v, bool pred) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %2, 0;\n\t@p st.shared.f32 [%0], %1;\n\t}" ::"r"(addr), "f"(v), "r"((unsigned)pred) : "memory");
+}
+__device__ __forceinline__ unsigned smem_addr(const void *ptr) {
+  unsigned a = (unsigned)__cvta_generic_to_shared(ptr);
+  asm volatile("mov.u32 %0, %0;" : "+r"(a)); // opaque: keep it in a register
+  return a;
+}
+
+// unit shift with several warps per atom (G = 32 W lanes): rotation by one lane inside each warp (shuffles); the value
+// that crosses a warp boundary goes through shared memory rows [warp][set][NS + 2], written by the SENDING warp into
+// the row of the receiving one: "up" rows hold the new order 0 in entry 1 and slot s of the sender's lane 31 in
+// entry s + 2 (warp 0 reads from entry 1: its lane 0 takes slot s - 1 of the last warp), "down" rows hold slot s of
+// the sender's lane 0 in entry s followed by a zero (the last warp reads from entry 1).  One named barrier per shift;
+// the rows are double-buffered by the caller.  Arguments are shared-memory byte addresses.
+template <typename real, int NS, int SETS, int K>
+__device__ __forceinline__ void rj_shift_mw(real (&U)[SETS][NS], real (&D)[SETS][NS], int G, int lq, int srcUp, int srcDn, bool c1lane,
+                                            bool has1, unsigned up_w, unsigned up_r, unsigned up_c1, unsigned dn_w, unsigned dn_r,
+                                            int barrier_id) {
+  const unsigned FULL = 0xffffffffu;
+  constexpr int NSX = NS + 2, RS = (int)sizeof(real);
+  if constexpr (K <= NS) {
+    const bool first = lq == 0, last = lq == 31;
+#pragma unroll
+    for (int q = 0; q < SETS; ++q) {
+#pragma unroll
+      for (int s = 0; s < K; ++s) sts_if(up_w + (q * NSX + s) * RS, U[q][s], last);
+#pragma unroll
+      for (int s = 0; s < K; ++s) sts_if(dn_w + (q * NSX + s) * RS, D[q][s], first);
+      sts_if(dn_w + (q * NSX + K) * RS, real(0), first);
+      sts_if(up_c1 + q * NSX * RS, has1 ? D[q][0] : real(0), c1lane);
+    }
+    asm volatile("bar.sync %0, %1;" ::"r"(barrier_id), "r"(G) : "memory");
+#pragma unroll
+    for (int q = 0; q < SETS; ++q)
+#pragma unroll
+      for (int s = 0; s < K; ++s) {
+        real v = __shfl_sync(FULL, U[q][s], srcUp);
+        lds_if(v, up_r + (q * NSX + s) * RS, first);
+        U[q][s] = v;
+      }
+#pragma unroll
+    for (int q = 0; q < SETS; ++q)
+#pragma unroll
+      for (int s = 0; s < K; ++s) {
+        real v = __shfl_sync(FULL, D[q][s], srcDn);
+        lds_if(v, dn_r + (q * NSX + s) * RS, last);
+        D[q][s] = v;
+      }
   }
 }
 
@@ -245,7 +282,7 @@ __device__ __forceinline__ void rj_trj(real (&P)[SETS][NS], real (&M)[SETS][NS],
   }
 }
 
-template <typename real, int NS, int NV>
+template <typename real, int NS, int NV, bool MW>
 __global__ void __launch_bounds__(256) realjac_kernel(const KParams p) {
   typedef typename vec2<real>::type real2;
   constexpr int SETS = 1 + NV;
@@ -256,14 +293,13 @@ __global__ void __launch_bounds__(256) realjac_kernel(const KParams p) {
   const int al = tid / G;
   const int lane = tid - al * G;
   const int lw = tid & 31;
-  const int W = G > 32 ? G >> 5 : 1;
-  const int GW = G > 32 ? 32 : G;
-  const int wq = G > 32 ? lane >> 5 : 0;
+  const int W = MW ? G >> 5 : 1; // MW: several warps per atom (G = 32 W), else one warp or less
+  const int GW = MW ? 32 : G;
+  const int wq = MW ? lane >> 5 : 0;
   const int gbase = lw & ~(GW - 1);
   const int lq = lw - gbase;
   const int srcUp = gbase | ((lq - 1) & (GW - 1));
   const int srcDn = gbase | ((lq + 1) & (GW - 1));
-  const unsigned FULL = 0xffffffffu;
   const bool is_first = lq == 0, is_last = lq == GW - 1;
   int lgG = 0;
   while ((1 << lgG) < G) ++lgG;
@@ -274,12 +310,19 @@ __global__ void __launch_bounds__(256) realjac_kernel(const KParams p) {
   const int v0 = blockIdx.y * NV;
   const real *__restrict__ coef = (const real *)p.coef;
 
-  // shared memory: tape window, pattern offsets [A][npattern], boundary exchange [2][A][W][SETS][2][NS],
+  // shared memory: tape window, pattern offsets [A][npattern], boundary exchange [2][A][up | down][W][SETS][NS + 2],
   // TRJ coefficients [A][TRJ_PER_WINDOW][SETS][8]
   int4 *tbuf = (int4 *)smem_raw;
   int *patoff = (int *)(tbuf + 2 * TAPE_CHUNK * 2) + al * p.npattern;
   real *xbuf = (real *)((int *)(tbuf + 2 * TAPE_CHUNK * 2) + ((p.A * p.npattern + 3) & ~3));
-  real *trjc = xbuf + (W > 1 ? (size_t)2 * p.A * W * SETS * 2 * NS : 0) + (size_t)al * TRJ_PER_WINDOW * TRJ_REALS;
+  constexpr int NSX = NS + 2, ROW = SETS * NSX; // boundary exchange rows (rj_shift_mw)
+  const int par_stride = p.A * W * 2 * ROW;
+  real *trjc = xbuf + (MW ? (size_t)2 * par_stride : 0) + (size_t)al * TRJ_PER_WINDOW * TRJ_REALS;
+  real *const xup = xbuf + (size_t)al * W * 2 * ROW, *const xdn = xup + W * ROW;
+  const unsigned up_w = smem_addr(xup + (wq + 1 == W ? 0 : wq + 1) * ROW + 2), up_c1 = smem_addr(xup + 1);
+  const unsigned up_r = smem_addr(xup + wq * ROW + (wq == 0 ? 1 : 2));
+  const unsigned dn_w = smem_addr(xdn + (wq == 0 ? W - 1 : wq - 1) * ROW);
+  const unsigned dn_r = smem_addr(xdn + wq * ROW + (wq == W - 1 ? 1 : 0));
   {
     int idx[EPGX_MAX_DIMS];
     long long r = atom;
@@ -373,10 +416,15 @@ __global__ void __launch_bounds__(256) realjac_kernel(const KParams p) {
       if (lane == 0) Z[0][0] = m0;                                                                                     \
     } else if (shift != 0) {                                                                                           \
       const int nsl = (n_new >> lgG) + 1;                                                                              \
-      real *xb = xbuf + (size_t)(parity * p.A + al) * W * SETS * 2 * NS;                                               \
-      if (shift > 0) { RJ_DISPATCH(nsl, rj_shift, P, M, G, W, wq, lq, gbase, srcUp, srcDn, is_first, is_last, n_old >= 1, xb, 1 + al) } \
-      else { RJ_DISPATCH(nsl, rj_shift, M, P, G, W, wq, lq, gbase, srcUp, srcDn, is_first, is_last, n_old >= 1, xb, 1 + al) } \
-      if (W > 1) parity ^= 1;                                                                                          \
+      if constexpr (MW) {                                                                                              \
+        const unsigned po = parity * par_stride * (int)sizeof(real);                                                                           \
+        if (shift > 0) { RJ_DISPATCH(nsl, rj_shift_mw, P, M, G, lq, srcUp, srcDn, lane == 1, n_old >= 1, up_w + po, up_r + po, up_c1 + po, dn_w + po, dn_r + po, 1 + al) } \
+        else { RJ_DISPATCH(nsl, rj_shift_mw, M, P, G, lq, srcUp, srcDn, lane == 1, n_old >= 1, up_w + po, up_r + po, up_c1 + po, dn_w + po, dn_r + po, 1 + al) } \
+        parity ^= 1;                                                                                                   \
+      } else {                                                                                                         \
+        if (shift > 0) { RJ_DISPATCH(nsl, rj_shift, P, M, G, gbase, srcUp, srcDn, is_first, is_last, n_old >= 1) } \
+        else { RJ_DISPATCH(nsl, rj_shift, M, P, G, gbase, srcUp, srcDn, is_first, is_last, n_old >= 1) } \
+      }                                                                                                                \
       if (sflags & EPGX_SEG_MASK_TOP) {                                                                                \
         _Pragma("unroll") for (int q = 0; q < SETS; ++q)                                                               \
           _Pragma("unroll") for (int s = 0; s < NS; ++s)                                                               \
