@@ -282,6 +282,64 @@ __device__ __forceinline__ void rj_trj(real (&P)[SETS][NS], real (&M)[SETS][NS],
   }
 }
 
+// per-thread constants of the whole-TR fast loop
+template <typename real> struct RjCtx {
+  int G, lgG, lane, lq, gbase, srcUp, srcDn, barrier_id, nvar;
+  bool is_first, is_last, valid;
+  unsigned up_w, up_r, up_c1, dn_w, dn_r, par_bytes; // shared-memory byte addresses (rj_shift_mw)
+  typename vec2<real>::type *sig, *jac;               // output rows of this atom
+  long long sig_stride, jac_stride;
+};
+
+// consecutive plain whole-TR groups (unit shift +1, no segment flags) of the current tape window, executed with K
+// slots: the slot count is a compile-time constant of the LOOP, not of each TR, so the state never leaves its
+// registers between TRs.  K covers orders 0..min(n_new, nact + 1): orders above nact + 1 are unobservable
+// (lowering.py) and need not move.  On entry r is the first record of a group that qualifies; on exit it is the
+// last record of the last group done.
+template <typename real, int NS, int SETS, bool MW, int K>
+__device__ __forceinline__ void rj_trj_run(real (&P)[SETS][NS], real (&M)[SETS][NS], real (&Z)[SETS][NS], const RjCtx<real> &c,
+                                           const int4 *tb, const real *trjc, real m0, int cnt, int &r, int &nact, int &parity) {
+  typedef typename vec2<real>::type real2;
+  if constexpr (K <= NS) {
+    for (;;) {
+      const int4 h0 = tb[2 * r], q0 = tb[2 * r + 2], q1 = tb[2 * r + 3];
+      const real *cf = trjc + (r / 5) * (SETS * 8);
+      rj_trj<real, NS, SETS, K>(P, M, Z, cf);
+      if (c.lane == 0) {
+#pragma unroll
+        for (int q = 0; q < SETS; ++q) {
+          const real f = cf[8 * q + 5] * m0;
+          P[q][0] += f; M[q][0] += f; Z[q][0] += cf[8 * q + 6] * m0;
+        }
+        if (c.valid) {
+          c.sig[(long long)q0.y * c.sig_stride] = real2{P[0][0], real(0)};
+          if (h0.x & (EPGX_FLAG_PARTIALS << 16)) {
+#pragma unroll
+            for (int q = 1; q < SETS; ++q)
+              if (q - 1 < c.nvar) c.jac[((long long)q1.w * c.nvar + q - 1) * c.jac_stride] = real2{P[q][0], real(0)};
+          }
+        }
+      }
+      const int n_old = (int)((unsigned)q1.x >> 16);
+      if constexpr (MW) {
+        const unsigned po = parity * c.par_bytes;
+        rj_shift_mw<real, NS, SETS, K>(P, M, c.G, c.lq, c.srcUp, c.srcDn, c.lane == 1, n_old >= 1, c.up_w + po, c.up_r + po,
+                                       c.up_c1 + po, c.dn_w + po, c.dn_r + po, c.barrier_id);
+        parity ^= 1;
+      } else {
+        rj_shift<real, NS, SETS, K>(P, M, c.G, c.gbase, c.srcUp, c.srcDn, c.is_first, c.is_last, n_old >= 1);
+      }
+      nact = q1.z;
+      r += 5;
+      if (r + 5 > cnt) break;
+      const int4 g0 = tb[2 * r], g2 = tb[2 * r + 2], g3 = tb[2 * r + 3];
+      if ((g0.x & 0xffff) != EPGX_OP_TRJ || ((g2.x >> 16) & 0xffff) != 2 || nact < 0) break;
+      if (((min((int)((unsigned)g3.x & 0xffff), nact + 1) >> c.lgG) + 1) != K) break;
+    }
+    r -= 1;
+  }
+}
+
 template <typename real, int NS, int NV, bool MW>
 __global__ void __launch_bounds__(256) realjac_kernel(const KParams p) {
   typedef typename vec2<real>::type real2;
@@ -323,6 +381,14 @@ __global__ void __launch_bounds__(256) realjac_kernel(const KParams p) {
   const unsigned up_r = smem_addr(xup + wq * ROW + (wq == 0 ? 1 : 2));
   const unsigned dn_w = smem_addr(xdn + (wq == 0 ? W - 1 : wq - 1) * ROW);
   const unsigned dn_r = smem_addr(xdn + wq * ROW + (wq == W - 1 ? 1 : 0));
+  RjCtx<real> ctx;
+  ctx.G = G; ctx.lgG = lgG; ctx.lane = lane; ctx.lq = lq; ctx.gbase = gbase; ctx.srcUp = srcUp; ctx.srcDn = srcDn;
+  ctx.barrier_id = 1 + al; ctx.nvar = p.nvar;
+  ctx.is_first = is_first; ctx.is_last = is_last; ctx.valid = valid;
+  ctx.up_w = up_w; ctx.up_r = up_r; ctx.up_c1 = up_c1; ctx.dn_w = dn_w; ctx.dn_r = dn_r;
+  ctx.par_bytes = (unsigned)par_stride * (unsigned)sizeof(real);
+  ctx.sig = (typename vec2<real>::type *)p.signal + a_rel; ctx.jac = (typename vec2<real>::type *)p.jac + a_rel;
+  ctx.sig_stride = p.sig_stride; ctx.jac_stride = p.jac_stride;
   {
     int idx[EPGX_MAX_DIMS];
     long long r = atom;
@@ -504,6 +570,16 @@ __global__ void __launch_bounds__(256) realjac_kernel(const KParams p) {
         DO_SEG((int)off0, (int)off1, (int)off2, r1.z, aux)
         break;
       case EPGX_OP_TRJ: { // one whole TR with its injections, ADC and the segment's close (coefficients: trjc)
+        if (((tb[2 * r + 2].x >> 16) & 0xffff) == 2 && nact >= 0 && v0 == 0) { // plain TRs: per-slot-count loops
+          const int ks = (min((int)((unsigned)tb[2 * r + 3].x & 0xffff), nact + 1) >> lgG) + 1;
+#define RUN(K) case K: rj_trj_run<real, NS, SETS, MW, K>(P, M, Z, ctx, tb, trjc, m0, cnt, r, nact, parity); break;
+          switch (ks) { RUN(1) RUN(2) RUN(3) RUN(4) RUN(5) RUN(6) RUN(7) RUN(8) default: break; }
+#undef RUN
+          if (ks <= NS) {
+            nslot = nact < 0 ? 0 : (nact >> lgG) + 1;
+            break;
+          }
+        }
         const real *cf = trjc + (r / 5) * (SETS * 8);
         RJ_DISPATCH(nslot, rj_trj, P, M, Z, cf)
         if (lane == 0 && nslot > 0) {
