@@ -90,6 +90,8 @@ def main():
     ap.add_argument("--only", nargs="*", default=None)
     ap.add_argument("--dtype", default="f64")
     ap.add_argument("--reps", type=int, default=3)
+    ap.add_argument("--lanes", type=int, default=0, help="force lanes per atom (tuning)")
+    ap.add_argument("--atoms-per-cta", type=int, default=0, help="force atoms per CTA (tuning)")
     args = ap.parse_args()
     import torch
 
@@ -106,6 +108,8 @@ def main():
         low = lowering.lower(seq, init=init, probe=probe, options=opts, dtype=args.dtype)
         t_host = time.perf_counter() - t0
         plan = engine.Plan(low)
+        if args.lanes or args.atoms_per_cta:
+            plan.set_variant(lanes_per_atom=args.lanes, atoms_per_cta=args.atoms_per_cta)
         cfg = plan.config()
         dev = torch.cuda.current_device()
         sig, jc = plan.run(dev)  # warm-up (allocates)

@@ -104,7 +104,7 @@ static int choose_variant(epgx_plan *pl, int kernel, int lanes, int vars, int at
     return fail(EPGX_ERR_UNSUPPORTED, "the real-valued derivative kernel needs a real-valued tape with order-1 variables");
   if (pl->realjac_ok && (kernel == 0 || kernel == 4)) {
     // ---- real-valued register kernel with 3 resident partial states: G = 32 W lanes x NS slots >= C orders
-    const int ns_max = t.dtype == EPGX_F64 ? 4 : 8;
+    const int ns_max = 4; // 4 slots x (1 + 3) state sets x 3 reals: the most that leaves three (FP64) / four (FP32) CTAs per SM
     int G = lanes > 0 ? pow2ceil(lanes) : pow2ceil((C + ns_max - 1) / ns_max);
     if (G > 256) G = 256;
     const int need = (C + G - 1) / G;
@@ -115,9 +115,10 @@ static int choose_variant(epgx_plan *pl, int kernel, int lanes, int vars, int at
       const int W = G > 32 ? G / 32 : 1;
       int A = atoms > 0 ? atoms : (128 / G > 0 ? 128 / G : 1);
       if (W > 1 && A > 15) A = 15;
-      if (A > 16 && atoms <= 0) A = 16; // per-atom TRJ coefficient windows in shared memory
+      const bool trj = t.nvar <= 3; // whole-TR groups (EPGX_OP_TRJ): per-atom coefficient windows in shared memory
+      if (trj && A > 16 && atoms <= 0) A = 16;
       while (A * G > 256 && A > 1) --A;
-      while (A > 1 && A * epgx::kTrjPerWindow * epgx::kTrjReals * rsz > 32 * 1024) --A;
+      while (trj && A > 1 && A * epgx::kTrjPerWindow * epgx::kTrjReals * rsz > 32 * 1024) --A;
       if (A * G <= 256) {
         c.kernel = 3;
         c.lanes_per_atom = G;
@@ -127,7 +128,7 @@ static int choose_variant(epgx_plan *pl, int kernel, int lanes, int vars, int at
         c.atoms_per_cta = A;
         c.threads_per_cta = A * G;
         c.smem_bytes = 2 * epgx::kTapeChunk * 32 + ((A * t.npattern + 3) & ~3) * 4 + (W > 1 ? 2 * A * W * 4 * 2 * (NS + 2) * rsz : 0) +
-                       A * epgx::kTrjPerWindow * epgx::kTrjReals * rsz + 32;
+                       (trj ? A * epgx::kTrjPerWindow * epgx::kTrjReals * rsz : 0) + 32;
         c.ring = C;
         return EPGX_OK;
       }

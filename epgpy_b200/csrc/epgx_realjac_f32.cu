@@ -8,7 +8,10 @@ template <> cudaError_t launch_realjac<float>(int slots, const KParams &kp, dim3
   switch (slots) {
   case 1: mw ? realjac_kernel<float, 1, 3, true><<<grid, threads, smem, st>>>(kp) : realjac_kernel<float, 1, 3, false><<<grid, threads, smem, st>>>(kp); break;
   case 2: mw ? realjac_kernel<float, 2, 3, true><<<grid, threads, smem, st>>>(kp) : realjac_kernel<float, 2, 3, false><<<grid, threads, smem, st>>>(kp); break;
-  case 4: mw ? realjac_kernel<float, 4, 3, true><<<grid, threads, smem, st>>>(kp) : realjac_kernel<float, 4, 3, false><<<grid, threads, smem, st>>>(kp); break;
+  case 4:
+    if (threads <= 128) mw ? realjac_kernel<float, 4, 3, true, 128><<<grid, threads, smem, st>>>(kp) : realjac_kernel<float, 4, 3, false, 128><<<grid, threads, smem, st>>>(kp);
+    else mw ? realjac_kernel<float, 4, 3, true><<<grid, threads, smem, st>>>(kp) : realjac_kernel<float, 4, 3, false><<<grid, threads, smem, st>>>(kp);
+    break;
   case 8: mw ? realjac_kernel<float, 8, 3, true><<<grid, threads, smem, st>>>(kp) : realjac_kernel<float, 8, 3, false><<<grid, threads, smem, st>>>(kp); break;
   default: return cudaErrorInvalidValue;
   }

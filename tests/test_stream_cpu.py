@@ -1,0 +1,69 @@
+"""Host-side checks of the merged record stream the register kernels execute (epgx_plan_stream; no GPU needed):
+whole-TR grouping of forward and derivative FISP tapes (csrc/epgx.cu, csrc/epgx_common.cuh)."""
+
+import collections
+
+import numpy as np
+import pytest
+
+import cases
+from util import product_namespace
+
+OP_SEG, OP_TR, OP_TRC, OP_TRJ, OP_CONT, OP_NOP = 64, 65, 66, 67, 13, 0
+
+
+@pytest.fixture(scope="module")
+def epg():
+    return product_namespace()
+
+
+def _stream(epg, case, **kw):
+    from epgpy_b200 import engine, lowering
+    probe = [None, epg.Jacobian(case["jac"])] if case.get("jac") else None
+    low = lowering.lower(case["seq"], probe=probe, options=dict(case.get("options", {})), **kw)
+    plan = engine.Plan(low)
+    return low, plan, plan.stream()
+
+
+def test_forward_fisp_collapses_to_whole_tr_records(epg):
+    low, plan, st = _stream(epg, cases.fisp_unbounded(epg))
+    count = collections.Counter(st["code"].tolist())
+    assert plan.config()["kernel"] == 2
+    assert count[OP_TR] >= low.nadc - 2  # every TR but the first and the last is one record pair
+
+
+def test_fisp_jacobian_collapses_to_whole_tr_groups(epg):
+    case = cases.fisp_jac_global(epg, ntr=40)
+    low, plan, st = _stream(epg, case)
+    assert plan.config()["kernel"] == 3
+    heads = np.flatnonzero(st["code"] == OP_TRJ)
+    assert len(heads) == low.nadc - 2  # generic records: the first TR (with the inversion pulse) and the last one (trailing E)
+    # groups of five records, aligned to multiples of five inside a 64-record window, never split by a window
+    assert np.all(heads % 64 % 5 == 0) and np.all(heads % 64 <= 59)
+    for h in heads:
+        assert np.all(st["code"][h + 1:h + 5] == OP_CONT)
+        grp = st[h:h + 5]
+        assert grp[0]["flags"] & 0x182 == 0x182  # PRE | POST | PARTIALS
+        assert grp[1]["flags"] == 2  # unit shift +1, no segment flags
+        # B1 is injected at the pulse, T1 and T2 before both relaxation operators; one slot per variable
+        pre, pulse, post = int(grp[2]["flags"]), int(grp[3]["flags"]), int(grp[4]["flags"])
+        assert pre == post and pre | pulse == 7 and pre & pulse == 0 and bin(pulse).count("1") == 1
+    # windows holding groups are flagged for the coefficient assembly pass
+    for w0 in range(0, len(st), 64):
+        has = np.any(st["code"][w0:w0 + 64] == OP_TRJ)
+        assert bool(st["flags"][w0] & 0x2000) == bool(has)
+    # signal and Jacobian rows ride in CONT'
+    rows = [(int(st[h + 1]["aux"]), int(st[h + 1]["rsv1"])) for h in heads]
+    assert rows == [(i, i) for i in range(1, low.nadc - 1)]
+
+
+def test_more_than_three_variables_keep_generic_records(epg):
+    case = cases.fisp_jac_pulses(epg)
+    low, plan, st = _stream(epg, case)
+    assert low.nvar > 3 and not np.any(st["code"] == OP_TRJ)
+
+
+def test_complex_injections_are_not_grouped(epg):
+    case = cases.mse_jac(epg)  # T(150, 0): complex couplings, ring kernel
+    low, plan, st = _stream(epg, case)
+    assert plan.config()["kernel"] == 0 and not np.any(st["code"] == OP_TRJ)
