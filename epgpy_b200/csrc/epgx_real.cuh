@@ -172,13 +172,14 @@ __global__ void __launch_bounds__(256, (sizeof(real) * NS <= 64 ? 3 : sizeof(rea
 #define DO_SEG(SHIFT_, NOLD_, NNEW_, SFLAGS_, NEXT_)                                                       \
   {                                                                                                        \
     const int shift = (SHIFT_), n_old = (NOLD_), n_new = (NNEW_), sflags = (SFLAGS_);                      \
+    const int n_move = max(min(n_new, nact + 1), 0); /* orders above nact + 1 are unobservable: they stay */ \
     nact = (NEXT_);                                                                                        \
     nslot = nact < 0 ? 0 : (nact >> lgG) + 1;                                                              \
     if (sflags & EPGX_SEG_RESET) {                                                                         \
       _Pragma("unroll") for (int s = 0; s < NS; ++s) P[s] = M[s] = Z[s] = real(0);                         \
       if (lane == 0) Z[0] = m0;                                                                            \
     } else if (shift != 0) {                                                                               \
-      const int nsl = (n_new >> lgG) + 1;                                                                  \
+      const int nsl = (n_move >> lgG) + 1;                                                                 \
       if (shift > 0) SHIFT_REAL(P, M) else SHIFT_REAL(M, P)                                                \
       if (sflags & EPGX_SEG_MASK_TOP) {                                                                    \
         _Pragma("unroll") for (int s = 0; s < NS; ++s)                                                     \
@@ -241,8 +242,11 @@ __global__ void __launch_bounds__(256, (sizeof(real) * NS <= 64 ? 3 : sizeof(rea
                                           fl & EPGX_FLAG_POST, ldc(cb), ldc(cb + 1),
                                           ldc(coef + (unsigned)b0.w + patoff[(b1.y >> 8) & 0xff]), false, m0);
       const int rowv = b0.y, nnewv = (int)((unsigned)b1.x & 0xffff), nextv = b1.z;
-      // largest slot count any TR of the window needs (apply: nact, shift: n_new)
-      int need = max(nnewv >> 5, nextv < 0 ? -1 : nextv >> 5) + 1;
+      // largest slot count any TR of the window needs: it applies to orders 0..nact and shifts orders
+      // 0..min(n_new, nact + 1) -- what lies above nact + 1 is unobservable (lowering.py) and need not move
+      int curv = __shfl_up_sync(FULL, nextv, 1); // nact of TR j = the "next nact" of TR j - 1
+      if (lw == 0) curv = nact;
+      int need = (max(min(nnewv, curv + 1), 0) >> 5) + 1;
       need = max(__reduce_max_sync(FULL, need), nslot);
 #define TRW(K_) case K_: tr_window<real, NS, K_>(P, M, Z, fv, rowv, lane == 0, valid, is_first, is_last, srcUp, srcDn, sig, p.sig_stride, a_rel); break;
       switch (need) {

@@ -476,6 +476,7 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 128 ? 3 : 1) realjac_kernel(cons
 #define DO_SEG(SHIFT, NOLD, NNEW, SFLAGS, NEXT_NACT)                                                                  \
   {                                                                                                                    \
     const int shift = (SHIFT), n_old = (NOLD), n_new = (NNEW), sflags = (SFLAGS);                                      \
+    const int n_move = max(min(n_new, nact + 1), 0); /* orders above nact + 1 are unobservable: they stay */           \
     nact = (NEXT_NACT);                                                                                                \
     nslot = nact < 0 ? 0 : (nact >> lgG) + 1;                                                                          \
     if (sflags & EPGX_SEG_RESET) {                                                                                     \
@@ -483,7 +484,7 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 128 ? 3 : 1) realjac_kernel(cons
         _Pragma("unroll") for (int s = 0; s < NS; ++s) P[q][s] = M[q][s] = Z[q][s] = real(0);                          \
       if (lane == 0) Z[0][0] = m0;                                                                                     \
     } else if (shift != 0) {                                                                                           \
-      const int nsl = (n_new >> lgG) + 1;                                                                              \
+      const int nsl = (n_move >> lgG) + 1;                                                                             \
       if constexpr (MW) {                                                                                              \
         const unsigned po = parity * par_stride * (int)sizeof(real);                                                                           \
         if (shift > 0) { RJ_DISPATCH(nsl, rj_shift_mw, P, M, G, lq, srcUp, srcDn, lane == 1, n_old >= 1, up_w + po, up_r + po, up_c1 + po, dn_w + po, dn_r + po, 1 + al) } \

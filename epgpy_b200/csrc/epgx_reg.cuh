@@ -236,6 +236,7 @@ __global__ void __launch_bounds__(256, (6 * NS * sizeof(real) <= 192 ? 2 : 1)) r
 #define DO_SEG(SHIFT_, NOLD_, NNEW_, SFLAGS_, NEXT_) \
   { \
     const int shift = (SHIFT_), n_old = (NOLD_), n_new = (NNEW_), sflags = (SFLAGS_); \
+    const int n_move = max(min(n_new, nact + 1), 0); /* orders above nact + 1 are unobservable: they stay */ \
     nact = (NEXT_); \
     nslot = nact < 0 ? 0 : (nact >> lgG) + 1; \
         if (sflags & EPGX_SEG_RESET) { \
@@ -243,7 +244,7 @@ _Pragma("unroll") \
           for (int s = 0; s < NS; ++s) Pr[s] = Pi[s] = Mr[s] = Mi[s] = Zr[s] = Zi[s] = real(0); \
           if (lane == 0) Zr[0] = m0; \
         } else if (shift != 0) { \
-      const int nsl = (n_new >> lgG) + 1; \
+      const int nsl = (n_move >> lgG) + 1; \
       if (W == 1) { \
         if (shift > 0) SHIFT_W1(Pr, Pi, Mr, Mi) else SHIFT_W1(Mr, Mi, Pr, Pi) \
       } else { \
@@ -281,7 +282,7 @@ _Pragma("unroll") \
     if (G == 32 && (tb[0].x & EPGX_CHUNK_PURE_TRC)) {
       // ---- fast path: the window holds TRC_PER_WINDOW whole-TR triples.  Phase 1: lane j decodes TR j, gathers and
       // fuses its coefficients and stages them in shared memory; phase 2 (trc_window) runs the TRs in order.
-      int need = 0;
+      int need = 0, nnew = 0, nxt = -1;
       if (lw < TRC_PER_WINDOW) {
         const int4 a0 = tb[6 * lw], a1 = tb[6 * lw + 1], b0 = tb[6 * lw + 2], b1 = tb[6 * lw + 3];
         const int4 c0 = tb[6 * lw + 4], c1 = tb[6 * lw + 5];
@@ -300,10 +301,14 @@ _Pragma("unroll") \
         c[8] = f.fzr; c[9] = f.fzi; c[10] = f.zz; c[11] = fr; c[12] = fi;
         cibuf[4 * lw] = b0.y;                                                                  // ADC row
         cibuf[4 * lw + 1] = (f2 & 2) ? (int)((unsigned)c0.w + (unsigned)patoff[(c1.y >> 8) & 0xff]) : -1; // D table
-        const int nnew = (int)((unsigned)b1.x & 0xffff), nxt = b1.z;
-        need = max(nnew >> 5, nxt < 0 ? -1 : nxt >> 5) + 1;
+        nnew = (int)((unsigned)b1.x & 0xffff); nxt = b1.z;
         if (lw == TRC_PER_WINDOW - 1) cibuf[4 * lw + 2] = nxt;
       }
+      // slots a TR needs: it applies to orders 0..nact and shifts orders 0..min(n_new, nact + 1) (what lies above
+      // nact + 1 is unobservable and need not move); nact of TR j is the "next nact" of TR j - 1
+      int curv = __shfl_up_sync(FULL, nxt, 1);
+      if (lw == 0) curv = nact;
+      if (lw < TRC_PER_WINDOW) need = (max(min(nnew, curv + 1), 0) >> 5) + 1;
       need = max(__reduce_max_sync(FULL, need), nslot);
       __syncwarp();
 #define TRCW(K_) case K_: trc_window<real, NS, K_>(Pr, Pi, Mr, Mi, Zr, Zi, cwbuf, cibuf, TRC_PER_WINDOW, coef, p.C, lane, valid, is_first, is_last, srcUp, srcDn, sig, p.sig_stride, a_rel); break;
