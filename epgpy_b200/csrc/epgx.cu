@@ -156,7 +156,7 @@ static int choose_variant(epgx_plan *pl, int kernel, int lanes, int vars, int at
       c.var_tiles = 1;
       c.atoms_per_cta = A;
       c.threads_per_cta = A * G;
-      c.smem_bytes = 2 * epgx::kTapeChunk * 32 + ((A * t.npattern + 3) & ~3) * 4 + 32;
+      c.smem_bytes = 2 * epgx::kTapeChunk * 32 + ((A * t.npattern + 3) & ~3) * 4 + ((A * G + 31) / 32) * 32 * 9 * rsz + 32;
       c.ring = C;
       return EPGX_OK;
     }

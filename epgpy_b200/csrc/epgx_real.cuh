@@ -22,37 +22,21 @@ namespace epgx {
 
 // One tape window of TAPE_CHUNK / 2 whole-TR records (fused E.T.E, plain ADC, unit shift +1) for one atom
 // per warp, with a COMPILE-TIME number K of active slots: the per-TR body is a single basic block (no slot
-// dispatch), so the scheduler overlaps the coefficient broadcasts, the 9 K FMAs and the 4 K shuffles /
-// selects of the shift.  K is the largest slot count of the window; a slot above the populated orders
-// holds zeros, so over-covering by (at most) one slot changes nothing.
+// dispatch), so the scheduler overlaps the coefficient loads, the 9 K FMAs and the 4 K shuffles / selects
+// of the shift.  K is the largest slot count of the window; a slot above the populated orders holds zeros,
+// so over-covering by (at most) one slot changes nothing.  The fused coefficients of the window's TRs wait
+// in the warp's shared-memory rows cw[TR][8] (written by lane TR); lane 0 leaves the echo of TR j in sb[j].
 template <typename real, int NS, int K>
-__device__ __forceinline__ void tr_window(real (&P)[NS], real (&M)[NS], real (&Z)[NS], const Fused5<real> &fv, int rowv,
-                                          bool lane0, bool valid, bool is_first, bool is_last, int srcUp, int srcDn,
-                                          typename vec2<real>::type *sig, long long sig_stride, long long a_rel) {
+__device__ __forceinline__ void tr_window(real (&P)[NS], real (&M)[NS], real (&Z)[NS], const real *cw, real *sb, bool lane0,
+                                          bool is_first, bool is_last, int srcUp, int srcDn) {
   typedef typename vec2<real>::type real2;
   const unsigned FULL = 0xffffffffu;
   if constexpr (K <= NS) {
-#ifdef EPGX_PIPELINE_BCAST
-    // software pipeline: the coefficients of TR j + 1 are broadcast while TR j computes
-    real a = __shfl_sync(FULL, fv.a, 0), w = __shfl_sync(FULL, fv.w, 0), b = __shfl_sync(FULL, fv.b, 0);
-    real u = __shfl_sync(FULL, fv.u, 0), h = __shfl_sync(FULL, fv.h, 0);
-    real fz = __shfl_sync(FULL, fv.fz, 0), zz = __shfl_sync(FULL, fv.zz, 0);
-    int row = __shfl_sync(FULL, rowv, 0);
 #pragma unroll 1
     for (int j = 0; j < TAPE_CHUNK / 2; ++j) {
-      const int jn = (j + 1) & (TAPE_CHUNK / 2 - 1);
-      const real na = __shfl_sync(FULL, fv.a, jn), nw = __shfl_sync(FULL, fv.w, jn), nb = __shfl_sync(FULL, fv.b, jn);
-      const real nu = __shfl_sync(FULL, fv.u, jn), nh = __shfl_sync(FULL, fv.h, jn);
-      const real nfz = __shfl_sync(FULL, fv.fz, jn), nzz = __shfl_sync(FULL, fv.zz, jn);
-      const int nrow = __shfl_sync(FULL, rowv, jn);
-#else
-#pragma unroll 1
-    for (int j = 0; j < TAPE_CHUNK / 2; ++j) {
-      const real a = __shfl_sync(FULL, fv.a, j), w = __shfl_sync(FULL, fv.w, j), b = __shfl_sync(FULL, fv.b, j);
-      const real u = __shfl_sync(FULL, fv.u, j), h = __shfl_sync(FULL, fv.h, j);
-      const real fz = __shfl_sync(FULL, fv.fz, j), zz = __shfl_sync(FULL, fv.zz, j);
-      const int row = __shfl_sync(FULL, rowv, j);
-#endif
+      // coefficients of TR j: four broadcast loads from the warp's staging rows (a, w | b, u | h, fz | zz, -)
+      const real2 c0 = ((const real2 *)cw)[4 * j], c1v = ((const real2 *)cw)[4 * j + 1], c2 = ((const real2 *)cw)[4 * j + 2];
+      const real a = c0.x, w = c0.y, b = c1v.x, u = c1v.y, h = c2.x;
 #pragma unroll
       for (int s = 0; s < K; ++s) {
         const real p_ = P[s], m_ = M[s], z_ = Z[s];
@@ -60,8 +44,11 @@ __device__ __forceinline__ void tr_window(real (&P)[NS], real (&M)[NS], real (&Z
         M[s] = a * m_ + b * p_ + u * z_;
         Z[s] = w * z_ + h * (p_ + m_);
       }
-      if (lane0) { P[0] += fz; M[0] += fz; Z[0] += zz; }
-      if (lane0 && valid) sig[(long long)row * sig_stride + a_rel] = real2{P[0], real(0)};
+      if (lane0) {
+        const real fz = c2.y, zz = cw[8 * j + 6];
+        P[0] += fz; M[0] += fz; Z[0] += zz;
+        sb[j] = P[0]; // the echo of TR j; written to HBM by lane j after the window
+      }
       // unit shift +1: F+ up (last lane takes over its previous slot, then rotate), F- down (first lane sends its
       // next slot), F+(0) <- F-(1)
       const real c1 = __shfl_sync(FULL, M[0], 1);
@@ -77,9 +64,6 @@ __device__ __forceinline__ void tr_window(real (&P)[NS], real (&M)[NS], real (&Z
         M[s] = __shfl_sync(FULL, is_first ? keep : cur, srcDn);
         keep = cur;
       }
-#ifdef EPGX_PIPELINE_BCAST
-      a = na; w = nw; b = nb; u = nu; h = nh; fz = nfz; zz = nzz; row = nrow;
-#endif
     }
   }
 }
@@ -109,6 +93,9 @@ __global__ void __launch_bounds__(256, (sizeof(real) * NS <= 64 ? 3 : sizeof(rea
 
   int4 *tbuf = (int4 *)smem_raw;
   int *patoff = (int *)(tbuf + 2 * TAPE_CHUNK * 2) + al * p.npattern;
+  // whole-TR windows (G == 32): per warp, coefficient rows [32][8] and the echoes of the window [32]
+  real *cw = (real *)((int *)(tbuf + 2 * TAPE_CHUNK * 2) + ((p.A * p.npattern + 3) & ~3)) + (size_t)(tid >> 5) * (32 * 9);
+  real *sb = cw + 32 * 8;
   {
     int idx[EPGX_MAX_DIMS];
     long long r = atom;
@@ -242,18 +229,25 @@ __global__ void __launch_bounds__(256, (sizeof(real) * NS <= 64 ? 3 : sizeof(rea
                                           fl & EPGX_FLAG_POST, ldc(cb), ldc(cb + 1),
                                           ldc(coef + (unsigned)b0.w + patoff[(b1.y >> 8) & 0xff]), false, m0);
       const int rowv = b0.y, nnewv = (int)((unsigned)b1.x & 0xffff), nextv = b1.z;
+      {
+        real2 *c = (real2 *)(cw + 8 * lw);
+        c[0] = real2{fv.a, fv.w}; c[1] = real2{fv.b, fv.u}; c[2] = real2{fv.h, fv.fz}; c[3] = real2{fv.zz, real(0)};
+      }
       // largest slot count any TR of the window needs: it applies to orders 0..nact and shifts orders
       // 0..min(n_new, nact + 1) -- what lies above nact + 1 is unobservable (lowering.py) and need not move
       int curv = __shfl_up_sync(FULL, nextv, 1); // nact of TR j = the "next nact" of TR j - 1
       if (lw == 0) curv = nact;
       int need = (max(min(nnewv, curv + 1), 0) >> 5) + 1;
       need = max(__reduce_max_sync(FULL, need), nslot);
-#define TRW(K_) case K_: tr_window<real, NS, K_>(P, M, Z, fv, rowv, lane == 0, valid, is_first, is_last, srcUp, srcDn, sig, p.sig_stride, a_rel); break;
+      __syncwarp();
+#define TRW(K_) case K_: tr_window<real, NS, K_>(P, M, Z, cw, sb, lane == 0, is_first, is_last, srcUp, srcDn); break;
       switch (need) {
         TRW(1) TRW(2) TRW(3) TRW(4) TRW(5) TRW(6) TRW(7) TRW(8) TRW(9) TRW(10) TRW(11) TRW(12) TRW(13) TRW(14) TRW(15) TRW(16)
         TRW(17) TRW(18) TRW(19) TRW(20) TRW(21) TRW(22) TRW(23) TRW(24) TRW(25) TRW(26) TRW(27) TRW(28) TRW(29) TRW(30) TRW(31) TRW(32)
       default: break;
       }
+      __syncwarp();
+      if (valid) sig[(long long)rowv * p.sig_stride + a_rel] = real2{sb[lw], real(0)}; // lane j: the echo of TR j
 #undef TRW
       nact = __shfl_sync(FULL, nextv, TAPE_CHUNK / 2 - 1);
       nslot = nact < 0 ? 0 : (nact >> lgG) + 1;
