@@ -144,7 +144,7 @@ static int choose_variant(epgx_plan *pl, int kernel, int lanes, int vars, int at
     if (G > 32) G = 32;
     const int need = (C + G - 1) / G;
     int NS = 0;
-    for (int o : {1, 2, 4, 8, 16, 32})
+    for (int o : {2, 4, 8, 16, 32}) // register slots come in pairs: blocks of two orders per lane
       if (o >= need && !NS) NS = o;
     if (NS && NS <= ns_max) {
       int A = atoms > 0 ? atoms : 128 / G;

@@ -6,8 +6,13 @@
 // reference computes them anyway and returns ~1e-17 round-off, epgpy/transition.py:114-151).  The MRF
 // FISP / phase-alternated bSSFP families are of this kind.  This kernel keeps three reals per order
 // instead of six: half the FMAs, half the shuffles of the unit shift, half the registers (so twice the
-// resident warps) of epgx_reg.cuh, same layout otherwise: order k in slot k / G of lane k % G, tape
-// streamed through shared memory, shifts by rotate-by-one-lane.  One warp (or a sub-warp group) per atom.
+// resident warps) of epgx_reg.cuh.  One warp (or a sub-warp group of G lanes) per atom.
+//
+// Layout: orders are dealt to the lanes in BLOCKS OF TWO -- order k = 2 b + i lives in lane b % G, register
+// slot 2 (b / G) + i.  A unit shift moves F+(k - 1) to F+(k): inside a block that is a change of register
+// (free), only the value that leaves a block crosses to the next lane.  In the whole-TR fast path the register
+// roles alternate with the parity of the TR (tr_window), so a shift costs ONE shuffled register per block
+// and component instead of two; the generic record path keeps the canonical roles and copies.
 #pragma once
 #include <cuda_pipeline.h>
 
@@ -21,48 +26,66 @@
 namespace epgx {
 
 // One tape window of TAPE_CHUNK / 2 whole-TR records (fused E.T.E, plain ADC, unit shift +1) for one atom
-// per warp, with a COMPILE-TIME number K of active slots: the per-TR body is a single basic block (no slot
-// dispatch), so the scheduler overlaps the coefficient loads, the 9 K FMAs and the 4 K shuffles / selects
-// of the shift.  K is the largest slot count of the window; a slot above the populated orders holds zeros,
-// so over-covering by (at most) one slot changes nothing.  The fused coefficients of the window's TRs wait
-// in the warp's shared-memory rows cw[TR][8] (written by lane TR); lane 0 leaves the echo of TR j in sb[j].
-template <typename real, int NS, int K>
+// per warp, with a COMPILE-TIME number KP of active register pairs: the per-TR body is a single basic block (no
+// slot dispatch), so the scheduler overlaps the coefficient loads, the 18 KP FMAs and the 2 KP shuffles /
+// selects of the shift.  KP is the largest pair count of the window; registers above the populated orders
+// hold zeros (or unobservable values), so over-covering changes nothing.  The fused coefficients of the
+// window's TRs wait in the warp's shared-memory rows cw[TR][8] (written by lane TR); lane 0 leaves the echo of
+// TR j in sb[j].
+//
+// Two TRs per iteration.  Even TR ("phase 0"): the even order of a block is in register 2 sp, the odd one in
+// 2 sp + 1 (canonical).  Its shift rotates the ODD F+ registers up one lane (they become the even orders of
+// the next block) and the EVEN F- registers down one lane (they become the odd orders of the previous block);
+// the other registers stay where they are and change role.  Odd TR ("phase 1"): roles swapped, its shift
+// rotates the even F+ and the odd F- registers and restores the canonical roles.  Z never moves.
+template <typename real, int NS, int KP>
 __device__ __forceinline__ void tr_window(real (&P)[NS], real (&M)[NS], real (&Z)[NS], const real *cw, real *sb, bool lane0,
                                           bool is_first, bool is_last, int srcUp, int srcDn) {
   typedef typename vec2<real>::type real2;
   const unsigned FULL = 0xffffffffu;
-  if constexpr (K <= NS) {
+  if constexpr (2 * KP <= NS) {
 #pragma unroll 1
-    for (int j = 0; j < TAPE_CHUNK / 2; ++j) {
-      // coefficients of TR j: four broadcast loads from the warp's staging rows (a, w | b, u | h, fz | zz, -)
-      const real2 c0 = ((const real2 *)cw)[4 * j], c1v = ((const real2 *)cw)[4 * j + 1], c2 = ((const real2 *)cw)[4 * j + 2];
-      const real a = c0.x, w = c0.y, b = c1v.x, u = c1v.y, h = c2.x;
+    for (int j = 0; j < TAPE_CHUNK / 2; j += 2) {
 #pragma unroll
-      for (int s = 0; s < K; ++s) {
-        const real p_ = P[s], m_ = M[s], z_ = Z[s];
-        P[s] = a * p_ + b * m_ + u * z_;
-        M[s] = a * m_ + b * p_ + u * z_;
-        Z[s] = w * z_ + h * (p_ + m_);
-      }
-      if (lane0) {
-        const real fz = c2.y, zz = cw[8 * j + 6];
-        P[0] += fz; M[0] += fz; Z[0] += zz;
-        sb[j] = P[0]; // the echo of TR j; written to HBM by lane j after the window
-      }
-      // unit shift +1: F+ up (last lane takes over its previous slot, then rotate), F- down (first lane sends its
-      // next slot), F+(0) <- F-(1)
-      const real c1 = __shfl_sync(FULL, M[0], 1);
+      for (int ph = 0; ph < 2; ++ph) {
+        // coefficients of the TR: broadcast loads from the warp's staging rows (a, w | b, u | h, fz | zz, -)
+        const real2 c0 = ((const real2 *)cw)[4 * (j + ph)], c1v = ((const real2 *)cw)[4 * (j + ph) + 1],
+                    c2 = ((const real2 *)cw)[4 * (j + ph) + 2];
+        const real a = c0.x, w = c0.y, b = c1v.x, u = c1v.y, h = c2.x;
 #pragma unroll
-      for (int s = K - 1; s >= 0; --s) {
-        const real v = is_last ? (s > 0 ? P[s > 0 ? s - 1 : 0] : c1) : P[s];
-        P[s] = __shfl_sync(FULL, v, srcUp);
-      }
-      real keep = real(0);
+        for (int sp = 0; sp < KP; ++sp)
 #pragma unroll
-      for (int s = K - 1; s >= 0; --s) {
-        const real cur = M[s];
-        M[s] = __shfl_sync(FULL, is_first ? keep : cur, srcDn);
-        keep = cur;
+          for (int i = 0; i < 2; ++i) {
+            const int r = 2 * sp + (i ^ ph); // register of F+- (k = 2 b + i) in this phase; Z(k) is in 2 sp + i
+            const real p_ = P[r], m_ = M[r], z_ = Z[2 * sp + i];
+            P[r] = a * p_ + b * m_ + u * z_;
+            M[r] = a * m_ + b * p_ + u * z_;
+            Z[2 * sp + i] = w * z_ + h * (p_ + m_);
+          }
+        if (lane0) {
+          const real fz = c2.y, zz = cw[8 * (j + ph) + 6];
+          P[ph] += fz; M[ph] += fz; Z[0] += zz;
+          sb[j + ph] = P[ph]; // the echo of the TR; written to HBM by lane j + ph after the window
+        }
+        // unit shift +1.  F+: registers of the odd orders (2 sp + 1 - ph) rotate up one lane, the last lane sending
+        // the value of its previous pair; order 0 <- F-(1), which lane 0 holds itself.  F-: registers of the even
+        // orders (2 sp + ph) rotate down one lane, the first lane sending the value of its next pair.
+        const real f1 = M[1 - ph];
+#pragma unroll
+        for (int sp = KP - 1; sp >= 0; --sp) {
+          const int r = 2 * sp + 1 - ph;
+          const real v = (is_last && sp > 0) ? P[sp > 0 ? r - 2 : r] : P[r];
+          P[r] = __shfl_sync(FULL, v, srcUp);
+        }
+        if (is_first) P[1 - ph] = f1;
+        real keep = real(0);
+#pragma unroll
+        for (int sp = KP - 1; sp >= 0; --sp) {
+          const int r = 2 * sp + ph;
+          const real cur = M[r];
+          M[r] = __shfl_sync(FULL, is_first ? keep : cur, srcDn);
+          keep = cur;
+        }
       }
     }
   }
@@ -112,13 +135,18 @@ __global__ void __launch_bounds__(256, (sizeof(real) * NS <= 64 ? 3 : sizeof(rea
   }
   __syncthreads();
 
+  static_assert(NS % 2 == 0, "register slots come in pairs (blocks of two orders)");
+  // order held by register slot s of this lane (canonical roles): k = 2 ((s / 2) G + lane) + s % 2
+#define ORDER_OF(s) (((((s) >> 1) << lgG) + lane) * 2 + ((s) & 1))
+// register slots (whole pairs) that hold orders 0..n
+#define SLOTS_FOR(n) ((((n) >> (lgG + 1)) + 1) * 2)
   real P[NS], M[NS], Z[NS];
   real m0 = ldc(coef + p.m0_off + patoff[p.m0_pat]);
   {
     const real *ib = coef + p.init_off + patoff[p.init_pat];
 #pragma unroll
     for (int s = 0; s < NS; ++s) {
-      const int k = s * G + lane;
+      const int k = ORDER_OF(s);
       const bool in = k <= p.init_n;
       P[s] = in ? ldc(ib + 6 * k) : real(0);
       M[s] = in ? ldc(ib + 6 * k + 2) : real(0);
@@ -161,39 +189,54 @@ __global__ void __launch_bounds__(256, (sizeof(real) * NS <= 64 ? 3 : sizeof(rea
     const int shift = (SHIFT_), n_old = (NOLD_), n_new = (NNEW_), sflags = (SFLAGS_);                      \
     const int n_move = max(min(n_new, nact + 1), 0); /* orders above nact + 1 are unobservable: they stay */ \
     nact = (NEXT_);                                                                                        \
-    nslot = nact < 0 ? 0 : (nact >> lgG) + 1;                                                              \
+    nslot = nact < 0 ? 0 : SLOTS_FOR(nact);                                                                \
     if (sflags & EPGX_SEG_RESET) {                                                                         \
       _Pragma("unroll") for (int s = 0; s < NS; ++s) P[s] = M[s] = Z[s] = real(0);                         \
       if (lane == 0) Z[0] = m0;                                                                            \
     } else if (shift != 0) {                                                                               \
-      const int nsl = (n_move >> lgG) + 1;                                                                 \
+      const int npair = (n_move >> (lgG + 1)) + 1;                                                         \
       if (shift > 0) SHIFT_REAL(P, M) else SHIFT_REAL(M, P)                                                \
       if (sflags & EPGX_SEG_MASK_TOP) {                                                                    \
         _Pragma("unroll") for (int s = 0; s < NS; ++s)                                                     \
-          if (s * G + lane > n_new) {                                                                      \
+          if (ORDER_OF(s) > n_new) {                                                                       \
             if (shift > 0) P[s] = real(0); else M[s] = real(0);                                            \
           }                                                                                                \
       }                                                                                                    \
     }                                                                                                      \
   }
-// U: the component whose orders move up (F+ for shift > 0), D: the other one; new order 0 of U is old
-// order 1 of D (real state: no conjugation).  up: the LAST lane first takes over the value of its previous
-// slot, then one rotate-by-one-lane delivers every order to its new owner (descending = in place);
-// dn: rotate the other way, the FIRST lane sends the value of its NEXT slot to the last lane.
+// U: the component whose orders move up (F+ for shift > 0), D: the other one; the new order 0 of U is the old
+// order 1 of D (real state: no conjugation), which lane 0 holds itself.  Canonical roles before and after:
+// up: the odd register of every pair rotates one lane up (the LAST lane sending the value of its previous pair)
+// and becomes the even one, the old even one becomes the odd one; dn: mirrored.
+#define PAIR_CASE(K, ...)                           \
+  case (K) + 1:                                     \
+    if (NS > 2 * (K)) {                             \
+      constexpr int sp = 2 * (K) < NS ? (K) : 0;    \
+      __VA_ARGS__                                   \
+    }
+#define DUFFP(n, ...)                                                                                       \
+  switch (n) {                                                                                              \
+    PAIR_CASE(15, __VA_ARGS__) PAIR_CASE(14, __VA_ARGS__) PAIR_CASE(13, __VA_ARGS__) PAIR_CASE(12, __VA_ARGS__) \
+    PAIR_CASE(11, __VA_ARGS__) PAIR_CASE(10, __VA_ARGS__) PAIR_CASE(9, __VA_ARGS__) PAIR_CASE(8, __VA_ARGS__)   \
+    PAIR_CASE(7, __VA_ARGS__) PAIR_CASE(6, __VA_ARGS__) PAIR_CASE(5, __VA_ARGS__) PAIR_CASE(4, __VA_ARGS__)     \
+    PAIR_CASE(3, __VA_ARGS__) PAIR_CASE(2, __VA_ARGS__) PAIR_CASE(1, __VA_ARGS__) PAIR_CASE(0, __VA_ARGS__)     \
+  default:                                                                                                  \
+    break;                                                                                                  \
+  }
 #define SHIFT_REAL(U, D)                                                                                   \
   {                                                                                                        \
-    real c1;                                                                                               \
-    if (G == 1) c1 = NS > 1 ? D[NS > 1 ? 1 : 0] : real(0);                                                 \
-    else c1 = __shfl_sync(FULL, D[0], gbase | 1);                                                          \
-    if (n_old < 1) c1 = real(0);                                                                           \
-    DUFF(nsl, {                                                                                            \
-      const real v = is_last ? (s > 0 ? U[s > 0 ? s - 1 : 0] : c1) : U[s];                                 \
-      U[s] = __shfl_sync(FULL, v, srcUp);                                                                  \
+    const real f1 = n_old < 1 ? real(0) : D[1];                                                            \
+    DUFFP(npair, {                                                                                         \
+      const real v = (is_last && sp > 0) ? U[sp > 0 ? 2 * sp - 1 : 1] : U[2 * sp + 1];                     \
+      U[2 * sp + 1] = U[2 * sp];                                                                           \
+      U[2 * sp] = __shfl_sync(FULL, v, srcUp);                                                             \
     })                                                                                                     \
-    real keep = real(0); /* old value of the slot above (zero above the populated orders) */               \
-    DUFF(nsl, {                                                                                            \
-      const real cur = D[s];                                                                               \
-      D[s] = __shfl_sync(FULL, is_first ? keep : cur, srcDn);                                              \
+    if (is_first) U[0] = f1;                                                                               \
+    real keep = real(0); /* old even value of the pair above (zero above the populated orders) */          \
+    DUFFP(npair, {                                                                                         \
+      const real cur = D[2 * sp];                                                                          \
+      D[2 * sp] = D[2 * sp + 1];                                                                           \
+      D[2 * sp + 1] = __shfl_sync(FULL, is_first ? keep : cur, srcDn);                                     \
       keep = cur;                                                                                          \
     })                                                                                                     \
   }
@@ -237,20 +280,19 @@ __global__ void __launch_bounds__(256, (sizeof(real) * NS <= 64 ? 3 : sizeof(rea
       // 0..min(n_new, nact + 1) -- what lies above nact + 1 is unobservable (lowering.py) and need not move
       int curv = __shfl_up_sync(FULL, nextv, 1); // nact of TR j = the "next nact" of TR j - 1
       if (lw == 0) curv = nact;
-      int need = (max(min(nnewv, curv + 1), 0) >> 5) + 1;
-      need = max(__reduce_max_sync(FULL, need), nslot);
+      int need = (max(min(nnewv, curv + 1), 0) >> 6) + 1; // register pairs (64 orders each)
+      need = max(__reduce_max_sync(FULL, need), nslot >> 1);
       __syncwarp();
 #define TRW(K_) case K_: tr_window<real, NS, K_>(P, M, Z, cw, sb, lane == 0, is_first, is_last, srcUp, srcDn); break;
       switch (need) {
         TRW(1) TRW(2) TRW(3) TRW(4) TRW(5) TRW(6) TRW(7) TRW(8) TRW(9) TRW(10) TRW(11) TRW(12) TRW(13) TRW(14) TRW(15) TRW(16)
-        TRW(17) TRW(18) TRW(19) TRW(20) TRW(21) TRW(22) TRW(23) TRW(24) TRW(25) TRW(26) TRW(27) TRW(28) TRW(29) TRW(30) TRW(31) TRW(32)
       default: break;
       }
       __syncwarp();
       if (valid) sig[(long long)rowv * p.sig_stride + a_rel] = real2{sb[lw], real(0)}; // lane j: the echo of TR j
 #undef TRW
       nact = __shfl_sync(FULL, nextv, TAPE_CHUNK / 2 - 1);
-      nslot = nact < 0 ? 0 : (nact >> lgG) + 1;
+      nslot = nact < 0 ? 0 : SLOTS_FOR(nact);
       continue;
     }
     for (int r = 0; r < cnt; ++r) {
@@ -287,7 +329,7 @@ __global__ void __launch_bounds__(256, (sizeof(real) * NS <= 64 ? 3 : sizeof(rea
       case EPGX_OP_D: {
         const real *c = coef + off0 + patoff[pat0];
         DUFF(nslot, {
-          const int k = min(s * G + lane, p.C - 1);
+          const int k = min(ORDER_OF(s), p.C - 1);
           P[s] *= ldc(c + 3 * k); M[s] *= ldc(c + 3 * k + 1); Z[s] *= ldc(c + 3 * k + 2);
         })
       } break;
@@ -337,6 +379,10 @@ __global__ void __launch_bounds__(256, (sizeof(real) * NS <= 64 ? 3 : sizeof(rea
 #undef SHIFT_REAL
 #undef DUFF
 #undef SLOT_CASE
+#undef DUFFP
+#undef PAIR_CASE
+#undef ORDER_OF
+#undef SLOTS_FOR
 }
 
 } // namespace epgx

@@ -5,7 +5,6 @@
 namespace epgx {
 template <> cudaError_t launch_real<float>(int slots, const KParams &kp, dim3 grid, int threads, int smem, cudaStream_t st) {
   switch (slots) {
-  case 1: real_kernel<float, 1><<<grid, threads, smem, st>>>(kp); break;
   case 2: real_kernel<float, 2><<<grid, threads, smem, st>>>(kp); break;
   case 4: real_kernel<float, 4><<<grid, threads, smem, st>>>(kp); break;
   case 8: real_kernel<float, 8><<<grid, threads, smem, st>>>(kp); break;
