@@ -19,10 +19,6 @@
 #include "epgx_common.cuh"
 #include "epgx_reg.cuh"
 
-#ifndef EPGX_MINB_128
-#define EPGX_MINB_128 2
-#endif
-
 namespace epgx {
 
 // One tape window of TAPE_CHUNK / 2 whole-TR records (fused E.T.E, plain ADC, unit shift +1) for one atom
@@ -91,8 +87,15 @@ __device__ __forceinline__ void tr_window(real (&P)[NS], real (&M)[NS], real (&Z
   }
 }
 
-template <typename real, int NS>
-__global__ void __launch_bounds__(256, (sizeof(real) * NS <= 64 ? 3 : sizeof(real) * NS <= 128 ? EPGX_MINB_128 : 1)) real_kernel(const KParams p) {
+// register budget: CTAs of at most 128 threads (MAXT = 128, the default launch shape: four warps) get 168 registers
+// when the state takes 96 of them (FP64 NS = 16: three CTAs per SM; measured 246 ms against 282 ms at 128 registers
+// and 258 ms uncapped for the 1 M-atom FISP dictionary) and 128 registers for the smaller states
+constexpr int real_min_blocks(int state_bytes, int maxt) {
+  return maxt <= 128 ? (state_bytes <= 64 ? 4 : state_bytes <= 128 ? 3 : 2) : (state_bytes <= 64 ? 3 : state_bytes <= 128 ? 2 : 1);
+}
+
+template <typename real, int NS, int MAXT = 256>
+__global__ void __launch_bounds__(MAXT, real_min_blocks(sizeof(real) * NS, MAXT)) real_kernel(const KParams p) {
   typedef typename vec2<real>::type real2;
   extern __shared__ __align__(16) unsigned char smem_raw[];
 

@@ -7,8 +7,14 @@ template <> cudaError_t launch_real<float>(int slots, const KParams &kp, dim3 gr
   switch (slots) {
   case 2: real_kernel<float, 2><<<grid, threads, smem, st>>>(kp); break;
   case 4: real_kernel<float, 4><<<grid, threads, smem, st>>>(kp); break;
-  case 8: real_kernel<float, 8><<<grid, threads, smem, st>>>(kp); break;
-  case 16: real_kernel<float, 16><<<grid, threads, smem, st>>>(kp); break;
+  case 8:
+    if (threads <= 128) real_kernel<float, 8, 128><<<grid, threads, smem, st>>>(kp);
+    else real_kernel<float, 8><<<grid, threads, smem, st>>>(kp);
+    break;
+  case 16:
+    if (threads <= 128) real_kernel<float, 16, 128><<<grid, threads, smem, st>>>(kp);
+    else real_kernel<float, 16><<<grid, threads, smem, st>>>(kp);
+    break;
   case 32: real_kernel<float, 32><<<grid, threads, smem, st>>>(kp); break;
   default: return cudaErrorInvalidValue;
   }
