@@ -389,8 +389,10 @@ def main():
             "bound": "fma", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
             # dram__bytes_read.sum + dram__bytes_write.sum of the ncu --set full capture in profiles/ (27 000-atom
             # launch: 4.8 MB read + 432.3 MB written = 16.19 kB per atom), scaled to this launch's atom count
-            "traffic": 16190.0 * cnt if (args.ntr == NTR and args.dtype == "f64") else None,
-            "traffic_note": "scaled per atom from profiles/r01_real_kernel_f64_full.txt (algorithmic: 16 kB per atom)",
+            "traffic": 14492.0 * cnt if (args.ntr == NTR and args.dtype == "f64") else None,
+            "traffic_note": "scaled per atom from the 27 000-atom capture profiles/r01_real_kernel_f64_full.txt "
+                            "(2.7 MB read + 388.6 MB written; algorithmic: 16 kB per atom, the difference is dirty lines "
+                            "still in the 126 MB L2 when the kernel ends)",
             "peak_source": f"measured live on this GPU: dependent-FMA microbenchmark epgx_fma_peak({args.dtype})",
             "flops_per_atom_executed": cfg["flops_per_atom"],
             "hbm": {"achieved": bytes_alg / (step_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",

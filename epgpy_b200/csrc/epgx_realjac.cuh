@@ -150,14 +150,23 @@ __device__ __forceinline__ void rj_shift_mw(real (&U)[SETS][NS], real (&D)[SETS]
   constexpr int NSX = NS + 2, RS = (int)sizeof(real);
   if constexpr (K <= NS) {
     const bool first = lq == 0, last = lq == 31;
+    if (last) { // one divergent region per sender (ptxas turns predicated stores into a branch each)
 #pragma unroll
-    for (int q = 0; q < SETS; ++q) {
+      for (int q = 0; q < SETS; ++q)
 #pragma unroll
-      for (int s = 0; s < K; ++s) sts_if(up_w + (q * NSX + s) * RS, U[q][s], last);
+        for (int s = 0; s < K; ++s) sts_if(up_w + (q * NSX + s) * RS, U[q][s], true);
+    }
+    if (first) {
 #pragma unroll
-      for (int s = 0; s < K; ++s) sts_if(dn_w + (q * NSX + s) * RS, D[q][s], first);
-      sts_if(dn_w + (q * NSX + K) * RS, real(0), first);
-      sts_if(up_c1 + q * NSX * RS, has1 ? D[q][0] : real(0), c1lane);
+      for (int q = 0; q < SETS; ++q) {
+#pragma unroll
+        for (int s = 0; s < K; ++s) sts_if(dn_w + (q * NSX + s) * RS, D[q][s], true);
+        sts_if(dn_w + (q * NSX + K) * RS, real(0), true);
+      }
+    }
+    if (c1lane) {
+#pragma unroll
+      for (int q = 0; q < SETS; ++q) sts_if(up_c1 + q * NSX * RS, has1 ? D[q][0] : real(0), true);
     }
     asm volatile("bar.sync %0, %1;" ::"r"(barrier_id), "r"(G) : "memory");
 #pragma unroll
