@@ -38,6 +38,7 @@ struct epgx_plan {
   int64_t natoms;
   double flops_cplx, flops_real, updates; // executed real flops per atom (complex / real-valued kernels)
   bool realjac_ok; // real-valued graph with real-valued derivative injections
+  int64_t ntrj = 0; // whole-TR derivative groups (EPGX_OP_TRJ) in the merged stream
   bool real_ok; // real-valued phase graph: eligible for the three-reals-per-order kernel
   epgx_config cfg;
   // workspace layout (bytes)
@@ -100,8 +101,33 @@ static int choose_variant(epgx_plan *pl, int kernel, int lanes, int vars, int at
   const bool reg_ok = t.nvar == 0 && t.npool == 1;
   if (kernel == 2 && !reg_ok)
     return fail(EPGX_ERR_UNSUPPORTED, "the register kernel runs forward simulations of one pool only");
-  if (kernel == 4 && !pl->realjac_ok)
-    return fail(EPGX_ERR_UNSUPPORTED, "the real-valued derivative kernel needs a real-valued tape with order-1 variables");
+  if ((kernel == 4 || kernel == 5) && !pl->realjac_ok)
+    return fail(EPGX_ERR_UNSUPPORTED, "the real-valued derivative kernels need a real-valued tape with order-1 variables");
+  if (kernel == 5 && t.nvar > 3)
+    return fail(EPGX_ERR_UNSUPPORTED, "the warp-per-state-set derivative kernel holds at most three variables");
+  // ---- one warp per state set (epgx_setjac.cuh): whole-TR derivative groups, 32 NS orders.  Automatic choice when
+  // most of the segments are such groups and the orders would not fit one warp of the orders-over-warps kernel
+  if (pl->realjac_ok && t.nvar <= 3 && (kernel == 5 || (kernel == 0 && C > 128 && 2 * pl->ntrj >= t.nseg))) {
+    const int need = (C + 31) / 32;
+    int NS = 0;
+    for (int o : {2, 4, 8, 16})
+      if (o >= need && !NS) NS = o;
+    if (NS) {
+      const int W = 1 + t.nvar;
+      c.kernel = 4;
+      c.lanes_per_atom = 32;
+      c.slots_per_lane = NS;
+      c.vars_per_pass = t.nvar;
+      c.var_tiles = 1;
+      c.atoms_per_cta = 1;
+      c.threads_per_cta = 32 * W;
+      c.smem_bytes = 2 * epgx::kTapeChunk * 32 + ((t.npattern + 3) & ~3) * 4 + 2 * 3 * NS * 32 * rsz +
+                     W * (epgx::kTrjPerWindow * epgx::kSjRow + 16) * rsz + 64;
+      c.ring = C;
+      return EPGX_OK;
+    }
+    if (kernel == 5) return fail(EPGX_ERR_CAPACITY, "no warp-per-state-set instance holds " + std::to_string(C) + " orders");
+  }
   if (pl->realjac_ok && (kernel == 0 || kernel == 4)) {
     // ---- real-valued register kernel with 3 resident partial states: G = 32 W lanes x NS slots >= C orders
     const int ns_max = 4; // 4 slots x (1 + 3) state sets x 3 reals: the most that leaves three (FP64) / four (FP32) CTAs per SM
@@ -540,9 +566,14 @@ extern "C" int epgx_plan_create(const epgx_tape *t, epgx_plan **out) {
       if (purec) st[b0].flags |= 0x4000;
     }
     for (size_t b0 = 0; b0 < st.size(); b0 += CH) { // windows holding TRJ groups: coefficient assembly pass
-      bool anyj = false;
-      for (size_t j = b0; !anyj && j < st.size() && j < b0 + CH; j += 5) anyj = st[j].code == EPGX_OP_TRJ;
-      if (anyj) st[b0].flags |= 0x2000;
+      int nj = 0, nplain = 0;
+      for (size_t j = b0; j + 1 < st.size() && j < b0 + CH; j += 5)
+        if (st[j].code == EPGX_OP_TRJ) { ++nj; if (st[j + 1].flags == 2) ++nplain; }
+      pl->ntrj += nj;
+      if (nj) st[b0].flags |= 0x2000;
+      bool pure = nplain == epgx::kTrjPerWindow && b0 + CH <= st.size();
+      for (int j = 5 * epgx::kTrjPerWindow; pure && j < CH; ++j) pure = st[b0 + j].code == EPGX_OP_NOP;
+      if (pure) st[b0].flags |= 0x1000;
     }
   }
   pl->tape.ops = pl->ops.data();
@@ -628,6 +659,8 @@ static int dispatch(const epgx_plan *pl, const KParams &kp, cudaStream_t st) {
   dim3 grid((unsigned)((kp.atom_count + c.atoms_per_cta - 1) / c.atoms_per_cta), (unsigned)c.var_tiles);
   cudaError_t e;
   switch (c.kernel) {
+  case 4: e = f64 ? launch_setjac<double>(c.slots_per_lane, kp, grid, c.threads_per_cta, c.smem_bytes, st)
+                  : launch_setjac<float>(c.slots_per_lane, kp, grid, c.threads_per_cta, c.smem_bytes, st); break;
   case 3: e = f64 ? launch_realjac<double>(c.slots_per_lane, kp, grid, c.threads_per_cta, c.smem_bytes, st)
                   : launch_realjac<float>(c.slots_per_lane, kp, grid, c.threads_per_cta, c.smem_bytes, st); break;
   case 2: e = f64 ? launch_real<double>(c.slots_per_lane, kp, grid, c.threads_per_cta, c.smem_bytes, st)

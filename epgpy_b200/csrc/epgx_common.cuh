@@ -33,6 +33,8 @@
 // first record of a window says that it holds at least one of them.
 #define EPGX_OP_TRJ 67
 #define EPGX_CHUNK_ANY_TRJ 0x20000000
+// flags bit 12: the window is made of 12 plain groups (unit shift +1, no segment flags) followed by NOP records
+#define EPGX_CHUNK_PURE_TRJ 0x10000000
 #define EPGX_CHUNK_PURE_TRC 0x40000000
 
 namespace epgx {

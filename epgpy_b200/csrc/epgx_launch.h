@@ -10,9 +10,11 @@ template <typename real> cudaError_t launch_ring(int npool, int nvt, const KPara
 template <typename real> cudaError_t launch_reg(int slots, const KParams &kp, dim3 grid, int threads, int smem, cudaStream_t st);
 template <typename real> cudaError_t launch_real(int slots, const KParams &kp, dim3 grid, int threads, int smem, cudaStream_t st);
 template <typename real> cudaError_t launch_realjac(int slots, const KParams &kp, dim3 grid, int threads, int smem, cudaStream_t st);
+template <typename real> cudaError_t launch_setjac(int slots, const KParams &kp, dim3 grid, int threads, int smem, cudaStream_t st);
 constexpr int kTapeChunk = 64;      // == TAPE_CHUNK of epgx_reg.cuh (checked there)
 constexpr int kTrcPerWindow = 21;   // == TRC_PER_WINDOW
 constexpr int kTrcReals = 14;       // == TRC_REALS
 constexpr int kTrjPerWindow = 12;   // == TRJ_PER_WINDOW of epgx_realjac.cuh
 constexpr int kTrjReals = 32;       // == TRJ_REALS: (1 + 3) state sets x 8
+constexpr int kSjRow = 16;          // == SJ_ROW of epgx_setjac.cuh
 } // namespace epgx

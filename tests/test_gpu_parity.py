@@ -243,6 +243,11 @@ def test_realjac_whole_tr_groups(lanes, atoms, dtype, variables, max_nstate, epg
     except MemoryError:
         pytest.skip("more orders than lanes x slots of any instance")
     assert cfg["kernel"] == 3 and cfg["var_tiles"] == 1
+    if lanes == 0:  # the same tape through the warp-per-state-set kernel
+        alt, acfg = run(5, dtype)
+        assert acfg["kernel"] == 4 and acfg["threads_per_cta"] == 32 * (1 + len(variables))
+        assert rel_err(alt[0], got[0]) < (1e-11 if dtype == "f64" else RTOL32)
+        assert rel_err(alt[1], got[1]) < (1e-11 if dtype == "f64" else 5 * RTOL32)
     tol = 1e-11 if dtype == "f64" else RTOL32
     assert rel_err(got[0], ring[0]) < tol
     for i in range(len(variables)):

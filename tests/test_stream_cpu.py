@@ -67,3 +67,23 @@ def test_complex_injections_are_not_grouped(epg):
     case = cases.mse_jac(epg)  # T(150, 0): complex couplings, ring kernel
     low, plan, st = _stream(epg, case)
     assert plan.config()["kernel"] == 0 and not np.any(st["code"] == OP_TRJ)
+
+
+def test_kernel_choice_for_derivative_tapes(epg):
+    from epgpy_b200 import engine, lowering
+    # few orders: the orders-over-lanes kernel; many orders and whole-TR groups: one warp per state set
+    _, small, _ = _stream(epg, cases.fisp_jac_global(epg, ntr=40))
+    assert small.config()["kernel"] == 3
+    low, big, st = _stream(epg, cases.fisp_jac_global(epg, ntr=400))
+    cfg = big.config()
+    assert low.max_order + 1 > 128 and cfg["kernel"] == 4 and cfg["threads_per_cta"] == 128 and cfg["atoms_per_cta"] == 1
+    # pure windows: 12 plain groups + 4 NOP records
+    pure = [w0 for w0 in range(0, len(st) - 63, 64) if st["flags"][w0] & 0x1000]
+    assert len(pure) >= (low.nadc - 2) // 12 - 2
+    for w0 in pure:
+        assert np.all(st["code"][w0:w0 + 60:5] == OP_TRJ) and np.all(st["flags"][w0 + 1:w0 + 60:5] == 2)
+        assert np.all(st["code"][w0 + 60:w0 + 64] == OP_NOP)
+    big.set_variant(kernel=4)
+    assert big.config()["kernel"] == 3
+    big.set_variant(kernel=5)
+    assert big.config()["kernel"] == 4
