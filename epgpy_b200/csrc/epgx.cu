@@ -175,6 +175,7 @@ static int choose_variant(epgx_plan *pl, int kernel, int lanes, int vars, int at
     if (NS && NS <= ns_max) {
       int A = atoms > 0 ? atoms : 128 / G;
       while (A * G > 256 && A > 1) --A;
+      while (G >= 8 && A > 1 && A * 32 * 9 * rsz > 40 * 1024) --A; // staging rows of the whole-TR windows
       c.kernel = 2;
       c.lanes_per_atom = G;
       c.slots_per_lane = NS;
@@ -182,7 +183,7 @@ static int choose_variant(epgx_plan *pl, int kernel, int lanes, int vars, int at
       c.var_tiles = 1;
       c.atoms_per_cta = A;
       c.threads_per_cta = A * G;
-      c.smem_bytes = 2 * epgx::kTapeChunk * 32 + ((A * t.npattern + 3) & ~3) * 4 + ((A * G + 31) / 32) * 32 * 9 * rsz + 32;
+      c.smem_bytes = 2 * epgx::kTapeChunk * 32 + ((A * t.npattern + 3) & ~3) * 4 + (G >= 8 ? A * 32 * 9 * rsz : 0) + 32;
       c.ring = C;
       return EPGX_OK;
     }
@@ -559,7 +560,8 @@ extern "C" int epgx_plan_create(const epgx_tape *t, epgx_plan **out) {
     }
     for (size_t b0 = 0; b0 + CH <= st.size(); b0 += CH) {
       bool pure = true;
-      for (int j = 0; pure && j < CH; j += 2) pure = st[b0 + j].code == EPGX_OP_TR && st[b0 + j + 1].flags == 2;
+      for (int j = 0; pure && j < CH; j += 2) // unit shift +1, no segment flag but (possibly) the truncation at max_nstate
+        pure = st[b0 + j].code == EPGX_OP_TR && (st[b0 + j + 1].flags & ~(EPGX_SEG_MASK_TOP << 2)) == 2;
       if (pure) st[b0].flags |= 0x8000;
       bool purec = st[b0 + CH - 1].code == EPGX_OP_NOP;
       for (int j = 0; purec && j + 3 <= CH - 1; j += 3) purec = st[b0 + j].code == EPGX_OP_TRC && st[b0 + j + 1].flags == 2;
@@ -702,6 +704,7 @@ extern "C" int epgx_simulate_strided(const epgx_plan *pl, const void *ws, int64_
   kp.pats = (const int *)(w + pl->off_pats);
   kp.stream = w + pl->off_stream;
   kp.nstream = (int)pl->stream.size();
+  for (const epgx_segment &sg : pl->segs) kp.bounded |= (sg.flags & EPGX_SEG_MASK_TOP) ? 1 : 0;
   kp.coef = w + pl->off_coef;
   kp.signal = signal;
   kp.jac = jacobian;

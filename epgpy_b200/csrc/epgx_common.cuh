@@ -262,6 +262,7 @@ struct KParams {
   int shape[EPGX_MAX_DIMS];
   int ndim, npattern, nseg;
   int G, A, C, nvar;
+  int bounded; // the tape has segments that truncate at max_nstate (EPGX_SEG_MASK_TOP)
   unsigned init_off, m0_off;
   int init_pat, m0_pat, init_n;
 };

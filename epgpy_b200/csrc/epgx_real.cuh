@@ -27,16 +27,16 @@ namespace epgx {
 // selects of the shift.  KP is the largest pair count of the window; registers above the populated orders
 // hold zeros (or unobservable values), so over-covering changes nothing.  The fused coefficients of the
 // window's TRs wait in the warp's shared-memory rows cw[TR][8] (written by lane TR); lane 0 leaves the echo of
-// TR j in sb[j].
+// TR j in sb[j]; cw[TR][7] != 0 flags a shift that truncates at max_nstate.
 //
 // Two TRs per iteration.  Even TR ("phase 0"): the even order of a block is in register 2 sp, the odd one in
 // 2 sp + 1 (canonical).  Its shift rotates the ODD F+ registers up one lane (they become the even orders of
 // the next block) and the EVEN F- registers down one lane (they become the odd orders of the previous block);
 // the other registers stay where they are and change role.  Odd TR ("phase 1"): roles swapped, its shift
 // rotates the even F+ and the odd F- registers and restores the canonical roles.  Z never moves.
-template <typename real, int NS, int KP>
+template <typename real, int NS, int KP, bool MASK>
 __device__ __forceinline__ void tr_window(real (&P)[NS], real (&M)[NS], real (&Z)[NS], const real *cw, real *sb, bool lane0,
-                                          bool is_first, bool is_last, int srcUp, int srcDn) {
+                                          bool is_first, bool is_last, int srcUp, int srcDn, unsigned mtop) {
   typedef typename vec2<real>::type real2;
   const unsigned FULL = 0xffffffffu;
   if constexpr (2 * KP <= NS) {
@@ -82,6 +82,15 @@ __device__ __forceinline__ void tr_window(real (&P)[NS], real (&M)[NS], real (&Z
           M[r] = __shfl_sync(FULL, is_first ? keep : cur, srcDn);
           keep = cur;
         }
+        // truncation at max_nstate (EPGX_SEG_MASK_TOP, flag staged with the coefficients): F+ of the order that moved
+        // above the cap reads as zero.  mtop: bit of its canonical register in this lane (0: another lane / not held);
+        // in the roles after this shift the register is (canonical ^ (1 - ph))
+        if constexpr (MASK) {
+          if (cw[8 * (j + ph) + 7] != real(0)) { // (bit tests: an index comparison would turn P[] into a local array)
+#pragma unroll
+            for (int r = 0; r < 2 * KP; ++r) P[r] = ((mtop >> (r ^ (1 - ph))) & 1u) ? real(0) : P[r];
+          }
+        }
       }
     }
   }
@@ -94,7 +103,9 @@ constexpr int real_min_blocks(int state_bytes, int maxt) {
   return maxt <= 128 ? (state_bytes <= 64 ? 4 : state_bytes <= 128 ? 3 : 2) : (state_bytes <= 64 ? 3 : state_bytes <= 128 ? 2 : 1);
 }
 
-template <typename real, int NS, int MAXT = 256>
+// BOUNDED: the tape truncates at max_nstate (EPGX_SEG_MASK_TOP segments) -- only these instances carry the masking
+// code of the whole-TR windows (it costs the unbounded FISP dictionary 10 % through register pressure otherwise)
+template <typename real, int NS, int MAXT = 256, bool BOUNDED = false>
 __global__ void __launch_bounds__(MAXT, real_min_blocks(sizeof(real) * NS, MAXT)) real_kernel(const KParams p) {
   typedef typename vec2<real>::type real2;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -119,8 +130,8 @@ __global__ void __launch_bounds__(MAXT, real_min_blocks(sizeof(real) * NS, MAXT)
 
   int4 *tbuf = (int4 *)smem_raw;
   int *patoff = (int *)(tbuf + 2 * TAPE_CHUNK * 2) + al * p.npattern;
-  // whole-TR windows (G == 32): per warp, coefficient rows [32][8] and the echoes of the window [32]
-  real *cw = (real *)((int *)(tbuf + 2 * TAPE_CHUNK * 2) + ((p.A * p.npattern + 3) & ~3)) + (size_t)(tid >> 5) * (32 * 9);
+  // whole-TR windows (G >= 8): per atom, coefficient rows [32][8] and the echoes of the window [32]
+  real *cw = (real *)((int *)(tbuf + 2 * TAPE_CHUNK * 2) + ((p.A * p.npattern + 3) & ~3)) + (size_t)al * (32 * 9);
   real *sb = cw + 32 * 8;
   {
     int idx[EPGX_MAX_DIMS];
@@ -143,6 +154,8 @@ __global__ void __launch_bounds__(MAXT, real_min_blocks(sizeof(real) * NS, MAXT)
 #define ORDER_OF(s) (((((s) >> 1) << lgG) + lane) * 2 + ((s) & 1))
 // register slots (whole pairs) that hold orders 0..n
 #define SLOTS_FOR(n) ((((n) >> (lgG + 1)) + 1) * 2)
+  // bit of the canonical register of order C = max_order + 1 (the one a truncating shift must clear) if this lane holds it
+  const unsigned mtop = (((p.C >> 1) & (G - 1)) == lane && ((p.C >> 1) >> lgG) * 2 + 1 < NS) ? 1u << (((p.C >> 1) >> lgG) * 2 + (p.C & 1)) : 0u;
   real P[NS], M[NS], Z[NS];
   real m0 = ldc(coef + p.m0_off + patoff[p.m0_pat]);
   {
@@ -261,40 +274,42 @@ __global__ void __launch_bounds__(MAXT, real_min_blocks(sizeof(real) * NS, MAXT)
     }
     const int4 *tb = tbuf + (chunk & 1) * 2 * TAPE_CHUNK;
     const int cnt = min(TAPE_CHUNK, p.nstream - base);
-    if (G == 32 && (tb[0].x & EPGX_CHUNK_PURE_TR)) {
-      // ---- fast path: the window holds TAPE_CHUNK / 2 whole-TR records (shift +1, no flags).  Phase 1: lane j
-      // decodes TR j, gathers its coefficients and fuses them -- one vectorised pass for 32 TRs.  Phase 2: every
-      // TR broadcasts its coefficients from its lane; no global load and no decode on the per-TR path.
-      const int4 a0 = tb[4 * lw], a1 = tb[4 * lw + 1], b0 = tb[4 * lw + 2], b1 = tb[4 * lw + 3];
-      const int fl = (a0.x >> 16) & 0xffff;
-      const real *ct = coef + (unsigned)a0.z + patoff[a1.y & 0xff];
-      const real *ca = coef + (unsigned)a0.w + patoff[(a1.y >> 8) & 0xff];
-      const real *cb = coef + (unsigned)b0.z + patoff[b1.y & 0xff];
-      const Fused5<real> fv = fuse5<real>(ldc(ct), ldc(ct + 1), ldc(ct + 2), ldc(ct + 3), fl & EPGX_FLAG_PRE, ldc(ca),
-                                          ldc(ca + 1), ldc(coef + (unsigned)a1.x + patoff[(a1.y >> 16) & 0xff]),
-                                          fl & EPGX_FLAG_POST, ldc(cb), ldc(cb + 1),
-                                          ldc(coef + (unsigned)b0.w + patoff[(b1.y >> 8) & 0xff]), false, m0);
-      const int rowv = b0.y, nnewv = (int)((unsigned)b1.x & 0xffff), nextv = b1.z;
-      {
-        real2 *c = (real2 *)(cw + 8 * lw);
-        c[0] = real2{fv.a, fv.w}; c[1] = real2{fv.b, fv.u}; c[2] = real2{fv.h, fv.fz}; c[3] = real2{fv.zz, real(0)};
+    if (G >= 8 && (tb[0].x & EPGX_CHUNK_PURE_TR)) {
+      // ---- fast path: the window holds TAPE_CHUNK / 2 whole-TR records (shift +1, no flags).  Phase 1: the G lanes
+      // of an atom decode the TRs (lane, lane + G, ...), gather their coefficients, fuse them and stage them in the
+      // atom's shared-memory rows -- one vectorised pass for 32 TRs.  Phase 2 (tr_window) runs the TRs in order: no
+      // global load and no decode on the per-TR path.  need: register pairs (2 G orders each) the window needs -- a TR
+      // applies to orders 0..nact and shifts orders 0..min(n_new, nact + 1); what lies above nact + 1 is unobservable
+      // (lowering.py) and need not move; nact of TR j is the "next nact" of TR j - 1
+      int need = 0;
+      for (int j = lane; j < TAPE_CHUNK / 2; j += G) {
+        const int4 a0 = tb[4 * j], a1 = tb[4 * j + 1], b0 = tb[4 * j + 2], b1 = tb[4 * j + 3];
+        const int fl = (a0.x >> 16) & 0xffff;
+        const real *ct = coef + (unsigned)a0.z + patoff[a1.y & 0xff];
+        const real *ca = coef + (unsigned)a0.w + patoff[(a1.y >> 8) & 0xff];
+        const real *cb = coef + (unsigned)b0.z + patoff[b1.y & 0xff];
+        const Fused5<real> fv = fuse5<real>(ldc(ct), ldc(ct + 1), ldc(ct + 2), ldc(ct + 3), fl & EPGX_FLAG_PRE, ldc(ca),
+                                            ldc(ca + 1), ldc(coef + (unsigned)a1.x + patoff[(a1.y >> 16) & 0xff]),
+                                            fl & EPGX_FLAG_POST, ldc(cb), ldc(cb + 1),
+                                            ldc(coef + (unsigned)b0.w + patoff[(b1.y >> 8) & 0xff]), false, m0);
+        real2 *c = (real2 *)(cw + 8 * j);
+        c[0] = real2{fv.a, fv.w}; c[1] = real2{fv.b, fv.u}; c[2] = real2{fv.h, fv.fz};
+        c[3] = real2{fv.zz, ((b0.x >> 18) & EPGX_SEG_MASK_TOP) ? real(1) : real(0)};
+        const int cur = j == 0 ? nact : tb[4 * j - 1].z;
+        need = max(need, (max(min((int)((unsigned)b1.x & 0xffff), cur + 1), 0) >> (lgG + 1)) + 1);
       }
-      // largest slot count any TR of the window needs: it applies to orders 0..nact and shifts orders
-      // 0..min(n_new, nact + 1) -- what lies above nact + 1 is unobservable (lowering.py) and need not move
-      int curv = __shfl_up_sync(FULL, nextv, 1); // nact of TR j = the "next nact" of TR j - 1
-      if (lw == 0) curv = nact;
-      int need = (max(min(nnewv, curv + 1), 0) >> 6) + 1; // register pairs (64 orders each)
       need = max(__reduce_max_sync(FULL, need), nslot >> 1);
       __syncwarp();
-#define TRW(K_) case K_: tr_window<real, NS, K_>(P, M, Z, cw, sb, lane == 0, is_first, is_last, srcUp, srcDn); break;
+#define TRW(K_) case K_: tr_window<real, NS, K_, BOUNDED>(P, M, Z, cw, sb, lane == 0, is_first, is_last, srcUp, srcDn, mtop); break;
       switch (need) {
         TRW(1) TRW(2) TRW(3) TRW(4) TRW(5) TRW(6) TRW(7) TRW(8) TRW(9) TRW(10) TRW(11) TRW(12) TRW(13) TRW(14) TRW(15) TRW(16)
       default: break;
       }
-      __syncwarp();
-      if (valid) sig[(long long)rowv * p.sig_stride + a_rel] = real2{sb[lw], real(0)}; // lane j: the echo of TR j
 #undef TRW
-      nact = __shfl_sync(FULL, nextv, TAPE_CHUNK / 2 - 1);
+      __syncwarp();
+      if (valid) // lane j (+ G, ...) stores the echoes of its TRs
+        for (int j = lane; j < TAPE_CHUNK / 2; j += G) sig[(long long)tb[4 * j + 2].y * p.sig_stride + a_rel] = real2{sb[j], real(0)};
+      nact = tb[4 * (TAPE_CHUNK / 2 - 1) + 3].z;
       nslot = nact < 0 ? 0 : SLOTS_FOR(nact);
       continue;
     }

@@ -3,21 +3,23 @@
 #include "epgx_real.cuh"
 
 namespace epgx {
+#define LAUNCH(NS, MAXT)                                                                         \
+  if (kp.bounded) real_kernel<float, NS, MAXT, true><<<grid, threads, smem, st>>>(kp);           \
+  else real_kernel<float, NS, MAXT, false><<<grid, threads, smem, st>>>(kp);
 template <> cudaError_t launch_real<float>(int slots, const KParams &kp, dim3 grid, int threads, int smem, cudaStream_t st) {
   switch (slots) {
-  case 2: real_kernel<float, 2><<<grid, threads, smem, st>>>(kp); break;
-  case 4: real_kernel<float, 4><<<grid, threads, smem, st>>>(kp); break;
+  case 2: LAUNCH(2, 256) break;
+  case 4: LAUNCH(4, 256) break;
   case 8:
-    if (threads <= 128) real_kernel<float, 8, 128><<<grid, threads, smem, st>>>(kp);
-    else real_kernel<float, 8><<<grid, threads, smem, st>>>(kp);
+    if (threads <= 128) { LAUNCH(8, 128) } else { LAUNCH(8, 256) }
     break;
   case 16:
-    if (threads <= 128) real_kernel<float, 16, 128><<<grid, threads, smem, st>>>(kp);
-    else real_kernel<float, 16><<<grid, threads, smem, st>>>(kp);
+    if (threads <= 128) { LAUNCH(16, 128) } else { LAUNCH(16, 256) }
     break;
-  case 32: real_kernel<float, 32><<<grid, threads, smem, st>>>(kp); break;
+  case 32: LAUNCH(32, 256) break;
   default: return cudaErrorInvalidValue;
   }
   return cudaGetLastError();
 }
+#undef LAUNCH
 } // namespace epgx
