@@ -74,6 +74,23 @@ def cfg_mt_bssfp(epg, ntr=500):
     return seq, {"init": epg.StateMatrix(density=f)}, None
 
 
+def cfg_mt_bssfp_pulse_jac(epg, ntr=200):
+    """BASELINE configs[4] with its Jacobian: per-pulse flip-angle variables (both pools), partial states carried through
+    the exchange operator; 101 off-resonance x 16 flip-angle atoms"""
+    T1, T2, khi, f = [779.0, 779.0], [45.0, 12e-3], 4.3e-3, [1 - 0.117, 0.117]
+    kmat = epg.exchange_matrix(khi, densities=f)
+    offres = 1 / 5.0 * np.linspace(-0.5, 0.5, 101)
+    FA = np.linspace(5, 60, 16)[None, None, :]
+    pool = np.array([1.0, 0.0])[:, None, None]
+    sat = epg.R(rL=[0, 0.0316])
+    exg = epg.X(5.0, kmat, T1=T1, T2=T2, g=[offres])
+    names = [f"a{i:04d}" for i in range(ntr)]
+    seq = []
+    for i in range(ntr):
+        seq += [epg.T(FA * pool, 0.0 if i % 2 == 0 else 180.0, order1={names[i]: {"alpha": pool}}) @ sat, exg, epg.Adc(reduce=0)]
+    return seq, {"init": epg.StateMatrix(density=f), "propagate_nondiff": True}, names
+
+
 CONFIGS = {
     "C1_readme_mse": cfg_readme,
     "C2_mse_grid_200k": cfg_mse,
@@ -82,6 +99,7 @@ CONFIGS = {
     "C3J_fisp_pulse_jac_64_atoms_1000_vars": cfg_fisp_pulse_jac,
     "C4_gre_diffusion_40k": cfg_gre_diffusion,
     "C5_mt_bssfp_20k": cfg_mt_bssfp,
+    "C5J_mt_bssfp_pulse_jac_1616_atoms_200_vars": cfg_mt_bssfp_pulse_jac,
 }
 
 
@@ -104,8 +122,9 @@ def main():
         seq, opts, jac = fn(epg)
         opts = dict(opts)
         init = opts.pop("init", None)
+        extra = {"propagate_nondiff": True} if opts.pop("propagate_nondiff", False) else {}
         probe = [None, epg.Jacobian(jac)] if jac else None
-        low = lowering.lower(seq, init=init, probe=probe, options=opts, dtype=args.dtype)
+        low = lowering.lower(seq, init=init, probe=probe, options=opts, dtype=args.dtype, **extra)
         t_host = time.perf_counter() - t0
         plan = engine.Plan(low)
         if args.lanes or args.atoms_per_cta:

@@ -440,6 +440,7 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 128 ? 3 : 1) realjac_kernel(cons
   for (int i = tid; i < 2 * TAPE_CHUNK && i < 2 * p.nstream; i += nthreads) __pipeline_memcpy_async(tbuf + i, stream + i, 16);
   __pipeline_commit();
   int nact = -1, nslot = 0;
+  bool alive = false; // has a derivative been injected into this tile's partial states yet?
   for (int base = 0, chunk = 0; base < p.nstream; base += TAPE_CHUNK, ++chunk) {
     __pipeline_wait_prior(0);
     __syncthreads();
@@ -465,9 +466,12 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 128 ? 3 : 1) realjac_kernel(cons
       const int code = r0.x & 0xffff, flags = (r0.x >> 16) & 0xffff, aux = r0.y;
       const unsigned off0 = (unsigned)r0.z, off1 = (unsigned)r0.w, off2 = (unsigned)r1.x;
       const int pat0 = r1.y & 0xff, pat1 = (r1.y >> 8) & 0xff;
-      const bool on_base = flags & EPGX_FLAG_BASE, on_part = flags & EPGX_FLAG_PARTIALS;
       const bool inject = flags & EPGX_FLAG_INJECT;
       const int iset = aux - v0 + 1; // target set of an injection
+      // the partial states of this variable tile are exactly zero until its first injection (per-pulse variables: most
+      // of the sequence for the late tiles): linear operators leave them zero, so they are skipped
+      if (inject && iset >= 1 && iset < SETS) alive = true;
+      const bool on_base = flags & EPGX_FLAG_BASE, on_part = (flags & EPGX_FLAG_PARTIALS) && alive;
       const bool aff0 = (flags & EPGX_FLAG_AFFINE) && lane == 0 && nslot > 0;
       (void)off2;
 
@@ -566,7 +570,7 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 128 ? 3 : 1) realjac_kernel(cons
             const real x = z0 ? Z[0][0] : P[0][0];
             sig[(long long)aux * p.sig_stride + a_rel] = real2{x * fr, x * fi};
           }
-          if (on_part) {
+          if (flags & EPGX_FLAG_PARTIALS) {
 #pragma unroll
             for (int q = 1; q < SETS; ++q) {
               const int v = v0 + q - 1;
@@ -604,7 +608,7 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 128 ? 3 : 1) realjac_kernel(cons
         const int4 q0 = tb[2 * r + 2], q1 = tb[2 * r + 3];
         if (lane == 0 && valid) {
           if (blockIdx.y == 0) sig[(long long)q0.y * p.sig_stride + a_rel] = real2{P[0][0], real(0)};
-          if (on_part) {
+          if (flags & EPGX_FLAG_PARTIALS) {
 #pragma unroll
             for (int q = 1; q < SETS; ++q) {
               const int v = v0 + q - 1;

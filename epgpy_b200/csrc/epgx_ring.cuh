@@ -73,6 +73,7 @@ __global__ void __launch_bounds__(256) ring_kernel(const KParams p) {
   if (G > 32) __syncthreads(); else __syncwarp();
 
   int baseP = 0, baseM = 0; // logical order k of F+ sits at ring slot (baseP + k) mod C
+  bool alive = false;       // has a derivative been injected into this tile's partial states yet?
   real2 *sig = (real2 *)p.signal;
   real2 *jac = (real2 *)p.jac;
 
@@ -82,6 +83,15 @@ __global__ void __launch_bounds__(256) ring_kernel(const KParams p) {
     const int first = s0.x, count = s0.y, nact = s0.z, shift = s0.w;
     const int n_old = s1.x, n_new = s1.y, sflags = s1.z;
 
+    // the partial states of this variable tile are exactly zero until its first injection (per-pulse variables: most
+    // of the sequence for the late tiles): linear operators leave them zero, so they are skipped.  Decided per
+    // segment by every thread alike (a lane without an order in this segment must learn it too)
+    if (NVT > 0 && !alive)
+      for (int r = first; r < first + count; ++r) {
+        const int2 h = __ldg((const int2 *)(p.ops + r));
+        const int iset = h.y - v0 + 1;
+        if (((h.x >> 16) & EPGX_FLAG_INJECT) && iset >= 1 && iset < NSET) alive = true;
+      }
     if (count > 0) {
       for (int k = lane; k <= nact; k += G) {
         int iP = baseP + k; if (iP >= C) iP -= C;
@@ -103,9 +113,9 @@ __global__ void __launch_bounds__(256) ring_kernel(const KParams p) {
           const unsigned off0 = (unsigned)r0.z, off1 = (unsigned)r0.w, off2 = (unsigned)r1.x;
           const int pat0 = r1.y & 0xff, pat1 = (r1.y >> 8) & 0xff, pat2 = (r1.y >> 16) & 0xff;
           const int aux1 = r1.z;
-          const bool on_base = flags & EPGX_FLAG_BASE, on_part = flags & EPGX_FLAG_PARTIALS;
           const bool inject = flags & EPGX_FLAG_INJECT;
           const int iset = aux - v0 + 1; // target set of an injection
+          const bool on_base = flags & EPGX_FLAG_BASE, on_part = (flags & EPGX_FLAG_PARTIALS) && alive;
           const bool aff = (flags & EPGX_FLAG_AFFINE) && k == 0;
 
           // linear forms: out = form(in) for the selected sets, or partial += form(base)
@@ -292,7 +302,7 @@ __global__ void __launch_bounds__(256) ring_kernel(const KParams p) {
                   const real xr = z0 ? st[0][q].zr : st[0][q].pr, xi = z0 ? st[0][q].zi : st[0][q].pi;
                   sig[((long long)aux * p.sig_stride + a_rel) * NP + q] = real2{xr * fr - xi * fi, xr * fi + xi * fr};
                 }
-                if (on_part) {
+                if (flags & EPGX_FLAG_PARTIALS) {
 #pragma unroll
                   for (int s = 1; s < NSET; ++s) {
                     const int v = v0 + s - 1;

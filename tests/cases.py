@@ -178,6 +178,24 @@ def bssfp_mt(epg, ntr=40, noff=7):
     return dict(seq=seq, density=f)
 
 
+def bssfp_mt_pulse_jac(epg, ntr=8, noff=5, dalpha=None, diff=True):
+    """BASELINE configs[4] with its Jacobian: two-pool MT bSSFP, one order-1 variable per pulse (flip angle of both
+    pools).  Not in CASES: the reference does not propagate partial states through X, so the oracle for
+    this Jacobian is the central finite difference of the forward signal (`dalpha`: per-pulse perturbation, degrees)."""
+    T1, T2, khi, f = _mt_model()
+    kmat = epg.exchange_matrix(khi, densities=f)
+    FA, TR = 10.0, 5
+    offres = 1 / TR * np.linspace(-0.5, 0.5, noff)
+    sat = epg.R(rL=[0, 0.0316])
+    exg = epg.X(TR, kmat, T1=T1, T2=T2, g=[offres])
+    seq = []
+    for i in range(ntr):
+        d = 0.0 if dalpha is None else float(dalpha[i])
+        kw = dict(order1={f"a{i}": "alpha"}) if diff else {}
+        seq += [epg.T([FA + d, d], 0 if i % 2 == 0 else 180, **kw) @ sat, exg, epg.Adc(reduce=0)]
+    return dict(seq=seq, density=f, jac=[f"a{i}" for i in range(ntr)] if diff else None)
+
+
 def spgr_exchange(epg, ntr=30):
     """two-pool water exchange SPGR with RF spoiling + shift (gre_exchange.py:73-87, model1)"""
     T1, T2, khi, f = [1000.0, 500.0], [100.0, 20.0], 2e-3, [0.8, 0.2]

@@ -344,6 +344,26 @@ def test_partials_through_nondiff_ops_gpu(epg):
     assert rel_err(sig, rs) < RTOL64 and rel_err(jac, rj) < RTOL64
 
 
+@pytest.mark.parametrize("vars_per_pass", [0, 1])
+def test_mt_bssfp_pulse_jacobian_gpu(vars_per_pass, epg):
+    """BASELINE configs[4]: two-pool MT bSSFP + per-pulse flip-angle Jacobian (ring kernel, exchange, tiled variables)
+    against central finite differences of the oracle's forward signal and the forward signal itself"""
+    from epgpy_b200 import engine, functions, lowering
+    from test_lowering_cpu import _mt_jacobian_by_finite_differences
+    ntr, noff = 12, 5
+    case = cases.bssfp_mt_pulse_jac(epg, ntr, noff)
+    low = lowering.lower(case["seq"], probe=[None, epg.Jacobian(case["jac"])], init=epg.StateMatrix(density=case["density"]),
+                         propagate_nondiff=True)
+    plan = engine.Plan(low)
+    if vars_per_pass:
+        plan.set_variant(kernel=1, vars_per_pass=vars_per_pass)
+    parts, _ = functions.run_lowered(low, plan=plan)
+    sig, jac = functions._assemble(low, parts)
+    ref = oracle_api.O.simulate(cases.bssfp_mt_pulse_jac(oracle_api.epg, ntr, noff, diff=False)["seq"], density=case["density"])
+    assert rel_err(sig, np.asarray(ref)) < RTOL64
+    assert rel_err(jac.sum(axis=1), _mt_jacobian_by_finite_differences(ntr, noff)) < 1e-7
+
+
 def test_larger_grid_vs_oracle(epg):
     """FISP at a size the oracle still finishes in seconds: 12 x 10 x 8 atoms, 120 TRs, unbounded"""
     case = cases.fisp(epg, 120, sizes=(12, 10, 8))

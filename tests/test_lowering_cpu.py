@@ -211,3 +211,27 @@ def test_modify_like_reference():
     sig = interp_simulate(new)
     ref = interp_simulate([pulse, epg.E(1, 1e10, 100), grad, epg.E(5, 1e10, 100), pulse, epg.E(1, 1e10, 100), epg.ADC])
     assert np.allclose(sig, ref)
+
+
+def _mt_jacobian_by_finite_differences(ntr, noff, h=1e-5):
+    import oracle_api
+
+    def fwd(d):
+        case = cases.bssfp_mt_pulse_jac(oracle_api.epg, ntr, noff, dalpha=d, diff=False)
+        return np.asarray(oracle_api.O.simulate(case["seq"], density=case["density"]))
+
+    eye = np.eye(ntr)
+    return np.stack([(fwd(h * eye[i]) - fwd(-h * eye[i])) / (2 * h) for i in range(ntr)], axis=-1)
+
+
+def test_mt_bssfp_pulse_jacobian_matches_finite_differences():
+    """BASELINE configs[4]: exchange / MT bSSFP with a per-pulse flip-angle Jacobian, partial states carried through X
+    (propagate_nondiff), against central finite differences of the oracle's forward signal"""
+    epg = product_namespace()
+    ntr, noff = 8, 5
+    case = cases.bssfp_mt_pulse_jac(epg, ntr, noff)
+    sig, jac = interp_simulate(case["seq"], probe=[None, epg.Jacobian(case["jac"])], init=epg.StateMatrix(density=case["density"]),
+                               propagate_nondiff=True)
+    fd = _mt_jacobian_by_finite_differences(ntr, noff)
+    assert jac.shape == (ntr, 2, noff, ntr)  # the Jacobian probe is not reduced over the pools
+    assert rel_err(jac.sum(axis=1), fd) < 1e-7
