@@ -84,8 +84,16 @@ __device__ __forceinline__ void trc_window(real (&Pr)[NS], real (&Pi)[NS], real 
   }
 }
 
-template <typename real, int NS>
-__global__ void __launch_bounds__(256, (6 * NS * sizeof(real) <= 192 ? 2 : 1)) reg_kernel(const KParams p) {
+// MAXT = 128: instances for CTAs of at most 128 threads with a register budget chosen by measurement (as in
+// epgx_real.cuh): REG_MINB_128 CTAs per SM when the state takes 96 registers (FP64 NS = 8, FP32 NS = 16)
+#ifndef REG_MINB_128
+#define REG_MINB_128 3
+#endif
+constexpr int reg_min_blocks(int state_bytes, int maxt) {
+  return maxt <= 128 ? (state_bytes <= 192 ? 4 : state_bytes <= 384 ? REG_MINB_128 : 1) : (state_bytes <= 192 ? 2 : 1);
+}
+template <typename real, int NS, int MAXT = 256>
+__global__ void __launch_bounds__(MAXT, reg_min_blocks(6 * NS * sizeof(real), MAXT)) reg_kernel(const KParams p) {
   typedef typename vec2<real>::type real2;
   extern __shared__ __align__(16) unsigned char smem_raw[];
 

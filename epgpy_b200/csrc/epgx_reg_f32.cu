@@ -8,9 +8,18 @@ template <> cudaError_t launch_reg<float>(int slots, const KParams &kp, dim3 gri
   switch (slots) {
   case 1: reg_kernel<float, 1><<<grid, threads, smem, st>>>(kp); break;
   case 2: reg_kernel<float, 2><<<grid, threads, smem, st>>>(kp); break;
-  case 4: reg_kernel<float, 4><<<grid, threads, smem, st>>>(kp); break;
-  case 8: reg_kernel<float, 8><<<grid, threads, smem, st>>>(kp); break;
-  case 16: reg_kernel<float, 16><<<grid, threads, smem, st>>>(kp); break;
+  case 4:
+    if (threads <= 128) reg_kernel<float, 4, 128><<<grid, threads, smem, st>>>(kp);
+    else reg_kernel<float, 4><<<grid, threads, smem, st>>>(kp);
+    break;
+  case 8:
+    if (threads <= 128) reg_kernel<float, 8, 128><<<grid, threads, smem, st>>>(kp);
+    else reg_kernel<float, 8><<<grid, threads, smem, st>>>(kp);
+    break;
+  case 16:
+    if (threads <= 128) reg_kernel<float, 16, 128><<<grid, threads, smem, st>>>(kp);
+    else reg_kernel<float, 16><<<grid, threads, smem, st>>>(kp);
+    break;
   default: return cudaErrorInvalidValue;
   }
   return cudaGetLastError();
