@@ -48,16 +48,36 @@ __device__ __forceinline__ void tr_window(real (&P)[NS], real (&M)[NS], real (&Z
         const real2 c0 = ((const real2 *)cw)[4 * (j + ph)], c1v = ((const real2 *)cw)[4 * (j + ph) + 1],
                     c2 = ((const real2 *)cw)[4 * (j + ph) + 2];
         const real a = c0.x, w = c0.y, b = c1v.x, u = c1v.y, h = c2.x;
+        if constexpr (sizeof(real) == 4) {
+          // FP32: the two orders of a block sit in adjacent registers and take the same coefficients -- Blackwell's
+          // packed FFMA2 / FMUL2 / FADD2 (sm_100: fma.rn.f32x2) update both at once, 8 instructions per register pair
+          // instead of 18; the scalar coefficients are broadcast operands and the role swap of the odd TRs is the
+          // LO_HI operand swizzle on the Z pair (both free).  The kernel is issue-bound in FP32.
 #pragma unroll
-        for (int sp = 0; sp < KP; ++sp)
-#pragma unroll
-          for (int i = 0; i < 2; ++i) {
-            const int r = 2 * sp + (i ^ ph); // register of F+- (k = 2 b + i) in this phase; Z(k) is in 2 sp + i
-            const real p_ = P[r], m_ = M[r], z_ = Z[2 * sp + i];
-            P[r] = a * p_ + b * m_ + u * z_;
-            M[r] = a * m_ + b * p_ + u * z_;
-            Z[2 * sp + i] = w * z_ + h * (p_ + m_);
+          for (int sp = 0; sp < KP; ++sp) {
+            const float2 p2 = make_float2(P[2 * sp], P[2 * sp + 1]), m2 = make_float2(M[2 * sp], M[2 * sp + 1]);
+            const float2 z2 = ph ? make_float2(Z[2 * sp + 1], Z[2 * sp]) : make_float2(Z[2 * sp], Z[2 * sp + 1]);
+            const float2 a2 = make_float2(a, a), b2 = make_float2(b, b), u2 = make_float2(u, u), w2 = make_float2(w, w),
+                         h2 = make_float2(h, h);
+            const float2 t2 = __fmul2_rn(u2, z2);
+            const float2 np = __ffma2_rn(a2, p2, __ffma2_rn(b2, m2, t2));
+            const float2 nm = __ffma2_rn(a2, m2, __ffma2_rn(b2, p2, t2));
+            const float2 nz = __ffma2_rn(w2, z2, __fmul2_rn(h2, __fadd2_rn(p2, m2)));
+            P[2 * sp] = np.x; P[2 * sp + 1] = np.y; M[2 * sp] = nm.x; M[2 * sp + 1] = nm.y;
+            if (ph) { Z[2 * sp + 1] = nz.x; Z[2 * sp] = nz.y; } else { Z[2 * sp] = nz.x; Z[2 * sp + 1] = nz.y; }
           }
+        } else {
+#pragma unroll
+          for (int sp = 0; sp < KP; ++sp)
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+              const int r = 2 * sp + (i ^ ph); // register of F+- (k = 2 b + i) in this phase; Z(k) is in 2 sp + i
+              const real p_ = P[r], m_ = M[r], z_ = Z[2 * sp + i];
+              P[r] = a * p_ + b * m_ + u * z_;
+              M[r] = a * m_ + b * p_ + u * z_;
+              Z[2 * sp + i] = w * z_ + h * (p_ + m_);
+            }
+        }
         if (lane0) {
           const real fz = c2.y, zz = cw[8 * (j + ph) + 6];
           P[ph] += fz; M[ph] += fz; Z[0] += zz;
