@@ -56,7 +56,38 @@ __device__ __forceinline__ void sj_apply(real (&P)[NS], real (&M)[NS], real (&Z)
   typedef typename vec2<real>::type real2;
   const real2 c0 = ((const real2 *)cf)[0], c1v = ((const real2 *)cf)[1], c2 = ((const real2 *)cf)[2];
   const real a = c0.x, w = c0.y, b = c1v.x, u = c1v.y, h = c2.x;
-  if (q == 0) {
+  if constexpr (sizeof(real) == 4) {
+    // FP32, canonical roles (ph == 0 for every caller of the float instances): packed f32x2 arithmetic on the two
+    // orders of a block (epgx_real.cuh), 8 (base) / 18 (partial) instructions per register pair instead of 18 / 36
+    const float2 a2 = make_float2(a, a), b2 = make_float2(b, b), u2 = make_float2(u, u), w2 = make_float2(w, w), h2 = make_float2(h, h);
+    if (q == 0) {
+#pragma unroll
+      for (int sp = 0; sp < KP; ++sp) {
+        const float2 p2 = make_float2(P[2 * sp], P[2 * sp + 1]), m2 = make_float2(M[2 * sp], M[2 * sp + 1]);
+        const float2 z2 = make_float2(Z[2 * sp], Z[2 * sp + 1]);
+        const float2 t2 = __fmul2_rn(u2, z2);
+        const float2 np = __ffma2_rn(a2, p2, __ffma2_rn(b2, m2, t2)), nm = __ffma2_rn(a2, m2, __ffma2_rn(b2, p2, t2));
+        const float2 nz = __ffma2_rn(w2, z2, __fmul2_rn(h2, __fadd2_rn(p2, m2)));
+        P[2 * sp] = np.x; P[2 * sp + 1] = np.y; M[2 * sp] = nm.x; M[2 * sp + 1] = nm.y; Z[2 * sp] = nz.x; Z[2 * sp + 1] = nz.y;
+      }
+    } else {
+      const float2 j0 = ((const float2 *)cf)[4], j1 = ((const float2 *)cf)[5], j2 = ((const float2 *)cf)[6];
+      const float2 ja2 = make_float2(j0.x, j0.x), jw2 = make_float2(j0.y, j0.y), jb2 = make_float2(j1.x, j1.x),
+                   ju2 = make_float2(j1.y, j1.y), jh2 = make_float2(j2.x, j2.x);
+      const float2 *xp = (const float2 *)xb, *xm = xp + NS * 16, *xz = xm + NS * 16;
+#pragma unroll
+      for (int sp = 0; sp < KP; ++sp) {
+        const float2 vp = xp[32 * sp + lane], vm = xm[32 * sp + lane], vz = xz[32 * sp + lane];
+        const float2 p2 = make_float2(P[2 * sp], P[2 * sp + 1]), m2 = make_float2(M[2 * sp], M[2 * sp + 1]);
+        const float2 z2 = make_float2(Z[2 * sp], Z[2 * sp + 1]);
+        const float2 t2 = __ffma2_rn(u2, z2, __fmul2_rn(ju2, vz)); // u Z + ju x_Z, shared by F+ and F-
+        const float2 np = __ffma2_rn(a2, p2, __ffma2_rn(b2, m2, __ffma2_rn(ja2, vp, __ffma2_rn(jb2, vm, t2))));
+        const float2 nm = __ffma2_rn(a2, m2, __ffma2_rn(b2, p2, __ffma2_rn(ja2, vm, __ffma2_rn(jb2, vp, t2))));
+        const float2 nz = __ffma2_rn(w2, z2, __ffma2_rn(h2, __fadd2_rn(p2, m2), __ffma2_rn(jw2, vz, __fmul2_rn(jh2, __fadd2_rn(vp, vm)))));
+        P[2 * sp] = np.x; P[2 * sp + 1] = np.y; M[2 * sp] = nm.x; M[2 * sp + 1] = nm.y; Z[2 * sp] = nz.x; Z[2 * sp + 1] = nz.y;
+      }
+    }
+  } else if (q == 0) {
 #pragma unroll
     for (int sp = 0; sp < KP; ++sp)
 #pragma unroll
