@@ -58,7 +58,7 @@ def test_random_jacobian(seed):
     rs, rj = oracle_api.O.simulate(ref_seq, kvalue=opts["kvalue"], max_nstate=opts.get("max_nstate"), jacobian=jac,
                                    propagate_nondiff=True)
     ss, sj = max(1.0, np.abs(rs).max()), max(1.0, np.abs(rj).max())
-    for kernel in (0, 1, 4):  # auto, ring, realjac
+    for kernel in (0, 1, 4, 5):  # auto, ring, realjac (orders over warps), setjac (one warp per state set)
         for dtype, tol in (("f64", 1e-10), ("f32", 1e-4)):
             for lanes in (0, 2, 32, 128):
                 try:
