@@ -60,6 +60,35 @@ def test_c3_fisp_dictionary_1000_tr(epg):
     assert rel_err(sigb[sub], refb) < RTOL64
 
 
+def test_c3_fisp_jacobian_1000_tr(epg):
+    """configs[2] "plus its flip-angle Jacobian" (SURVEY 8d, M3J(i)): 1000 TRs, variables B1 (the flip-angle scale), T1,
+    T2; a 12 x 10 x 8 slab on the device through the warp-per-state-set kernel (83 pure whole-TR windows), a
+    2 x 2 x 2 sub-grid against the oracle, FP64 and FP32, and the orders-over-warps kernel on the same tape"""
+    import bench
+    from epgpy_b200 import engine, functions, lowering
+
+    T1, T2, B1 = bench.grid_axes((100, 100, 100))
+    T1, T2, B1 = T1[::9][:12], T2[::10][:10], B1[::13][:8]
+    names = ["B1", "T1", "T2"]
+    seq = bench.fisp_sequence(epg, T1, T2, B1, 1000, jac=True)
+    sub = (slice(None), slice(1, 12, 8), slice(2, 10, 6), slice(0, 8, 5))
+    rs, rj = O.simulate(bench.fisp_sequence(oracle_api.epg, T1[sub[1]], T2[sub[2]], B1[sub[3]], 1000, jac=True), jacobian=names)
+    rs, rj = np.asarray(rs), np.asarray(rj)
+    for dtype, tol in (("f64", RTOL64), ("f32", RTOL32)):
+        low = lowering.lower(seq, probe=[None, epg.Jacobian(names)], dtype=dtype)
+        for variant, kernel in ((0, 4), (4, 3)):  # automatic choice: one warp per state set; forced: orders over warps
+            plan = engine.Plan(low)
+            if variant:
+                plan.set_variant(kernel=variant)
+            assert plan.config()["kernel"] == kernel
+            parts, _ = functions.run_lowered(low, plan=plan)
+            sig, jac = functions._assemble(low, parts)
+            assert sig.shape == (1000, 12, 10, 8) and jac.shape == (1000, 12, 10, 8, 3)
+            assert rel_err(sig[sub], rs) < tol
+            for i in range(3):  # columns of very different magnitude: compare one by one
+                assert rel_err(jac[sub][..., i], rj[..., i]) < (tol if dtype == "f64" else 5 * tol)
+
+
 def test_c4_rf_spoiled_gre_3d_gradients_diffusion_500_tr(epg):
     """configs[3]: quadratic RF phase, 3-d (collinear) gradient shifts, isotropic diffusion, 500 TRs"""
     def build(e, T1, T2, ntr=500):
