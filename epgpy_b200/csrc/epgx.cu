@@ -242,6 +242,10 @@ static int choose_variant(epgx_plan *pl, int kernel, int lanes, int vars, int at
   while (A > 1 && A * per_atom > budget) --A;
   while (A * G > 256) --A;
   if (A < 1) A = 1;
+  if (atoms <= 0) { // small grids: smaller CTAs, so that every SM gets a few of them (latency-bound record loop)
+    const int tiles = nvt ? (t.nvar + nvt - 1) / nvt : 1;
+    while (A > 1 && A * G > 32 && ((pl->natoms + A - 1) / A) * tiles < 4 * 148) A = (A + 1) / 2;
+  }
   c.kernel = 0;
   c.lanes_per_atom = G;
   c.slots_per_lane = 0;

@@ -87,3 +87,23 @@ def test_kernel_choice_for_derivative_tapes(epg):
     assert big.config()["kernel"] == 3
     big.set_variant(kernel=5)
     assert big.config()["kernel"] == 4
+
+
+@pytest.mark.timeout(120)
+def test_variant_choice_terminates_on_tiny_grids(epg):
+    """host-side launch-shape heuristics (small grids get smaller CTAs) for every kernel / lanes / atoms request"""
+    from epgpy_b200 import engine, lowering
+    for case in (cases.readme_mse(epg), cases.fisp_jac_global(epg, ntr=12), cases.spgr_exchange(epg, ntr=6)):
+        probe = [None, epg.Jacobian(case["jac"])] if case.get("jac") else None
+        init = epg.StateMatrix(density=case["density"]) if case.get("density") is not None else None
+        low = lowering.lower(case["seq"], probe=probe, init=init, options=dict(case.get("options", {})))
+        for kernel in range(6):
+            for lanes in (0, 1, 2, 32, 64, 128, 256):
+                for atoms in (0, 1, 3, 16):
+                    plan = engine.Plan(low)
+                    try:
+                        plan.set_variant(kernel=kernel, lanes_per_atom=lanes, atoms_per_cta=atoms)
+                    except (NotImplementedError, MemoryError):
+                        continue
+                    cfg = plan.config()
+                    assert 1 <= cfg["atoms_per_cta"] and cfg["threads_per_cta"] <= 256
