@@ -39,6 +39,7 @@ struct epgx_plan {
   double flops_cplx, flops_real, updates; // executed real flops per atom (complex / real-valued kernels)
   bool realjac_ok; // real-valued graph with real-valued derivative injections
   int64_t ntrj = 0; // whole-TR derivative groups (EPGX_OP_TRJ) in the merged stream
+  bool bounded = false; // some segment truncates at max_nstate (EPGX_SEG_MASK_TOP)
   bool real_ok; // real-valued phase graph: eligible for the three-reals-per-order kernel
   epgx_config cfg;
   // workspace layout (bytes)
@@ -372,6 +373,7 @@ extern "C" int epgx_plan_create(const epgx_tape *t, epgx_plan **out) {
   pl->tape = *t;
   pl->ops.assign(t->ops, t->ops + t->nop);
   pl->segs.assign(t->segs, t->segs + t->nseg);
+  for (const epgx_segment &sg : pl->segs) pl->bounded = pl->bounded || (sg.flags & EPGX_SEG_MASK_TOP);
   if (t->dtype == EPGX_F64) pl->coef64.assign(t->coef, t->coef + t->ncoef);
   else {
     pl->coef32.resize(t->ncoef);
@@ -708,7 +710,7 @@ extern "C" int epgx_simulate_strided(const epgx_plan *pl, const void *ws, int64_
   kp.pats = (const int *)(w + pl->off_pats);
   kp.stream = w + pl->off_stream;
   kp.nstream = (int)pl->stream.size();
-  for (const epgx_segment &sg : pl->segs) kp.bounded |= (sg.flags & EPGX_SEG_MASK_TOP) ? 1 : 0;
+  kp.bounded = pl->bounded ? 1 : 0;
   kp.coef = w + pl->off_coef;
   kp.signal = signal;
   kp.jac = jacobian;

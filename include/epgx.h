@@ -46,7 +46,7 @@
 extern "C" {
 #endif
 
-#define EPGX_VERSION 102 /* 0.1.2 */
+#define EPGX_VERSION 103 /* 0.1.3: epgx_plan_stream, setjac kernel (variant 5) */
 #define EPGX_MAX_DIMS 8
 #define EPGX_MAX_PATTERNS 64
 #define EPGX_MAX_POOLS 2
