@@ -11,8 +11,12 @@ import numpy as np
 from epgpy_b200 import lowering as L
 
 
-def run(low):
-    """-> signal [nadc, natoms, npool], jac [njac, nvar, natoms, npool] (complex128)"""
+def run(low, stream=None):
+    """-> signal [nadc, natoms, npool], jac [njac, nvar, natoms, npool] (complex128).
+    With `stream` (Plan.stream(): the merged record stream of the register kernels, csrc/epgx_common.cuh) the
+    interpreter walks that stream instead of the tape's segments: segment markers, whole-TR records (TR / TRC) and the
+    whole-TR derivative groups (TRJ), the latter through the fused five-coefficient algebra of epgx_realjac.cuh
+    (trj_assemble) -- a host-side check of the stream builder and of that algebra."""
     coef = low.coef
     ashape, npool = low.atom_shape, low.npool
     natoms = low.natoms
@@ -68,9 +72,11 @@ def run(low):
                 out.append(e)
         return out
 
-    for seg in low.segs:
-        na = int(seg["nact"]) + 1
-        for rec in expand(low.ops[seg["first"]: seg["first"] + seg["count"]]):
+    st = {"m0": m0}
+
+    def apply(rec, na):
+        if True:
+            m0 = st["m0"]
             code, flags, aux, aux1 = int(rec["code"]), int(rec["flags"]), int(rec["aux"]), int(rec["aux1"])
             off, pat = rec["off"], rec["pat"]
             sets = []
@@ -82,7 +88,7 @@ def run(low):
                 if flags & L.F_PARTIALS:
                     sets += list(range(1, nset))
             if na <= 0 and code != L.OP_PD:
-                continue
+                return
             p, m, z = P[..., :na], M[..., :na], Z[..., :na]  # views [natoms, npool, nset, na]
 
             def linear(fn, affine):
@@ -152,7 +158,7 @@ def run(low):
                 for s in sets:
                     p[:, :, s] = 0; m[:, :, s] = 0
             elif code == L.OP_PD:
-                m0 = blk(off[0], pat[0], 1)[..., 0]
+                st["m0"] = blk(off[0], pat[0], 1)[..., 0]
             elif code == L.OP_ADC:
                 f = 1.0
                 if flags & L.F_SCALE:
@@ -163,10 +169,10 @@ def run(low):
                 if flags & L.F_PARTIALS:
                     for v in range(low.nvar):
                         jac[aux1, v] = src[:, :, 1 + v, 0] * f
-        n_old, n_new, sh = int(seg["n_old"]), int(seg["n_new"]), int(seg["shift"])
-        if seg["flags"] & L.SEG_RESET:
+    def close(sh, n_old, n_new, sflags):
+        if sflags & L.SEG_RESET:
             P[:] = 0; M[:] = 0; Z[:] = 0
-            Z[:, :, 0, 0] = m0
+            Z[:, :, 0, 0] = st["m0"]
         elif sh:
             up, dn = (P, M) if sh > 0 else (M, P)
             new0 = dn[..., 1].conj() if (n_old >= 1 and C > 1) else 0 * dn[..., 0]
@@ -176,6 +182,122 @@ def run(low):
             dn[..., -1] = 0
             dn[..., n_old:] = 0
             up[..., n_new + 1:] = 0
+
+    if stream is None:
+        for seg in low.segs:
+            for rec in expand(low.ops[seg["first"]: seg["first"] + seg["count"]]):
+                apply(rec, int(seg["nact"]) + 1)
+            close(int(seg["shift"]), int(seg["n_old"]), int(seg["n_new"]), int(seg["flags"]))
+        return sig, jac
+
+    # ---- the merged stream (internal codes: csrc/epgx_common.cuh)
+    OP_SEG, OP_TR, OP_TRC, OP_TRJ = 64, 65, 66, 67
+
+    def mkrec(code, flags, offs=(), pats=(), aux=0, aux1=0):
+        r = np.zeros((), dtype=L.OP_DTYPE)
+        r["code"], r["flags"], r["aux"], r["aux1"] = code, flags, aux, aux1
+        for i, (o, q) in enumerate(zip(offs, pats)):
+            r["off"][i], r["pat"][i] = o, q
+        return r
+
+    def close_from(cont):
+        w = int(cont["flags"])
+        close((w & 3) - 1, int(cont["off"][2]) >> 16, int(cont["off"][2]) & 0xffff, w >> 2)
+        return int(cont["aux1"])
+
+    nact, i, n = -1, 0, len(stream)
+    while i < n:
+        rec = stream[i]
+        code, flags = int(rec["code"]), int(rec["flags"]) & 0x0fff  # bits 12..15 of a window's first record: window flags
+        if code == OP_SEG:
+            sh = int(rec["off"][0])
+            close(sh - (1 << 32) if sh >= 1 << 31 else sh, int(rec["off"][1]), int(rec["off"][2]), int(rec["aux1"]))
+            nact = int(rec["aux"])
+            i += 1
+        elif code in (OP_TR, OP_TRC):
+            cont = stream[i + 1]
+            if code == OP_TRC:
+                c2 = stream[i + 2]
+                if int(c2["flags"]) & 2:
+                    apply(mkrec(L.OP_D, L.F_BASE, [c2["off"][1]], [c2["pat"][1]]), nact + 1)
+            f = rec.copy()
+            f["code"], f["flags"] = L.OP_FUSED, flags
+            for r in expand([f, mkrec(L.OP_CONT, 0, cont["off"][:2], cont["pat"][:2])]):
+                apply(r, nact + 1)
+            adc = mkrec(L.OP_ADC, L.F_BASE, aux=int(cont["aux"]))
+            if code == OP_TRC and int(stream[i + 2]["flags"]) & 1:
+                adc = mkrec(L.OP_ADC, L.F_BASE | L.F_SCALE, [stream[i + 2]["off"][0]], [stream[i + 2]["pat"][0]], aux=int(cont["aux"]))
+            apply(adc, nact + 1)
+            nact = close_from(cont)
+            i += 2 if code == OP_TR else 3
+        elif code == OP_TRJ:
+            g = stream[i:i + 5]
+            na = nact + 1
+            one = np.ones((natoms, npool))
+            tb = blk(g[0]["off"][0], g[0]["pat"][0], 4)
+            ta, tw, tbb, tu = (tb[..., k] for k in range(4))
+            th = -0.5 * tu
+            al1 = al2 = be1 = be2 = one
+            ra = rb = 0 * one
+            if flags & L.F_PRE:
+                b0 = blk(g[0]["off"][1], g[0]["pat"][1], 2)
+                al1, ra, al2 = b0[..., 0], b0[..., 1], blk(g[0]["off"][2], g[0]["pat"][2], 1)[..., 0]
+            if flags & L.F_POST:
+                b0 = blk(g[1]["off"][0], g[1]["pat"][0], 2)
+                be1, rb, be2 = b0[..., 0], b0[..., 1], blk(g[1]["off"][1], g[1]["pat"][1], 1)[..., 0]
+            F = dict(a=be2 * al2 * ta, b=be2 * al2 * tbb, u=be2 * al1 * tu, h=be1 * al2 * th, w=be1 * al1 * tw,
+                     f=be2 * tu * ra, z=be1 * tw * ra + rb)
+            x = [P[:, :, 0, :na].copy(), M[:, :, 0, :na].copy(), Z[:, :, 0, :na].copy()]
+            m0 = st["m0"]
+
+            def lin(c, p_, m_, z_):
+                a, b, u, h, w = (c[k][..., None] for k in "abuhw")
+                return a * p_ + b * m_ + u * z_, a * m_ + b * p_ + u * z_, w * z_ + h * (p_ + m_)
+
+            for s in range(nset):
+                o = lin(F, P[:, :, s, :na], M[:, :, s, :na], Z[:, :, s, :na])
+                if s == 0:
+                    J = F
+                else:
+                    v = s - 1
+                    pp = pz = p0 = ga = gw = gb = gu = qq = qz = q0 = 0 * one
+                    if int(g[2]["flags"]) >> v & 1:
+                        c = blk(g[2]["off"][v], g[2]["pat"][v], 8); pp, pz, p0 = c[..., 0], c[..., 4], c[..., 6]
+                    if int(g[3]["flags"]) >> v & 1:
+                        c = blk(g[3]["off"][v], g[3]["pat"][v], 4); ga, gw, gb, gu = (c[..., k] for k in range(4))
+                    if int(g[4]["flags"]) >> v & 1:
+                        c = blk(g[4]["off"][v], g[4]["pat"][v], 8); qq, qz, q0 = c[..., 0], c[..., 4], c[..., 6]
+                    gh = -0.5 * gu
+                    A = ta * ga + tbb * gb + tu * gh
+                    B = ta * gb + tbb * ga + tu * gh
+                    U = (ta + tbb) * gu + tu * gw
+                    H = th * (ga + gb) + tw * gh
+                    W = 2 * th * gu + tw * gw
+                    J = dict(a=F["a"] * (pp + qq) + be2 * al2 * A, w=F["w"] * (pz + qz) + be1 * al1 * W,
+                             b=F["b"] * (pp + qq) + be2 * al2 * B, u=F["u"] * (pz + qq) + be2 * al1 * U,
+                             h=F["h"] * (pp + qz) + be1 * al2 * H, f=F["u"] * p0 + be2 * (U + qq * tu) * ra,
+                             z=F["w"] * p0 + be1 * ((W + qz * tw) * ra + q0))
+                    o = [a_ + b_ for a_, b_ in zip(o, lin(J, *x))]
+                o = [np.array(t) for t in o]
+                if na > 0:
+                    o[0][..., 0] += J["f"] * m0; o[1][..., 0] += J["f"] * m0; o[2][..., 0] += J["z"] * m0
+                P[:, :, s, :na], M[:, :, s, :na], Z[:, :, s, :na] = o
+            sig[int(g[1]["aux"])] = P[:, :, 0, 0]
+            if flags & L.F_PARTIALS:
+                for v in range(low.nvar):
+                    jac[int(g[1]["rsv1"]), v] = P[:, :, 1 + v, 0]
+            nact = close_from(g[1])
+            i += 5
+        elif code == L.OP_FUSED:
+            for r in expand([rec, stream[i + 1]]):
+                apply(r, nact + 1)
+            i += 2
+        else:
+            if code != L.OP_NOP:
+                r = rec.copy()
+                r["flags"] = flags
+                apply(r, nact + 1)
+            i += 1
     return sig, jac
 
 

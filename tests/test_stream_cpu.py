@@ -107,3 +107,37 @@ def test_variant_choice_terminates_on_tiny_grids(epg):
                         continue
                     cfg = plan.config()
                     assert 1 <= cfg["atoms_per_cta"] and cfg["threads_per_cta"] <= 256
+
+
+def _both_ways(epg, seq, jac=None, options=None, init=None, **kw):
+    """the tape through the numpy interpreter, segment by segment and through the merged stream"""
+    import tape_interp
+    from epgpy_b200 import engine, lowering
+    low = lowering.lower(seq, probe=[None, epg.Jacobian(jac)] if jac else None, init=init, options=dict(options or {}), **kw)
+    st = engine.Plan(low).stream()
+    return low, st, tape_interp.run(low), tape_interp.run(low, stream=st)
+
+
+@pytest.mark.parametrize("name", sorted(cases.CASES))
+def test_merged_stream_reproduces_the_tape(name, epg):
+    """every golden case: the stream the register kernels execute (segment markers, whole-TR records and groups with
+    their fused five-coefficient algebra, hopped E records) gives what the plain tape gives"""
+    case = cases.CASES[name](epg)
+    init = epg.StateMatrix(density=case["density"]) if case.get("density") is not None else None
+    low, st, (s0, j0), (s1, j1) = _both_ways(epg, case["seq"], case.get("jac"), case.get("options"), init)
+    assert np.abs(s1 - s0).max() <= 1e-13 * max(1.0, np.abs(s0).max())
+    if low.nvar:
+        assert np.abs(j1 - j0).max() <= 1e-12 * max(1.0, np.abs(j0).max())
+
+
+@pytest.mark.parametrize("variables,max_nstate", [(["B1", "T1", "T2"], None), (["B1", "T1", "T2"], 9), (["T2", "B1"], None),
+                                                  (["tau", "T1"], None), (["B1"], 20)])
+def test_whole_tr_groups_on_the_host(variables, max_nstate, epg):
+    """the derivative train of tests/test_gpu_parity.py (whole-TR groups mixed with TRs that are not): stream == tape"""
+    import test_gpu_parity as tg
+    options = {"kvalue": 2500.0, **({"max_nstate": max_nstate} if max_nstate else {})}
+    low, st, (s0, j0), (s1, j1) = _both_ways(epg, tg._trj_sequence(epg, variables), variables, options, propagate_nondiff=True)
+    assert np.count_nonzero(st["code"] == OP_TRJ) >= 60
+    assert np.abs(s1 - s0).max() <= 1e-13 * max(1.0, np.abs(s0).max())
+    for v in range(low.nvar):
+        assert np.abs(j1[:, v] - j0[:, v]).max() <= 1e-12 * max(1e-30, np.abs(j0[:, v]).max())
