@@ -49,6 +49,12 @@ class Config(ctypes.Structure):
 
 _lib = None
 _lock = threading.Lock()
+LAUNCHES = 0  # kernel launches issued through this binding (bench.py reports the count of its timed regions)
+
+
+def _count(n=1):
+    global LAUNCHES
+    LAUNCHES += n
 
 EXPORTS = [
     "epgx_version", "epgx_device_count", "epgx_last_error", "epgx_plan_create", "epgx_plan_destroy",
@@ -137,7 +143,8 @@ class Plan:
         t.nadc, t.njac, t.nvar, t.max_order = low.nadc, low.njac, low.nvar, low.max_order
         self._h = ctypes.c_void_p()
         _check(L.epgx_plan_create(ctypes.byref(t), ctypes.byref(self._h)))
-        self._ws = {}  # device index -> workspace tensor
+        self._ws = {}  # device index -> (workspace tensor, upload event)
+        self._ws_lock = threading.Lock()
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
@@ -173,19 +180,48 @@ class Plan:
 
     # ---- device side
     def upload(self, device, force=False):
-        """H2D of tape + coefficient table (cached per device unless `force`); returns the workspace tensor"""
+        """H2D of tape + coefficient table (cached per device unless `force`); returns the workspace tensor.
+        The copies are enqueued on torch's current stream of the device; an event recorded behind them is waited on by
+        every later launch stream (`_wait_upload`), so a run on another stream / thread never reads a partly
+        uploaded table."""
         import torch
 
         dev = torch.device("cuda", device)
-        if device not in self._ws or force:
-            with torch.cuda.device(dev):
-                ws = self._ws.get(device)
-                if ws is None:
-                    ws = torch.empty(self.workspace_bytes(), dtype=torch.uint8, device=dev)
-                st = torch.cuda.current_stream(dev).cuda_stream
-                _check(lib().epgx_plan_upload(self._h, ws.data_ptr(), st))
-            self._ws[device] = ws
-        return self._ws[device]
+        with self._ws_lock:
+            if device not in self._ws or force:
+                with torch.cuda.device(dev):
+                    ws = self._ws.get(device, (None, None))[0]
+                    if ws is None:
+                        ws = torch.empty(self.workspace_bytes(), dtype=torch.uint8, device=dev)
+                    stream = torch.cuda.current_stream(dev)
+                    _check(lib().epgx_plan_upload(self._h, ws.data_ptr(), stream.cuda_stream))
+                    ev = torch.cuda.Event()
+                    ev.record(stream)
+                self._ws[device] = (ws, ev)
+            return self._ws[device][0]
+
+    def _wait_upload(self, device, stream):
+        ev = self._ws[device][1]
+        stream.wait_event(ev)
+
+    def _check_buffer(self, t, name, rows, atoms, device=None):
+        """caller-supplied buffers: dtype, contiguity, size (and device) -- a wrong buffer would be written out of bounds"""
+        import torch
+
+        cdt = torch.complex128 if self.low.dtype == "f64" else torch.complex64
+        need = rows * atoms * self.low.npool
+        if isinstance(t, np.ndarray):
+            ok = t.dtype == (np.complex128 if self.low.dtype == "f64" else np.complex64) and t.flags.c_contiguous and t.size >= need
+            if device is not None:
+                raise ValueError(f"{name}: expected a CUDA tensor")
+        else:
+            ok = t.dtype == cdt and t.is_contiguous() and t.numel() >= need
+            if device is not None and (not t.is_cuda or t.device.index != device):
+                raise ValueError(f"{name}: expected a tensor on cuda:{device}, got {t.device}")
+            if device is None and t.is_cuda:
+                raise ValueError(f"{name}: expected a host buffer, got {t.device}")
+        if not ok:
+            raise ValueError(f"{name}: need a contiguous {cdt} buffer of at least {rows} x {atoms} x {self.low.npool} elements")
 
     def run(self, device, atom_begin=0, atom_count=None, signal=None, jacobian=None):
         """launch the fused kernel for an atom range on torch's current stream of `device`.
@@ -198,63 +234,112 @@ class Plan:
             atom_count = low.natoms - atom_begin
         dev = torch.device("cuda", device)
         cdt = torch.complex128 if low.dtype == "f64" else torch.complex64
+        has_jac = bool(low.nvar and low.njac)
         with torch.cuda.device(dev):
             ws = self.upload(device)
             if signal is None:
                 signal = torch.empty((low.nadc, atom_count, low.npool), dtype=cdt, device=dev)
-            if jacobian is None and low.nvar and low.njac:
+            else:
+                self._check_buffer(signal, "signal", low.nadc, atom_count, device)
+            if jacobian is None and has_jac:
                 jacobian = torch.empty((low.njac, low.nvar, atom_count, low.npool), dtype=cdt, device=dev)
-            st = torch.cuda.current_stream(dev).cuda_stream
+            elif has_jac:
+                self._check_buffer(jacobian, "jacobian", low.njac * low.nvar, atom_count, device)
+            if atom_count == 0:
+                return signal, jacobian
+            stream = torch.cuda.current_stream(dev)
+            self._wait_upload(device, stream)
             _check(lib().epgx_simulate(self._h, ws.data_ptr(), atom_begin, atom_count,
                                        signal.data_ptr() if signal is not None and signal.numel() else None,
-                                       jacobian.data_ptr() if jacobian is not None and jacobian.numel() else None, st))
+                                       jacobian.data_ptr() if jacobian is not None and jacobian.numel() else None,
+                                       stream.cuda_stream))
+            _count()
         return signal, jacobian
 
+    def run_strided(self, device, atom_begin, atom_count, signal, signal_stride, jacobian=None, jacobian_stride=0):
+        """epgx_simulate_strided on torch's current stream: rows of `signal` are `signal_stride` atoms apart, so that
+        launches over atom sub-ranges fill one [row][atoms][npool] buffer (pass the view that starts at the range's
+        first column)"""
+        import torch
+
+        require_cuda()
+        dev = torch.device("cuda", device)
+        with torch.cuda.device(dev):
+            ws = self.upload(device)
+            stream = torch.cuda.current_stream(dev)
+            self._wait_upload(device, stream)
+            _check(lib().epgx_simulate_strided(self._h, ws.data_ptr(), atom_begin, atom_count, signal.data_ptr(), signal_stride,
+                                               jacobian.data_ptr() if jacobian is not None else None,
+                                               jacobian_stride or signal_stride, stream.cuda_stream))
+            _count()
+
     def run_to_host(self, device, out_signal, atom_begin=0, atom_count=None, nchunk=8, out_jacobian=None,
-                    dev_signal=None, dev_jacobian=None):
+                    dev_signal=None, dev_jacobian=None, host_col=0, host_atoms=None):
         """pipelined end-to-end run: H2D of the tape, then the atom range is cut in `nchunk` column ranges;
         range i+1 is computed while range i is copied to the (pinned) host buffers with pitched D2H copies.
-        out_signal: host torch tensor / numpy array [nadc][atom_count][npool] complex (pinned for overlap).
-        Synchronises before returning."""
+        out_signal: host torch tensor / numpy array [nadc][host_atoms][npool] complex (pinned for overlap); the range
+        lands in columns [host_col, host_col + atom_count) (host_atoms defaults to atom_count: the buffer holds exactly
+        this range).  out_jacobian: [njac * nvar][host_atoms][npool], required when the plan has derivative rows.
+        Synchronises before returning.  Returns the device slabs (dev_signal, dev_jacobian)."""
         import torch
 
         require_cuda()
         low = self.low
         if atom_count is None:
             atom_count = low.natoms - atom_begin
+        if host_atoms is None:
+            host_atoms = atom_count
+        if host_col < 0 or host_col + atom_count > host_atoms:
+            raise ValueError("host column range outside the host buffer")
         dev = torch.device("cuda", device)
         cdt = torch.complex128 if low.dtype == "f64" else torch.complex64
         csz = 16 if low.dtype == "f64" else 8
+        has_jac = bool(low.nvar and low.njac)
+        if low.nadc:
+            if out_signal is None:
+                raise ValueError("out_signal is required: the plan has read-out rows")
+            self._check_buffer(out_signal, "out_signal", low.nadc, host_atoms)
+        if has_jac:
+            if out_jacobian is None:
+                raise ValueError("out_jacobian is required: the plan has derivative rows")
+            self._check_buffer(out_jacobian, "out_jacobian", low.njac * low.nvar, host_atoms)
         L = lib()
         with torch.cuda.device(dev):
             ws = self.upload(device, force=True)
             if dev_signal is None:
                 dev_signal = torch.empty((low.nadc, atom_count, low.npool), dtype=cdt, device=dev)
-            has_jac = bool(low.nvar and low.njac)
+            else:
+                self._check_buffer(dev_signal, "dev_signal", low.nadc, atom_count, device)
             if has_jac and dev_jacobian is None:
                 dev_jacobian = torch.empty((low.njac * low.nvar, atom_count, low.npool), dtype=cdt, device=dev)
+            elif has_jac:
+                self._check_buffer(dev_jacobian, "dev_jacobian", low.njac * low.nvar, atom_count, device)
+            if atom_count == 0:
+                return dev_signal, dev_jacobian
             compute = torch.cuda.current_stream(dev)
+            self._wait_upload(device, compute)
             copy = torch.cuda.Stream(dev)
             per = -(-atom_count // max(1, nchunk))
-            hs = out_signal.data_ptr() if hasattr(out_signal, "data_ptr") else out_signal.ctypes.data
-            hj = None
-            if has_jac:
-                hj = out_jacobian.data_ptr() if hasattr(out_jacobian, "data_ptr") else out_jacobian.ctypes.data
+            ptr = lambda t: t.data_ptr() if hasattr(t, "data_ptr") else t.ctypes.data
+            hs = ptr(out_signal) + host_col * low.npool * csz if low.nadc else None
+            hj = ptr(out_jacobian) + host_col * low.npool * csz if has_jac else None
             pitch = atom_count * low.npool * csz
+            hpitch = host_atoms * low.npool * csz
             for b in range(0, atom_count, per):
                 c = min(per, atom_count - b)
                 colb = b * low.npool * csz
                 _check(L.epgx_simulate_strided(
                     self._h, ws.data_ptr(), atom_begin + b, c, dev_signal.data_ptr() + colb, atom_count,
                     (dev_jacobian.data_ptr() + colb) if has_jac else None, atom_count, compute.cuda_stream))
+                _count()
                 ev = torch.cuda.Event()
                 ev.record(compute)
                 copy.wait_event(ev)
                 if low.nadc:
-                    _check(L.epgx_copy2d_to_host(hs + colb, pitch, dev_signal.data_ptr() + colb, pitch, c * low.npool * csz,
+                    _check(L.epgx_copy2d_to_host(hs + colb, hpitch, dev_signal.data_ptr() + colb, pitch, c * low.npool * csz,
                                                  low.nadc, copy.cuda_stream))
                 if has_jac:
-                    _check(L.epgx_copy2d_to_host(hj + colb, pitch, dev_jacobian.data_ptr() + colb, pitch,
+                    _check(L.epgx_copy2d_to_host(hj + colb, hpitch, dev_jacobian.data_ptr() + colb, pitch,
                                                  c * low.npool * csz, low.njac * low.nvar, copy.cuda_stream))
             copy.synchronize()
             compute.synchronize()

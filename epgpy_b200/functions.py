@@ -56,68 +56,137 @@ def _devices(device):
     return [d.index if d.index is not None else torch.cuda.current_device()]
 
 
-def run_lowered(low, plan=None, device=None, atom_range=None):
-    """run a lowered sequence on one or several devices of this process (atoms split in contiguous
-    slabs, no inter-device traffic); returns (signal, jacobian, plan) with signal a device tensor list
-    per device: [(begin, count, sig, jac)]"""
+def _split(begin, count, n):
+    per = -(-count // n)
+    return [(begin + i * per, min(per, begin + count - (begin + i * per))) for i in range(n) if begin + i * per < begin + count]
+
+
+def _host_buffer(shape, cdt):
+    """output buffer of a run: PINNED host memory (the pitched D2H copies of `Plan.run_to_host` overlap with the
+    kernels only into page-locked memory).  torch's caching host allocator keeps the pages when the returned array is
+    dropped, so repeated simulations of the same size do not pin again.  Pageable memory is the fallback when the
+    host refuses to pin that much."""
+    import torch
+
+    try:
+        return torch.empty(shape, dtype=cdt, pin_memory=True)
+    except RuntimeError:
+        return torch.empty(shape, dtype=cdt)
+
+
+def run_lowered(low, plan=None, device=None, atom_range=None, nchunk=None, keep_device=None):
+    """run a lowered sequence on one or several devices of this process: the atom range is cut in one contiguous
+    slab per device (no inter-device traffic) and every slab in column chunks, chunk i + 1 being computed while chunk i
+    is copied into the pinned host result (engine.Plan.run_to_host).
+    Returns (result, plan); result.sig_host / result.jac_host: host arrays complex [nadc][count][npool] and
+    [njac][nvar][count][npool] (numpy views of pinned tensors; None when the tape has no such rows), result.parts: the
+    device slabs [(device, begin, count, sig_dev, jac_dev)]."""
+    import threading
+
     import torch
 
     engine.require_cuda()
     plan = plan or engine.Plan(low)
     devs = _devices(device)
     begin, count = atom_range if atom_range is not None else (0, low.natoms)
-    per = -(-count // len(devs))
-    parts = []
-    for i, d in enumerate(devs):
-        b = begin + i * per
-        c = min(per, begin + count - b)
-        if c <= 0:
-            continue
-        sig, jac = plan.run(d, b, c)
-        parts.append((d, b, c, sig, jac))
-    return parts, plan
+    if begin < 0 or count < 0 or begin + count > low.natoms:
+        raise ValueError(f"atom range ({begin}, {count}) outside the grid of {low.natoms} atoms")
+    cdt = torch.complex128 if low.dtype == "f64" else torch.complex64
+    csz = 16 if low.dtype == "f64" else 8
+    has_jac = bool(low.nvar and low.njac)
+    sig_t = _host_buffer((low.nadc, count, low.npool), cdt) if low.nadc else None
+    jac_t = _host_buffer((low.njac * low.nvar, count, low.npool), cdt) if has_jac else None
+    slabs = _split(begin, count, len(devs)) if count else []
+    if nchunk is None:  # chunks of >= 32 MB of output, at most 16 per device
+        per_dev = low.nbytes_out(natoms=-(-count // max(1, len(slabs)))) if slabs else 0
+        nchunk = int(min(16, max(1, per_dev // (32 << 20))))
+    parts, errors = [None] * len(slabs), []
+
+    def work(i, d, b, c):
+        try:
+            col = b - begin
+            sig_d, jac_d = plan.run_to_host(d, sig_t, b, c, nchunk=nchunk, out_jacobian=jac_t, host_col=col, host_atoms=count)
+            parts[i] = (d, b, c, sig_d, jac_d)
+        except BaseException as ex:  # re-raised in the calling thread
+            errors.append(ex)
+
+    if len(slabs) == 1:
+        work(0, devs[0], *slabs[0])
+    else:
+        threads = [threading.Thread(target=work, args=(i, d, b, c)) for i, (d, (b, c)) in enumerate(zip(devs, slabs))]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+    if errors:
+        raise errors[0]
+    sig_host = sig_t.numpy() if sig_t is not None else None
+    jac_host = jac_t.numpy().reshape(low.njac, low.nvar, count, low.npool) if jac_t is not None else None
+    return RunResult(sig_host, jac_host, [p for p in parts if p is not None]), plan
 
 
-def _assemble(low, parts, asarray=True):
-    """device slabs -> per-probe host arrays shaped like the reference's output (nADC, *grid)"""
-    import torch
+class RunResult:
+    def __init__(self, sig_host, jac_host, parts):
+        self.sig_host, self.jac_host, self.parts = sig_host, jac_host, parts
 
+
+def _assemble(low, res, count=None, asarray=True):
+    """host slabs -> per-probe arrays shaped like the reference's output (nADC, *grid).  A probe whose rows are plain
+    read-outs comes back as a reshaped VIEW of the [nadc][atoms] result buffer (no copy).  With `count` (a slab of the
+    flattened grid, `simulate(shard=...)`) the grid axes are replaced by one flat atom axis."""
+    if isinstance(res, list):  # one device slab [(device, begin, count, sig, jac)] (tests/tape_interp.py)
+        (_, _, _, sig, jac), = res
+        res = RunResult(None if sig is None else sig.cpu().numpy(), None if jac is None else jac.cpu().numpy(), res)
+    sig_host, jac_host, parts = res.sig_host, res.jac_host, res.parts
     grid, ax, npool = tuple(low.grid), low.pool_axis, low.npool
-    store_shape = tuple(d for i, d in enumerate(grid) if i != ax) + ((npool,) if ax is not None else ())
-    order = [i for i in range(len(grid)) if i != ax] + ([ax] if ax is not None else [])  # grid axis of each storage axis
+    flat_mode = count is not None
+    if flat_mode:
+        store_shape = (count,) + ((npool,) if ax is not None else ())
+        grid = store_shape
+        ax = 1 if ax is not None else None
+        order = [0] + ([1] if ax is not None else [])
+    else:
+        store_shape = tuple(d for i, d in enumerate(grid) if i != ax) + ((npool,) if ax is not None else ())
+        order = [i for i in range(len(grid)) if i != ax] + ([ax] if ax is not None else [])  # grid axis of each storage axis
     cdt = np.complex128 if low.dtype == "f64" else np.complex64
 
-    def to_grid(flat):
-        a = flat.reshape(store_shape)
+    def to_grid(flat, lead=0):
+        a = flat.reshape(flat.shape[:lead] + store_shape)
         if ax is not None:
-            a = np.moveaxis(a, -1, ax)
-        return a.reshape(grid)
+            a = np.moveaxis(a, -1, lead + ax)
+        return a.reshape(flat.shape[:lead] + grid)
 
-    sig_host = jac_host = sig_dev = None
-    if low.nadc:
-        if len(parts) == 1:
-            sig_host = parts[0][3].cpu().numpy()
-        else:
-            sig_host = np.empty((low.nadc, low.natoms, npool), dtype=cdt)
-            for d, b, c, sig, jac in parts:
-                sig_host[:, b:b + c] = sig.cpu().numpy()
+    sig_dev = None
+    if low.nadc and any(r.kind == "sig" and r.reduce is not None for rows in low.rows for r in rows):
         # reduction of rows on the device (probe.py:148-153)
-        if any(r.kind == "sig" and r.reduce is not None for rows in low.rows for r in rows):
-            sig_dev = parts[0][3] if len(parts) == 1 else torch.cat([p[3].to(parts[0][3].device) for p in parts], dim=1)
-    if low.nvar and low.njac:
+        if flat_mode:
+            raise NotImplementedError("Adc(reduce=...) over a shard of the grid")
         if len(parts) == 1:
-            jac_host = parts[0][4].cpu().numpy()
+            sig_dev = parts[0][3]
         else:
-            jac_host = np.empty((low.njac, low.nvar, low.natoms, npool), dtype=cdt)
-            for d, b, c, sig, jac in parts:
-                jac_host[:, :, b:b + c] = jac.cpu().numpy()
+            import torch
+
+            sig_dev = torch.cat([p[3].to(parts[0][3].device) for p in parts], dim=1)
 
     values = [[] for _ in range(low.nprobe)]
+    plain = [all(rows[ip].kind == "sig" and rows[ip].reduce is None and rows[ip].post is None for rows in low.rows)
+             for ip in range(low.nprobe)]
+    for ip in range(low.nprobe):
+        if not (asarray and plain[ip] and low.rows):
+            continue
+        idx = [rows[ip].index for rows in low.rows]
+        step = idx[1] - idx[0] if len(idx) > 1 else 1
+        if step > 0 and all(b - a == step for a, b in zip(idx, idx[1:])):
+            values[ip] = to_grid(sig_host[idx[0]:idx[-1] + 1:step].reshape(len(idx), -1), lead=1)  # a view
+        else:
+            plain[ip] = False
     for rows in low.rows:
         for ip, row in enumerate(rows):
+            if asarray and plain[ip]:
+                continue
             if row.kind == "sig":
                 if row.reduce is None:
-                    arr = to_grid(sig_host[row.index])
+                    arr = to_grid(sig_host[row.index].reshape(-1))
                 else:
                     t = sig_dev[row.index].reshape(store_shape)
                     red = list(range(len(grid))) if row.reduce is True else sorted({r % len(grid) for r in row.reduce})
@@ -130,26 +199,26 @@ def _assemble(low, parts, asarray=True):
                     arr = np.asarray(row.post(arr)).astype(cdt, copy=False)
                 values[ip].append(arr)
             elif row.kind == "expr":
-                val = row.jac._eval(to_grid(sig_host[row.index]), to_grid(sig_host[row.index + 1]))
+                val = row.jac._eval(to_grid(sig_host[row.index].reshape(-1)), to_grid(sig_host[row.index + 1].reshape(-1)))
                 values[ip].append(row.post(val) if row.post is not None else val)
             else:
                 jrow, cols = row.jac
                 out = np.zeros(grid + (len(cols),), dtype=cdt)
                 for ic, (kind, vi) in enumerate(cols):
                     if kind == "mag":
-                        out[..., ic] = to_grid(sig_host[row.index])
+                        out[..., ic] = to_grid(sig_host[row.index].reshape(-1))
                     elif kind == "var":
-                        out[..., ic] = to_grid(jac_host[jrow, vi])
+                        out[..., ic] = to_grid(jac_host[jrow, vi].reshape(-1))
                 if row.post is not None:
                     out = np.asarray(row.post(out)).astype(cdt, copy=False)
                 values[ip].append(out)
     if asarray:
-        return tuple(np.asarray(v) for v in values)
+        return tuple(v if isinstance(v, np.ndarray) else np.asarray(v) for v in values)
     return tuple(tuple(v) for v in values)
 
 
 def simulate(sequence, *, adc_time=False, init=None, squeeze=False, probe=None, callback=None, asarray=True,
-             disp=False, dtype="float64", device=None, propagate_nondiff=False, **options):
+             disp=False, dtype="float64", device=None, propagate_nondiff=False, shard=None, **options):
     """simulate a sequence; values are returned at the probe operators (epgpy/functions.py:50-170)
 
     Parameters (reference-compatible):
@@ -165,6 +234,9 @@ def simulate(sequence, *, adc_time=False, init=None, squeeze=False, probe=None, 
         propagate_nondiff: False reproduces the reference, whose D / X / SPOILER never touch the
             order-1 partial states (epgpy/operator.py:96-104); True applies them to the partials too
             (the exact chain rule).
+        shard: (index, count): simulate only slab `index` of the `count` contiguous slabs of the flattened grid
+            (one process per GPU, sharding.slab); the grid axes of the result are then ONE flat atom axis:
+            (nADC, slab atoms).  sharding.simulate adds the final NCCL gather.
     Returns: values | (times, values) -- ndarray (nADC, *grid) per probe, a tuple if several probes
     """
     if squeeze:
@@ -175,8 +247,13 @@ def simulate(sequence, *, adc_time=False, init=None, squeeze=False, probe=None, 
     low = lowering.lower(sequence, init=init, probe=probe, options=options, dtype=engine.norm_dtype(dtype),
                          propagate_nondiff=propagate_nondiff)
     LOGGER.info("Simulate sequence: num. operators: %d, shape: %s, max order: %d", len(low.ops), low.grid, low.max_order)
-    parts, plan = run_lowered(low, device=device)
-    values = _assemble(low, parts, asarray=asarray)
+    atom_range = None
+    if shard is not None:
+        from . import sharding
+
+        atom_range = sharding.slab(low.natoms, int(shard[0]), int(shard[1]))
+    res, plan = run_lowered(low, device=device, atom_range=atom_range)
+    values = _assemble(low, res, count=None if shard is None else atom_range[1], asarray=asarray)
     times = np.asarray(low.times) if asarray else low.times
     if len(values) == 1:
         values = values[0]

@@ -237,6 +237,18 @@ class DiffOperator(Operator):
     def _form(self):
         raise NotImplementedError
 
+    def _lowered_form(self):
+        """the coefficient form of the operator itself as the tape takes it (pulses reduced to their real-coupling
+        kinds), computed once per operator object: T and E build it in their constructors, like the reference computes
+        its coefficient arrays eagerly (epgpy/transition.py:32-36, evolution.py:107-118)"""
+        f = self.__dict__.get("_lform")
+        if f is None:
+            f = self._form()
+            if f[0] == "tgen":
+                f = reduce_pulse(f)
+            self._lform = f
+        return f
+
     def _dform(self, param):
         raise NotImplementedError
 
@@ -330,6 +342,19 @@ class CombinableOperator(DiffOperator):
 
     def combine(self, other, *, right=False, name=None, duration=None):
         return _combine(other, self, name, duration) if right else _combine(self, other, name, duration)
+
+
+def reduce_pulse(form):
+    """('tgen', blk6) -> ('tre' | 'tim', blk4) when B and U are real / B real and U imaginary (phi = +-90 / 0, 180 deg)"""
+    blk = form[1]
+    if not np.any(blk[..., 3]):
+        if not np.any(blk[..., 5]):
+            return ("tre", np.ascontiguousarray(blk[..., [0, 1, 2, 4]]))
+        if not np.any(blk[..., 4]):
+            b4 = blk[..., [0, 1, 2, 5]].copy()
+            b4[..., 3] *= -1  # U = -i u
+            return ("tim", b4)
+    return form
 
 
 def _cplx_block(*cols):
@@ -490,6 +515,7 @@ class T(CombinableOperator):
             name = common.repr_operator("T", ["alpha", "phi"], [alpha, phi], [".1f", ".1f"])
         super().__init__(name=name, duration=duration, **kwargs)
         self._shape = op_shape(self.alpha, self.phi)
+        self._lowered_form()
 
     @property
     def shape(self):
@@ -504,7 +530,11 @@ class T(CombinableOperator):
         a, phi = self._ap()
         B = np.sin(a / 2) ** 2 * _cis_deg(phi, 2)
         U = -1j * _snap(np.sin(a)) * _cis_deg(phi)  # sin(180 deg) = 1.2e-16 -> 0
-        return ("tgen", _cplx_block(np.cos(a / 2) ** 2 + 0 * B.real, _snap(np.cos(a)) + 0 * B.real, B, U))
+        blk = np.empty(np.broadcast_shapes(a.shape, phi.shape) + (6,))
+        blk[..., 0] = np.cos(a / 2) ** 2
+        blk[..., 1] = _snap(np.cos(a))
+        blk[..., 2], blk[..., 3], blk[..., 4], blk[..., 5] = B.real, B.imag, U.real, U.imag
+        return ("tgen", blk)
 
     def _dform(self, param):
         a, phi = self._ap()
@@ -658,6 +688,7 @@ class E(_Evolution):
         duration = self.tau if duration is True else duration
         super().__init__(name=name, duration=duration, **kwargs)
         self._shape = op_shape(self.tau, self.T1, self.T2, self.g)
+        self._lowered_form()
 
     @property
     def shape(self):
@@ -669,12 +700,14 @@ class E(_Evolution):
     def _form(self):
         tau, T1, T2, g = self._params()
         e1 = np.exp(-tau / T1)
-        blk0 = _cplx_block(e1, 1 - e1)
-        blk1 = _cplx_block(np.exp(-tau / T2))
+        blk0 = np.empty(e1.shape + (2,))
+        blk0[..., 0], blk0[..., 1] = e1, 1 - e1
+        blk1 = np.exp(-tau / T2)[..., None]
         blk2 = None
         if np.any(g != 0):
             ph = 2 * np.pi * g * tau
-            blk2 = _cplx_block(np.cos(ph), np.sin(ph))
+            blk2 = np.empty(ph.shape + (2,))
+            blk2[..., 0], blk2[..., 1] = np.cos(ph), np.sin(ph)
         return ("e", blk0, blk1, blk2, True)
 
     def _arrs(self):

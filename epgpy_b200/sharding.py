@@ -44,3 +44,63 @@ def gather_rows(local, natoms, group=None):
     for r, (b, c) in enumerate(parts):
         out[:, b:b + c] = recv[r, :, :c]
     return out
+
+
+def run_gather(plan, device, group=None, nchunk=4, out=None):
+    """the north-star multi-GPU step: every rank runs ITS slab of the plan's atoms (sharding.slab) and the signal
+    slabs are all-gathered over NCCL / NVLink, so that every rank ends with the whole [nadc][natoms][npool] signal in
+    its HBM.  The slab is cut in `nchunk` column chunks: the all-gather of chunk j (NCCL's own stream,
+    async_op=True) overlaps with the kernel of chunk j + 1; the chunks are then scattered to their columns of `out`
+    (one strided device copy per rank and chunk).  Ragged slabs are padded to the largest one for the collective.
+    Enqueues on torch's current stream and returns `out` without synchronising."""
+    import torch
+    import torch.distributed as dist
+
+    low = plan.low
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    parts = slabs(low.natoms, world)
+    begin, count = parts[rank]
+    cmax = max(c for _, c in parts)
+    nchunk = max(1, min(int(nchunk), cmax))
+    per = -(-cmax // nchunk)
+    dev = torch.device("cuda", device)
+    cdt = torch.complex128 if low.dtype == "f64" else torch.complex64
+    if low.nvar and low.njac:
+        raise NotImplementedError("run_gather gathers read-out rows only; gather Jacobian slabs with gather_rows")
+    if out is None:
+        out = torch.empty((low.nadc, low.natoms, low.npool), dtype=cdt, device=dev)
+    flat = lambda t: torch.view_as_real(t).reshape(-1)
+    works = []
+    for b in range(0, cmax, per):
+        w = min(per, cmax - b)               # columns of this chunk (same on every rank)
+        c = max(0, min(w, count - b))        # atoms this rank really has in it
+        send = torch.empty((low.nadc, w, low.npool), dtype=cdt, device=dev)
+        recv = torch.empty((world, low.nadc, w, low.npool), dtype=cdt, device=dev)
+        if c < w:
+            send.zero_()
+        if c:
+            plan.run_strided(device, begin + b, c, send, w)
+        works.append((dist.all_gather_into_tensor(flat(recv), flat(send), group=group, async_op=True), recv, b, w))
+    for work, recv, b, w in works:
+        work.wait()
+        for r, (rb, rc) in enumerate(parts):
+            c = max(0, min(w, rc - b))
+            if c:
+                out[:, rb + b:rb + b + c] = recv[r, :, :c]
+    return out
+
+
+def simulate(sequence, *, group=None, device=None, nchunk=4, dtype="float64", **kwargs):
+    """distributed `simulate` (one process per GPU, torch.distributed initialised): every rank lowers the sequence,
+    simulates its slab of the flattened grid and the slabs are all-gathered on the devices (run_gather).
+    Returns the device tensor complex [nadc][natoms][npool] -- the whole dictionary in the HBM of every rank, ready
+    for device-side matching -- together with the Lowered description (grid shape, ADC times)."""
+    import torch
+
+    from . import engine, lowering
+
+    options = {k: kwargs.pop(k) for k in ("max_nstate", "kvalue") if k in kwargs}
+    low = lowering.lower(sequence, options=options, dtype=engine.norm_dtype(dtype), **kwargs)
+    plan = engine.Plan(low)
+    dev = torch.cuda.current_device() if device is None else int(device)
+    return run_gather(plan, dev, group=group, nchunk=nchunk), low

@@ -471,29 +471,46 @@ def resize(states, n):
     return states[..., d:-d, :].copy()
 
 
-def apply_matrix(states, mat, eq=None, mat0=None):
-    """states[g,s,:] <- M[g] . states[g,s,:] (+ mat0 . equilibrium)   (epgpy/opmatrix.py:199-221)"""
+def apply_matrix(states, mat, eq=None, mat0=None, inplace=False):
+    """states[g,s,:] <- M[g] . states[g,s,:] (+ mat0 . equilibrium)   (epgpy/opmatrix.py:199-221)
+    Written as the row-vector product states[g] (s x 3) @ M[g]^T (3 x 3): one small GEMM per atom instead of
+    one 3x3 matvec per order.  inplace=True overwrites `states` like the reference (`out=states`, opmatrix.py:208-221)."""
     nd = states.ndim - 2
-    m = _left(mat, nd, tail=2)[..., None, :, :]
-    out = np.matmul(m, states[..., None])[..., 0]
+    mt = np.swapaxes(_left(mat, nd, tail=2), -1, -2)
+    if inplace and np.broadcast_shapes(mt.shape[:-2], states.shape[:-2]) == states.shape[:-2]:
+        out = np.matmul(states, mt, out=states)
+    else:
+        out = np.matmul(states, mt)
     if mat0 is not None:
-        m0 = _left(mat0, nd, tail=2)[..., None, :, :]
-        out = out + np.matmul(m0, np.broadcast_to(eq, states.shape)[..., None])[..., 0]
+        m0t = np.swapaxes(_left(mat0, nd, tail=2), -1, -2)
+        n = nstate(states)
+        # the equilibrium is non-zero at k = 0 only (statematrix.py:94-100): one row instead of the whole state
+        out[..., n, :] += np.matmul(np.broadcast_to(eq, states.shape)[..., n:n + 1, :], m0t)[..., 0, :]
     return out
 
 
-def apply_diag(states, arr, eq=None, arr0=None):
-    """states *= arr ; states += arr0 * equilibrium   (epgpy/opscalar.py:213-232)"""
+def apply_diag(states, arr, eq=None, arr0=None, inplace=False):
+    """states *= arr ; states += arr0 * equilibrium   (epgpy/opscalar.py:213-232)
+    inplace=True multiplies in place like the reference (`states *= arr`, opscalar.py:222-232)."""
     nd = states.ndim - 2
-    out = states * _left(arr, nd, tail=1)[..., None, :]
+    a = _left(arr, nd, tail=1)[..., None, :]
+    if inplace and np.broadcast_shapes(a.shape, states.shape) == states.shape:
+        states *= a
+        out = states
+    else:
+        out = states * a
     if arr0 is not None:
-        out = out + _left(arr0, nd, tail=1)[..., None, :] * eq
+        n = nstate(out)
+        neq = nstate(eq)
+        # the equilibrium is non-zero at k = 0 only: add its row instead of a whole-state pass
+        out[..., n, :] += _left(arr0, nd, tail=1) * eq[..., neq, :]
     return out
 
 
-def shift_int(states, k):
-    """1-d integer shift on an already resized array (epgpy/shift.py:283-292)"""
-    out = states.copy()
+def shift_int(states, k, inplace=False):
+    """1-d integer shift on an already resized array (epgpy/shift.py:283-292); the reference shifts in place
+    (overlapping slice assignments, which numpy buffers)"""
+    out = states if inplace else states.copy()
     n = k
     if n > 0:
         out[..., n:, 0] = states[..., :-n, 0]
@@ -662,7 +679,7 @@ def _apply_linear(sim, op):
     base = sim.states
     # 1. propagate the existing partials (their equilibrium is zero: no affine term)
     for v in list(sim.partials):
-        sim.partials[v] = app(sim.partials[v], c)
+        sim.partials[v] = app(sim.partials[v], c, inplace=True)
     # 2. new contributions from the pre-operator base state (diff.py:279-286,556-579)
     for v, pc in op.order1.items():
         acc = None
@@ -678,8 +695,8 @@ def _apply_linear(sim, op):
             continue
         acc = np.broadcast_to(acc, base.shape)
         sim.partials[v] = sim.partials[v] + acc if v in sim.partials else acc.copy()
-    # 3. the operator itself
-    sim.states = app(base, c, sim.eq, c0)
+    # 3. the operator itself (in place, like the reference: opscalar.py:222-232, opmatrix.py:208-221)
+    sim.states = app(base, c, sim.eq, c0, inplace=True)
 
 
 def _apply_shift(sim, op):
@@ -706,7 +723,7 @@ def _apply_shift(sim, op):
             s = s.copy()
             s[..., :2] = 0
         else:
-            s = shift_int(s, k)
+            s = shift_int(s, k, inplace=s.flags.writeable)
         sim.set(v, s)
 
 
