@@ -197,7 +197,7 @@ def main():
     ap.add_argument("--lanes", type=int, default=0)
     ap.add_argument("--atoms-per-cta", type=int, default=0)
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"])
-    ap.add_argument("--gather-chunks", type=int, default=4)
+    ap.add_argument("--gather-chunks", type=int, default=8)
     ap.add_argument("--no-gather", action="store_true", help="N > 1: leave the final NCCL all-gather out of the timed step")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")

@@ -367,6 +367,11 @@ def lower(sequence, *, init=None, probe=None, options=None, dtype="f64", propaga
 
     # ---- order schedule: maximum order of the whole tape
     init_n = sm.nstate
+    crop = 0
+    if max_nstate and init_n > max_nstate and any(isinstance(op, S) for op in seq):
+        # the first shift crops the state to max_nstate orders (shift.py:98, statematrix.resize); the orders above
+        # never reach k = 0 before that, so cropping the initial state gives the same read-outs
+        crop, init_n = init_n - max_nstate, max_nstate
     n, max_order = init_n, init_n
     for op in seq:
         if isinstance(op, S):
@@ -379,7 +384,7 @@ def lower(sequence, *, init=None, probe=None, options=None, dtype="f64", propaga
         max_order = init_n
 
     # ---- init / equilibrium blocks (half storage: orders 0..init_n)
-    st = sm.states
+    st = sm.states[..., crop:sm.states.shape[-2] - crop, :]
     half = st[..., init_n:, :]
     init_blk = np.stack([half[..., 0].real, half[..., 0].imag, half[..., 1].real, half[..., 1].imag,
                          half[..., 2].real, half[..., 2].imag], axis=-1).reshape(half.shape[:-2] + (6 * (init_n + 1),))
@@ -449,6 +454,9 @@ def lower(sequence, *, init=None, probe=None, options=None, dtype="f64", propaga
             cap = max_nstate or op.nmax or None
             for _ in range(abs(m)):
                 n_new = n + 1 if cap is None else min(n + 1, max(cap, 0))
+                if n_new < n:
+                    raise NotImplementedError(f"{op!r}: nmax={cap} is below the current number of states ({n}); a state matrix "
+                                              "that shrinks in mid-sequence is not lowered (use the max_nstate option)")
                 close_segment(1 if m > 0 else -1, n, n_new, SEG_MASK_TOP if n_new == n else 0)
                 n = n_new
         elif isinstance(op, (X, D, Spoiler)):

@@ -46,12 +46,12 @@ def gather_rows(local, natoms, group=None):
     return out
 
 
-def run_gather(plan, device, group=None, nchunk=4, out=None):
+def run_gather(plan, device, group=None, nchunk=8, out=None):
     """the north-star multi-GPU step: every rank runs ITS slab of the plan's atoms (sharding.slab) and the signal
     slabs are all-gathered over NCCL / NVLink, so that every rank ends with the whole [nadc][natoms][npool] signal in
     its HBM.  The slab is cut in `nchunk` column chunks: the all-gather of chunk j (NCCL's own stream,
-    async_op=True) overlaps with the kernel of chunk j + 1; the chunks are then scattered to their columns of `out`
-    (one strided device copy per rank and chunk).  Ragged slabs are padded to the largest one for the collective.
+    async_op=True) overlaps with the kernel of chunk j + 1, and so does the scatter of chunk j to its columns of `out`
+    (one strided device copy per rank and chunk, on a side stream).  Ragged slabs are padded to the largest one for the collective.
     Enqueues on torch's current stream and returns `out` without synchronising."""
     import torch
     import torch.distributed as dist
@@ -70,7 +70,8 @@ def run_gather(plan, device, group=None, nchunk=4, out=None):
     if out is None:
         out = torch.empty((low.nadc, low.natoms, low.npool), dtype=cdt, device=dev)
     flat = lambda t: torch.view_as_real(t).reshape(-1)
-    works = []
+    cur = torch.cuda.current_stream(dev)
+    side = torch.cuda.Stream(dev)  # scatters chunk j to its columns of `out` while the kernel of chunk j + 1 runs
     for b in range(0, cmax, per):
         w = min(per, cmax - b)               # columns of this chunk (same on every rank)
         c = max(0, min(w, count - b))        # atoms this rank really has in it
@@ -80,13 +81,16 @@ def run_gather(plan, device, group=None, nchunk=4, out=None):
             send.zero_()
         if c:
             plan.run_strided(device, begin + b, c, send, w)
-        works.append((dist.all_gather_into_tensor(flat(recv), flat(send), group=group, async_op=True), recv, b, w))
-    for work, recv, b, w in works:
-        work.wait()
-        for r, (rb, rc) in enumerate(parts):
-            c = max(0, min(w, rc - b))
-            if c:
-                out[:, rb + b:rb + b + c] = recv[r, :, :c]
+        work = dist.all_gather_into_tensor(flat(recv), flat(send), group=group, async_op=True)
+        with torch.cuda.stream(side):
+            work.wait()
+            recv.record_stream(side)
+            for r, (rb, rc) in enumerate(parts):
+                cr = max(0, min(w, rc - b))
+                if cr:
+                    out[:, rb + b:rb + b + cr] = recv[r, :, :cr]
+    cur.wait_stream(side)
+    out.record_stream(side)
     return out
 
 

@@ -241,6 +241,78 @@ def adc_reduce(epg):
     return dict(seq=seq)
 
 
+def gre_diffusion_tensor(epg, ntr=24):
+    """anisotropic diffusion TENSOR with collinear 3-d shifts (diffusion.py:140-145), ramp term included"""
+    T1 = np.array([600.0, 1200.0])
+    T2 = np.array([[40.0, 80.0, 120.0]])
+    Dten = np.array([[2.0, 0.1, 0.0], [0.1, 1.0, 0.2], [0.0, 0.2, 0.5]]) * 1e-3
+    seq, kv = [], [2, 1, -1]
+    for n in range(ntr):
+        ph = 117.0 * n * (n + 1) / 2
+        seq.append([epg.T(15, ph), epg.E(2, T1, T2), epg.Adc(phase=-ph), epg.E(8, T1, T2), epg.D(3.0, Dten),
+                    epg.S(kv), epg.D(10, Dten, k=kv)])
+    return dict(seq=seq, options={"kvalue": 500.0}, kvec=kv)
+
+
+def _valid_state(n, seed, real=False):
+    """a random (2n+1) x 3 state obeying F-(k) = conj F+(-k), Z(k) = conj Z(-k) (statematrix.py:418-421)"""
+    rng = np.random.RandomState(seed)
+    half = rng.randn(n + 1, 3) + (0 if real else 1j) * rng.randn(n + 1, 3)
+    half[0, 2] = half[0, 2].real
+    full = np.zeros((2 * n + 1, 3), dtype=complex)
+    full[n:, :] = half
+    full[:n, 0] = half[:0:-1, 1].conj()
+    full[:n, 1] = half[:0:-1, 0].conj()
+    full[:n, 2] = half[:0:-1, 2].conj()
+    full[n, 1] = full[n, 0].conj()
+    return 0.3 * full
+
+
+def init_states(epg, ntr=14):
+    """initial state with n = 3 populated orders and complex entries (functions.py:113-144): complex kernels"""
+    T2 = np.array([40.0, 80.0, 120.0])
+    g = np.array([[0.0, 0.03]])
+    seq = []
+    for i in range(ntr):
+        seq.append([epg.T(25 + i, 30.0 * i), epg.E(4, 900.0, T2, g), epg.ADC, epg.Adc("Z0"), epg.S(1 if i % 4 else -2)])
+    return dict(seq=seq, init=_valid_state(3, 11))
+
+
+def init_states_real(epg, ntr=14):
+    """real initial state with n = 3 populated orders under +-90 degree pulses: the real-valued kernels;
+    max_nstate below the initial order count crops it at the first shift (statematrix.resize, shift.py:98)"""
+    T2 = np.array([40.0, 80.0, 120.0])
+    seq = []
+    for i in range(ntr):
+        seq.append([epg.T(25 + i, 90 if i % 3 else 270), epg.E(4, 900.0, T2), epg.ADC, epg.Adc("Z0"), epg.S(1 if i % 4 else -1)])
+    return dict(seq=seq, init=_valid_state(3, 12, real=True))
+
+
+def init_states_cropped(epg):
+    """max_nstate BELOW the order count of the initial state: the first shift crops it (shift.py:98, statematrix.resize)"""
+    case = init_states_real(epg)
+    case["options"] = {"max_nstate": 2}
+    return case
+
+
+def init_states_jac(epg, ntr=10):
+    """initial state with populated orders + order-1 variables: the partial states start from zero (diff.py:103-109)"""
+    T2 = np.array([40.0, 80.0, 120.0])
+    seq = []
+    for i in range(ntr):
+        seq.append([epg.T(25 + i, 90, order1={"B1": {"alpha": 25.0 + i}}), epg.E(4, 900.0, T2, order1=["T2"]), epg.ADC, epg.S(1)])
+    return dict(seq=seq, init=_valid_state(2, 13, real=True), jac=["magnitude", "B1", "T2"])
+
+
+def init_states_jac_complex(epg, ntr=10):
+    T2 = np.array([40.0, 80.0, 120.0])
+    seq = []
+    for i in range(ntr):
+        seq.append([epg.T(25 + i, 20.0 * i, order1={"B1": {"alpha": 25.0 + i}}), epg.E(4, 900.0, T2, 0.02, order1=["T2"]), epg.ADC,
+                    epg.S(1)])
+    return dict(seq=seq, init=_valid_state(2, 14), jac=["B1", "T2"])
+
+
 CASES = {
     "readme_mse": readme_mse,
     "mse_grid": mse_grid,
@@ -258,7 +330,40 @@ CASES = {
     "hyperecho": hyperecho,
     "misc_ops": misc_ops,
     "adc_reduce": adc_reduce,
+    "gre_diffusion_tensor": gre_diffusion_tensor,
+    "init_states": init_states,
+    "init_states_real": init_states_real,
+    "init_states_cropped": init_states_cropped,
+    "init_states_jac": init_states_jac,
+    "init_states_jac_complex": init_states_jac_complex,
 }
+
+
+def fisp_equal_axes(epg, ntr=30, n=3):
+    """FISP + (B1, T1, T2) Jacobian on an n x n x n grid: EQUAL axis sizes, like the headline 100 x 100 x 100
+    dictionary.  The reference's own vectorised run is wrong on such grids, so the golden file is
+    assembled from n^3 per-atom SCALAR runs of the unmodified reference (tests/golden/make_golden.py)."""
+    fa, tr = _fisp_schedule(ntr)
+    T1 = np.linspace(300, 3000, n)
+    T2 = np.linspace(20, 300, n)
+    B1 = np.linspace(0.7, 1.2, n)
+    return dict(axes=(T1, T2, B1), jac=["B1", "T1", "T2"], build=lambda T1, T2, B1: _fisp_jac_seq(epg, fa, tr, T1, T2, B1))
+
+
+def _fisp_jac_seq(epg, fa, tr, T1, T2, B1):
+    o1 = ["T1", "T2"]
+    seq = [epg.T(180, 0), epg.E(20, T1, T2, order1=o1)]
+    for i in range(len(fa)):
+        seq.append([epg.T(fa[i] * B1, 90, order1={"B1": {"alpha": fa[i]}}), epg.E(3, T1, T2, order1=o1), epg.ADC,
+                    epg.E(tr[i] - 3, T1, T2, order1=o1), epg.S(1)])
+    return seq
+
+
+def probe_expr(epg):
+    """`probe=` expressions over F0 / Z0 superseding the in-sequence ADCs (probe.py:7-66; functions.py:118-127)"""
+    case = misc_ops(epg)
+    case["probe"] = ["abs(F0)", "Z0.real + 2 * F0", "F0"]
+    return case
 
 
 def namespace(pkg):
@@ -276,6 +381,8 @@ def run_api(epg, case):
     opts = dict(case.get("options") or {})
     if case.get("density") is not None:
         opts["init"] = epg.StateMatrix(density=case["density"])
+    if case.get("init") is not None:
+        opts["init"] = np.array(case["init"])
     if case.get("jac"):
         sig, jac = epg.simulate(case["seq"], probe=[None, epg.Jacobian(case["jac"])], **opts)
         return np.asarray(sig), np.asarray(jac)

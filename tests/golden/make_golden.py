@@ -42,6 +42,31 @@ def main():
         np.savez_compressed(os.path.join(HERE, f"{name}.npz"), **out)
         print(f"{name:20s} signal {sig.shape} jac {None if jac is None else jac.shape}")
 
+    # ---- equal-size grid axes: per-atom SCALAR runs of the reference (its vectorised run is wrong there)
+    case = cases.fisp_equal_axes(ns)
+    T1, T2, B1 = case["axes"]
+    sig = jac = None
+    for i, t1 in enumerate(T1):
+        for j, t2 in enumerate(T2):
+            for k, b1 in enumerate(B1):
+                s1, j1 = epgpy.simulate(case["build"](float(t1), float(t2), float(b1)), probe=[None, epgpy.core.Jacobian(case["jac"])])
+                s1, j1 = np.asarray(s1), np.asarray(j1)
+                if sig is None:
+                    sig = np.zeros((s1.shape[0], len(T1), len(T2), len(B1)), dtype=complex)
+                    jac = np.zeros(sig.shape + (j1.shape[-1],), dtype=complex)
+                sig[:, i, j, k], jac[:, i, j, k] = s1[:, 0], j1[:, 0]
+    vec = np.asarray(epgpy.simulate(case["build"](T1, T2[None, :], B1[None, None, :]), probe=None))
+    np.savez_compressed(os.path.join(HERE, "fisp_equal_axes.npz"), signal=sig, jacobian=jac,
+                        reference_vectorised_rel_diff=np.abs(vec - sig).max() / np.abs(sig).max())
+    print(f"fisp_equal_axes      signal {sig.shape} jac {jac.shape}; the reference's own vectorised run differs by "
+          f"{np.abs(vec - sig).max() / np.abs(sig).max():.3f} (relative)")
+
+    # ---- `probe=` expressions
+    case = cases.probe_expr(ns)
+    vals = epgpy.simulate(case["seq"], probe=case["probe"])
+    np.savez_compressed(os.path.join(HERE, "probe_expr.npz"), **{f"probe{i}": np.asarray(v) for i, v in enumerate(vals)})
+    print("probe_expr          ", [np.asarray(v).shape for v in vals])
+
     # ---- operator-level primitives
     rng = np.random.RandomState(1)
     alpha = rng.uniform(-180, 180, (4, 1))

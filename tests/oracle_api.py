@@ -29,6 +29,7 @@ def run(case, **extra):
         kvec=case.get("kvec"),
         density=case.get("density") if case.get("density") is not None else 1.0,
         jacobian=case.get("jac"),
+        init=case.get("init"),
     )
     kw.update(extra)
     res = O.simulate(case["seq"], **kw)

@@ -27,6 +27,8 @@ def run_case(simulate, epg, case, **extra):
     opts.update(extra)
     if case.get("density") is not None:
         opts["init"] = epg.StateMatrix(density=case["density"])
+    if case.get("init") is not None:
+        opts["init"] = np.array(case["init"])
     if case.get("jac"):
         sig, jac = simulate(case["seq"], probe=[None, epg.Jacobian(case["jac"])], **opts)
         return np.asarray(sig), np.asarray(jac)
