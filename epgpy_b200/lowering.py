@@ -345,7 +345,8 @@ def lower(sequence, *, init=None, probe=None, options=None, dtype="f64", propaga
 
     # ---- derivative variables: only those a Jacobian probe asks for
     jprobes = [pb for pb in (probes or []) if isinstance(pb, Jacobian)]
-    jprobes += [op for op in seq if isinstance(op, Jacobian)] if probes is None else []
+    if probes is None or any(pb is None for pb in probes):  # a None entry keeps the in-sequence probes, Jacobians included
+        jprobes += [op for op in seq if isinstance(op, Jacobian)]
     defined = []
     for op in seq:
         for var in getattr(op, "order1", None) or {}:

@@ -1,6 +1,7 @@
-"""Drop-in check against the REAL reference (only where it is importable: the build container).  Sequences are
-built with the reference's own operator classes, converted with `compat.from_reference`, run through the
-lowering (tape interpreter here, the GPU in `-m gpu`), and compared with the reference's own `simulate`."""
+"""Drop-in check against the REAL reference (where it is importable: /root/reference in the build container,
+baseline/_ref -- the pip --target install made by __graft_entry__.build() -- on the GPU box).  Sequences are built
+with the reference's own operator classes, converted with `compat.from_reference`, run through the lowering -- by the
+tape interpreter in the CPU suite, by the CUDA ENGINE in `-m gpu` -- and compared with the reference's own `simulate`."""
 
 import os
 import sys
@@ -12,29 +13,46 @@ import cases
 import tape_interp
 from util import RTOL64, rel_err
 
-REF = os.environ.get("EPGPY_REFERENCE", "/root/reference")
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CANDIDATES = [os.environ.get("EPGPY_REFERENCE"), "/root/reference", os.path.join(ROOT, "baseline", "_ref")]
 
 
 @pytest.fixture(scope="module")
 def ref():
-    if not os.path.isdir(os.path.join(REF, "epgpy")):
-        pytest.skip("the reference package is not available on this machine")
-    sys.path.insert(0, REF)
-    try:
-        import epgpy
-    finally:
-        sys.path.remove(REF)
-    return epgpy
+    for root in CANDIDATES:
+        if root and os.path.isdir(os.path.join(root, "epgpy")):
+            sys.path.insert(0, root)
+            try:
+                import epgpy
+            finally:
+                sys.path.remove(root)
+            return epgpy
+    pytest.skip("the reference package is not available on this machine")
+
+
+def _engine_simulate(engine):
+    """`simulate` of the path under test: the numpy tape interpreter (CPU suite) or the CUDA engine (-m gpu)"""
+    if engine == "interp":
+        return lambda seq, **kw: tape_interp.simulate(None, seq, **kw)
+    import epgpy_b200
+
+    return epgpy_b200.epg.simulate
+
+
+ENGINES = ["interp", pytest.param("cuda", marks=pytest.mark.gpu)]
 
 
 NAMES = ["readme_mse", "mse_grid", "fisp_bounded", "fisp_jac_global", "mse_jac", "jac_all_params", "gre_diffusion_1d",
-         "bssfp_mt", "spgr_exchange", "hyperecho", "misc_ops", "adc_reduce"]
+         "gre_diffusion_tensor", "bssfp_mt", "spgr_exchange", "hyperecho", "misc_ops", "adc_reduce"]
 
 
+@pytest.mark.parametrize("engine", ENGINES)
 @pytest.mark.parametrize("name", NAMES)
-def test_reference_objects_run_on_the_engine_path(name, ref):
+def test_reference_objects_run_on_the_engine_path(name, engine, ref):
     import epgpy_b200
     from epgpy_b200 import compat
+
+    simulate = _engine_simulate(engine)
 
     rns = cases.namespace(ref)
     case = cases.CASES[name](rns)                      # operators of the reference
@@ -45,12 +63,15 @@ def test_reference_objects_run_on_the_engine_path(name, ref):
     if case.get("density") is not None:
         opts["init"] = epg.StateMatrix(density=case["density"])
     if case.get("jac"):
-        sig, jac = tape_interp.simulate(None, seq, probe=[None, epg.Jacobian(case["jac"])], **opts)
+        sig, jac = simulate(seq, probe=[None, epg.Jacobian(case["jac"])], **opts)
         assert rel_err(jac, want_jac) < RTOL64
     else:
-        sig = tape_interp.simulate(None, seq, **opts)
+        sig = simulate(seq, **opts)
     assert rel_err(np.asarray(sig), want_sig) < RTOL64
-    assert epg.get_adc_times(seq) == pytest.approx(ref.core.get_adc_times(case["seq"])) or True
+    got_t, want_t = epg.get_adc_times(seq), ref.core.get_adc_times(case["seq"])
+    assert len(got_t) == len(want_t)
+    for a, b in zip(got_t, want_t):
+        assert np.allclose(np.asarray(a, dtype=float), np.asarray(b, dtype=float), rtol=1e-13, atol=0)
 
 
 def test_identity_is_preserved(ref):
@@ -62,7 +83,8 @@ def test_identity_is_preserved(ref):
     assert out[1][1] is out[1][4] and type(out[1][1]).__name__ == "E"
 
 
-def test_reference_sequence_layer_runs_unchanged_on_the_engine_path(ref, monkeypatch):
+@pytest.mark.parametrize("engine", ENGINES)
+def test_reference_sequence_layer_runs_unchanged_on_the_engine_path(engine, ref, monkeypatch):
     """the reference's symbolic `Sequence` layer (signal / jacobian / crlb) only calls
     `functions.simulate`; with that one call routed through `compat.from_reference` + the lowering, it runs
     unchanged (reference test/test_sequence.py:6-61 restated)."""
@@ -81,6 +103,7 @@ def test_reference_sequence_layer_runs_unchanged_on_the_engine_path(ref, monkeyp
     want_crlb = seq.crlb(["T2", "B1"])(T2=30, B1=0.8)
 
     calls = []
+    simulate = _engine_simulate(engine)
 
     def routed(sequence, **kw):
         calls.append(len(sequence))
@@ -88,7 +111,7 @@ def test_reference_sequence_layer_runs_unchanged_on_the_engine_path(ref, monkeyp
         if probe is not None:
             probe = [compat.from_reference(p) if p is not None else None for p in (probe if isinstance(probe, (list, tuple)) else [probe])]
         kw.pop("asarray", None)
-        return tape_interp.simulate(None, compat.from_reference(sequence), probe=probe, **kw)
+        return simulate(compat.from_reference(sequence), probe=probe, **kw)
 
     import epgpy.sequence as refseq
 

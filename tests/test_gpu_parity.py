@@ -44,11 +44,39 @@ def test_fp32_matches_reference(name, golden, epg):
                 assert np.abs(jac[..., i] - col).max() < 1e-3 * np.abs(ref["jacobian"]).max()
 
 
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+def test_equal_axes_grid_matches_per_atom_reference_runs(dtype, golden, epg):
+    """grid axes of EQUAL size, like the headline 100 x 100 x 100 dictionary: the golden file holds n^3 per-atom scalar
+    runs of the unmodified reference (its own vectorised run is wrong there)"""
+    ref = golden("fisp_equal_axes")
+    case = cases.fisp_equal_axes(epg)
+    T1, T2, B1 = case["axes"]
+    seq = case["build"](T1, T2[None, :], B1[None, None, :])
+    tol = RTOL64 if dtype == "float64" else RTOL32
+    sig = epg.simulate(seq, dtype=dtype)  # forward: the real-valued whole-TR kernel of the headline
+    assert sig.shape == ref["signal"].shape and rel_err(sig, ref["signal"]) < tol
+    sig, jac = epg.simulate(seq, probe=[None, epg.Jacobian(case["jac"])], dtype=dtype)
+    assert rel_err(sig, ref["signal"]) < tol
+    for i in range(jac.shape[-1]):
+        assert rel_err(jac[..., i], ref["jacobian"][..., i]) < (tol if dtype == "float64" else 5 * tol)
+
+
+def test_probe_expressions(golden, epg):
+    ref = golden("probe_expr")
+    case = cases.probe_expr(epg)
+    vals = epg.simulate(case["seq"], probe=case["probe"])
+    assert len(vals) == 3
+    for i, v in enumerate(vals):
+        assert rel_err(np.asarray(v), ref[f"probe{i}"]) < RTOL64
+
+
 def _run_variant(epg, case, dtype="f64", **variant):
     from epgpy_b200 import engine, functions, lowering
 
     opts = dict(case.get("options") or {})
     init = epg.StateMatrix(density=case["density"]) if case.get("density") is not None else None
+    if case.get("init") is not None:
+        init = np.array(case["init"])
     probe = [None, epg.Jacobian(case["jac"])] if case.get("jac") else None
     low = lowering.lower(case["seq"], init=init, probe=probe, options=opts, dtype=dtype)
     plan = engine.Plan(low)
@@ -60,7 +88,8 @@ def _run_variant(epg, case, dtype="f64", **variant):
 
 
 @pytest.mark.parametrize("lanes,atoms", [(1, 1), (1, 32), (2, 3), (8, 16), (32, 2), (64, 1), (128, 2), (256, 1)])
-@pytest.mark.parametrize("name", ["fisp_unbounded", "fisp_bounded", "misc_ops", "spgr_exchange", "fisp_jac_global"])
+@pytest.mark.parametrize("name", ["fisp_unbounded", "fisp_bounded", "misc_ops", "spgr_exchange", "fisp_jac_global",
+                                  "gre_diffusion_tensor", "init_states", "init_states_jac", "init_states_jac_complex"])
 def test_ring_kernel_variants(name, lanes, atoms, golden, epg):
     """ring kernel: every lanes-per-atom / atoms-per-CTA mapping gives the same answer (ragged tails included)"""
     ref = golden(name)
@@ -72,7 +101,8 @@ def test_ring_kernel_variants(name, lanes, atoms, golden, epg):
 
 
 FORWARD = ["readme_mse", "mse_grid", "fisp_unbounded", "fisp_bounded", "bssfp_offres", "gre_diffusion",
-           "gre_diffusion_1d", "hyperecho", "misc_ops", "adc_reduce"]
+           "gre_diffusion_1d", "hyperecho", "misc_ops", "adc_reduce", "gre_diffusion_tensor", "init_states",
+           "init_states_real", "init_states_cropped"]
 
 
 @pytest.mark.parametrize("dtype", ["f64", "f32"])
@@ -136,6 +166,30 @@ def test_real_kernel_variants(lanes, atoms, dtype, max_nstate, epg):
     assert rel_err(got[0], ring[0]) < (1e-12 if dtype == "f64" else RTOL32)
     ref = oracle_api.O.simulate(_real_sequence(oracle_api.epg), kvalue=2500.0, max_nstate=max_nstate)
     assert rel_err(ring[0], ref) < RTOL64
+
+
+@pytest.mark.parametrize("dtype", ["f64", "f32"])
+@pytest.mark.parametrize("lanes", [0, 1, 4, 32])
+@pytest.mark.parametrize("name", ["init_states_real", "init_states_cropped"])
+def test_real_kernel_initial_states(name, lanes, dtype, golden, epg):
+    """initial state with populated orders n > 0 in the real-valued register kernel"""
+    ref = golden(name)
+    got, cfg = _run_variant(epg, cases.CASES[name](epg), dtype=dtype, kernel=3, lanes_per_atom=lanes)
+    assert cfg["kernel"] == 2
+    assert rel_err(got[0], ref["signal"]) < (RTOL64 if dtype == "f64" else RTOL32)
+
+
+@pytest.mark.parametrize("dtype", ["f64", "f32"])
+@pytest.mark.parametrize("kernel,lanes", [(4, 0), (4, 2), (4, 32), (4, 64), (5, 0)])
+def test_realjac_kernels_initial_states(kernel, lanes, dtype, golden, epg):
+    """initial state with populated orders in the real-valued derivative kernels (orders over warps, warp per state set)"""
+    ref = golden("init_states_jac")
+    got, cfg = _run_variant(epg, cases.init_states_jac(epg), dtype=dtype, kernel=kernel, lanes_per_atom=lanes)
+    assert cfg["kernel"] == kernel - 1
+    tol = RTOL64 if dtype == "f64" else RTOL32
+    assert rel_err(got[0], ref["signal"]) < tol
+    for i in range(ref["jacobian"].shape[-1]):
+        assert rel_err(got[1][..., i], ref["jacobian"][..., i]) < (tol if dtype == "f64" else 5 * tol)
 
 
 def _real_jac_sequence(epg, ntr=50):

@@ -39,6 +39,46 @@ def test_tape_transformations_are_exact(name, fuse, pre_inject, golden):
         assert rel_err(jac, ref["jacobian"]) < RTOL64
 
 
+def test_equal_axes_grid(golden):
+    """left-aligned broadcasting on a grid with EQUAL axis sizes, against per-atom runs of the unmodified reference"""
+    ref = golden("fisp_equal_axes")
+    epg = product_namespace()
+    case = cases.fisp_equal_axes(epg)
+    T1, T2, B1 = case["axes"]
+    sig, jac = interp_simulate(case["build"](T1, T2[None, :], B1[None, None, :]), probe=[None, epg.Jacobian(case["jac"])])
+    assert rel_err(sig, ref["signal"]) < RTOL64 and rel_err(jac, ref["jacobian"]) < RTOL64
+
+
+def test_probe_expressions(golden):
+    """probe=[...] expressions over F0 / Z0 supersede the in-sequence ADCs but keep their phase compensation"""
+    ref = golden("probe_expr")
+    epg = product_namespace()
+    case = cases.probe_expr(epg)
+    vals = interp_simulate(case["seq"], probe=case["probe"])
+    assert len(vals) == 3
+    for i, v in enumerate(vals):
+        assert rel_err(np.asarray(v), ref[f"probe{i}"]) < RTOL64
+
+
+def test_in_sequence_jacobian_survives_probe_none():
+    """probe=[None, ...] keeps the in-sequence probes: an in-sequence Jacobian must still see its variables
+    (round-1 advisor finding: the derivatives silently came back as zeros)"""
+    epg = product_namespace()
+    rf = epg.T(30, 90, order1="alpha")
+    seq = [rf, epg.E(5, 800.0, 60.0), epg.Jacobian(["magnitude", "alpha"]), epg.S(1), rf, epg.E(5, 800.0, 60.0),
+           epg.Jacobian(["magnitude", "alpha"])]
+    a = interp_simulate(seq)
+    b = interp_simulate(seq, probe=[None])
+    assert np.abs(np.asarray(a)[..., 1]).max() > 1e-3
+    assert rel_err(np.asarray(b), np.asarray(a)) < 1e-14
+
+
+def test_shrinking_cap_is_refused_clearly():
+    epg = product_namespace()
+    with pytest.raises(NotImplementedError, match="shrinks"):
+        interp_simulate([epg.T(30, 90), epg.S(3), epg.S(1, nmax=2), epg.ADC])
+
+
 def test_api_surface_and_shapes(golden):
     epg = product_namespace()
     for name, fn in cases.CASES.items():
