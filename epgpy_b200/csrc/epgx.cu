@@ -54,10 +54,11 @@ static int pow2ceil(int x) {
   return p;
 }
 
-static int nvt_choice(int nvar, int want) {
+static int nvt_choice(int nvar, int want, int npool) {
   // instantiated tile sizes of the ring kernel
   const int opts[3] = {0, 1, 3};
   if (nvar == 0) return 0;
+  if (npool > 2) return 1; // three / four pools: one resident partial state
   if (want > 0) {
     for (int o : opts)
       if (o == want) return o;
@@ -94,9 +95,8 @@ static double form_flops_real(int code) {
   }
 }
 
-static int choose_variant(epgx_plan *pl, int kernel, int lanes, int vars, int atoms) {
+static int choose_variant(const epgx_plan *pl, epgx_config &c, int kernel, int lanes, int vars, int atoms) {
   const epgx_tape &t = pl->tape;
-  epgx_config &c = pl->cfg;
   const int rsz = t.dtype == EPGX_F64 ? 8 : 4;
   const int C = t.max_order + 1;
   const bool reg_ok = t.nvar == 0 && t.npool == 1;
@@ -176,7 +176,8 @@ static int choose_variant(epgx_plan *pl, int kernel, int lanes, int vars, int at
     if (NS && NS <= ns_max) {
       int A = atoms > 0 ? atoms : 128 / G;
       while (A * G > 256 && A > 1) --A;
-      while (G >= 8 && A > 1 && A * 32 * 9 * rsz > 40 * 1024) --A; // staging rows of the whole-TR windows
+      const int raw_reals = G == 32 ? 32 * 10 : 0; // prefetched coefficient entries of the next window (one warp per atom)
+      while (G >= 8 && A > 1 && A * (32 * 9 + raw_reals) * rsz > 40 * 1024) --A; // staging rows of the whole-TR windows
       c.kernel = 2;
       c.lanes_per_atom = G;
       c.slots_per_lane = NS;
@@ -184,7 +185,7 @@ static int choose_variant(epgx_plan *pl, int kernel, int lanes, int vars, int at
       c.var_tiles = 1;
       c.atoms_per_cta = A;
       c.threads_per_cta = A * G;
-      c.smem_bytes = 2 * epgx::kTapeChunk * 32 + ((A * t.npattern + 3) & ~3) * 4 + (G >= 8 ? A * 32 * 9 * rsz : 0) + 32;
+      c.smem_bytes = 3 * epgx::kTapeChunk * 32 + ((A * t.npattern + 3) & ~3) * 4 + (G >= 8 ? A * (32 * 9 + raw_reals) * rsz : 0) + 32;
       c.ring = C;
       return EPGX_OK;
     }
@@ -227,7 +228,7 @@ static int choose_variant(epgx_plan *pl, int kernel, int lanes, int vars, int at
   }
   int G = lanes > 0 ? pow2ceil(lanes) : pow2ceil((C + 3) / 4);
   if (G > 256) G = 256;
-  int nvt = nvt_choice(t.nvar, vars);
+  int nvt = nvt_choice(t.nvar, vars, t.npool);
   int64_t per_atom;
   for (;;) {
     per_atom = (int64_t)(1 + nvt) * t.npool * 3 * C * 2 * rsz + (int64_t)t.npattern * 4;
@@ -589,7 +590,7 @@ extern "C" int epgx_plan_create(const epgx_tape *t, epgx_plan **out) {
   pl->tape.coef = nullptr;
   pl->natoms = natoms;
   memset(&pl->cfg, 0, sizeof(pl->cfg));
-  int rc = choose_variant(pl, 0, 0, 0, 0);
+  int rc = choose_variant(pl, pl->cfg, 0, 0, 0, 0);
   if (rc != EPGX_OK) {
     delete pl;
     return rc;
@@ -624,7 +625,7 @@ extern "C" int epgx_plan_config(const epgx_plan *pl, epgx_config *cfg) {
 
 extern "C" int epgx_plan_set_variant(epgx_plan *pl, int kernel, int lanes, int vars, int atoms) {
   if (!pl) return fail(EPGX_ERR_INVALID, "null plan");
-  int rc = choose_variant(pl, kernel, lanes, vars, atoms);
+  int rc = choose_variant(pl, pl->cfg, kernel, lanes, vars, atoms);
   pl->cfg.flops_per_atom = pl->cfg.kernel >= 2 ? pl->flops_real : pl->flops_cplx;
   pl->cfg.updates_per_atom = pl->updates;
   return rc;
@@ -661,8 +662,7 @@ extern "C" int epgx_plan_upload(const epgx_plan *pl, void *ws, void *stream) {
   return EPGX_OK;
 }
 
-static int dispatch(const epgx_plan *pl, const KParams &kp, cudaStream_t st) {
-  const epgx_config &c = pl->cfg;
+static int dispatch(const epgx_plan *pl, const epgx_config &c, const KParams &kp, cudaStream_t st) {
   const bool f64 = pl->tape.dtype == EPGX_F64;
   dim3 grid((unsigned)((kp.atom_count + c.atoms_per_cta - 1) / c.atoms_per_cta), (unsigned)c.var_tiles);
   cudaError_t e;
@@ -691,9 +691,8 @@ extern "C" int epgx_simulate(const epgx_plan *pl, const void *ws, int64_t atom_b
   return epgx_simulate_strided(pl, ws, atom_begin, atom_count, signal, atom_count, jacobian, atom_count, stream);
 }
 
-extern "C" int epgx_simulate_strided(const epgx_plan *pl, const void *ws, int64_t atom_begin, int64_t atom_count,
-                                     void *signal, int64_t signal_stride, void *jacobian, int64_t jacobian_stride,
-                                     void *stream) {
+static int run_range(const epgx_plan *pl, const void *ws, int64_t atom_begin, int64_t atom_count, void *signal,
+                     int64_t signal_stride, void *jacobian, int64_t jacobian_stride, void *state, void *stream) {
   if (!pl || !ws) return fail(EPGX_ERR_INVALID, "null argument");
   if (signal_stride < atom_count || jacobian_stride < atom_count) return fail(EPGX_ERR_INVALID, "row stride < atom_count");
   if (atom_begin < 0 || atom_count < 0 || atom_begin + atom_count > pl->natoms)
@@ -702,6 +701,11 @@ extern "C" int epgx_simulate_strided(const epgx_plan *pl, const void *ws, int64_
   const epgx_tape &t = pl->tape;
   if (t.nadc && !signal) return fail(EPGX_ERR_INVALID, "null signal buffer");
   if (t.nvar && t.njac && !jacobian) return fail(EPGX_ERR_INVALID, "null jacobian buffer");
+  epgx_config cfg = pl->cfg;
+  if (state && cfg.kernel != 0) { // the state leaves the chip through the shared-memory kernel only
+    const int rc = choose_variant(pl, cfg, 1, 0, 0, 0);
+    if (rc != EPGX_OK) return rc;
+  }
   const char *w = (const char *)ws;
   KParams kp;
   memset(&kp, 0, sizeof(kp));
@@ -714,6 +718,7 @@ extern "C" int epgx_simulate_strided(const epgx_plan *pl, const void *ws, int64_
   kp.coef = w + pl->off_coef;
   kp.signal = signal;
   kp.jac = jacobian;
+  kp.state = state;
   kp.atom_begin = atom_begin;
   kp.atom_count = atom_count;
   kp.sig_stride = signal_stride;
@@ -722,17 +727,28 @@ extern "C" int epgx_simulate_strided(const epgx_plan *pl, const void *ws, int64_
   kp.ndim = t.ndim;
   kp.npattern = t.npattern;
   kp.nseg = (int)t.nseg;
-  kp.G = pl->cfg.lanes_per_atom;
-  kp.A = pl->cfg.atoms_per_cta;
-  kp.C = pl->cfg.ring;
+  kp.G = cfg.lanes_per_atom;
+  kp.A = cfg.atoms_per_cta;
+  kp.C = cfg.ring;
   kp.nvar = t.nvar;
   kp.init_off = t.init_off;
   kp.m0_off = t.m0_off;
   kp.init_pat = t.init_pat;
   kp.m0_pat = t.m0_pat;
   kp.init_n = t.init_n;
-  cudaStream_t st = (cudaStream_t)stream;
-  return dispatch(pl, kp, st);
+  return dispatch(pl, cfg, kp, (cudaStream_t)stream);
+}
+
+extern "C" int epgx_simulate_strided(const epgx_plan *pl, const void *ws, int64_t atom_begin, int64_t atom_count,
+                                     void *signal, int64_t signal_stride, void *jacobian, int64_t jacobian_stride,
+                                     void *stream) {
+  return run_range(pl, ws, atom_begin, atom_count, signal, signal_stride, jacobian, jacobian_stride, nullptr, stream);
+}
+
+extern "C" int epgx_simulate_state(const epgx_plan *pl, const void *ws, int64_t atom_begin, int64_t atom_count, void *signal,
+                                   int64_t signal_stride, void *jacobian, int64_t jacobian_stride, void *state, void *stream) {
+  if (!state) return fail(EPGX_ERR_INVALID, "null state buffer");
+  return run_range(pl, ws, atom_begin, atom_count, signal, signal_stride, jacobian, jacobian_stride, state, stream);
 }
 
 extern "C" int epgx_simulate_host(const epgx_plan *pl, int device, int64_t atom_begin, int64_t atom_count, void *signal,

@@ -257,6 +257,7 @@ struct KParams {
   const int *pats; // [npattern][EPGX_MAX_DIMS + 1]: axis strides then pool stride (reals)
   void *signal;
   void *jac;
+  void *state; // ring kernel: final base state complex[atom_count][npool][C][3], or null
   long long atom_begin, atom_count;
   long long sig_stride, jac_stride; // atoms per output row (>= atom_count)
   int shape[EPGX_MAX_DIMS];

@@ -403,6 +403,21 @@ __global__ void __launch_bounds__(256) ring_kernel(const KParams p) {
       if (G > 32) __syncthreads(); else __syncwarp();
     }
   }
+  // ---- final-state read-back (epgx_simulate_state): the base state in logical order, half storage
+  if (p.state != nullptr && blockIdx.y == 0) {
+    if (G > 32) __syncthreads(); else __syncwarp();
+    if (valid) {
+      real2 *out = (real2 *)p.state + (size_t)a_rel * NP * C * 3;
+#pragma unroll
+      for (int q = 0; q < NP; ++q)
+        for (int k = lane; k < C; k += G) {
+          int iP = baseP + k; if (iP >= C) iP -= C;
+          int iM = baseM + k; if (iM >= C) iM -= C;
+          real2 *o = out + ((size_t)q * C + k) * 3;
+          o[0] = RING(0, q, 0)[iP]; o[1] = RING(0, q, 1)[iM]; o[2] = RING(0, q, 2)[k];
+        }
+    }
+  }
 #undef RING
 #undef POFF
 }

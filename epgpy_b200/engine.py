@@ -59,7 +59,7 @@ def _count(n=1):
 EXPORTS = [
     "epgx_version", "epgx_device_count", "epgx_last_error", "epgx_plan_create", "epgx_plan_destroy",
     "epgx_plan_config", "epgx_plan_stream", "epgx_plan_set_variant", "epgx_plan_workspace_bytes", "epgx_plan_upload",
-    "epgx_simulate", "epgx_simulate_strided", "epgx_copy2d_to_host", "epgx_simulate_host", "epgx_reduce",
+    "epgx_simulate", "epgx_simulate_strided", "epgx_simulate_state", "epgx_copy2d_to_host", "epgx_simulate_host", "epgx_reduce",
     "epgx_fma_peak",
 ]
 
@@ -88,6 +88,7 @@ def lib():
             L.epgx_plan_upload.argtypes = [vp, vp, vp]
             L.epgx_simulate.argtypes = [vp, vp, i64, i64, vp, vp, vp]
             L.epgx_simulate_strided.argtypes = [vp, vp, i64, i64, vp, i64, vp, i64, vp]
+            L.epgx_simulate_state.argtypes = [vp, vp, i64, i64, vp, i64, vp, i64, vp, vp]
             L.epgx_copy2d_to_host.argtypes = [vp, i64, vp, i64, i64, i64, vp]
             L.epgx_simulate_host.argtypes = [vp, i32, i64, i64, vp, vp]
             L.epgx_reduce.argtypes = [i32, vp, vp, i64, i64, i64, vp]
@@ -255,6 +256,34 @@ class Plan:
                                        stream.cuda_stream))
             _count()
         return signal, jacobian
+
+    def run_state(self, device, atom_begin=0, atom_count=None):
+        """epgx_simulate_state: run the tape and read the FINAL base state of every atom back (the shared-memory kernel;
+        lower with prune_unobservable=False).  Returns device tensors (signal, jacobian, state) with
+        state complex [atoms][npool][max_order + 1][3] in half storage, columns (F+, F-, Z)."""
+        import torch
+
+        require_cuda()
+        low = self.low
+        if atom_count is None:
+            atom_count = low.natoms - atom_begin
+        dev = torch.device("cuda", device)
+        cdt = torch.complex128 if low.dtype == "f64" else torch.complex64
+        has_jac = bool(low.nvar and low.njac)
+        with torch.cuda.device(dev):
+            ws = self.upload(device)
+            signal = torch.empty((low.nadc, atom_count, low.npool), dtype=cdt, device=dev)
+            jacobian = torch.empty((low.njac, low.nvar, atom_count, low.npool), dtype=cdt, device=dev) if has_jac else None
+            state = torch.zeros((atom_count, low.npool, low.max_order + 1, 3), dtype=cdt, device=dev)
+            if atom_count:
+                stream = torch.cuda.current_stream(dev)
+                self._wait_upload(device, stream)
+                _check(lib().epgx_simulate_state(self._h, ws.data_ptr(), atom_begin, atom_count,
+                                                 signal.data_ptr() if signal.numel() else None, atom_count,
+                                                 jacobian.data_ptr() if has_jac and jacobian.numel() else None, atom_count,
+                                                 state.data_ptr(), stream.cuda_stream))
+                _count()
+        return signal, jacobian, state
 
     def run_strided(self, device, atom_begin, atom_count, signal, signal_stride, jacobian=None, jacobian_stride=0):
         """epgx_simulate_strided on torch's current stream: rows of `signal` are `signal_stride` atoms apart, so that

@@ -262,11 +262,44 @@ def simulate(sequence, *, adc_time=False, init=None, squeeze=False, probe=None, 
     return values
 
 
-def apply_operators(operators, sm):
-    raise NotImplementedError(
-        "applying an operator to a StateMatrix outside `simulate` needs the whole state on the host; "
-        "the device path only returns probe values"
-    )
+def apply_operators(operators, sm, *, dtype="float64", device=None):
+    """apply operators to a StateMatrix and return the new StateMatrix (the reference's `op(sm)`,
+    epgpy/operator.py:96-104): a probe-less tape on the engine whose final state is read back
+    (epgx_simulate_state; half storage -> the reference's [*grid, 2n+1, 3] by the symmetry of
+    statematrix.py:418-421).  The result can seed a later `simulate(init=sm)` (functions.py:133-144).
+    Order-1 partial states are not carried from one call to the next: differentiate inside one `simulate`."""
+    from .operators import PD, DiffOperator
+
+    seq = flatten_sequence(operators)
+    if any(isinstance(op, DiffOperator) and (getattr(op, "order1", None) or {}) for op in seq):
+        raise NotImplementedError("operators with order-1 variables applied outside `simulate`: the partial states stay on "
+                                  "the device; put the operators and a Jacobian probe in one `simulate` call")
+    if not isinstance(sm, StateMatrix):
+        sm = StateMatrix(sm)
+    low = lowering.lower(seq, init=sm, dtype=engine.norm_dtype(dtype), prune_unobservable=False, need_probe=False)
+    plan = engine.Plan(low)
+    dev = _devices(device)[0]
+    _, _, state = plan.run_state(dev)
+    half = state.cpu().numpy().astype(np.complex128)  # [atoms][npool][C][3]
+    n = low.final_n
+    half = half[:, :, :n + 1, :]
+    grid, ax = tuple(low.grid), low.pool_axis
+    half = half.reshape(tuple(low.atom_shape) + half.shape[1:])
+    half = np.moveaxis(half, len(low.atom_shape), ax) if ax is not None else half[..., 0, :, :]
+    half = half.reshape(grid + (n + 1, 3))
+    full = np.zeros(grid + (2 * n + 1, 3), dtype=np.complex128)
+    full[..., n:, :] = half
+    if n:
+        full[..., :n, 0] = half[..., :0:-1, 1].conj()
+        full[..., :n, 1] = half[..., :0:-1, 0].conj()
+        full[..., :n, 2] = half[..., :0:-1, 2].conj()
+    density = sm.density
+    for op in seq:  # PD replaces the equilibrium density (operator.py:315-341)
+        if isinstance(op, PD):
+            density = np.asarray(op.pd, dtype=float)
+    new = StateMatrix(full, density=np.broadcast_to(common.left(np.atleast_1d(density), len(grid)), grid), kvalue=sm.kvalue,
+                      tvalue=sm.tvalue, check=False, **sm.options)
+    return new
 
 
 # --------------------------------------------------------------------------------------------- #

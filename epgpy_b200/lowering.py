@@ -28,7 +28,7 @@ from .statematrix import StateMatrix
  OP_CONT) = range(14)
 F_BASE, F_PARTIALS, F_INJECT, F_G, F_AFFINE, F_Z0, F_SCALE, F_PRE, F_POST, F_IM, F_GEN = (1 << i for i in range(11))
 SEG_RESET, SEG_MASK_TOP = 1, 2
-MAX_DIMS, MAX_PATTERNS, MAX_POOLS = 8, 64, 2
+MAX_DIMS, MAX_PATTERNS, MAX_POOLS = 8, 64, 4
 
 OP_DTYPE = np.dtype([("code", "<u2"), ("flags", "<u2"), ("aux", "<i4"), ("off", "<u4", (3,)), ("pat", "u1", (3,)),
                      ("rsv", "u1"), ("aux1", "<i4"), ("rsv1", "<i4")])
@@ -293,11 +293,12 @@ def fuse_records(recs, segs):
 
 
 def lower(sequence, *, init=None, probe=None, options=None, dtype="f64", propagate_nondiff=False,
-          prune_unobservable=True, fuse=True, pre_inject=True):
-    """sequence -> Lowered"""
+          prune_unobservable=True, fuse=True, pre_inject=True, need_probe=True):
+    """sequence -> Lowered.  need_probe=False: a tape without read-out (functions.apply_operators reads the final
+    state back instead; it also passes prune_unobservable=False so that every order is kept up to date)"""
     options = dict(options or {})
     seq = flatten_sequence(sequence)
-    if not any(isinstance(op, Probe) for op in seq):
+    if need_probe and not any(isinstance(op, Probe) for op in seq):
         raise ValueError("Cannot simulate sequence without at least one Probe/ADC operator")
     for key in ("kgrid",):
         if options.get(key):
@@ -644,6 +645,7 @@ def lower(sequence, *, init=None, probe=None, options=None, dtype="f64", propaga
     low.init_ref, low.m0_ref, low.init_n = init_ref, m0_ref, init_n
     low.nadc, low.njac, low.nvar, low.max_order = nadc, njac, nvar, max_order
     low.variables = variables
+    low.final_n = n  # order count when the tape ends
     low.rows, low.times = rows_out, times
     low.nprobe = len(probes) if probes else 1
     low.keepalive = seq

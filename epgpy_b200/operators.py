@@ -60,10 +60,15 @@ class Operator:
         return MultiOperator([self, other])
 
     def __call__(self, sm, *, inplace=False):
-        """apply to a StateMatrix: one-operator tape on the engine (statematrix.StateMatrix.apply)"""
+        """apply to a StateMatrix (epgpy/operator.py:96-104): a one-operator tape on the engine whose final state is
+        read back (functions.apply_operators); inplace=True updates `sm` itself like the reference"""
         from .functions import apply_operators
 
-        return apply_operators([self], sm)
+        new = apply_operators([self], sm)
+        if inplace:
+            sm._states, sm._density = new._states, new._density
+            return sm
+        return new
 
     def copy(self, name=None, duration=None):
         import copy as _copy

@@ -46,10 +46,10 @@
 extern "C" {
 #endif
 
-#define EPGX_VERSION 103 /* 0.1.3: epgx_plan_stream, setjac kernel (variant 5) */
+#define EPGX_VERSION 104 /* 0.1.4: epgx_simulate_state (final-state read-back), up to 4 exchange pools */
 #define EPGX_MAX_DIMS 8
 #define EPGX_MAX_PATTERNS 64
-#define EPGX_MAX_POOLS 2
+#define EPGX_MAX_POOLS 4
 
 typedef enum {
   EPGX_OK = 0,
@@ -247,6 +247,19 @@ int epgx_simulate(const epgx_plan *plan, const void *workspace, int64_t atom_beg
 int epgx_simulate_strided(const epgx_plan *plan, const void *workspace, int64_t atom_begin, int64_t atom_count,
                           void *signal, int64_t signal_stride, void *jacobian, int64_t jacobian_stride,
                           void *stream);
+
+/* Same as epgx_simulate_strided, and the FINAL state of every atom is written too: what the reference hands back from
+ * Operator.__call__(sm) (epgpy/operator.py:96-104) and lets a later simulate(init=sm) resume from
+ * (epgpy/functions.py:133-144).  Half storage (orders k >= 0; F-(k) = conj F+(-k), Z(k) = conj Z(-k),
+ * epgpy/statematrix.py:418-421):
+ *   state  device, complex<real>[atom_count][npool][max_order + 1][3]   columns (F+, F-, Z) of the BASE state;
+ *          orders above the final order count of the tape read as zero.
+ * Runs the shared-memory (ring) kernel whatever variant the plan prefers for plain runs; the tape must have been
+ * lowered with every order kept up to date (no pruning of unobservable orders).  signal / jacobian may be NULL when
+ * the tape has no read-out rows. */
+int epgx_simulate_state(const epgx_plan *plan, const void *workspace, int64_t atom_begin, int64_t atom_count,
+                        void *signal, int64_t signal_stride, void *jacobian, int64_t jacobian_stride, void *state,
+                        void *stream);
 
 /* asynchronous pitched device->host copy (cudaMemcpy2DAsync) of `height` rows of `width` bytes: brings a
  * column range of the signal slab to (pinned) host memory while the next range is computed */

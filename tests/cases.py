@@ -207,6 +207,19 @@ def spgr_exchange(epg, ntr=30):
     return dict(seq=seq, density=f, options={"max_nstate": 8})
 
 
+def three_pool_exchange(epg, ntr=24):
+    """THREE exchanging compartments (exchange.py:14-81 is generic in N; exchange_matrix(..., ncomp=3)): spoiled
+    gradient echo with shifts, off-resonance axis, read-out summed over the pools"""
+    T1, T2, f = [1000.0, 700.0, 400.0], [90.0, 40.0, 8.0], [0.6, 0.3, 0.1]
+    kmat = epg.exchange_matrix(3e-3, ncomp=3, densities=f)
+    g = [np.linspace(-0.02, 0.02, 4)]
+    exg = epg.X(6, kmat, T1=T1, T2=T2, g=g)
+    adc = epg.Adc(reduce=0)
+    PH = np.array([50.0, 117.0, 150.0, 84.0])  # the pulse carries the second grid axis from the first operator on
+    seq = [[epg.T(12 + i % 5, [i * (i + 1) / 2 * PH]), adc, exg, epg.S(1)] for i in range(ntr)]
+    return dict(seq=seq, density=f, options={"max_nstate": 6})
+
+
 def hyperecho(epg, npulse=15):
     """reference test/test_core.py:9-32 (shorter); probe both F0 and Z0 through two ADCs"""
     grad = epg.S(1)
@@ -327,6 +340,7 @@ CASES = {
     "gre_diffusion_1d": gre_diffusion_1d,
     "bssfp_mt": bssfp_mt,
     "spgr_exchange": spgr_exchange,
+    "three_pool_exchange": three_pool_exchange,
     "hyperecho": hyperecho,
     "misc_ops": misc_ops,
     "adc_reduce": adc_reduce,

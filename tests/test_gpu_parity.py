@@ -467,3 +467,52 @@ def test_simulate_over_several_devices_of_one_process(golden, epg):
     sig, jac = epg.simulate(case["seq"], probe=[None, epg.Jacobian(case["jac"])], device=[1, 0])
     assert rel_err(sig, golden("fisp_jac_global")["signal"]) < RTOL64
     assert rel_err(jac, golden("fisp_jac_global")["jacobian"]) < RTOL64
+
+
+# ------------------------------------------------------------------------------------------------ #
+# final-state read-back: op(sm), simulate(init=previous state)
+# ------------------------------------------------------------------------------------------------ #
+
+
+def test_operator_call_returns_the_reference_state(golden, epg):
+    """`op(sm)` (epgpy/operator.py:96-104) through epgx_simulate_state against the reference's own states
+    (primitives.npz: state_<op> = op(StateMatrix(state0, kvalue=800)).states)"""
+    p = golden("primitives")
+    sm = epg.StateMatrix(p["state0"], kvalue=800.0)
+    ops = {"T": epg.T([30.0, 140.0], 25.0), "E": epg.E(7.0, 600.0, [40.0, 90.0], 0.03), "S+1": epg.S(1), "S-2": epg.S(-2),
+           "D": epg.D(4.0, 2e-3), "Dk": epg.D(4.0, 2e-3, k=1), "SPOILER": epg.SPOILER}
+    for label, op in ops.items():
+        out = op(sm)
+        want = p[f"state_{label}"]
+        assert out.states.shape == want.shape, label
+        assert rel_err(out.states, want) < RTOL64, label
+        assert np.array_equal(sm.states, p["state0"]), "the input state matrix must not change"
+    smn = epg.StateMatrix(p["state0"], max_nstate=3)
+    assert rel_err(epg.S(1)(smn).states, p["state_S+1_nmax3"]) < RTOL64
+    # in place
+    sm2 = epg.StateMatrix(p["state0"], kvalue=800.0)
+    assert ops["T"](sm2, inplace=True) is sm2 and rel_err(sm2.states, p["state_T"]) < RTOL64
+
+
+@pytest.mark.parametrize("name,cut", [("fisp_unbounded", 5 * 23 + 2), ("misc_ops", 9), ("spgr_exchange", 4 * 11), ("three_pool_exchange", 4 * 7)])
+def test_simulate_resumes_from_a_read_back_state(name, cut, golden, epg):
+    """run the head of a sequence with functions.apply_operators, read the state back, resume with
+    simulate(init=state) (the reference's 'resumable by hand' use, functions.py:133-144): the tail's read-outs equal
+    those of the one-piece run"""
+    from epgpy_b200 import functions
+    from epgpy_b200.lowering import flatten_sequence
+
+    case = cases.CASES[name](epg)
+    seq = flatten_sequence(case["seq"])
+    opts = dict(case.get("options") or {})
+    init = epg.StateMatrix(density=case["density"], **opts) if case.get("density") is not None else epg.StateMatrix([0, 0, 1], **opts)
+    head, tail = seq[:cut], seq[cut:]
+    nhead = sum(isinstance(op, type(epg.ADC)) for op in head)
+    whole = golden(name)["signal"]
+    # broadcast the initial state to the grid of the whole sequence, as simulate does (functions.py:136-141)
+    grid = epg.getshape(seq)
+    sm0 = epg.StateMatrix(init.states, density=init.density, shape=grid, **opts)
+    mid = functions.apply_operators([op for op in head if not isinstance(op, type(epg.ADC))], sm0)
+    assert mid.shape == tuple(grid)
+    got = epg.simulate(tail, init=mid)
+    assert rel_err(np.asarray(got), whole[nhead:]) < RTOL64
