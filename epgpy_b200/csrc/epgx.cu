@@ -176,8 +176,7 @@ static int choose_variant(const epgx_plan *pl, epgx_config &c, int kernel, int l
     if (NS && NS <= ns_max) {
       int A = atoms > 0 ? atoms : 128 / G;
       while (A * G > 256 && A > 1) --A;
-      const int raw_reals = G == 32 ? 32 * 10 : 0; // prefetched coefficient entries of the next window (one warp per atom)
-      while (G >= 8 && A > 1 && A * (32 * 9 + raw_reals) * rsz > 40 * 1024) --A; // staging rows of the whole-TR windows
+      while (G >= 8 && A > 1 && A * 32 * 9 * rsz > 40 * 1024) --A; // staging rows of the whole-TR windows
       c.kernel = 2;
       c.lanes_per_atom = G;
       c.slots_per_lane = NS;
@@ -185,7 +184,7 @@ static int choose_variant(const epgx_plan *pl, epgx_config &c, int kernel, int l
       c.var_tiles = 1;
       c.atoms_per_cta = A;
       c.threads_per_cta = A * G;
-      c.smem_bytes = 3 * epgx::kTapeChunk * 32 + ((A * t.npattern + 3) & ~3) * 4 + (G >= 8 ? A * (32 * 9 + raw_reals) * rsz : 0) + 32;
+      c.smem_bytes = 2 * epgx::kTapeChunk * 32 + ((A * t.npattern + 3) & ~3) * 4 + (G >= 8 ? A * 32 * 9 * rsz : 0) + 32;
       c.ring = C;
       return EPGX_OK;
     }

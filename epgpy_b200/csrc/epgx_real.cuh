@@ -19,15 +19,6 @@
 #include "epgx_common.cuh"
 #include "epgx_reg.cuh"
 
-// timing experiments only (wrong results): EPGX_EXP_NOPRO = 1 stages the coefficients of the first window only,
-// EPGX_EXP_NOPRO = 2 also drops the echo stores
-#ifndef EPGX_EXP_NOPRO
-#define EPGX_EXP_NOPRO 0
-#endif
-#ifndef EPGX_PREFETCH
-#define EPGX_PREFETCH 1
-#endif
-
 namespace epgx {
 
 // One tape window of TAPE_CHUNK / 2 whole-TR records (fused E.T.E, plain ADC, unit shift +1) for one atom
@@ -76,6 +67,7 @@ __device__ __forceinline__ void tr_window(real (&P)[NS], real (&M)[NS], real (&Z
             if (ph) { Z[2 * sp + 1] = nz.x; Z[2 * sp] = nz.y; } else { Z[2 * sp] = nz.x; Z[2 * sp + 1] = nz.y; }
           }
         } else {
+          const real fz0 = lane0 ? c2.y : real(0), zz0 = lane0 ? cw[8 * (j + ph) + 6] : real(0);
 #pragma unroll
           for (int sp = 0; sp < KP; ++sp)
 #pragma unroll
@@ -83,17 +75,29 @@ __device__ __forceinline__ void tr_window(real (&P)[NS], real (&M)[NS], real (&Z
               const int r = 2 * sp + (i ^ ph); // register of F+- (k = 2 b + i) in this phase; Z(k) is in 2 sp + i
               const real p_ = P[r], m_ = M[r], z_ = Z[2 * sp + i];
               // eight FP64 instructions per order: the product u Z is shared by F+ and F- (written out with fma();
-              // the plain expressions contract left to right into 1 DMUL + 2 DFMA each, nine per order)
-              const real t_ = u * z_;
-              P[r] = fma(a, p_, fma(b, m_, t_));
-              M[r] = fma(a, m_, fma(b, p_, t_));
-              Z[2 * sp + i] = fma(w, z_, h * (p_ + m_));
+              // the plain expressions contract left to right into 1 DMUL + 2 DFMA each, nine per order).  Order 0
+              // (pair 0, i = 0, lane 0) takes the affine terms of the two E operators as the addends of its first
+              // products, which costs two selects instead of three FP64 additions for the whole warp
+              if (sp == 0 && i == 0) {
+                const real t_ = fma(u, z_, fz0);
+                P[r] = fma(a, p_, fma(b, m_, t_));
+                M[r] = fma(a, m_, fma(b, p_, t_));
+                Z[0] = fma(w, z_, fma(h, p_ + m_, zz0));
+              } else {
+                const real t_ = u * z_;
+                P[r] = fma(a, p_, fma(b, m_, t_));
+                M[r] = fma(a, m_, fma(b, p_, t_));
+                Z[2 * sp + i] = fma(w, z_, h * (p_ + m_));
+              }
             }
+          if (lane0) sb[j + ph] = P[ph]; // the echo of the TR; written to HBM by lane j + ph after the window
         }
-        if (lane0) {
-          const real fz = c2.y, zz = cw[8 * (j + ph) + 6];
-          P[ph] += fz; M[ph] += fz; Z[0] += zz;
-          sb[j + ph] = P[ph]; // the echo of the TR; written to HBM by lane j + ph after the window
+        if constexpr (sizeof(real) == 4) {
+          if (lane0) {
+            const real fz = c2.y, zz = cw[8 * (j + ph) + 6];
+            P[ph] += fz; M[ph] += fz; Z[0] += zz;
+            sb[j + ph] = P[ph];
+          }
         }
         // unit shift +1.  F+: registers of the odd orders (2 sp + 1 - ph) rotate up one lane, the last lane sending
         // the value of its previous pair; order 0 <- F-(1), which lane 0 holds itself.  F-: registers of the even
@@ -160,16 +164,11 @@ __global__ void __launch_bounds__(MAXT, real_min_blocks(sizeof(real) * NS, MAXT)
   const long long atom = p.atom_begin + (valid ? a_rel : p.atom_count - 1);
   const real *__restrict__ coef = (const real *)p.coef;
 
-  // shared memory: THREE tape windows (the records of window w + 1 are on chip while window w runs, so the
-  // coefficients of its TRs can be prefetched), pattern offsets [A][npattern], then per atom the fused coefficient rows
-  // [32][8] + the echoes of the window [32] (G >= 8) and, with G = 32, the prefetched coefficient entries [32][RAWN] of the next window
   int4 *tbuf = (int4 *)smem_raw;
-  int *patoff = (int *)(tbuf + 3 * TAPE_CHUNK * 2) + al * p.npattern;
-  real *cw = (real *)((int *)(tbuf + 3 * TAPE_CHUNK * 2) + ((p.A * p.npattern + 3) & ~3)) + (size_t)al * (32 * 9);
+  int *patoff = (int *)(tbuf + 2 * TAPE_CHUNK * 2) + al * p.npattern;
+  // whole-TR windows (G >= 8): per atom, coefficient rows [32][8] and the echoes of the window [32]
+  real *cw = (real *)((int *)(tbuf + 2 * TAPE_CHUNK * 2) + ((p.A * p.npattern + 3) & ~3)) + (size_t)al * (32 * 9);
   real *sb = cw + 32 * 8;
-  constexpr int RAWN = 10; // T block (a, w, b, u), E_pre (e1, r0), (e2), E_post (e1, r0), (e2)
-  real *raw = (real *)((int *)(tbuf + 3 * TAPE_CHUNK * 2) + ((p.A * p.npattern + 3) & ~3)) + (size_t)p.A * (32 * 9) + (size_t)al * (32 * RAWN);
-  const bool prefetch = EPGX_PREFETCH && G == 32; // (sub-warp atoms: the rows of 16 atoms per CTA would not fit; they read the table directly)
   {
     int idx[EPGX_MAX_DIMS];
     long long r = atom;
@@ -296,49 +295,21 @@ __global__ void __launch_bounds__(MAXT, real_min_blocks(sizeof(real) * NS, MAXT)
 
   const int4 *stream = (const int4 *)p.stream;
   const int nthreads = blockDim.x;
-  // tape windows 0 and 1
-  for (int i = tid; i < 4 * TAPE_CHUNK && i < 2 * p.nstream; i += nthreads) __pipeline_memcpy_async(tbuf + i, stream + i, 16);
+  for (int i = tid; i < 2 * TAPE_CHUNK && i < 2 * p.nstream; i += nthreads) __pipeline_memcpy_async(tbuf + i, stream + i, 16);
   __pipeline_commit();
   int nact = -1, nslot = 0;
-  int raw_for = -1; // tape window whose coefficient entries wait in raw
   for (int base = 0, chunk = 0; base < p.nstream; base += TAPE_CHUNK, ++chunk) {
-    __pipeline_wait_prior(0); // window chunk + 1 (issued one window ago) and the prefetched entries of this window
+    __pipeline_wait_prior(0);
     __syncthreads();
     {
-      const int nb = base + 2 * TAPE_CHUNK; // window chunk + 2 takes the place of window chunk - 1
-      int4 *dst = tbuf + ((chunk + 2) % 3) * 2 * TAPE_CHUNK;
+      const int nb = base + TAPE_CHUNK;
+      int4 *dst = tbuf + ((chunk + 1) & 1) * 2 * TAPE_CHUNK;
       for (int i = tid; i < 2 * TAPE_CHUNK && nb * 2 + i < 2 * p.nstream; i += nthreads)
         __pipeline_memcpy_async(dst + i, stream + (size_t)nb * 2 + i, 16);
-    }
-    const int4 *tb = tbuf + (chunk % 3) * 2 * TAPE_CHUNK;
-    const int cnt = min(TAPE_CHUNK, p.nstream - base);
-    // coefficient entries of the NEXT window's TRs: cp.async global -> shared needs no register to hold what is in
-    // flight, and the latency of the (L2) gathers disappears behind this window's TRs.  Lane j serves TR j and reads
-    // back its own copies only (no barrier involved); a pure window calls this after it has consumed its own row.
-    auto prefetch_next = [&]() {
-      if (prefetch && base + 2 * TAPE_CHUNK <= p.nstream) {
-        const int4 *tn = tbuf + ((chunk + 1) % 3) * 2 * TAPE_CHUNK;
-        if (tn[0].x & EPGX_CHUNK_PURE_TR) {
-          const int j = lane;
-          const int4 a0 = tn[4 * j], a1 = tn[4 * j + 1], b0 = tn[4 * j + 2], b1 = tn[4 * j + 3];
-          const real *ct = coef + (unsigned)a0.z + patoff[a1.y & 0xff];
-          const real *ca = coef + (unsigned)a0.w + patoff[(a1.y >> 8) & 0xff];
-          const real *ea = coef + (unsigned)a1.x + patoff[(a1.y >> 16) & 0xff];
-          const real *cb = coef + (unsigned)b0.z + patoff[b1.y & 0xff];
-          const real *eb = coef + (unsigned)b0.w + patoff[(b1.y >> 8) & 0xff];
-          real *dst = raw + j * RAWN;
-          __pipeline_memcpy_async(dst + 0, ct + 0, sizeof(real)); __pipeline_memcpy_async(dst + 1, ct + 1, sizeof(real));
-          __pipeline_memcpy_async(dst + 2, ct + 2, sizeof(real)); __pipeline_memcpy_async(dst + 3, ct + 3, sizeof(real));
-          __pipeline_memcpy_async(dst + 4, ca + 0, sizeof(real)); __pipeline_memcpy_async(dst + 5, ca + 1, sizeof(real));
-          __pipeline_memcpy_async(dst + 6, ea, sizeof(real));
-          __pipeline_memcpy_async(dst + 7, cb + 0, sizeof(real)); __pipeline_memcpy_async(dst + 8, cb + 1, sizeof(real));
-          __pipeline_memcpy_async(dst + 9, eb, sizeof(real));
-          raw_for = chunk + 1;
-        }
-      }
       __pipeline_commit();
-    };
-    if (!(G >= 8 && (tb[0].x & EPGX_CHUNK_PURE_TR))) prefetch_next();
+    }
+    const int4 *tb = tbuf + (chunk & 1) * 2 * TAPE_CHUNK;
+    const int cnt = min(TAPE_CHUNK, p.nstream - base);
     if (G >= 8 && (tb[0].x & EPGX_CHUNK_PURE_TR)) {
       // ---- fast path: the window holds TAPE_CHUNK / 2 whole-TR records (shift +1, no flags).  Phase 1: the G lanes
       // of an atom decode the TRs (lane, lane + G, ...), gather their coefficients, fuse them and stage them in the
@@ -349,25 +320,16 @@ __global__ void __launch_bounds__(MAXT, real_min_blocks(sizeof(real) * NS, MAXT)
       // (the window runs as two halves of 16 TRs, each with its own pair count: 0.13 pair less per TR on average)
       constexpr int HALF = TAPE_CHUNK / 4;
       int need0 = 0, need1 = 0;
-#if EPGX_EXP_NOPRO
-      if (chunk > 1) { need0 = need1 = ((max(nact, 0) + 32) >> (lgG + 1)) + 1; } else
-#endif
       for (int j = lane; j < TAPE_CHUNK / 2; j += G) {
         const int4 a0 = tb[4 * j], a1 = tb[4 * j + 1], b0 = tb[4 * j + 2], b1 = tb[4 * j + 3];
         const int fl = (a0.x >> 16) & 0xffff;
-        Fused5<real> fv;
-        if (raw_for == chunk) { // entries prefetched while the previous window ran (G = 32: j = lane)
-          const real *rw = raw + j * RAWN;
-          fv = fuse5<real>(rw[0], rw[1], rw[2], rw[3], fl & EPGX_FLAG_PRE, rw[4], rw[5], rw[6], fl & EPGX_FLAG_POST, rw[7], rw[8],
-                           rw[9], false, m0);
-        } else {
-          const real *ct = coef + (unsigned)a0.z + patoff[a1.y & 0xff];
-          const real *ca = coef + (unsigned)a0.w + patoff[(a1.y >> 8) & 0xff];
-          const real *cb = coef + (unsigned)b0.z + patoff[b1.y & 0xff];
-          fv = fuse5<real>(ldc(ct), ldc(ct + 1), ldc(ct + 2), ldc(ct + 3), fl & EPGX_FLAG_PRE, ldc(ca), ldc(ca + 1),
-                           ldc(coef + (unsigned)a1.x + patoff[(a1.y >> 16) & 0xff]), fl & EPGX_FLAG_POST, ldc(cb), ldc(cb + 1),
-                           ldc(coef + (unsigned)b0.w + patoff[(b1.y >> 8) & 0xff]), false, m0);
-        }
+        const real *ct = coef + (unsigned)a0.z + patoff[a1.y & 0xff];
+        const real *ca = coef + (unsigned)a0.w + patoff[(a1.y >> 8) & 0xff];
+        const real *cb = coef + (unsigned)b0.z + patoff[b1.y & 0xff];
+        const Fused5<real> fv = fuse5<real>(ldc(ct), ldc(ct + 1), ldc(ct + 2), ldc(ct + 3), fl & EPGX_FLAG_PRE, ldc(ca),
+                                            ldc(ca + 1), ldc(coef + (unsigned)a1.x + patoff[(a1.y >> 16) & 0xff]),
+                                            fl & EPGX_FLAG_POST, ldc(cb), ldc(cb + 1),
+                                            ldc(coef + (unsigned)b0.w + patoff[(b1.y >> 8) & 0xff]), false, m0);
         real2 *c = (real2 *)(cw + 8 * j);
         c[0] = real2{fv.a, fv.w}; c[1] = real2{fv.b, fv.u}; c[2] = real2{fv.h, fv.fz};
         c[3] = real2{fv.zz, ((b0.x >> 18) & EPGX_SEG_MASK_TOP) ? real(1) : real(0)};
@@ -375,7 +337,6 @@ __global__ void __launch_bounds__(MAXT, real_min_blocks(sizeof(real) * NS, MAXT)
         const int nd = (max(max(min((int)((unsigned)b1.x & 0xffff), cur + 1), cur), 0) >> (lgG + 1)) + 1;
         if (j < HALF) need0 = max(need0, nd); else need1 = max(need1, nd);
       }
-      prefetch_next();
       need0 = __reduce_max_sync(FULL, need0);
       need1 = __reduce_max_sync(FULL, need1);
       __syncwarp();
@@ -389,11 +350,7 @@ __global__ void __launch_bounds__(MAXT, real_min_blocks(sizeof(real) * NS, MAXT)
       }
 #undef TRW
       __syncwarp();
-#if EPGX_EXP_NOPRO == 2
-      if (valid && chunk < 2)
-#else
       if (valid) // lane j (+ G, ...) stores the echoes of its TRs
-#endif
         for (int j = lane; j < TAPE_CHUNK / 2; j += G) sig[(long long)tb[4 * j + 2].y * p.sig_stride + a_rel] = real2{sb[j], real(0)};
       nact = tb[4 * (TAPE_CHUNK / 2 - 1) + 3].z;
       nslot = nact < 0 ? 0 : SLOTS_FOR(nact);

@@ -10,4 +10,3 @@ print('$lib', '$dt', round(d['ms_per_step'],2), 'ms  frac', round(d['roofline'][
 PY
   done
 done
-python -m pytest tests/test_gpu_parity.py tests/test_gpu_baseline_sizes.py -x -q -k "real_kernel or fp64_matches or fp32_matches or equal_axes or c3_fisp or initial_states" 2>&1 | tail -3
