@@ -34,6 +34,8 @@ struct epgx_plan {
   std::vector<double> coef64;
   std::vector<float> coef32;
   std::vector<int> pats; // [npattern][MAX_DIMS+1]
+  std::vector<int> tiles; // [ntile][3] variables resident per tile of the shared-memory kernel (order-2 tapes)
+  bool order2 = false;    // injections from partial states / P1, P2 records: the shared-memory kernel only
   std::vector<epgx_op> stream; // segments + records merged (register kernel)
   int64_t natoms;
   double flops_cplx, flops_real, updates; // executed real flops per atom (complex / real-valued kernels)
@@ -43,7 +45,7 @@ struct epgx_plan {
   bool real_ok; // real-valued phase graph: eligible for the three-reals-per-order kernel
   epgx_config cfg;
   // workspace layout (bytes)
-  int64_t off_ops, off_segs, off_pats, off_stream, off_coef, ws_bytes;
+  int64_t off_ops, off_segs, off_pats, off_stream, off_tiles, off_coef, ws_bytes;
 };
 
 static const int kSmemLimit = 227 * 1024;
@@ -228,10 +230,19 @@ static int choose_variant(const epgx_plan *pl, epgx_config &c, int kernel, int l
   int G = lanes > 0 ? pow2ceil(lanes) : pow2ceil((C + 3) / 4);
   if (G > 256) G = 256;
   int nvt = nvt_choice(t.nvar, vars, t.npool);
+  const bool tiled = !pl->tiles.empty();
+  if (tiled) {
+    if (t.npool > 2) return fail(EPGX_ERR_UNSUPPORTED, "order-2 partial states with more than two exchange pools");
+    nvt = 3; // a pair tile holds (a, b, ab)
+  } else if (pl->order2 && (t.nvar > 3 || t.npool > 2)) {
+    return fail(EPGX_ERR_INVALID, "order-2 tape without variable tiles");
+  } else if (pl->order2) {
+    nvt = 3;
+  }
   int64_t per_atom;
   for (;;) {
     per_atom = (int64_t)(1 + nvt) * t.npool * 3 * C * 2 * rsz + (int64_t)t.npattern * 4;
-    if (per_atom <= kSmemLimit - 1024 || nvt <= 1) break;
+    if (per_atom <= kSmemLimit - 1024 || nvt <= 1 || pl->order2) break;
     nvt = nvt == 3 ? 1 : 0;
   }
   if (per_atom > kSmemLimit - 1024)
@@ -244,14 +255,14 @@ static int choose_variant(const epgx_plan *pl, epgx_config &c, int kernel, int l
   while (A * G > 256) --A;
   if (A < 1) A = 1;
   if (atoms <= 0) { // small grids: smaller CTAs, so that every SM gets a few of them (latency-bound record loop)
-    const int tiles = nvt ? (t.nvar + nvt - 1) / nvt : 1;
+    const int tiles = tiled ? (int)(pl->tiles.size() / 3) : nvt ? (t.nvar + nvt - 1) / nvt : 1;
     while (A > 1 && A * G > 32 && ((pl->natoms + A - 1) / A) * tiles < 4 * 148) A = (A + 1) / 2;
   }
   c.kernel = 0;
   c.lanes_per_atom = G;
   c.slots_per_lane = 0;
   c.vars_per_pass = nvt;
-  c.var_tiles = nvt ? (t.nvar + nvt - 1) / nvt : 1;
+  c.var_tiles = tiled ? (int)(pl->tiles.size() / 3) : nvt ? (t.nvar + nvt - 1) / nvt : 1;
   c.atoms_per_cta = A;
   c.threads_per_cta = A * G;
   c.smem_bytes = (int)(A * per_atom + 16);
@@ -301,8 +312,12 @@ extern "C" int epgx_plan_create(const epgx_tape *t, epgx_plan **out) {
   if (t->nop < 0 || t->nseg < 0 || t->ncoef < 1 || !t->coef || (t->nop && !t->ops) || (t->nseg && !t->segs))
     return fail(EPGX_ERR_INVALID, "empty or null tape arrays");
   if (t->ncoef >= (int64_t)1 << 31) return fail(EPGX_ERR_CAPACITY, "coefficient table too large (>= 2^31 reals)");
-  if (t->max_order < 0 || t->init_n < 0 || t->init_n > t->max_order || t->nvar < 0 || t->nadc < 0)
+  if (t->max_order < 0 || t->init_n < 0 || t->init_n > t->max_order || t->nvar < 0 || t->nadc < 0 || t->nvar1 < 0 ||
+      t->nvar1 > t->nvar)
     return fail(EPGX_ERR_INVALID, "bad order / variable counts");
+  if (t->ntile < 0 || (t->ntile > 0 && !t->tiles)) return fail(EPGX_ERR_INVALID, "bad variable tiles");
+  for (int64_t i = 0; i < 3 * (int64_t)t->ntile; ++i)
+    if (t->tiles[i] < -1 || t->tiles[i] >= t->nvar) return fail(EPGX_ERR_INVALID, "variable tile refers to an unknown variable");
   int64_t natoms = 1;
   for (int d = 0; d < t->ndim; ++d) {
     if (t->shape[d] < 1) return fail(EPGX_ERR_INVALID, "bad grid shape");
@@ -338,6 +353,8 @@ extern "C" int epgx_plan_create(const epgx_tape *t, epgx_plan **out) {
       return fail(EPGX_ERR_INVALID, "FUSED record without its CONT record at " + std::to_string(i));
     if ((o.flags & EPGX_FLAG_INJECT) && (o.aux < 0 || o.aux >= t->nvar))
       return fail(EPGX_ERR_INVALID, "injection into unknown variable in record " + std::to_string(i));
+    if ((o.flags & EPGX_FLAG_INJECT) && (o.aux1 < 0 || o.aux1 > t->nvar))
+      return fail(EPGX_ERR_INVALID, "injection from unknown state set in record " + std::to_string(i));
     if (o.code == EPGX_OP_ADC) {
       if ((o.flags & EPGX_FLAG_BASE) && (o.aux < 0 || o.aux >= t->nadc))
         return fail(EPGX_ERR_INVALID, "ADC row out of range in record " + std::to_string(i));
@@ -379,6 +396,13 @@ extern "C" int epgx_plan_create(const epgx_tape *t, epgx_plan **out) {
     pl->coef32.resize(t->ncoef);
     for (int64_t i = 0; i < t->ncoef; ++i) pl->coef32[i] = (float)t->coef[i];
   }
+  if (t->ntile) pl->tiles.assign(t->tiles, t->tiles + 3 * (size_t)t->ntile);
+  pl->tape.tiles = nullptr;
+  if (pl->tape.nvar1 == 0) pl->tape.nvar1 = t->nvar;
+  pl->order2 = t->ntile > 0 || pl->tape.nvar1 < t->nvar;
+  for (int64_t i = 0; i < t->nop; ++i)
+    if (((t->ops[i].flags & EPGX_FLAG_INJECT) && t->ops[i].aux1 > 0) || (t->ops[i].flags & (EPGX_FLAG_P1 | EPGX_FLAG_P2)))
+      pl->order2 = true;
   pl->pats.assign((size_t)t->npattern * (EPGX_MAX_DIMS + 1), 0);
   for (int q = 0; q < t->npattern; ++q) {
     for (int d = 0; d < t->ndim; ++d) pl->pats[q * (EPGX_MAX_DIMS + 1) + d] = t->stride[q][d];
@@ -403,7 +427,7 @@ extern "C" int epgx_plan_create(const epgx_tape *t, epgx_plan **out) {
     }
     pl->real_ok = ok;
     // the same with order-1 partial states: injections must be real as well
-    bool okj = t->nvar > 0 && t->npool == 1;
+    bool okj = t->nvar > 0 && t->npool == 1 && !pl->order2;
     for (int64_t i = 0; okj && i < t->nop; ++i) {
       const epgx_op &o = t->ops[i];
       switch (o.code) {
@@ -605,7 +629,8 @@ extern "C" int epgx_plan_create(const epgx_tape *t, epgx_plan **out) {
   pl->off_segs = align(pl->off_ops + (int64_t)sizeof(epgx_op) * (t->nop ? t->nop : 1));
   pl->off_pats = align(pl->off_segs + (int64_t)sizeof(epgx_segment) * (t->nseg ? t->nseg : 1));
   pl->off_stream = align(pl->off_pats + (int64_t)pl->pats.size() * 4);
-  pl->off_coef = align(pl->off_stream + (int64_t)sizeof(epgx_op) * pl->stream.size());
+  pl->off_tiles = align(pl->off_stream + (int64_t)sizeof(epgx_op) * pl->stream.size());
+  pl->off_coef = align(pl->off_tiles + (int64_t)pl->tiles.size() * 4);
   pl->ws_bytes = align(pl->off_coef + t->ncoef * rsz);
   *out = pl;
   return EPGX_OK;
@@ -654,6 +679,8 @@ extern "C" int epgx_plan_upload(const epgx_plan *pl, void *ws, void *stream) {
     CUDA_TRY(cudaMemcpyAsync(w + pl->off_segs, pl->segs.data(), sizeof(epgx_segment) * t.nseg, cudaMemcpyHostToDevice, st));
   CUDA_TRY(cudaMemcpyAsync(w + pl->off_pats, pl->pats.data(), pl->pats.size() * 4, cudaMemcpyHostToDevice, st));
   CUDA_TRY(cudaMemcpyAsync(w + pl->off_stream, pl->stream.data(), sizeof(epgx_op) * pl->stream.size(), cudaMemcpyHostToDevice, st));
+  if (!pl->tiles.empty())
+    CUDA_TRY(cudaMemcpyAsync(w + pl->off_tiles, pl->tiles.data(), pl->tiles.size() * 4, cudaMemcpyHostToDevice, st));
   if (t.dtype == EPGX_F64)
     CUDA_TRY(cudaMemcpyAsync(w + pl->off_coef, pl->coef64.data(), t.ncoef * 8, cudaMemcpyHostToDevice, st));
   else
@@ -730,6 +757,8 @@ static int run_range(const epgx_plan *pl, const void *ws, int64_t atom_begin, in
   kp.A = cfg.atoms_per_cta;
   kp.C = cfg.ring;
   kp.nvar = t.nvar;
+  kp.nvar1 = t.nvar1;
+  kp.tiles = pl->tiles.empty() ? nullptr : (const int *)(w + pl->off_tiles);
   kp.init_off = t.init_off;
   kp.m0_off = t.m0_off;
   kp.init_pat = t.init_pat;

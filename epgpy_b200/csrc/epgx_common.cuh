@@ -263,6 +263,8 @@ struct KParams {
   int shape[EPGX_MAX_DIMS];
   int ndim, npattern, nseg;
   int G, A, C, nvar;
+  int nvar1;        // order-1 variables among the nvar partial state sets (the rest: order-2 pairs)
+  const int *tiles; // ring kernel: [gridDim.y][3] variables resident per tile (-1: empty), or null: consecutive
   int bounded; // the tape has segments that truncate at max_nstate (EPGX_SEG_MASK_TOP)
   unsigned init_off, m0_off;
   int init_pat, m0_pat, init_n;

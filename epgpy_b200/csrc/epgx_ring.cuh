@@ -28,7 +28,21 @@ __global__ void __launch_bounds__(256) ring_kernel(const KParams p) {
   const long long a_rel = (long long)blockIdx.x * p.A + al;
   const bool valid = a_rel < p.atom_count;
   const long long atom = p.atom_begin + (valid ? a_rel : p.atom_count - 1);
-  const int v0 = blockIdx.y * NVT; // first variable of this tile
+  // variables resident in this tile (set s holds variable tv[s - 1]; -1: empty slot)
+  int tv[NVT > 0 ? NVT : 1];
+#pragma unroll
+  for (int s = 0; s < NVT; ++s) {
+    if (p.tiles != nullptr) tv[s] = s < 3 ? __ldg(p.tiles + blockIdx.y * 3 + s) : -1;
+    else tv[s] = (int)(blockIdx.y * NVT + s) < p.nvar ? (int)(blockIdx.y * NVT + s) : -1;
+  }
+  // set (1..NVT) that holds variable v, 0 if it is not resident
+  auto set_of = [&](int v) {
+    int r = 0;
+#pragma unroll
+    for (int s = 0; s < NVT; ++s)
+      if (tv[s] == v && v >= 0) r = s + 1;
+    return r;
+  };
   const real *__restrict__ coef = (const real *)p.coef;
 
   // shared memory: rings [A][NSET][NP][3][C] complex, then pattern offsets [A][npattern] int
@@ -89,8 +103,7 @@ __global__ void __launch_bounds__(256) ring_kernel(const KParams p) {
     if (NVT > 0 && !alive)
       for (int r = first; r < first + count; ++r) {
         const int2 h = __ldg((const int2 *)(p.ops + r));
-        const int iset = h.y - v0 + 1;
-        if (((h.x >> 16) & EPGX_FLAG_INJECT) && iset >= 1 && iset < NSET) alive = true;
+        if (((h.x >> 16) & EPGX_FLAG_INJECT) && set_of(h.y) >= 1) alive = true;
       }
     if (count > 0) {
       for (int k = lane; k <= nact; k += G) {
@@ -114,23 +127,33 @@ __global__ void __launch_bounds__(256) ring_kernel(const KParams p) {
           const int pat0 = r1.y & 0xff, pat1 = (r1.y >> 8) & 0xff, pat2 = (r1.y >> 16) & 0xff;
           const int aux1 = r1.z;
           const bool inject = flags & EPGX_FLAG_INJECT;
-          const int iset = aux - v0 + 1; // target set of an injection
+          const int iset = inject ? set_of(aux) : 0;                  // target set of an injection (0: not resident)
+          const int isrc = inject && aux1 > 0 ? set_of(aux1 - 1) : 0; // its source set: 0 = the base state
+          const bool src_ok = !inject || aux1 == 0 || isrc >= 1;
           const bool on_base = flags & EPGX_FLAG_BASE, on_part = (flags & EPGX_FLAG_PARTIALS) && alive;
-          const bool aff = (flags & EPGX_FLAG_AFFINE) && k == 0;
+          // order-1 / order-2 partial states only (EPGX_FLAG_P1 / P2)
+          bool sel[NSET];
+          sel[0] = on_base;
+#pragma unroll
+          for (int s = 1; s < NSET; ++s)
+            sel[s] = on_part && tv[s - 1] >= 0 && !((flags & EPGX_FLAG_P1) && tv[s - 1] >= p.nvar1) &&
+                     !((flags & EPGX_FLAG_P2) && tv[s - 1] < p.nvar1);
+          const bool aff = (flags & EPGX_FLAG_AFFINE) && k == 0 && isrc == 0;
 
           // linear forms: out = form(in) for the selected sets, or partial += form(base)
 #define APPLY_FORM(EXPR, AFFINE_STMT)                                         \
   {                                                                            \
     if (inject) {                                                              \
-      if (iset >= 1 && iset < NSET) {                                          \
-        const Tri<real> &s_ = st[0][q];                                        \
+      if (iset >= 1 && iset < NSET && src_ok) {                                \
+        Tri<real> s_ = st[0][q];                                               \
+        _Pragma("unroll") for (int s = 1; s < NSET; ++s) if (s == isrc) s_ = st[s][q]; \
         Tri<real> o_ = EXPR;                                                   \
         if (aff) { AFFINE_STMT; }                                              \
         _Pragma("unroll") for (int s = 1; s < NSET; ++s) if (s == iset) tri_add(st[s][q], o_); \
       }                                                                        \
     } else {                                                                   \
       _Pragma("unroll") for (int s = 0; s < NSET; ++s) {                       \
-        if (s == 0 ? on_base : on_part) {                                      \
+        if (sel[s]) {                                                          \
           const Tri<real> s_ = st[s][q];                                       \
           Tri<real> o_ = EXPR;                                                 \
           if (s == 0 && aff) { AFFINE_STMT; }                                  \
@@ -215,7 +238,7 @@ __global__ void __launch_bounds__(256) ring_kernel(const KParams p) {
               const real dp = ldc(c), dm = ldc(c + 1), dl = ldc(c + 2);
 #pragma unroll
               for (int s = 0; s < NSET; ++s)
-                if (s == 0 ? on_base : on_part) {
+                if (sel[s]) {
                   st[s][q].pr *= dp; st[s][q].pi *= dp; st[s][q].mr *= dm; st[s][q].mi *= dm;
                   st[s][q].zr *= dl; st[s][q].zi *= dl;
                 }
@@ -229,7 +252,7 @@ __global__ void __launch_bounds__(256) ring_kernel(const KParams p) {
             for (int i = 0; i < NP * NP * 2; ++i) { mt[i] = ldc(c + i); ml[i] = ldc(c + NP * NP * 2 + i); }
 #pragma unroll
             for (int s = 0; s < NSET; ++s)
-              if (s == 0 ? on_base : on_part) {
+              if (sel[s]) {
                 Tri<real> o[NP];
 #pragma unroll
                 for (int i = 0; i < NP; ++i) {
@@ -282,7 +305,7 @@ __global__ void __launch_bounds__(256) ring_kernel(const KParams p) {
             for (int q = 0; q < NP; ++q)
 #pragma unroll
               for (int s = 0; s < NSET; ++s)
-                if (s == 0 ? on_base : on_part) st[s][q].pr = st[s][q].pi = st[s][q].mr = st[s][q].mi = real(0);
+                if (sel[s]) st[s][q].pr = st[s][q].pi = st[s][q].mr = st[s][q].mi = real(0);
             break;
           case EPGX_OP_PD:
 #pragma unroll
@@ -305,8 +328,8 @@ __global__ void __launch_bounds__(256) ring_kernel(const KParams p) {
                 if (flags & EPGX_FLAG_PARTIALS) {
 #pragma unroll
                   for (int s = 1; s < NSET; ++s) {
-                    const int v = v0 + s - 1;
-                    if (v < p.nvar) {
+                    const int v = tv[s - 1];
+                    if (v >= 0 && v < p.nvar) {
                       const real xr = z0 ? st[s][q].zr : st[s][q].pr, xi = z0 ? st[s][q].zi : st[s][q].pi;
                       jac[(((long long)aux1 * p.nvar + v) * p.jac_stride + a_rel) * NP + q] =
                           real2{xr * fr - xi * fi, xr * fi + xi * fr};

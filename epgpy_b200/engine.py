@@ -31,7 +31,7 @@ class _Tape(ctypes.Structure):
         ("init_off", ctypes.c_uint32), ("m0_off", ctypes.c_uint32), ("init_pat", ctypes.c_uint8),
         ("m0_pat", ctypes.c_uint8), ("rsv0", ctypes.c_uint8 * 2), ("init_n", ctypes.c_int32),
         ("nadc", ctypes.c_int32), ("njac", ctypes.c_int32), ("nvar", ctypes.c_int32), ("max_order", ctypes.c_int32),
-        ("rsv", ctypes.c_int32 * 3),
+        ("nvar1", ctypes.c_int32), ("rsv", ctypes.c_int32 * 2), ("ntile", ctypes.c_int32), ("tiles", ctypes.c_void_p),
     ]
 
 
@@ -142,6 +142,9 @@ class Plan:
         t.m0_off, t.m0_pat = low.m0_ref
         t.init_n = low.init_n
         t.nadc, t.njac, t.nvar, t.max_order = low.nadc, low.njac, low.nvar, low.max_order
+        t.nvar1 = getattr(low, "nvar1", low.nvar)
+        self._tiles = np.ascontiguousarray(getattr(low, "tiles", np.zeros((0, 3))), dtype=np.int32)
+        t.ntile, t.tiles = len(self._tiles), (self._tiles.ctypes.data if len(self._tiles) else None)
         self._h = ctypes.c_void_p()
         _check(L.epgx_plan_create(ctypes.byref(t), ctypes.byref(self._h)))
         self._ws = {}  # device index -> (workspace tensor, upload event)

@@ -201,6 +201,16 @@ def _assemble(low, res, count=None, asarray=True):
             elif row.kind == "expr":
                 val = row.jac._eval(to_grid(sig_host[row.index].reshape(-1)), to_grid(sig_host[row.index + 1].reshape(-1)))
                 values[ip].append(row.post(val) if row.post is not None else val)
+            elif row.kind == "hess":
+                jrow, entries = row.jac
+                out = np.zeros(grid + (len(entries), len(entries[0]) if entries else 0), dtype=cdt)
+                for i1, ent in enumerate(entries):
+                    for i2, vi in enumerate(ent):
+                        if vi >= 0 and jrow >= 0:
+                            out[..., i1, i2] = to_grid(jac_host[jrow, vi].reshape(-1))
+                if row.post is not None:
+                    out = np.asarray(row.post(out)).astype(cdt, copy=False)
+                values[ip].append(out)
             else:
                 jrow, cols = row.jac
                 out = np.zeros(grid + (len(cols),), dtype=cdt)

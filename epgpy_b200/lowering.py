@@ -19,14 +19,14 @@ import numpy as np
 
 from . import common, operators as ops_mod
 from .exchange import X
-from .operators import (PD, Adc, D, DiffOperator, EmptyOperator, Jacobian, MultiOperator, Operator, Probe, Reset, S,
-                        Spoiler, reduce_pulse)
+from .operators import (PD, Adc, D, DiffOperator, EmptyOperator, Hessian, Jacobian, MultiOperator, Operator, Pair, Probe,
+                        Reset, S, Spoiler, reduce_pulse)
 from .statematrix import StateMatrix
 
 # opcodes / flags (include/epgx.h)
 (OP_NOP, OP_T_GEN, OP_T_RE, OP_T_IM, OP_E, OP_DIAG, OP_MATRIX, OP_D, OP_X, OP_SPOIL, OP_PD, OP_ADC, OP_FUSED,
  OP_CONT) = range(14)
-F_BASE, F_PARTIALS, F_INJECT, F_G, F_AFFINE, F_Z0, F_SCALE, F_PRE, F_POST, F_IM, F_GEN = (1 << i for i in range(11))
+F_BASE, F_PARTIALS, F_INJECT, F_G, F_AFFINE, F_Z0, F_SCALE, F_PRE, F_POST, F_IM, F_GEN, F_P1, F_P2 = (1 << i for i in range(13))
 SEG_RESET, SEG_MASK_TOP = 1, 2
 MAX_DIMS, MAX_PATTERNS, MAX_POOLS = 8, 64, 4
 
@@ -162,29 +162,29 @@ def _cmul_block(blk, z):
     raise NotImplementedError("complex chain-rule coefficients")
 
 
-def _emit_form(bld, form, flags, aux=0):
-    """emit one record for a coefficient form; returns nothing"""
+def _emit_form(bld, form, flags, aux=0, aux1=0):
+    """emit one record for a coefficient form (aux / aux1: target variable and source set of an injection)"""
     kind = form[0]
     if kind == "tgen":
         form = reduce_pulse(form)
         kind = form[0]
     if kind == "tre":
-        bld.record(OP_T_RE, flags, [bld.block(form[1])], aux)
+        bld.record(OP_T_RE, flags, [bld.block(form[1])], aux, aux1)
     elif kind == "tim":
-        bld.record(OP_T_IM, flags, [bld.block(form[1])], aux)
+        bld.record(OP_T_IM, flags, [bld.block(form[1])], aux, aux1)
     elif kind == "tgen":
-        bld.record(OP_T_GEN, flags, [bld.block(form[1])], aux)
+        bld.record(OP_T_GEN, flags, [bld.block(form[1])], aux, aux1)
     elif kind == "e":
         _, b0, b1, b2, affine = form
         fl = flags | (F_G if b2 is not None else 0) | (F_AFFINE if affine else 0)
-        bld.record(OP_E, fl, [bld.block(b0), bld.block(b1), None if b2 is None else bld.block(b2)], aux)
+        bld.record(OP_E, fl, [bld.block(b0), bld.block(b1), None if b2 is None else bld.block(b2)], aux, aux1)
     elif kind == "diag":
         _, blk, affine = form
-        bld.record(OP_DIAG, flags | (F_AFFINE if affine else 0), [bld.block(blk)], aux)
+        bld.record(OP_DIAG, flags | (F_AFFINE if affine else 0), [bld.block(blk)], aux, aux1)
     elif kind == "matrix":
         _, blk, blk0 = form
         bld.record(OP_MATRIX, flags | (F_AFFINE if blk0 is not None else 0),
-                   [bld.block(blk), None if blk0 is None else bld.block(blk0)], aux)
+                   [bld.block(blk), None if blk0 is None else bld.block(blk0)], aux, aux1)
     else:
         raise ValueError(kind)
 
@@ -344,19 +344,34 @@ def lower(sequence, *, init=None, probe=None, options=None, dtype="f64", propaga
     atom_shape = tuple(d for i, d in enumerate(grid) if i != pool_axis) or (1,)
     bld = _Builder(grid, pool_axis)
 
-    # ---- derivative variables: only those a Jacobian probe asks for
+    # ---- derivative variables: only those a Jacobian / Hessian probe asks for
     jprobes = [pb for pb in (probes or []) if isinstance(pb, Jacobian)]
+    hprobes = [pb for pb in (probes or []) if isinstance(pb, Hessian)]
     if probes is None or any(pb is None for pb in probes):  # a None entry keeps the in-sequence probes, Jacobians included
         jprobes += [op for op in seq if isinstance(op, Jacobian)]
+        hprobes += [op for op in seq if isinstance(op, Hessian)]
     defined = []
     for op in seq:
         for var in getattr(op, "order1", None) or {}:
             if var not in defined:
                 defined.append(var)
+    wanted_pairs = {pair for pb in hprobes for pair in pb.pairs() if pair[0] in defined and pair[1] in defined}
     wanted = {v for pb in jprobes for v in pb.variables if v != "magnitude"}
+    wanted |= {v for pb in hprobes for v in pb.first()} | {v for pair in wanted_pairs for v in pair}
     variables = [v for v in defined if v in wanted]
     vindex = {v: i for i, v in enumerate(variables)}
-    nvar = len(variables)
+    nvar1 = len(variables)
+    # order-2 partial states: one more state set per unordered pair of variables, numbered behind the order-1 ones
+    # (epgpy/diff.py:290-378).  The shared-memory kernel keeps three partial states resident per tile: (a, b, ab)
+    pairs = sorted(wanted_pairs, key=lambda pr: (vindex[pr[0]], vindex[pr[1]]))
+    pindex = {pair: nvar1 + i for i, pair in enumerate(pairs)}
+    nvar = nvar1 + len(pairs)
+    tiles = None
+    if pairs:
+        tiles = [[vindex[a], vindex[b] if b != a else pindex[(a, b)], pindex[(a, b)] if b != a else -1] for a, b in pairs]
+        covered = {v for pair in pairs for v in pair}
+        rest = [vindex[v] for v in variables if v not in covered]
+        tiles += [(rest[i:i + 3] + [-1, -1])[:3] for i in range(0, len(rest), 3)]
 
     # ---- shifts: 1-d integers, or collinear integer vectors
     vecs = [op.k for op in seq if isinstance(op, S) and not common.isscalar(op.k)]
@@ -437,7 +452,9 @@ def lower(sequence, *, init=None, probe=None, options=None, dtype="f64", propaga
     times, tic = [], 0
     nadc = njac = 0
     n = init_n
-    alive = False          # any partial state non-zero so far
+    alive = False          # any order-1 partial state non-zero so far
+    alive2 = False         # any order-2 partial state non-zero so far
+    alive_vars = set()     # order-1 variables injected so far
     seg_first = 0
 
     def close_segment(shift, n_old, n_new, flags=0):
@@ -446,7 +463,7 @@ def lower(sequence, *, init=None, probe=None, options=None, dtype="f64", propaga
         seg_first = len(bld.records)
 
     def part_flag():
-        return F_PARTIALS if (nvar and alive) else 0
+        return F_PARTIALS if (nvar and (alive or alive2)) else 0
 
     for op in seq:
         if isinstance(op, Jacobian) and probes is not None:
@@ -505,7 +522,46 @@ def lower(sequence, *, init=None, probe=None, options=None, dtype="f64", propaga
             form = bld.cache[key]
             inj = [(vindex[var], param, coeff) for var, pc in op.order1.items() if var in vindex
                    for param, coeff in pc.items()] if nvar else []
-            if not inj:
+            if pairs and not inj and not (getattr(op, "order2", None) or {}):
+                _emit_or_reuse(bld, op, form, F_BASE | part_flag())  # no derivative of its own: one record for all state sets
+            elif pairs:
+                # order 2 (diff.py:290-378, every cross term): Op on the order-2 states, their injections from the
+                # PRE-operator order-1 / base states, then the order-1 update, then the base state
+                #   x_ab <- Op x_ab + sum_p c_ap dOp_p x_b + sum_p c_bp dOp_p x_a + sum_pq c_ap c_bq d2Op_pq x_0 + sum_p c2_ab,p dOp_p x_0
+                if alive2:
+                    _emit_or_reuse(bld, op, form, F_PARTIALS | F_P2)
+                dforms = {}
+
+                def dform(param):
+                    if param not in dforms:
+                        dforms[param] = op._dform(param)
+                    return dforms[param]
+
+                for (a, b) in pairs:
+                    dst = pindex[(a, b)]
+                    for src, var in ((b, a), (a, b)):  # a == b: both terms, the factor 2 of diff.py:349-362
+                        if var in op.order1 and src in alive_vars:
+                            for param, coeff in op.order1[var].items():
+                                _emit_form(bld, _scaled_form(dform(param), coeff), F_INJECT, aux=dst, aux1=1 + vindex[src])
+                                alive2 = True
+                    if a in op.order1 and b in op.order1:
+                        for p_, ca in op.order1[a].items():
+                            for q_, cb in op.order1[b].items():
+                                d2 = op._d2form(p_, q_)
+                                if d2 is not None:
+                                    _emit_form(bld, _scaled_form(_scaled_form(d2, ca), cb), F_INJECT, aux=dst)
+                                    alive2 = True
+                    for param, c2 in (getattr(op, "order2", None) or {}).get(Pair(a, b), {}).items():
+                        _emit_form(bld, _scaled_form(dform(param), c2), F_INJECT, aux=dst)
+                        alive2 = True
+                if alive:
+                    _emit_or_reuse(bld, op, form, F_PARTIALS | F_P1)
+                for vi, param, coeff in inj:
+                    _emit_form(bld, _scaled_form(dform(param), coeff), F_INJECT, aux=vi)
+                    alive = True
+                    alive_vars.add(variables[vi])
+                _emit_or_reuse(bld, op, form, F_BASE)
+            elif not inj:
                 _emit_or_reuse(bld, op, form, F_BASE | part_flag())
             else:
                 gens = [op._gform(param) for _, param, _ in inj] if pre_inject else [None]
@@ -539,7 +595,29 @@ def lower(sequence, *, init=None, probe=None, options=None, dtype="f64", propaga
                 custom_post = None
                 if not isinstance(op, Adc) and getattr(op, "_post", None):
                     custom_post = op._post
-                if isinstance(eff, Jacobian):
+                if isinstance(eff, Hessian):
+                    fl = F_PARTIALS | (F_Z0 if eff.probe == "Z0" else 0)
+                    blocks = []
+                    if phase is not None:
+                        ph = np.atleast_1d(np.exp(1j * np.asarray(phase, dtype=float) * common.DEG))
+                        blocks = [bld.block(np.stack([ph.real, ph.imag], axis=-1))]
+                        fl |= F_SCALE
+                    entries = []
+                    for a in eff.variables1:
+                        row = []
+                        for b in eff.variables2:
+                            if a == "magnitude" or b == "magnitude":  # first derivatives w.r.t. the other one (diff.py:451-464)
+                                v = b if a == "magnitude" else a
+                                row.append(vindex.get(v, -1))
+                            else:
+                                row.append(pindex.get(Pair(a, b), -1))
+                        entries.append(row)
+                    jrow = -1
+                    if nvar:
+                        jrow, njac = njac, njac + 1
+                        bld.record(OP_ADC, fl, blocks, aux=0, aux1=jrow)
+                    rows.append(Row("hess", -1, post=custom_post, jac=(jrow, entries)))
+                elif isinstance(eff, Jacobian):
                     attr = eff.probe
                     fl = (F_Z0 if attr == "Z0" else 0)
                     blocks = []
@@ -645,6 +723,8 @@ def lower(sequence, *, init=None, probe=None, options=None, dtype="f64", propaga
     low.init_ref, low.m0_ref, low.init_n = init_ref, m0_ref, init_n
     low.nadc, low.njac, low.nvar, low.max_order = nadc, njac, nvar, max_order
     low.variables = variables
+    low.nvar1, low.pairs = nvar1, pairs
+    low.tiles = np.array(tiles, dtype=np.int32).reshape(-1, 3) if tiles else np.zeros((0, 3), dtype=np.int32)
     low.final_n = n  # order count when the tape ends
     low.rows, low.times = rows_out, times
     low.nprobe = len(probes) if probes else 1
@@ -658,7 +738,7 @@ def _emit_or_reuse(bld, op, form, flags):
     key = (id(op), "rec")
     rec = bld.cache.get(key)
     if rec is not None:
-        bld.records.append((rec[0], (rec[1] & ~(F_BASE | F_PARTIALS | F_INJECT)) | flags) + rec[2:])
+        bld.records.append((rec[0], (rec[1] & ~(F_BASE | F_PARTIALS | F_INJECT | F_P1 | F_P2)) | flags) + rec[2:])
         return
     _emit_form(bld, form, flags)
     bld.cache[key] = bld.records[-1]

@@ -216,23 +216,65 @@ def parse_order1(order1, parameters):
     return order1
 
 
+def Pair(p1, p2=None):
+    """sorted pair (epgpy/diff.py:534-540)"""
+    if p2 is None:
+        p1, p2 = p1
+    return (p2, p1) if p1 > p2 else (p1, p2)
+
+
+def parse_order2(order1, order2, parameters1, parameters2):
+    """normalise the `order2` keyword to {(var1, var2): {parameter: coefficient}} (epgpy/diff.py:197-262).
+    The coefficients are the SECOND derivatives of the operator's parameters with respect to the pair of variables
+    (empty for parameters that are linear in the variables).  Which pairs are actually propagated is decided by the
+    Hessian probe of the simulation, not by this keyword: every pair of variables it asks for gets its exact chain-rule
+    update at every operator, the `auto_cross_derivatives` case of the reference (diff.py:333-362)."""
+    if not order2:
+        return {}
+    if not order1:
+        raise ValueError("order1 must be set.")
+    if order2 is True:
+        order2 = {Pair(pair): {} for pair in parameters2}
+    elif isinstance(order2, str):
+        order2 = {(order2, order2): {}}
+    elif not isinstance(order2, dict) and all(isinstance(item, str) for item in order2):
+        items = list(order2)
+        order2 = {Pair(a, b): {} for a in items for b in items}
+    elif not isinstance(order2, dict) and all(isinstance(pair, tuple) for pair in order2):
+        order2 = {Pair(pair): {} for pair in order2}
+    elif isinstance(order2, dict) and all(isinstance(pair, tuple) and isinstance(order2[pair], dict) for pair in order2):
+        order2 = {Pair(pair): dict(order2[pair]) for pair in order2}
+    else:
+        raise ValueError(f"Invalid parameter 'order2' value: {order2}")
+    invalid = {pair for pair in order2 if not (set(pair) & set(order1))}
+    if invalid:
+        raise ValueError(f"Invalid variable pair(s), no match in order1 variables: {invalid}")
+    invalid = {pair for pair in order2 if (set(pair) - set(order1)) and order2[pair]}
+    if invalid:
+        raise ValueError(f"Invalid variable pair(s), expecting no coefficient: {invalid}")
+    invalid = {param for pair in order2 for param in (set(order2[pair]) - set(parameters1))}
+    if invalid:
+        raise ValueError(f"Unknown parameter(s) in order2: {invalid}")
+    return order2
+
+
 class DiffOperator(Operator):
-    """operator with order-1 partial derivatives (epgpy/diff.py:20-139)
+    """operator with order-1 and order-2 partial derivatives (epgpy/diff.py:20-378)
 
     order1: False | True | parameter name(s) | {alias: parameter} | {variable: {parameter: coeff}}
+    order2: False | True | parameter name(s) | [(var1, var2), ...] | {(var1, var2): {parameter: coeff2}}
     The partial state matrices are propagated on the device in the same pass as the base state.
     """
 
     PARAMETERS_ORDER1 = set()
+    PARAMETERS_ORDER2 = set()
 
     def __init__(self, *, order1=False, order2=False, name=None, duration=None):
         super().__init__(name=name, duration=duration)
-        if order2:
-            raise NotImplementedError(
-                "second-order derivatives (order2 / Hessian, epgpy/diff.py:290-378) are not part of the B200 hot path yet"
-            )
+        if (not order1) and isinstance(order2, (bool, str)):  # order2 alone names the variables (diff.py:158-159)
+            order1 = order2
         self.order1 = parse_order1(order1, self.PARAMETERS_ORDER1)
-        self.order2 = {}
+        self.order2 = parse_order2(self.order1, order2, self.PARAMETERS_ORDER1, self.PARAMETERS_ORDER2)
 
     @property
     def parameters_order1(self):
@@ -260,6 +302,10 @@ class DiffOperator(Operator):
     def _gform(self, param):
         """Op^-1 dOp/dparam as a coefficient form when it has a closed form (pre-injection), else None"""
         return None
+
+    def _d2form(self, p1, p2):
+        """d2 Op / dp1 dp2 as a coefficient form; None when it vanishes identically"""
+        raise NotImplementedError(f"second derivatives of {type(self).__name__} w.r.t. ({p1}, {p2})")
 
     # generic dense coefficients (for `@` and for the public .mat / .arr attributes)
     def _dense(self):
@@ -379,11 +425,12 @@ class MatrixOp(CombinableOperator):
 
     def __init__(self, mat, mat0=None, *, dmats=None, d2mats=None, axes=None, check=True, **kwargs):
         dmats = dmats or {}
+        d2mats = d2mats or {}
         self.PARAMETERS_ORDER1 = set(kwargs.pop("parameters_order1", None) or dmats)
-        if d2mats:
-            raise NotImplementedError("second-order derivative matrices are not supported")
+        self.PARAMETERS_ORDER2 = {Pair(pair) for pair in (kwargs.pop("parameters_order2", None) or d2mats)}
         super().__init__(**kwargs)
         self.mat, self.mat0 = _matrix_setup(mat, mat0, check=check)
+        self.d2mats = {Pair(p): _matrix_setup(*(d if isinstance(d, tuple) else (d, None)), check=check) for p, d in d2mats.items()}
         self.dmats = {p: _matrix_setup(*(d if isinstance(d, tuple) else (d, None)), check=check) for p, d in dmats.items()}
         if axes is not None:
             raise NotImplementedError("the `axes` keyword is not supported: give parameters their grid axes directly")
@@ -413,6 +460,10 @@ class MatrixOp(CombinableOperator):
     def _dform(self, param):
         return self._matrix_form(*self.dmats[param])
 
+    def _d2form(self, p1, p2):
+        d2 = self.d2mats.get(Pair(p1, p2))
+        return None if d2 is None else self._matrix_form(*d2)
+
 
 def _matrix_setup(mat, mat0=None, check=True):
     """epgpy/opmatrix.py:140-170"""
@@ -439,11 +490,12 @@ class ScalarOp(CombinableOperator):
 
     def __init__(self, arr, arr0=None, *, darrs=None, d2arrs=None, axes=None, check=True, **kwargs):
         darrs = darrs or {}
+        d2arrs = d2arrs or {}
         self.PARAMETERS_ORDER1 = set(kwargs.pop("parameters_order1", None) or darrs)
-        if d2arrs:
-            raise NotImplementedError("second-order derivative arrays are not supported")
+        self.PARAMETERS_ORDER2 = {Pair(pair) for pair in (kwargs.pop("parameters_order2", None) or d2arrs)}
         super().__init__(**kwargs)
         self.arr, self.arr0 = _scalar_setup(arr, arr0, check=check)
+        self.d2arrs = {Pair(p): _scalar_setup(*(d if isinstance(d, tuple) else (d, None)), check=check) for p, d in d2arrs.items()}
         self.darrs = {p: _scalar_setup(*(d if isinstance(d, tuple) else (d, None)), check=check) for p, d in darrs.items()}
         if axes is not None:
             raise NotImplementedError("the `axes` keyword is not supported: give parameters their grid axes directly")
@@ -469,6 +521,10 @@ class ScalarOp(CombinableOperator):
 
     def _dform(self, param):
         return self._diag_form(*self.darrs[param])
+
+    def _d2form(self, p1, p2):
+        d2 = self.d2arrs.get(Pair(p1, p2))
+        return None if d2 is None else self._diag_form(*d2)
 
 
 def _scalar_setup(arr, arr0=None, check=True):
@@ -553,6 +609,26 @@ class T(CombinableOperator):
             return ("tgen", _cplx_block(0 * B.real, 0 * B.real, B, U))
         raise ValueError(param)
 
+    PARAMETERS_ORDER2 = {("alpha", "alpha"), ("alpha", "phi"), ("phi", "phi")}
+
+    def _d2form(self, p1, p2):
+        """second derivatives per degree^2 (epgpy/transition.py:203-247): with a = cos^2(alpha/2), w = cos(alpha),
+        B = sin^2(alpha/2) e^{2 i phi}, U = -i sin(alpha) e^{i phi} the pulse is linear in (a, w, B, U), hence so are
+        its derivatives"""
+        a, phi = self._ap()
+        z1, z2 = _cis_deg(phi), _cis_deg(phi, 2)
+        pair = Pair(p1, p2)
+        if pair == ("alpha", "alpha"):
+            B, U = 0.5 * np.cos(a) * z2, 1j * np.sin(a) * z1
+            return ("tgen", _cplx_block(-0.5 * np.cos(a) * DEG**2 + 0 * B.real, -np.cos(a) * DEG**2 + 0 * B.real, B * DEG**2, U * DEG**2))
+        if pair == ("alpha", "phi"):
+            B, U = 1j * np.sin(a) * z2, np.cos(a) * z1
+            return ("tgen", _cplx_block(0 * B.real, 0 * B.real, B * DEG**2, U * DEG**2))
+        if pair == ("phi", "phi"):
+            B, U = -4 * np.sin(a / 2) ** 2 * z2, 1j * np.sin(a) * z1
+            return ("tgen", _cplx_block(0 * B.real, 0 * B.real, B * DEG**2, U * DEG**2))
+        raise ValueError(pair)
+
     def _gform(self, param):
         """generator N = T^-1 dT/dparam, when it has a closed form: dT/dalpha = T . Rz(phi) Rx'(0) Rz(-phi), so a
         derivative injection can be done BEFORE the pulse (x_v += c N x_0) and the pulse then applied to all
@@ -620,11 +696,17 @@ class Phi(CombinableOperator):
             return np.stack([1j * z * DEG, -1j * z.conj() * DEG, 0 * z], axis=-1)
         return np.stack([z, z.conj(), 1 + 0 * z], axis=-1)
 
+    PARAMETERS_ORDER2 = {("phi", "phi")}
+
     def _form(self):
         return ScalarOp._diag_form(self._arrs(), None)
 
     def _dform(self, param):
         return ScalarOp._diag_form(self._arrs(True), None)
+
+    def _d2form(self, p1, p2):
+        z = np.atleast_1d(_cis_deg(self.phi))
+        return ScalarOp._diag_form(np.stack([-z * DEG**2, -z.conj() * DEG**2, 0 * z], axis=-1), None)
 
     def _dense(self):
         return "diag", self._arrs(), None
@@ -738,6 +820,41 @@ class E(_Evolution):
             return _diag_gen(rM.conj(), rM, 0 * rM, False)
         return None
 
+    PARAMETERS_ORDER2 = {("tau", "tau"), ("T1", "T1"), ("T2", "T2"), ("g", "g"), ("T1", "tau"), ("T2", "tau"), ("g", "tau"),
+                         ("T2", "g")}
+
+    def _d2form(self, p1, p2):
+        """second derivatives (epgpy/evolution.py:405-488); pairs outside PARAMETERS_ORDER2 vanish (T1 acts on Z only,
+        T2 and g on F+- only)"""
+        tau, T1, T2, g = self._params()
+        rT, rL = tau * (1 / T2 + 2j * np.pi * g), tau / T1
+        eM, e1 = np.exp(-rT), np.exp(-rL)  # factors of F- and Z
+        zero = 0 * (eM * e1)
+        pair = Pair(p1, p2)
+        fM = fZ = None
+        if pair == ("tau", "tau"):
+            fM, fZ = (rT / tau) ** 2 * eM, e1 / T1**2
+        elif pair == ("T1", "T1"):
+            fZ = e1 * (tau**2 / T1**4 - 2 * tau / T1**3)
+        elif pair == ("T2", "T2"):
+            fM = eM * (tau**2 / T2**4 - 2 * tau / T2**3)
+        elif pair == ("g", "g"):
+            fM = (-2j * np.pi * tau) ** 2 * eM
+        elif pair == ("T1", "tau"):
+            fZ = e1 * (1 - rL) / T1**2
+        elif pair == ("T2", "tau"):
+            fM = eM * (1 - rT) / T2**2
+        elif pair == ("g", "tau"):
+            fM = -2j * np.pi * (1 - rT) * eM
+        elif pair == ("T2", "g"):
+            fM = -2j * np.pi * (tau / T2) ** 2 * eM
+        else:
+            return None
+        fM = zero if fM is None else fM + zero
+        fZ = zero if fZ is None else fZ + zero
+        # the recovery term 1 - e1 differentiates to minus the Z factor
+        return ("diag", _cplx_block(np.conj(fM), fM, fZ + 0j, -fZ + 0j), bool(np.any(fZ != 0)))
+
     def _darrs(self, param):
         """first derivatives (epgpy/evolution.py:360-399)"""
         tau, T1, T2, g = self._params()
@@ -813,6 +930,21 @@ class P(_Evolution):
         rM = -2j * np.pi * (g if param == "tau" else tau) + 0 * (tau + g)
         return _diag_gen(rM.conj(), rM, 0 * rM, False)
 
+    PARAMETERS_ORDER2 = {("tau", "tau"), ("g", "g"), ("g", "tau")}
+
+    def _d2form(self, p1, p2):
+        """epgpy/evolution.py:331-355"""
+        tau, g = self._params()
+        eM = np.exp(-2j * np.pi * g * tau)
+        pair = Pair(p1, p2)
+        if pair == ("tau", "tau"):
+            fM = (-2j * np.pi * g) ** 2 * eM
+        elif pair == ("g", "g"):
+            fM = (-2j * np.pi * tau) ** 2 * eM
+        else:
+            fM = -2j * np.pi * (1 - 2j * np.pi * g * tau) * eM
+        return ("diag", _cplx_block(np.conj(fM), fM, 0 * fM, 0 * fM), False)
+
     def _darrs(self, param):
         """epgpy/evolution.py:313-328"""
         tau, g = self._params()
@@ -846,6 +978,15 @@ class R(_Evolution):
 
     def _form(self):
         return ScalarOp._diag_form(*self._arrs())
+
+    PARAMETERS_ORDER2 = {("rT", "rT"), ("rL", "rL"), ("r0", "r0")}
+
+    def _d2form(self, p1, p2):
+        """epgpy/evolution.py:283-310: the second derivative of e^{-r} is e^{-r}; mixed pairs vanish"""
+        if p1 != p2:
+            return None
+        d, d0 = self._darrs(p1)
+        return ScalarOp._diag_form(-d, None if d0 is None else -d0)
 
     def _darrs(self, param):
         """epgpy/evolution.py:263-280"""
@@ -1050,8 +1191,38 @@ class Jacobian(Probe):
 
 
 class Hessian(Probe):
-    def __init__(self, *args, **kwargs):
-        raise NotImplementedError("Hessian probe (epgpy/diff.py:419-476): second-order derivatives are not on the B200 hot path yet")
+    """probe returning the second derivatives of the signal (epgpy/diff.py:419-476): (..., nvar1, nvar2); a
+    'magnitude' entry in either list selects the first derivatives with respect to the other variable"""
+
+    def __init__(self, variables1, variables2=None, *, probe="F0"):
+        if probe not in ("F0", "Z0"):
+            raise NotImplementedError("Hessian probes 'F0' or 'Z0' only")
+        self.probe = probe
+        variables1 = variables1 if isinstance(variables1, list) else [variables1]
+        if not variables2:
+            variables2 = variables1
+        elif not isinstance(variables2, list):
+            variables2 = [variables2]
+        self.variables1, self.variables2 = list(variables1), list(variables2)
+        self.phase = self.reduce = self.weights = None
+        self.duration = 0
+        self.name = f"Hessian({probe})"
+
+    def __repr__(self):
+        return self.name
+
+    def pairs(self):
+        """unordered pairs of variables whose second derivatives this probe reads"""
+        return {Pair(a, b) for a in self.variables1 for b in self.variables2 if "magnitude" not in (a, b)}
+
+    def first(self):
+        """variables whose first derivatives this probe reads (partners of 'magnitude')"""
+        out = set()
+        if "magnitude" in self.variables1:
+            out |= set(self.variables2)
+        if "magnitude" in self.variables2:
+            out |= set(self.variables1)
+        return out - {"magnitude"}
 
 
 from .exchange import X  # noqa: E402  (needs Operator)

@@ -46,7 +46,7 @@
 extern "C" {
 #endif
 
-#define EPGX_VERSION 104 /* 0.1.4: epgx_simulate_state (final-state read-back), up to 4 exchange pools */
+#define EPGX_VERSION 105 /* 0.1.5: order-2 partial states (injection source sets, variable tiles), epgx_simulate_state, 4 pools */
 #define EPGX_MAX_DIMS 8
 #define EPGX_MAX_PATTERNS 64
 #define EPGX_MAX_POOLS 4
@@ -114,8 +114,9 @@ typedef enum {
 enum {
   EPGX_FLAG_BASE = 1 << 0,     /* apply to the base state                                      */
   EPGX_FLAG_PARTIALS = 1 << 1, /* apply (without affine term) to the order-1 partial states    */
-  /* derivative injection (diff.py:279-286): partial[aux] += form(base), affine term included,
-   * where `form` is the record's code and `base` the current (pre-operator) base state */
+  /* derivative injection (diff.py:279-286): partial[aux] += form(source), where `form` is the record's code and the
+   * source is the current (pre-operator) base state when aux1 == 0 (affine term included) or the partial state of
+   * variable aux1 - 1 (order-2 cross terms, diff.py:333-362: no affine term, partial states have no equilibrium) */
   EPGX_FLAG_INJECT = 1 << 2,
   EPGX_FLAG_G = 1 << 3,      /* E: precession phasor present                  */
   EPGX_FLAG_AFFINE = 1 << 4, /* E/DIAG/MATRIX: equilibrium term present       */
@@ -124,7 +125,12 @@ enum {
   EPGX_FLAG_PRE = 1 << 7,    /* FUSED: E_pre present                          */
   EPGX_FLAG_POST = 1 << 8,   /* FUSED: E_post present (in the CONT record)    */
   EPGX_FLAG_IM = 1 << 9,     /* FUSED: T is of the T_IM kind (else T_RE)      */
-  EPGX_FLAG_GEN = 1 << 10    /* FUSED: T is of the T_GEN kind: blk0 = (a, w, B.re, B.im, U.re, U.im) */
+  EPGX_FLAG_GEN = 1 << 10,   /* FUSED: T is of the T_GEN kind: blk0 = (a, w, B.re, B.im, U.re, U.im) */
+  /* with EPGX_FLAG_PARTIALS: restrict the record to the order-1 partial states (variables < nvar1) or to the
+   * order-2 ones (variables >= nvar1): an operator is applied to the order-2 states, then their injections are made
+   * from the PRE-operator order-1 states, then the order-1 states follow (diff.py:119-131) */
+  EPGX_FLAG_P1 = 1 << 11,
+  EPGX_FLAG_P2 = 1 << 12
 };
 
 /* tape record, 32 bytes */
@@ -183,9 +189,15 @@ typedef struct {
   int32_t init_n;    /* highest order of the initial state */
   int32_t nadc;      /* rows of `signal`   */
   int32_t njac;      /* rows of `jacobian` */
-  int32_t nvar;      /* order-1 variables (0 = forward only) */
+  int32_t nvar;      /* partial state sets: order-1 variables, then order-2 pairs of variables (0 = forward only) */
   int32_t max_order; /* highest configuration order of the whole tape */
-  int32_t rsv[3];
+  int32_t nvar1;     /* order-1 variables among them (0: all of them) */
+  int32_t rsv[2];
+  /* variable tiles of the shared-memory kernel: tile i keeps the partial states tiles[3 i .. 3 i + 2] (-1: empty slot)
+   * resident next to the base state; an injection's source must sit in the tile of its target -- a pair tile is
+   * (a, b, ab).  ntile == 0: consecutive variables (order-1 tapes). */
+  int32_t ntile;
+  const int32_t *tiles;
 } epgx_tape;
 
 typedef struct epgx_plan epgx_plan;

@@ -47,9 +47,11 @@ def _arr(x):
     return None if x is None else np.asarray(x)
 
 
-def T(alpha, phi, order1=None, duration=0.0):
-    """RF pulse (epgpy/transition.py:7-65). order1: {var: {'alpha'|'phi': coeff}}"""
-    return Op(kind="T", alpha=_arr(alpha), phi=_arr(phi), order1=_parse_order1(order1, ("alpha", "phi")), duration=duration)
+def T(alpha, phi, order1=None, order2=None, duration=0.0):
+    """RF pulse (epgpy/transition.py:7-65). order1: {var: {'alpha'|'phi': coeff}};
+    order2: {(var1, var2): {param: second derivative of the parameter w.r.t. the pair}} (diff.py:225-227), usually empty"""
+    return Op(kind="T", alpha=_arr(alpha), phi=_arr(phi), order1=_parse_order1(order1, ("alpha", "phi")),
+              order2=_parse_order2(order2), duration=duration)
 
 
 def Phi(phi, order1=None, duration=0.0):
@@ -57,12 +59,12 @@ def Phi(phi, order1=None, duration=0.0):
     return Op(kind="Phi", phi=_arr(phi), order1=_parse_order1(order1, ("phi",)), duration=duration)
 
 
-def E(tau, T1, T2, g=0.0, order1=None, duration=0.0):
+def E(tau, T1, T2, g=0.0, order1=None, order2=None, duration=0.0):
     """relaxation/precession/recovery (epgpy/evolution.py:69-153)"""
     if duration is True:
         duration = tau
     return Op(kind="E", tau=_arr(tau), T1=_arr(T1), T2=_arr(T2), g=_arr(g),
-              order1=_parse_order1(order1, ("tau", "T1", "T2", "g")), duration=duration)
+              order1=_parse_order1(order1, ("tau", "T1", "T2", "g")), order2=_parse_order2(order2), duration=duration)
 
 
 def P(tau, g, order1=None, duration=0.0):
@@ -129,6 +131,14 @@ def MATRIX(mat, mat0=None, dmats=None, order1=None, duration=0.0):
     dmats = dmats or {}
     return Op(kind="MATRIX", mat=np.asarray(mat, dtype=complex), mat0=None if mat0 is None else np.asarray(mat0, dtype=complex),
               dmats=dmats, order1=_parse_order1(order1, tuple(dmats)), duration=duration)
+
+
+def _parse_order2(order2):
+    """{(var1, var2): {param: coeff}} with sorted pairs (epgpy/diff.py:225-227, 534-540); other spellings of the
+    keyword only SELECT pairs in the reference and carry no coefficient"""
+    if not isinstance(order2, dict):
+        return {}
+    return {tuple(sorted(pair)): dict(c) for pair, c in order2.items() if c}
 
 
 def _parse_order1(order1, parameters):
@@ -272,6 +282,72 @@ def rf_matrix_dphi(alpha, phi):
     """epgpy/transition.py:165-169"""
     alpha, phi = _pair(alpha, phi)
     return rot_z_d(phi) @ rot_x(alpha) @ rot_z(-phi) - rot_z(phi) @ rot_x(alpha) @ rot_z_d(-phi)
+
+
+def rot_x_d2(alpha):
+    """epgpy/transition.py:223-237 (per degree^2)"""
+    a = DEG * np.atleast_1d(alpha)
+    m = np.empty(a.shape + (3, 3), dtype=complex)
+    s, c = np.sin(a), np.cos(a)
+    m[..., 0, 0], m[..., 0, 1], m[..., 0, 2] = -0.5 * c, 0.5 * c, 1j * s
+    m[..., 1, 0], m[..., 1, 1], m[..., 1, 2] = 0.5 * c, -0.5 * c, -1j * s
+    m[..., 2, 0], m[..., 2, 1], m[..., 2, 2] = 0.5j * s, -0.5j * s, -c
+    return m * DEG**2
+
+
+def rot_z_d2(phi):
+    """epgpy/transition.py:240-247 (per degree^2)"""
+    p = DEG * np.atleast_1d(phi)
+    m = np.zeros(p.shape + (3, 3), dtype=complex)
+    m[..., 0, 0], m[..., 1, 1] = -np.exp(1j * p), -np.exp(-1j * p)
+    return m * DEG**2
+
+
+def rf_matrix_d2(alpha, phi, p1, p2):
+    """second derivatives of the RF pulse (epgpy/transition.py:203-220)"""
+    alpha, phi = _pair(alpha, phi)
+    pair = tuple(sorted((p1, p2)))
+    if pair == ("alpha", "alpha"):
+        return rot_z(phi) @ rot_x_d2(alpha) @ rot_z(-phi)
+    if pair == ("alpha", "phi"):
+        return rot_z_d(phi) @ rot_x_d(alpha) @ rot_z(-phi) - rot_z(phi) @ rot_x_d(alpha) @ rot_z_d(-phi)
+    if pair == ("phi", "phi"):
+        return (rot_z_d2(phi) @ rot_x(alpha) @ rot_z(-phi) + rot_z(phi) @ rot_x(alpha) @ rot_z_d2(-phi)
+                - 2 * rot_z_d(phi) @ rot_x(alpha) @ rot_z_d(-phi))
+    raise ValueError(pair)
+
+
+def relax_d2(p1, p2, tau, T1, T2, g=0.0):
+    """second derivatives of E: (d2arr, d2arr0) or None when the pair vanishes (epgpy/evolution.py:405-488)"""
+    tau, T1, T2, g = _e_params(tau, T1, T2, g)
+    rT = tau * (1 / T2 + 2j * np.pi * g)
+    rL = tau / T1
+    pair = tuple(sorted((p1, p2)))
+    arr, arr0 = evolution_arrays(rT, rL, rL)
+    fM = fZ = None
+    if pair == ("tau", "tau"):
+        fM, fZ = (rT / tau) ** 2, 1 / T1**2
+    elif pair == ("T1", "T1"):
+        fZ = tau**2 / T1**4 - 2 * tau / T1**3
+    elif pair == ("T2", "T2"):
+        fM = tau**2 / T2**4 - 2 * tau / T2**3
+    elif pair == ("g", "g"):
+        fM = (-2j * np.pi * tau) ** 2
+    elif pair == ("T1", "tau"):
+        fZ = (1 - rL) / T1**2
+    elif pair == ("T2", "tau"):
+        fM = (1 - rT) / T2**2
+    elif pair == ("g", "tau"):
+        fM = -2j * np.pi * (1 - rT)
+    elif pair == ("T2", "g"):
+        fM = -2j * np.pi * (tau / T2) ** 2
+    else:
+        return None
+    arr[..., 1] = 0 if fM is None else arr[..., 1] * fM
+    arr[..., 0] = arr[..., 1].conj()
+    arr[..., 2] = 0 if fZ is None else arr[..., 2] * fZ
+    arr0[..., 2] = -arr[..., 2]
+    return arr, (arr0 if fZ is not None else None)
 
 
 def evolution_arrays(rT, rL, r0=None):
@@ -591,6 +667,8 @@ class _Sim:
         self.grid = tuple(grid)
         self.states, self.eq = new_states(grid, init, density)
         self.partials = {}
+        self.partials2 = {}  # (var1, var2) sorted -> second-order partial state
+        self.pairs = []      # the pairs to propagate (those the Hessian asks for)
         self.max_nstate = max_nstate
         self.kvalue = kvalue
         self.kvec = kvec  # base shift vector (collinear n-d shifts) or None
@@ -600,10 +678,14 @@ class _Sim:
         yield None, self.states
         for v in self.partials:
             yield v, self.partials[v]
+        for pair in self.partials2:
+            yield pair, self.partials2[pair]
 
     def set(self, v, s):
         if v is None:
             self.states = s
+        elif isinstance(v, tuple):
+            self.partials2[v] = s
         else:
             self.partials[v] = s
 
@@ -647,6 +729,15 @@ def _linear_coeffs(op):
     raise ValueError(k)
 
 
+def _second_coeffs(op, p1, p2):
+    """(d2, d2_0) of a differentiable operator w.r.t. a pair of its parameters, None if it vanishes"""
+    if op.kind == "T":
+        return rf_matrix_d2(op.alpha, op.phi, p1, p2), None
+    if op.kind == "E":
+        return relax_d2(p1, p2, op.tau, op.T1, op.T2, op.g)
+    raise NotImplementedError(f"second derivatives of {op.kind}")
+
+
 def combine(op1, op2):
     """`op1 @ op2`: one 3x3 operator equal to op1 followed by op2, affine terms included
     (epgpy/operator.py:219-241, opmatrix.py:89-135,173-187; forward part only)"""
@@ -677,6 +768,40 @@ def _apply_linear(sim, op):
     app = apply_matrix if form == "mat" else apply_diag
     nd = len(sim.grid)
     base = sim.states
+
+    def scaled(part, coeff):
+        coeff = np.asarray(coeff)
+        if coeff.ndim:
+            coeff = _left(coeff, nd)[..., None, None]
+        return part * coeff
+
+    # 0. second-order partials (epgpy/diff.py:290-378 with every cross term, i.e. `auto_cross_derivatives`), from the
+    #    PRE-operator base and first-order states:
+    #    x_ab <- Op x_ab + sum_p c_ap dOp_p x_b + sum_p c_bp dOp_p x_a + sum_pq c_ap c_bq d2Op_pq x_0 + sum_p c2_ab,p dOp_p x_0
+    for a, b in sim.pairs:
+        acc = None
+        for src, var in ((b, a), (a, b)):  # a == b: both terms, hence the factor 2 of diff.py:349-362
+            if var in op.order1 and src in sim.partials:
+                for p_, coeff in op.order1[var].items():
+                    part = scaled(app(sim.partials[src], dcoef[p_][0]), coeff)
+                    acc = part if acc is None else acc + part
+        if a in op.order1 and b in op.order1:
+            for p_, ca in op.order1[a].items():
+                for q_, cb in op.order1[b].items():
+                    d2 = _second_coeffs(op, p_, q_)
+                    if d2 is None:
+                        continue
+                    part = scaled(scaled(app(base, d2[0], sim.eq, d2[1]), ca), cb)
+                    acc = part if acc is None else acc + part
+        for p_, c2 in (op.order2 or {}).get((a, b), {}).items():
+            d, d0 = dcoef[p_] if p_ in dcoef else _linear_coeffs(Op(op, order1={"_": {p_: 1}}))[3][p_]
+            part = scaled(app(base, d, sim.eq, d0), c2)
+            acc = part if acc is None else acc + part
+        if (a, b) in sim.partials2:
+            prev = app(sim.partials2[(a, b)], c)
+            sim.partials2[(a, b)] = prev if acc is None else prev + np.broadcast_to(acc, prev.shape)
+        elif acc is not None:
+            sim.partials2[(a, b)] = np.broadcast_to(acc, base.shape).copy()
     # 1. propagate the existing partials (their equilibrium is zero: no affine term)
     for v in list(sim.partials):
         sim.partials[v] = app(sim.partials[v], c, inplace=True)
@@ -778,10 +903,11 @@ def _apply_exchange(sim, op, propagate):
 
 
 def simulate(seq, *, init=None, density=1.0, max_nstate=None, kvalue=1.0, kvec=None,
-             jacobian=None, jacobian_probe=None, propagate_nondiff=False, adc_time=False, grid=None):
+             jacobian=None, jacobian_probe=None, hessian=None, propagate_nondiff=False, adc_time=False, grid=None):
     """forward simulation: values (nADC, *grid) complex128   (epgpy/functions.py:50-192)
 
     jacobian: list of variable names -> also returns (nADC, *grid, nvars)  (epgpy/diff.py:384-416)
+    hessian: (variables1, variables2) -> also returns (nADC, *grid, nvars1, nvars2)  (epgpy/diff.py:419-476)
     propagate_nondiff: False reproduces the reference, whose D / X / SPOILER / RESET / PD never
         touch the partial states (operator.py:96-104); True applies them to the partials too
         (the mathematically correct chain rule, which the CUDA path implements).
@@ -796,7 +922,10 @@ def simulate(seq, *, init=None, density=1.0, max_nstate=None, kvalue=1.0, kvec=N
         shape = broadcast_left(shape, np.shape(init)[:-2])
     sim = _Sim(shape, init, density, max_nstate, kvalue, kvec)
     nd = len(shape)
-    values, jacs, times, tic = [], [], [], 0
+    if hessian is not None:
+        v1s, v2s = hessian
+        sim.pairs = sorted({tuple(sorted((a, b))) for a in v1s for b in v2s if "magnitude" not in (a, b)})
+    values, jacs, hesss, times, tic = [], [], [], [], 0
     for op in seq:
         kind = op.kind
         if kind in ("T", "Phi", "E", "P", "R", "MATRIX"):
@@ -818,6 +947,8 @@ def simulate(seq, *, init=None, density=1.0, max_nstate=None, kvalue=1.0, kvec=N
             sim.states = np.broadcast_to(sim.eq, sim.grid + (1, 3)).copy()
             for v in list(sim.partials):
                 sim.partials[v] = resize(sim.partials[v], 0) if not propagate_nondiff else 0 * sim.states
+            for v in list(sim.partials2):
+                sim.partials2[v] = resize(sim.partials2[v], 0) if not propagate_nondiff else 0 * sim.states
         elif kind == "PD":
             n = nstate(sim.states)
             eq = np.zeros(sim.grid + (2 * n + 1, 3), dtype=complex)
@@ -847,8 +978,25 @@ def simulate(seq, *, init=None, density=1.0, max_nstate=None, kvalue=1.0, kvec=N
                     else:
                         cols.append(np.zeros(sim.grid, dtype=complex) * _acquire(sim.states, op, attr))
                 jacs.append(np.stack(np.broadcast_arrays(*cols), axis=-1))
+            if hessian is not None:
+                attr = jacobian_probe or "F0"
+                zero = np.zeros(sim.grid, dtype=complex)
+                rows = []
+                for a in hessian[0]:
+                    cols = []
+                    for b in hessian[1]:
+                        if a == "magnitude" or b == "magnitude":  # first derivatives w.r.t. the other one (diff.py:451-464)
+                            v = b if a == "magnitude" else a
+                            st = sim.partials.get(v)
+                        else:
+                            st = sim.partials2.get(tuple(sorted((a, b))))
+                        cols.append(zero if st is None else np.broadcast_to(_acquire(st, op, attr), sim.grid))
+                    rows.append(np.stack(cols, axis=-1))
+                hesss.append(np.stack(rows, axis=-2))
     out = np.asarray(values)
     res = (out,) if jacobian is None else (out, np.asarray(jacs))
+    if hessian is not None:
+        res = res + (np.asarray(hesss),)
     if adc_time:
         res = (np.asarray(times),) + res
     return res[0] if len(res) == 1 else res

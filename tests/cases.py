@@ -373,6 +373,48 @@ def _fisp_jac_seq(epg, fa, tr, T1, T2, B1):
     return seq
 
 
+def hessian_ssfp(epg, ntr=6):
+    """order-2 forward mode (epgpy/diff.py:290-378; reference test/test_diff.py:334-468): every differentiable
+    operator carries order2=True, the Hessian probe picks pairs of variables and, through 'magnitude', first derivatives"""
+    T2 = np.array([30.0, 50.0, 80.0])
+    B1 = np.array([[0.8, 1.1]])
+    seq = [epg.T(90, 90)]
+    for i in range(ntr):
+        seq += [epg.T((20 + 3 * i) * B1, 90 + 10 * i, order1=True, order2=True), epg.E(5, 1e3, T2, 0.01, order1=True, order2=True),
+                epg.S(1), epg.ADC]
+    return dict(seq=seq, hessian=(["alpha", "T2", "magnitude", "g"], ["T2", "phi", "tau", "alpha", "T1"]))
+
+
+def hessian_fisp(epg, ntr=20):
+    """FISP with global variables (B1 through a chain-rule coefficient, T1, T2): the Hessian of the dictionary atoms"""
+    fa, tr = _fisp_schedule(ntr)
+    T1 = np.linspace(300, 3000, 2)
+    T2 = np.linspace(20, 300, 3)[None, :]
+    B1 = np.linspace(0.7, 1.2, 2)[None, None, :]
+    # (pairs spelled out: the reference's list-of-names spelling of `order2` raises, diff.py:214)
+    pe = [("T1", "T1"), ("T1", "T2"), ("T2", "T2"), ("B1", "T1"), ("B1", "T2")]
+    pt = [("B1", "B1"), ("B1", "T1"), ("B1", "T2")]
+    seq = [epg.T(180, 0), epg.E(20, T1, T2, order1=["T1", "T2"], order2=pe)]
+    for i in range(ntr):
+        seq.append([epg.T(fa[i] * B1, 90, order1={"B1": {"alpha": fa[i]}}, order2=pt),
+                    epg.E(3, T1, T2, order1=["T1", "T2"], order2=pe), epg.ADC,
+                    epg.E(tr[i] - 3, T1, T2, order1=["T1", "T2"], order2=pe), epg.S(1)])
+    v = ["B1", "T1", "T2"]
+    return dict(seq=seq, hessian=(v, v), options={"max_nstate": 12})
+
+
+HESSIAN_CASES = {"hessian_ssfp": hessian_ssfp, "hessian_fisp": hessian_fisp}
+
+
+def run_hessian(epg, case, simulate=None, **extra):
+    """(signal, hessian) of a HESSIAN_CASES entry with a reference-compatible API"""
+    simulate = simulate or epg.simulate
+    opts = dict(case.get("options") or {})
+    opts.update(extra)
+    sig, hes = simulate(case["seq"], probe=[None, epg.Hessian(*case["hessian"])], **opts)
+    return np.asarray(sig), np.asarray(hes)
+
+
 def probe_expr(epg):
     """`probe=` expressions over F0 / Z0 superseding the in-sequence ADCs (probe.py:7-66; functions.py:118-127)"""
     case = misc_ops(epg)

@@ -61,6 +61,12 @@ def main():
     print(f"fisp_equal_axes      signal {sig.shape} jac {jac.shape}; the reference's own vectorised run differs by "
           f"{np.abs(vec - sig).max() / np.abs(sig).max():.3f} (relative)")
 
+    # ---- order-2 derivatives: Hessian probes
+    for name, fn in cases.HESSIAN_CASES.items():
+        sig, hes = cases.run_hessian(ns, fn(ns))
+        np.savez_compressed(os.path.join(HERE, f"{name}.npz"), signal=sig, hessian=hes)
+        print(f"{name:20s} signal {sig.shape} hessian {hes.shape}")
+
     # ---- `probe=` expressions
     case = cases.probe_expr(ns)
     vals = epgpy.simulate(case["seq"], probe=case["probe"])

@@ -80,13 +80,15 @@ def run(low, stream=None):
             code, flags, aux, aux1 = int(rec["code"]), int(rec["flags"]), int(rec["aux"]), int(rec["aux1"])
             off, pat = rec["off"], rec["pat"]
             sets = []
+            nvar1 = getattr(low, "nvar1", low.nvar)
             if flags & L.F_INJECT:
                 sets = ["inject"]
             else:
                 if flags & L.F_BASE:
                     sets.append(0)
-                if flags & L.F_PARTIALS:
-                    sets += list(range(1, nset))
+                if flags & L.F_PARTIALS:  # P1 / P2: order-1 / order-2 partial states only
+                    sets += [s for s in range(1, nset) if not ((flags & L.F_P1) and s - 1 >= nvar1)
+                             and not ((flags & L.F_P2) and s - 1 < nvar1)]
             if na <= 0 and code != L.OP_PD:
                 return
             p, m, z = P[..., :na], M[..., :na], Z[..., :na]  # views [natoms, npool, nset, na]
@@ -94,10 +96,10 @@ def run(low, stream=None):
             def linear(fn, affine):
                 """fn(p, m, z) -> (p', m', z') on [natoms, npool, na]; affine: (ap, am, az) at k = 0"""
                 for s in sets:
-                    src = 0 if s == "inject" else s
+                    src = aux1 if s == "inject" else s  # injection source: 0 = base state, 1 + v = partial state v
                     o = fn(p[:, :, src], m[:, :, src], z[:, :, src])
                     o = [np.array(x) for x in o]
-                    if affine is not None and (s == "inject" or s == 0) and (flags & L.F_AFFINE):
+                    if affine is not None and src == 0 and (flags & L.F_AFFINE):
                         for x, a in zip(o, affine):
                             x[..., 0] += a
                     if s == "inject":

@@ -61,6 +61,23 @@ def test_equal_axes_grid_matches_per_atom_reference_runs(dtype, golden, epg):
         assert rel_err(jac[..., i], ref["jacobian"][..., i]) < (tol if dtype == "float64" else 5 * tol)
 
 
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+@pytest.mark.parametrize("name", sorted(cases.HESSIAN_CASES))
+def test_order2_hessian_matches_reference(name, dtype, golden, epg):
+    """order-2 forward mode on the device (pair tiles of the shared-memory kernel) against the reference's Hessian probe"""
+    ref = golden(name)
+    sig, hes = cases.run_hessian(epg, cases.HESSIAN_CASES[name](epg), dtype=dtype)
+    tol = RTOL64 if dtype == "float64" else RTOL32
+    assert rel_err(sig, ref["signal"]) < tol
+    want = ref["hessian"]
+    for i in range(want.shape[-2]):
+        for j in range(want.shape[-1]):
+            col = want[..., i, j]
+            if dtype == "float64" or np.abs(col).max() > 1e-9 * np.abs(want).max():
+                scale = max(np.abs(col).max(), 1e-300)
+                assert np.abs(hes[..., i, j] - col).max() / scale < (tol if dtype == "float64" else 20 * tol) or np.abs(col).max() < 1e-14
+
+
 def test_probe_expressions(golden, epg):
     ref = golden("probe_expr")
     case = cases.probe_expr(epg)

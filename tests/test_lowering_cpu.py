@@ -49,6 +49,24 @@ def test_equal_axes_grid(golden):
     assert rel_err(sig, ref["signal"]) < RTOL64 and rel_err(jac, ref["jacobian"]) < RTOL64
 
 
+@pytest.mark.parametrize("name", sorted(cases.HESSIAN_CASES))
+def test_order2_hessian(name, golden):
+    """order-2 partial states as further state sets of the tape (pair tiles, injections sourced from order-1 states,
+    P1 / P2 records) against the reference's Hessian probe"""
+    ref = golden(name)
+    epg = product_namespace()
+    sig, hes = cases.run_hessian(epg, cases.HESSIAN_CASES[name](epg), simulate=interp_simulate)
+    assert rel_err(sig, ref["signal"]) < RTOL64 and rel_err(hes, ref["hessian"]) < RTOL64
+    from epgpy_b200 import lowering
+
+    case = cases.HESSIAN_CASES[name](epg)
+    low = lowering.lower(case["seq"], probe=[None, epg.Hessian(*case["hessian"])], options=dict(case.get("options") or {}))
+    assert low.nvar == low.nvar1 + len(low.pairs) and len(low.tiles) >= len(low.pairs)
+    for (a, b), tile in zip(low.pairs, low.tiles):  # a pair tile holds (a, b, ab): sources and target resident together
+        ia, ib, iab = low.variables.index(a), low.variables.index(b), low.nvar1 + low.pairs.index((a, b))
+        assert {ia, ib, iab} <= set(int(x) for x in tile)
+
+
 def test_probe_expressions(golden):
     """probe=[...] expressions over F0 / Z0 supersede the in-sequence ADCs but keep their phase compensation"""
     ref = golden("probe_expr")

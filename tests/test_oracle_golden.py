@@ -42,6 +42,17 @@ def test_equal_axes_grid_matches_per_atom_reference_runs(golden):
     assert rel_err(sig, ref["signal"]) < RTOL and rel_err(jac, ref["jacobian"]) < RTOL
 
 
+@pytest.mark.parametrize("name", sorted(cases.HESSIAN_CASES))
+def test_order2_hessian_matches_reference(name, golden):
+    """order-2 forward mode of the oracle (every cross term, diff.py:290-378) against the reference's Hessian probe"""
+    ref = golden(name)
+    case = cases.HESSIAN_CASES[name](oracle_api.epg)
+    opts = dict(case.get("options") or {})
+    sig, hes = O.simulate(case["seq"], hessian=case["hessian"], max_nstate=opts.get("max_nstate"))
+    assert rel_err(sig, ref["signal"]) < RTOL
+    assert rel_err(hes, ref["hessian"]) < RTOL
+
+
 def test_oracle_as_fast_as_the_reference_it_stands_for():
     """the oracle applies operators in place like the reference (opscalar.py:222-232, opmatrix.py:208-221): on the
     bench's own CPU sample (4 x 3 x 5 atoms of the FISP grid) it may not be more than 1.2 x slower than the unmodified
