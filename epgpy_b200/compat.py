@@ -25,20 +25,33 @@ def _order1(op):
     return {var: dict(pc) for var, pc in o1.items()} or False
 
 
+def _order2(op):
+    """{(var1, var2): {param: coeff2}} of the reference operator; a pair without coefficient only SELECTS the pair in the
+    reference (here the Hessian probe selects) but must stay listed so that `order2=` alone still names variables"""
+    o2 = getattr(op, "order2", None) or {}
+    if not isinstance(o2, dict):
+        o2 = {pair: {} for pair in o2}
+    return {tuple(pair): dict(c) for pair, c in o2.items()} or False
+
+
+def _diff(op):
+    return dict(order1=_order1(op), order2=_order2(op))
+
+
 def _convert(op):
     name = type(op).__name__
     dur = getattr(op, "duration", 0)
     dur = getattr(op, "_duration", dur) if getattr(op, "_duration", None) is True else dur
     if name in ("T", "Tx", "Ty"):
-        return ops.T(op.alpha, op.phi, order1=_order1(op), duration=dur, name=op.name)
+        return ops.T(op.alpha, op.phi, **_diff(op), duration=dur, name=op.name)
     if name == "Phi":
-        return ops.Phi(op.phi, order1=_order1(op), duration=dur, name=op.name)
+        return ops.Phi(op.phi, **_diff(op), duration=dur, name=op.name)
     if name == "E":
-        return ops.E(op.tau, op.T1, op.T2, op.g, order1=_order1(op), duration=dur, name=op.name)
+        return ops.E(op.tau, op.T1, op.T2, op.g, **_diff(op), duration=dur, name=op.name)
     if name == "P":
-        return ops.P(op.tau, op.g, order1=_order1(op), duration=dur, name=op.name)
+        return ops.P(op.tau, op.g, **_diff(op), duration=dur, name=op.name)
     if name == "R":
-        return ops.R(op.rT, op.rL, r0=op.r0, order1=_order1(op), duration=dur, name=op.name)
+        return ops.R(op.rT, op.rL, r0=op.r0, **_diff(op), duration=dur, name=op.name)
     if name == "S":
         k = op.k if isinstance(op.k, (int, np.integer)) else np.asarray(op.k)
         return ops.S(k, nmax=op.nmax, duration=dur, name=op.name)
@@ -50,6 +63,8 @@ def _convert(op):
         return ops.Adc(op.attr, phase=op.phase, reduce=op.reduce, weights=op.weights, name=op.name)
     if name == "Jacobian":
         return ops.Jacobian(list(op.variables), probe=op.probe)
+    if name == "Hessian":
+        return ops.Hessian(list(op.variables1), list(op.variables2), probe=op.probe)
     if name == "Probe":
         expr = getattr(op, "_expr", None)
         if expr is None:

@@ -123,3 +123,47 @@ def test_reference_sequence_layer_runs_unchanged_on_the_engine_path(engine, ref,
     assert rel_err(got_sig, want_sig) < RTOL64
     assert rel_err(got[0], want[0]) < RTOL64 and rel_err(got[1], want[1]) < RTOL64
     assert np.allclose(got_crlb, want_crlb, rtol=1e-8)
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+def test_reference_hessian_and_crlb_gradient_run_on_the_engine_path(engine, ref, monkeypatch):
+    """the reference's `Sequence.hessian` and `Sequence.crlb(..., gradient=...)` -- the inner loop of
+    its sequence optimisation (examples/differentiation/optim_mrf.py:127-149) -- with their one `simulate` call routed
+    through `compat.from_reference` + the lowering: order-2 partial states on the engine, CRLB and its gradient within
+    1e-8 of the reference's own."""
+    from epgpy_b200 import compat
+    from epgpy.sequence import Sequence, Variable, operators
+
+    T1, T2 = Variable("T1"), Variable("T2")
+    ntr = 12
+    alphas = [Variable(f"alpha_{i:02d}") for i in range(ntr)]
+    ops_ = [operators.T(180, 0), operators.E(20, T1, T2)]
+    for i in range(ntr):
+        ops_ += [operators.T(alphas[i], 90), operators.E(5, T1, T2), operators.ADC, operators.E(7, T1, T2), operators.S(1)]
+    seq = Sequence(ops_)
+    values = {"T1": 900.0, "T2": 70.0, **{f"alpha_{i:02d}": 15.0 + 3 * i for i in range(ntr)}}
+    avars = [f"alpha_{i:02d}" for i in range(ntr)]
+
+    want_h = seq.hessian(["T1", "T2"], avars, options={"max_nstate": 10})(values)
+    want_c = seq.crlb(["T1", "T2"], gradient=avars, options={"max_nstate": 10})(values)
+
+    calls = []
+    simulate = _engine_simulate(engine)
+
+    def routed(sequence, **kw):
+        calls.append(len(sequence))
+        probe = kw.pop("probe", None)
+        if probe is not None:
+            probe = [compat.from_reference(p) if p is not None else None for p in (probe if isinstance(probe, (list, tuple)) else [probe])]
+        kw.pop("asarray", None)
+        return simulate(compat.from_reference(sequence), probe=probe, **kw)
+
+    import epgpy.sequence as refseq
+
+    monkeypatch.setattr(refseq._functions, "simulate", routed)
+    got_h = seq.hessian(["T1", "T2"], avars, options={"max_nstate": 10})(values)
+    got_c = seq.crlb(["T1", "T2"], gradient=avars, options={"max_nstate": 10})(values)
+    assert calls
+    for g, w in zip(got_h, want_h):
+        assert rel_err(np.asarray(g), np.asarray(w)) < RTOL64
+    assert np.allclose(got_c[0], want_c[0], rtol=1e-8) and np.allclose(got_c[1], want_c[1], rtol=1e-8, atol=1e-8 * np.abs(want_c[1]).max())
