@@ -51,6 +51,18 @@ def cfg_fisp_pulse_jac(epg, ntr=1000, max_nstate=10):
     return seq, {"max_nstate": max_nstate}, names
 
 
+def cfg_optim_mrf(epg, ntr=400, max_nstate=10):
+    """the reference's sequence-optimisation inner loop (examples/differentiation/optim_mrf.py:96-149): ONE atom,
+    400 TRs, one flip-angle and one repetition-time variable per TR (800 variables), max_nstate = 10"""
+    fa, tr = bench.fisp_schedule(ntr)
+    names = [f"a{i:04d}" for i in range(ntr)] + [f"t{i:04d}" for i in range(ntr)]
+    seq = [epg.T(180, 0), epg.E(20, 1000.0, 80.0)]
+    for i in range(ntr):
+        seq.append([epg.T(fa[i], 90, order1={names[i]: "alpha"}), epg.E(3, 1000.0, 80.0), epg.ADC,
+                    epg.E(tr[i] - 3, 1000.0, 80.0, order1={names[ntr + i]: "tau"}), epg.S(1)])
+    return seq, {"max_nstate": max_nstate}, names
+
+
 def cfg_gre_diffusion(epg, ntr=500):
     T1 = np.linspace(400, 2000, 200)
     T2 = np.linspace(30, 200, 200)[None, :]
@@ -97,6 +109,7 @@ CONFIGS = {
     "C3_fisp_1M": cfg_fisp,
     "C3J_fisp_jac_B1_T1_T2_125k": lambda epg: cfg_fisp(epg, (50, 50, 50), 1000, jac=True),
     "C3J_fisp_pulse_jac_64_atoms_1000_vars": cfg_fisp_pulse_jac,
+    "C3J_optim_mrf_1_atom_800_vars_400_TR": cfg_optim_mrf,
     "C4_gre_diffusion_40k": cfg_gre_diffusion,
     "C5_mt_bssfp_20k": cfg_mt_bssfp,
     "C5J_mt_bssfp_pulse_jac_1616_atoms_200_vars": cfg_mt_bssfp_pulse_jac,

@@ -40,6 +40,7 @@ struct epgx_plan {
   int64_t natoms;
   double flops_cplx, flops_real, updates; // executed real flops per atom (complex / real-valued kernels)
   bool realjac_ok; // real-valued graph with real-valued derivative injections
+  bool pulsejac_ok = false; // ... whose variables are injected by exactly one record each (per-pulse variables)
   int64_t ntrj = 0; // whole-TR derivative groups (EPGX_OP_TRJ) in the merged stream
   bool bounded = false; // some segment truncates at max_nstate (EPGX_SEG_MASK_TOP)
   bool real_ok; // real-valued phase graph: eligible for the three-reals-per-order kernel
@@ -108,6 +109,22 @@ static int choose_variant(const epgx_plan *pl, epgx_config &c, int kernel, int l
     return fail(EPGX_ERR_UNSUPPORTED, "the real-valued derivative kernels need a real-valued tape with order-1 variables");
   if (kernel == 5 && t.nvar > 3)
     return fail(EPGX_ERR_UNSUPPORTED, "the warp-per-state-set derivative kernel holds at most three variables");
+  // ---- one thread per state set (epgx_pulsejac.cuh): per-pulse variables on bounded graphs
+  if (kernel == 6 && !(pl->pulsejac_ok && C <= 16))
+    return fail(EPGX_ERR_UNSUPPORTED, "the thread-per-state-set kernel needs a real-valued derivative tape of at most 16 orders "
+                                      "whose variables are injected once each");
+  if (pl->pulsejac_ok && C <= 16 && (kernel == 6 || (kernel == 0 && t.nvar >= 4))) {
+    c.kernel = 5;
+    c.lanes_per_atom = 1;
+    c.slots_per_lane = C <= 4 ? 4 : C <= 8 ? 8 : C <= 12 ? 12 : 16;
+    c.vars_per_pass = 128;
+    c.var_tiles = (t.nvar + 1 + 127) / 128;
+    c.atoms_per_cta = 1;
+    c.threads_per_cta = 128;
+    c.smem_bytes = 0;
+    c.ring = C;
+    return EPGX_OK;
+  }
   // ---- one warp per state set (epgx_setjac.cuh): whole-TR derivative groups, 32 NS orders.  Automatic choice when
   // most of the segments are such groups and the orders would not fit one warp of the orders-over-warps kernel
   if (pl->realjac_ok && t.nvar <= 3 && (kernel == 5 || (kernel == 0 && C > 128 && 2 * pl->ntrj >= t.nseg))) {
@@ -447,6 +464,14 @@ extern "C" int epgx_plan_create(const epgx_tape *t, epgx_plan **out) {
         if (((i - t->init_off) % 6) % 2 == 1 && t->coef[i] != 0.0) okj = false;
     }
     pl->realjac_ok = okj;
+    if (okj) { // every variable injected exactly once?
+      std::vector<int> ninj(t->nvar, 0);
+      for (int64_t i = 0; i < t->nop; ++i)
+        if (t->ops[i].flags & EPGX_FLAG_INJECT) ++ninj[t->ops[i].aux];
+      bool once = true;
+      for (int v = 0; v < t->nvar; ++v) once = once && ninj[v] == 1;
+      pl->pulsejac_ok = once;
+    }
   }
   {
     // merged stream: [SEG(open seg 0)] seg_0 seg_1 ... where every segment is emitted as
@@ -693,6 +718,8 @@ static int dispatch(const epgx_plan *pl, const epgx_config &c, const KParams &kp
   dim3 grid((unsigned)((kp.atom_count + c.atoms_per_cta - 1) / c.atoms_per_cta), (unsigned)c.var_tiles);
   cudaError_t e;
   switch (c.kernel) {
+  case 5: e = f64 ? launch_pulsejac<double>(c.slots_per_lane, kp, grid, c.threads_per_cta, c.smem_bytes, st)
+                  : launch_pulsejac<float>(c.slots_per_lane, kp, grid, c.threads_per_cta, c.smem_bytes, st); break;
   case 4: e = f64 ? launch_setjac<double>(c.slots_per_lane, kp, grid, c.threads_per_cta, c.smem_bytes, st)
                   : launch_setjac<float>(c.slots_per_lane, kp, grid, c.threads_per_cta, c.smem_bytes, st); break;
   case 3: e = f64 ? launch_realjac<double>(c.slots_per_lane, kp, grid, c.threads_per_cta, c.smem_bytes, st)

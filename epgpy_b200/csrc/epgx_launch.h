@@ -11,6 +11,7 @@ template <typename real> cudaError_t launch_reg(int slots, const KParams &kp, di
 template <typename real> cudaError_t launch_real(int slots, const KParams &kp, dim3 grid, int threads, int smem, cudaStream_t st);
 template <typename real> cudaError_t launch_realjac(int slots, const KParams &kp, dim3 grid, int threads, int smem, cudaStream_t st);
 template <typename real> cudaError_t launch_setjac(int slots, const KParams &kp, dim3 grid, int threads, int smem, cudaStream_t st);
+template <typename real> cudaError_t launch_pulsejac(int orders, const KParams &kp, dim3 grid, int threads, int smem, cudaStream_t st);
 constexpr int kTapeChunk = 64;      // == TAPE_CHUNK of epgx_reg.cuh (checked there)
 constexpr int kTrcPerWindow = 21;   // == TRC_PER_WINDOW
 constexpr int kTrcReals = 14;       // == TRC_REALS

@@ -85,8 +85,13 @@ def run_lowered(low, plan=None, device=None, atom_range=None, nchunk=None, keep_
 
     import torch
 
+    import os
+    import time
+
     engine.require_cuda()
+    t0 = time.perf_counter()
     plan = plan or engine.Plan(low)
+    t1 = time.perf_counter()
     devs = _devices(device)
     begin, count = atom_range if atom_range is not None else (0, low.natoms)
     if begin < 0 or count < 0 or begin + count > low.natoms:
@@ -96,6 +101,7 @@ def run_lowered(low, plan=None, device=None, atom_range=None, nchunk=None, keep_
     has_jac = bool(low.nvar and low.njac)
     sig_t = _host_buffer((low.nadc, count, low.npool), cdt) if low.nadc else None
     jac_t = _host_buffer((low.njac * low.nvar, count, low.npool), cdt) if has_jac else None
+    t2 = time.perf_counter()
     slabs = _split(begin, count, len(devs)) if count else []
     if nchunk is None:  # chunks of >= 32 MB of output, at most 16 per device
         per_dev = low.nbytes_out(natoms=-(-count // max(1, len(slabs)))) if slabs else 0
@@ -120,6 +126,9 @@ def run_lowered(low, plan=None, device=None, atom_range=None, nchunk=None, keep_
             t.join()
     if errors:
         raise errors[0]
+    if os.environ.get("EPGX_TIMING"):
+        print("epgx run: plan %.1f ms, host buffers %.1f ms, kernels + copies %.1f ms (%d chunks)" %
+              (1e3 * (t1 - t0), 1e3 * (t2 - t1), 1e3 * (time.perf_counter() - t2), nchunk), flush=True)
     sig_host = sig_t.numpy() if sig_t is not None else None
     jac_host = jac_t.numpy().reshape(low.njac, low.nvar, count, low.npool) if jac_t is not None else None
     return RunResult(sig_host, jac_host, [p for p in parts if p is not None]), plan
@@ -254,8 +263,13 @@ def simulate(sequence, *, adc_time=False, init=None, squeeze=False, probe=None, 
     if callback:
         raise NotImplementedError("`callback` needs the state matrix on the host after every operator; "
                                   "the fused device path has no such hook")
+    import os
+    import time
+
+    tm = [time.perf_counter()]
     low = lowering.lower(sequence, init=init, probe=probe, options=options, dtype=engine.norm_dtype(dtype),
                          propagate_nondiff=propagate_nondiff)
+    tm.append(time.perf_counter())
     LOGGER.info("Simulate sequence: num. operators: %d, shape: %s, max order: %d", len(low.ops), low.grid, low.max_order)
     atom_range = None
     if shard is not None:
@@ -263,7 +277,11 @@ def simulate(sequence, *, adc_time=False, init=None, squeeze=False, probe=None, 
 
         atom_range = sharding.slab(low.natoms, int(shard[0]), int(shard[1]))
     res, plan = run_lowered(low, device=device, atom_range=atom_range)
+    tm.append(time.perf_counter())
     values = _assemble(low, res, count=None if shard is None else atom_range[1], asarray=asarray)
+    tm.append(time.perf_counter())
+    if os.environ.get("EPGX_TIMING"):  # host-side breakdown of one call (ms): lowering | plan + upload + kernels + D2H | assembly
+        print("epgx simulate: lower %.1f ms, run %.1f ms, assemble %.1f ms" % tuple(1e3 * (b - a) for a, b in zip(tm, tm[1:])), flush=True)
     times = np.asarray(low.times) if asarray else low.times
     if len(values) == 1:
         values = values[0]

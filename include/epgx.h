@@ -207,7 +207,8 @@ typedef struct {
   int32_t kernel;         /* 0 = ring (state in shared memory), 1 = reg (state in registers), 2 = real (registers,
                              real-valued phase graphs: three reals per order), 3 = realjac (the same with
                              order-1 partial states, the orders of an atom over one or several warps),
-                             4 = setjac (the same, one warp per state set) */
+                             4 = setjac (the same, one warp per state set), 5 = pulsejac (the same for variables injected
+                             once each on bounded graphs: one thread per state set) */
   int32_t lanes_per_atom; /* G */
   int32_t slots_per_lane; /* reg kernel: orders held per lane */
   int32_t vars_per_pass;  /* partial states resident per atom */
@@ -232,7 +233,8 @@ int epgx_plan_config(const epgx_plan *plan, epgx_config *cfg);
 /* force a kernel variant (tuning / tests): a 0 / negative argument keeps the automatic choice;
  * kernel: 1 = ring (shared-memory state), 2 = reg (register state; forward, one pool only),
  * 3 = real (register state, real-valued phase graphs only), 4 = realjac (real-valued with partials, orders of an atom
- * over several warps), 5 = setjac (real-valued with at most three partials, one warp per state set) */
+ * over several warps), 5 = setjac (real-valued with at most three partials, one warp per state set), 6 = pulsejac
+ * (real-valued, at most 16 orders, every variable injected by one record: one thread per state set) */
 int epgx_plan_set_variant(epgx_plan *plan, int kernel, int lanes_per_atom, int vars_per_pass,
                           int atoms_per_cta);
 

@@ -533,3 +533,75 @@ def test_simulate_resumes_from_a_read_back_state(name, cut, golden, epg):
     assert mid.shape == tuple(grid)
     got = epg.simulate(tail, init=mid)
     assert rel_err(np.asarray(got), whole[nhead:]) < RTOL64
+
+
+# ------------------------------------------------------------------------------------------------ #
+# per-pulse variables: one thread per state set (epgx_pulsejac.cuh)
+# ------------------------------------------------------------------------------------------------ #
+
+
+def _pulse_sequence(epg, ntr, every=1, extras=True):
+    """FISP-like train with one flip-angle variable per pulse (examples/differentiation/optim_mrf.py:96-149), plus a few
+    TRs that are not of the plain form (negative shift, diffusion, spoiler, phase-compensated ADC, PD change)"""
+    fa, tr = cases._fisp_schedule(ntr)
+    T1 = np.linspace(300, 3000, 3)
+    T2 = np.linspace(20, 300, 4)[None, :]
+    names = []
+    seq = [epg.T(180, 90), epg.E(20, T1, T2)]
+    for i in range(ntr):
+        kw = {}
+        if i % every == 0:
+            names.append(f"a{i:04d}")
+            kw = dict(order1={names[-1]: "alpha"})
+        adc = epg.Adc(phase=30.0) if (extras and i == 9) else epg.ADC
+        seq += [epg.T(fa[i], 90 if i % 3 else 270, **kw), epg.E(3, T1, T2), adc, epg.E(tr[i] - 3, T1, T2),
+                epg.S(-1 if (extras and i == 13) else 1)]
+        if extras and i == 17:
+            seq += [epg.D(4.0, 1.2e-3, k=1)]
+        if extras and i == 21:
+            seq += [epg.SPOILER]
+        if extras and i == 25:
+            seq += [epg.PD(0.8, reset=False)]
+    return seq, names
+
+
+@pytest.mark.parametrize("dtype", ["f64", "f32"])
+@pytest.mark.parametrize("ntr,max_nstate,pre_inject", [(40, 10, True), (40, 3, True), (40, 15, False), (150, 7, True)])
+def test_pulsejac_kernel(ntr, max_nstate, pre_inject, dtype, epg):
+    """thread-per-state-set kernel against the shared-memory kernel and the oracle: signal + Jacobian with one variable
+    per pulse, D / SPOILER / negative shifts / PD in between, with and without derivative pre-injection"""
+    from epgpy_b200 import engine, functions, lowering
+
+    seq, names = _pulse_sequence(epg, ntr)
+    variables = ["magnitude"] + names
+
+    def run(kernel, dt):
+        low = lowering.lower(seq, probe=[None, epg.Jacobian(variables)], options={"max_nstate": max_nstate, "kvalue": 2500.0}, dtype=dt,
+                             propagate_nondiff=True, pre_inject=pre_inject)
+        plan = engine.Plan(low)
+        if kernel:
+            plan.set_variant(kernel=kernel)
+        res, _ = functions.run_lowered(low, plan=plan)
+        return functions._assemble(low, res), plan.config()
+
+    ring, _ = run(1, "f64")
+    got, cfg = run(0, dtype)  # the automatic choice
+    assert cfg["kernel"] == 5 and cfg["var_tiles"] == (len(names) + 1 + 127) // 128
+    tol = 1e-12 if dtype == "f64" else RTOL32
+    assert rel_err(got[0], ring[0]) < tol
+    for i in range(len(variables)):
+        col = ring[1][..., i]
+        assert np.abs(got[1][..., i] - col).max() <= (tol if dtype == "f64" else 5 * tol) * max(np.abs(ring[1]).max(), 1e-300)
+    oseq, _ = _pulse_sequence(oracle_api.epg, ntr)
+    rs, rj = oracle_api.O.simulate(oseq, jacobian=variables, kvalue=2500.0, max_nstate=max_nstate, propagate_nondiff=True)
+    assert rel_err(ring[0], rs) < RTOL64 and rel_err(ring[1], rj) < RTOL64
+
+
+def test_pulsejac_kernel_is_refused_for_repeated_variables(epg):
+    from epgpy_b200 import engine, lowering
+
+    case = cases.fisp_jac_global(epg)  # B1, T1, T2: injected at every operator
+    plan = engine.Plan(lowering.lower(case["seq"], probe=[None, epg.Jacobian(case["jac"])], options={"max_nstate": 8}))
+    assert plan.config()["kernel"] != 5
+    with pytest.raises(NotImplementedError):
+        plan.set_variant(kernel=6)
