@@ -5,7 +5,7 @@ derivatives) of py-baudin/epgpy: same operator API on the host, one fused CUDA k
 the device, reached through the C ABI of include/epgx.h (libepgx.so).  No CPU fallback.
 """
 
-from . import common, core, engine, exchange, functions, lowering, operators, sharding, statematrix, utils
+from . import common, core, engine, exchange, functions, lowering, operators, rfpulse, sharding, statematrix, utils
 from . import core as epg
 
 __version__ = "0.1.0"

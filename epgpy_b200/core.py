@@ -10,7 +10,7 @@ from .utils import Axes, get_wavenumber
 from .operators import (
     Operator, MultiOperator, EmptyOperator, Spoiler, Wait, Offset, Reset, PD, System,
     DiffOperator, MatrixOp, ScalarOp,
-    Probe, Adc, Jacobian, Hessian,
+    Probe, Adc, Jacobian, Hessian, PartialsPruner,
     E, P, R, T, Tx, Ty, Phi, S, D,
     ADC, NULL, SPOILER, RESET,
 )

@@ -260,9 +260,9 @@ def simulate(sequence, *, adc_time=False, init=None, squeeze=False, probe=None, 
     """
     if squeeze:
         raise NotImplementedError("Automatic sequence squeezing not implemented yet")
-    if callback:
+    if callback and not isinstance(callback, ops.PartialsPruner):
         raise NotImplementedError("`callback` needs the state matrix on the host after every operator; "
-                                  "the fused device path has no such hook")
+                                  "the fused device path has no such hook (a PartialsPruner is accepted: see its docstring)")
     import os
     import time
 

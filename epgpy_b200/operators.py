@@ -1225,4 +1225,22 @@ class Hessian(Probe):
         return out - {"magnitude"}
 
 
+class PartialsPruner:
+    """the reference's callback that drops partial states of negligible energy while a sequence runs
+    (epgpy/diff.py:479-527): a speed-for-accuracy trade of its CPU loop, where every live partial state costs a full pass
+    per operator.  On the device a partial state costs nothing before its injection (variables not yet injected are
+    skipped, csrc/epgx_ring.cuh `alive`; csrc/epgx_pulsejac.cuh) and is never dropped afterwards, so
+    `simulate(..., callback=PartialsPruner(...))` is accepted and returns the EXACT derivatives: they differ from the
+    reference's pruned ones by at most what the pruning itself discards (`condition`, relative to the state norm)."""
+
+    def __init__(self, *, condition=1e-5, variables=None):
+        if not (callable(condition) or np.isscalar(condition)):
+            raise TypeError(condition)
+        self.condition = condition
+        self.variables = set(variables) if variables else None
+
+    def __repr__(self):
+        return f"PartialsPruner({len(self.variables)} variables)" if self.variables else "PartialsPruner(all variables)"
+
+
 from .exchange import X  # noqa: E402  (needs Operator)

@@ -415,6 +415,19 @@ def run_hessian(epg, case, simulate=None, **extra):
     return np.asarray(sig), np.asarray(hes)
 
 
+def slice_profile(epg, nsample=41, nfreq=15):
+    """shaped RF pulse (rfpulse.py:37-197): a windowed sinc of 41 samples as a T / E chain over a frequency axis --
+    excitation profile (F0 and Z0) of a 60 degree pulse followed by a rephasing precession, with relaxation"""
+    t = np.linspace(-3, 3, nsample)
+    values = np.sinc(t) * np.hanning(nsample) * np.exp(1j * 0.3 * t)
+    freqs = np.linspace(-2.0, 2.0, nfreq)
+    pulse = epg.RFPulse(values, 4.0, alpha=60, phi=20.0, T1=900.0, T2=[[60.0], [120.0]], g=[freqs])
+    return dict(seq=[pulse, epg.P(-2.0, [freqs]), epg.ADC, epg.Adc("Z0")])
+
+
+CASES["slice_profile"] = slice_profile
+
+
 def probe_expr(epg):
     """`probe=` expressions over F0 / Z0 superseding the in-sequence ADCs (probe.py:7-66; functions.py:118-127)"""
     case = misc_ops(epg)
@@ -429,6 +442,9 @@ def namespace(pkg):
     core = pkg.core
     ns = types.SimpleNamespace(**{k: getattr(core, k) for k in dir(core) if not k.startswith("_")})
     ns.exchange_matrix = pkg.exchange.exchange_matrix
+    import importlib
+
+    ns.RFPulse = importlib.import_module(pkg.__name__ + ".rfpulse").RFPulse
     return ns
 
 

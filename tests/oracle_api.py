@@ -36,3 +36,45 @@ def run(case, **extra):
     if case.get("jac"):
         return np.asarray(res[0]), np.asarray(res[1])
     return np.asarray(res), None
+
+
+# ---- shaped RF pulse for the oracle (epgpy/rfpulse.py:104-197, 224-305): a plain list of oracle operators
+
+
+def _net_rotation(alphas, phis):
+    total = np.eye(3, dtype=complex)
+    for a, p in zip(alphas, phis):
+        total = O.rf_matrix(a, p)[0] @ total
+    return total
+
+
+def estimate_rf(values, alpha):
+    values = np.asarray(values, dtype=complex)
+    guess = alpha / 180.0 / np.abs(np.sum(values))
+    if np.all(np.isclose(np.diff(np.mod(np.angle(values, deg=True), 180)), 0, atol=1e-5)):
+        return guess
+    from scipy import optimize
+
+    eq = np.array([0, 0, 1], dtype=complex)
+    target = np.abs(O.rf_matrix(alpha, 90)[0] @ eq)
+    unit, phis = 180.0 * np.abs(values), np.angle(values, deg=True)
+    cost = lambda rf: float(np.sum((np.abs(_net_rotation(np.ravel(rf)[0] * unit, phis) @ eq) - target) ** 2))
+    return float(optimize.minimize(cost, guess, bounds=[(0, None)], tol=1e-8).x[0])
+
+
+def RFPulse(values, duration, *, rf=None, alpha=None, phi=None, T1=None, T2=None, g=None):
+    values = np.asarray(values, dtype=complex)
+    if rf is None:
+        rf = estimate_rf(values, alpha)
+    n = len(values)
+    seq = []
+    for v in values:
+        seq.append(O.T(180.0 * np.abs(v) * rf, np.angle(v, deg=True), duration=duration / n))
+        if not (T1 is None and T2 is None and g is None):
+            seq.append(O.E(duration / n, 1e10 if T1 is None else T1, 1e10 if T2 is None else T2, 0 if g is None else g))
+    if phi:
+        seq = [O.Phi(-phi)] + seq + [O.Phi(phi)]
+    return seq
+
+
+epg.RFPulse = RFPulse
