@@ -35,6 +35,8 @@ struct epgx_plan {
   std::vector<float> coef32;
   std::vector<int> pats; // [npattern][MAX_DIMS+1]
   std::vector<int> tiles; // [ntile][3] variables resident per tile of the shared-memory kernel (order-2 tapes)
+  std::vector<int> maps;  // gather maps of the lattice shifts
+  bool lattice = false;   // EPGX_SEG_LATTICE segments: the shared-memory kernel only
   bool order2 = false;    // injections from partial states / P1, P2 records: the shared-memory kernel only
   std::vector<epgx_op> stream; // segments + records merged (register kernel)
   int64_t natoms;
@@ -46,7 +48,7 @@ struct epgx_plan {
   bool real_ok; // real-valued phase graph: eligible for the three-reals-per-order kernel
   epgx_config cfg;
   // workspace layout (bytes)
-  int64_t off_ops, off_segs, off_pats, off_stream, off_tiles, off_coef, ws_bytes;
+  int64_t off_ops, off_segs, off_pats, off_stream, off_tiles, off_maps, off_coef, ws_bytes;
 };
 
 static const int kSmemLimit = 227 * 1024;
@@ -102,7 +104,7 @@ static int choose_variant(const epgx_plan *pl, epgx_config &c, int kernel, int l
   const epgx_tape &t = pl->tape;
   const int rsz = t.dtype == EPGX_F64 ? 8 : 4;
   const int C = t.max_order + 1;
-  const bool reg_ok = t.nvar == 0 && t.npool == 1;
+  const bool reg_ok = t.nvar == 0 && t.npool == 1 && !pl->lattice;
   if (kernel == 2 && !reg_ok)
     return fail(EPGX_ERR_UNSUPPORTED, "the register kernel runs forward simulations of one pool only");
   if ((kernel == 4 || kernel == 5) && !pl->realjac_ok)
@@ -258,7 +260,7 @@ static int choose_variant(const epgx_plan *pl, epgx_config &c, int kernel, int l
   }
   int64_t per_atom;
   for (;;) {
-    per_atom = (int64_t)(1 + nvt) * t.npool * 3 * C * 2 * rsz + (int64_t)t.npattern * 4;
+    per_atom = ((int64_t)(1 + nvt) * t.npool * 3 + (pl->lattice ? 1 : 0)) * C * 2 * rsz + (int64_t)t.npattern * 4;
     if (per_atom <= kSmemLimit - 1024 || nvt <= 1 || pl->order2) break;
     nvt = nvt == 3 ? 1 : 0;
   }
@@ -382,10 +384,24 @@ extern "C" int epgx_plan_create(const epgx_tape *t, epgx_plan **out) {
   double flops = 0, flops_r = 0, updates = 0;
   for (int64_t i = 0; i < t->nseg; ++i) {
     const epgx_segment &s = t->segs[i];
+    const bool lat = s.flags & EPGX_SEG_LATTICE;
     if (s.first < 0 || s.count < 0 || (int64_t)s.first + s.count > t->nop || s.nact < -1 || s.nact > t->max_order ||
-        s.shift < -1 || s.shift > 1 || s.n_old < 0 || s.n_new < s.n_old || s.n_new > t->max_order ||
-        s.n_new > s.n_old + 1)
+        s.n_old < 0 || s.n_new < 0 || s.n_new > t->max_order || s.n_old > t->max_order)
       return fail(EPGX_ERR_INVALID, "bad segment " + std::to_string(i));
+    if (!lat && (s.shift < -1 || s.shift > 1 || s.n_new < s.n_old || s.n_new > s.n_old + 1))
+      return fail(EPGX_ERR_INVALID, "bad segment " + std::to_string(i));
+    if (lat) {
+      if ((s.flags >> 16) < 0 || (s.flags >> 16) > s.n_old || (s.shift != 0 && s.shift != 2))
+        return fail(EPGX_ERR_INVALID, "bad lattice segment " + std::to_string(i));
+      if (s.shift == 2) {
+        const int64_t nn = s.n_new + 1;
+        if (!t->maps || s.rsv < 0 || (int64_t)s.rsv + 3 * nn > t->nmap)
+          return fail(EPGX_ERR_INVALID, "gather maps out of range in segment " + std::to_string(i));
+        for (int64_t j = 0; j < 3 * nn; ++j)
+          if (t->maps[s.rsv + j] < -1 || t->maps[s.rsv + j] > s.n_old)
+            return fail(EPGX_ERR_INVALID, "gather map refers to an unknown slot in segment " + std::to_string(i));
+      }
+    }
     for (int r = s.first; r < s.first + s.count; ++r) {
       const epgx_op &o = t->ops[r];
       if (o.code == EPGX_OP_FUSED && r + 1 >= s.first + s.count)
@@ -415,6 +431,9 @@ extern "C" int epgx_plan_create(const epgx_tape *t, epgx_plan **out) {
   }
   if (t->ntile) pl->tiles.assign(t->tiles, t->tiles + 3 * (size_t)t->ntile);
   pl->tape.tiles = nullptr;
+  if (t->nmap > 0 && t->maps) pl->maps.assign(t->maps, t->maps + t->nmap);
+  pl->tape.maps = nullptr;
+  for (const epgx_segment &sg : pl->segs) pl->lattice = pl->lattice || (sg.flags & EPGX_SEG_LATTICE);
   if (pl->tape.nvar1 == 0) pl->tape.nvar1 = t->nvar;
   pl->order2 = t->ntile > 0 || pl->tape.nvar1 < t->nvar;
   for (int64_t i = 0; i < t->nop; ++i)
@@ -426,7 +445,7 @@ extern "C" int epgx_plan_create(const epgx_tape *t, epgx_plan **out) {
     pl->pats[q * (EPGX_MAX_DIMS + 1) + EPGX_MAX_DIMS] = t->pool_stride[q];
   }
   {
-    bool ok = t->nvar == 0 && t->npool == 1;
+    bool ok = t->nvar == 0 && t->npool == 1 && !pl->lattice;
     for (int64_t i = 0; ok && i < t->nop; ++i) {
       const epgx_op &o = t->ops[i];
       switch (o.code) {
@@ -444,7 +463,7 @@ extern "C" int epgx_plan_create(const epgx_tape *t, epgx_plan **out) {
     }
     pl->real_ok = ok;
     // the same with order-1 partial states: injections must be real as well
-    bool okj = t->nvar > 0 && t->npool == 1 && !pl->order2;
+    bool okj = t->nvar > 0 && t->npool == 1 && !pl->order2 && !pl->lattice;
     for (int64_t i = 0; okj && i < t->nop; ++i) {
       const epgx_op &o = t->ops[i];
       switch (o.code) {
@@ -655,7 +674,8 @@ extern "C" int epgx_plan_create(const epgx_tape *t, epgx_plan **out) {
   pl->off_pats = align(pl->off_segs + (int64_t)sizeof(epgx_segment) * (t->nseg ? t->nseg : 1));
   pl->off_stream = align(pl->off_pats + (int64_t)pl->pats.size() * 4);
   pl->off_tiles = align(pl->off_stream + (int64_t)sizeof(epgx_op) * pl->stream.size());
-  pl->off_coef = align(pl->off_tiles + (int64_t)pl->tiles.size() * 4);
+  pl->off_maps = align(pl->off_tiles + (int64_t)pl->tiles.size() * 4);
+  pl->off_coef = align(pl->off_maps + (int64_t)pl->maps.size() * 4);
   pl->ws_bytes = align(pl->off_coef + t->ncoef * rsz);
   *out = pl;
   return EPGX_OK;
@@ -706,6 +726,8 @@ extern "C" int epgx_plan_upload(const epgx_plan *pl, void *ws, void *stream) {
   CUDA_TRY(cudaMemcpyAsync(w + pl->off_stream, pl->stream.data(), sizeof(epgx_op) * pl->stream.size(), cudaMemcpyHostToDevice, st));
   if (!pl->tiles.empty())
     CUDA_TRY(cudaMemcpyAsync(w + pl->off_tiles, pl->tiles.data(), pl->tiles.size() * 4, cudaMemcpyHostToDevice, st));
+  if (!pl->maps.empty())
+    CUDA_TRY(cudaMemcpyAsync(w + pl->off_maps, pl->maps.data(), pl->maps.size() * 4, cudaMemcpyHostToDevice, st));
   if (t.dtype == EPGX_F64)
     CUDA_TRY(cudaMemcpyAsync(w + pl->off_coef, pl->coef64.data(), t.ncoef * 8, cudaMemcpyHostToDevice, st));
   else
@@ -786,6 +808,8 @@ static int run_range(const epgx_plan *pl, const void *ws, int64_t atom_begin, in
   kp.nvar = t.nvar;
   kp.nvar1 = t.nvar1;
   kp.tiles = pl->tiles.empty() ? nullptr : (const int *)(w + pl->off_tiles);
+  kp.maps = pl->maps.empty() ? nullptr : (const int *)(w + pl->off_maps);
+  kp.lattice = pl->lattice ? 1 : 0;
   kp.init_off = t.init_off;
   kp.m0_off = t.m0_off;
   kp.init_pat = t.init_pat;
@@ -803,6 +827,7 @@ extern "C" int epgx_simulate_strided(const epgx_plan *pl, const void *ws, int64_
 extern "C" int epgx_simulate_state(const epgx_plan *pl, const void *ws, int64_t atom_begin, int64_t atom_count, void *signal,
                                    int64_t signal_stride, void *jacobian, int64_t jacobian_stride, void *state, void *stream) {
   if (!state) return fail(EPGX_ERR_INVALID, "null state buffer");
+  if (pl && pl->lattice) return fail(EPGX_ERR_UNSUPPORTED, "state read-back of a lattice tape (the half-storage format is 1-d)");
   return run_range(pl, ws, atom_begin, atom_count, signal, signal_stride, jacobian, jacobian_stride, state, stream);
 }
 

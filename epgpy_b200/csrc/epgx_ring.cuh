@@ -45,9 +45,11 @@ __global__ void __launch_bounds__(256) ring_kernel(const KParams p) {
   };
   const real *__restrict__ coef = (const real *)p.coef;
 
-  // shared memory: rings [A][NSET][NP][3][C] complex, then pattern offsets [A][npattern] int
+  // shared memory: rings [A][NSET][NP][3][C] complex (+ one ring per atom as the temporary of lattice gathers), then
+  // pattern offsets [A][npattern] int
   real2 *rings = (real2 *)smem_raw;
-  int *patoff_all = (int *)(rings + (size_t)p.A * NSET * NP * 3 * C);
+  real2 *gtmp = rings + (size_t)p.A * NSET * NP * 3 * C + (size_t)al * C;
+  int *patoff_all = (int *)(rings + (size_t)p.A * (NSET * NP * 3 + (p.lattice ? 1 : 0)) * C);
   real2 *ring = rings + (size_t)al * NSET * NP * 3 * C;
   int *patoff = patoff_all + al * p.npattern;
 #define RING(set, pool, comp) (ring + (((set) * NP + (pool)) * 3 + (comp)) * C)
@@ -96,6 +98,7 @@ __global__ void __launch_bounds__(256) ring_kernel(const KParams p) {
     const int4 s1 = __ldg((const int4 *)(p.segs + sg) + 1);
     const int first = s0.x, count = s0.y, nact = s0.z, shift = s0.w;
     const int n_old = s1.x, n_new = s1.y, sflags = s1.z;
+    const int kz = (sflags & EPGX_SEG_LATTICE) ? (sflags >> 16) : 0; // slot of the order k = 0
 
     // the partial states of this variable tile are exactly zero until its first injection (per-pulse variables: most
     // of the sequence for the late tiles): linear operators leave them zero, so they are skipped.  Decided per
@@ -138,7 +141,7 @@ __global__ void __launch_bounds__(256) ring_kernel(const KParams p) {
           for (int s = 1; s < NSET; ++s)
             sel[s] = on_part && tv[s - 1] >= 0 && !((flags & EPGX_FLAG_P1) && tv[s - 1] >= p.nvar1) &&
                      !((flags & EPGX_FLAG_P2) && tv[s - 1] < p.nvar1);
-          const bool aff = (flags & EPGX_FLAG_AFFINE) && k == 0 && isrc == 0;
+          const bool aff = (flags & EPGX_FLAG_AFFINE) && k == kz && isrc == 0;
 
           // linear forms: out = form(in) for the selected sets, or partial += form(base)
 #define APPLY_FORM(EXPR, AFFINE_STMT)                                         \
@@ -262,7 +265,7 @@ __global__ void __launch_bounds__(256) ring_kernel(const KParams p) {
                     const real tr = mt[(i * NP + j) * 2], ti = mt[(i * NP + j) * 2 + 1];
                     const real lr = ml[(i * NP + j) * 2], li = ml[(i * NP + j) * 2 + 1];
                     const Tri<real> &x = st[s][j];
-                    const real zr = x.zr - ((s == 0 && k == 0) ? m0[j] : real(0));
+                    const real zr = x.zr - ((s == 0 && k == kz) ? m0[j] : real(0));
                     o[i].pr += tr * x.pr - ti * x.pi;
                     o[i].pi += tr * x.pi + ti * x.pr;
                     o[i].mr += tr * x.mr + ti * x.mi;
@@ -270,7 +273,7 @@ __global__ void __launch_bounds__(256) ring_kernel(const KParams p) {
                     o[i].zr += lr * zr - li * x.zi;
                     o[i].zi += lr * x.zi + li * zr;
                   }
-                  if (s == 0 && k == 0) o[i].zr += m0[i];
+                  if (s == 0 && k == kz) o[i].zr += m0[i];
                 }
 #pragma unroll
                 for (int i = 0; i < NP; ++i) st[s][i] = o[i];
@@ -292,7 +295,7 @@ __global__ void __launch_bounds__(256) ring_kernel(const KParams p) {
               if (on_base) {
                 const Tri<real> s_ = st[0][q];
                 st[0][q] = form_t8(s_, f);
-                if (k == 0) {
+                if (k == kz) {
                   st[0][q].pr += f.fzr; st[0][q].pi += f.fzi; st[0][q].mr += f.fzr; st[0][q].mi -= f.fzi;
                   st[0][q].zr += f.zz;
                 }
@@ -312,7 +315,7 @@ __global__ void __launch_bounds__(256) ring_kernel(const KParams p) {
             for (int q = 0; q < NP; ++q) m0[q] = ldc(coef + off0 + POFF(pat0, q));
             break;
           case EPGX_OP_ADC:
-            if (k == 0 && valid) {
+            if (k == kz && valid) {
 #pragma unroll
               for (int q = 0; q < NP; ++q) {
                 real fr = real(1), fi = real(0);
@@ -381,6 +384,24 @@ __global__ void __launch_bounds__(256) ring_kernel(const KParams p) {
 #pragma unroll
           for (int q = 0; q < NP; ++q) RING(0, q, 2)[0] = real2{m0[q], real(0)};
         }
+      } else if (shift == 2) {
+        // lattice gather (EPGX_SEG_LATTICE): new slot j <- old slot map[j], per component, through the temporary ring
+        const int nn = n_new + 1;
+        const int *mp = p.maps + s1.w;
+        const real2 z = {real(0), real(0)};
+#pragma unroll 1
+        for (int sq = 0; sq < NSET * NP; ++sq)
+#pragma unroll 1
+          for (int c = 0; c < 3; ++c) {
+            real2 *r = ring + ((size_t)sq * 3 + c) * C;
+            for (int j = lane; j < nn; j += G) {
+              const int src = __ldg(mp + c * nn + j);
+              gtmp[j] = src >= 0 ? r[src] : z;
+            }
+            if (G > 32) __syncthreads(); else __syncwarp();
+            for (int j = lane; j < C; j += G) r[j] = j < nn ? gtmp[j] : z;
+            if (G > 32) __syncthreads(); else __syncwarp();
+          }
       } else if (shift > 0) {
         // F+(k) <- F+(k-1), F+(0) <- conj(F-(1)), F-(k) <- F-(k+1)
         if (lane == 0) {

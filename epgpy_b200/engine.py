@@ -32,6 +32,7 @@ class _Tape(ctypes.Structure):
         ("m0_pat", ctypes.c_uint8), ("rsv0", ctypes.c_uint8 * 2), ("init_n", ctypes.c_int32),
         ("nadc", ctypes.c_int32), ("njac", ctypes.c_int32), ("nvar", ctypes.c_int32), ("max_order", ctypes.c_int32),
         ("nvar1", ctypes.c_int32), ("rsv", ctypes.c_int32 * 2), ("ntile", ctypes.c_int32), ("tiles", ctypes.c_void_p),
+        ("nmap", ctypes.c_int64), ("maps", ctypes.c_void_p),
     ]
 
 
@@ -145,6 +146,8 @@ class Plan:
         t.nvar1 = getattr(low, "nvar1", low.nvar)
         self._tiles = np.ascontiguousarray(getattr(low, "tiles", np.zeros((0, 3))), dtype=np.int32)
         t.ntile, t.tiles = len(self._tiles), (self._tiles.ctypes.data if len(self._tiles) else None)
+        self._maps = np.ascontiguousarray(getattr(low, "maps", np.zeros(0)), dtype=np.int32)
+        t.nmap, t.maps = len(self._maps), (self._maps.ctypes.data if len(self._maps) else None)
         self._h = ctypes.c_void_p()
         _check(L.epgx_plan_create(ctypes.byref(t), ctypes.byref(self._h)))
         self._ws = {}  # device index -> (workspace tensor, upload event)

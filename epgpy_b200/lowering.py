@@ -27,7 +27,7 @@ from .statematrix import StateMatrix
 (OP_NOP, OP_T_GEN, OP_T_RE, OP_T_IM, OP_E, OP_DIAG, OP_MATRIX, OP_D, OP_X, OP_SPOIL, OP_PD, OP_ADC, OP_FUSED,
  OP_CONT) = range(14)
 F_BASE, F_PARTIALS, F_INJECT, F_G, F_AFFINE, F_Z0, F_SCALE, F_PRE, F_POST, F_IM, F_GEN, F_P1, F_P2 = (1 << i for i in range(13))
-SEG_RESET, SEG_MASK_TOP = 1, 2
+SEG_RESET, SEG_MASK_TOP, SEG_LATTICE = 1, 2, 4
 MAX_DIMS, MAX_PATTERNS, MAX_POOLS = 8, 64, 4
 
 OP_DTYPE = np.dtype([("code", "<u2"), ("flags", "<u2"), ("aux", "<i4"), ("off", "<u4", (3,)), ("pat", "u1", (3,)),
@@ -292,6 +292,63 @@ def fuse_records(recs, segs):
     return out, segs
 
 
+class _Lattice:
+    """the configuration lattice of general integer n-d shifts (the reference's `shift-nd` method,
+    epgpy/shift.py:103-117, 297-364).  Shifts are the same for every atom, so the set of configurations k that can be
+    populated after each operator is a pure function of the sequence: the host walks it ONCE, keeps one slot per
+    lattice point (full storage: both k and -k) and turns every shift into three gather maps for the device
+    (F+ moves to k + dk, F- to k - dk, Z stays; epgx.h EPGX_SEG_LATTICE).  Where the reference prunes rows whose values
+    fall below a tolerance after every shift (data dependent, 1e-8), the lattice drops the points that are
+    STRUCTURALLY empty -- never reached by any pathway -- which is exact; cropping at max_nstate is the reference's."""
+
+    def __init__(self, kdim):
+        self.kdim = kdim
+        self.zero = (0,) * kdim
+        self.coords = [self.zero]
+        self.occ = {self.zero: [True, True, True]}  # per point: F+, F-, Z possibly non-zero
+
+    def mix(self):  # a 3 x 3 operator couples the three components of a point
+        for o in self.occ.values():
+            if any(o):
+                o[0] = o[1] = o[2] = True
+
+    def spoil(self):
+        for o in self.occ.values():
+            o[0] = o[1] = False
+
+    def reset(self):
+        self.coords = [self.zero]
+        self.occ = {self.zero: [False, False, True]}
+
+    def shift(self, kvec, nmax):
+        """apply S(kvec); returns (mapP, mapM, mapZ): source slot of every new slot (-1: empty)"""
+        kvec = tuple(int(x) for x in kvec) + (0,) * (self.kdim - len(kvec))
+        new = {self.zero: [False, False, False]}
+        for c, (hp, hm, hz) in self.occ.items():
+            if hp:
+                new.setdefault(tuple(a + b for a, b in zip(c, kvec)), [False, False, False])[0] = True
+            if hm:
+                new.setdefault(tuple(a - b for a, b in zip(c, kvec)), [False, False, False])[1] = True
+            if hz:
+                new.setdefault(c, [False, False, False])[2] = True
+        if nmax is not None:  # crop (shift.py:331-343): points with a component above nmax fall off
+            new = {c: o for c, o in new.items() if all(abs(x) <= nmax for x in c)}
+        index = {c: i for i, c in enumerate(self.coords)}
+        coords = sorted(new)
+        maps = ([], [], [])
+        for c in coords:
+            srcs = (tuple(a - b for a, b in zip(c, kvec)), tuple(a + b for a, b in zip(c, kvec)), c)
+            for comp in range(3):
+                src = srcs[comp]
+                maps[comp].append(index[src] if (src in self.occ and self.occ[src][comp]) else -1)
+        self.coords, self.occ = coords, new
+        return maps
+
+    @property
+    def kzero(self):
+        return self.coords.index(self.zero)
+
+
 def lower(sequence, *, init=None, probe=None, options=None, dtype="f64", propagate_nondiff=False,
           prune_unobservable=True, fuse=True, pre_inject=True, need_probe=True):
     """sequence -> Lowered.  need_probe=False: a tape without read-out (functions.apply_operators reads the final
@@ -315,6 +372,7 @@ def lower(sequence, *, init=None, probe=None, options=None, dtype="f64", propaga
         kvalue = options.pop("kvalue", 1.0)
         sm = StateMatrix(init)
     max_nstate = options.pop("max_nstate", None) or None
+    lattice_opt = bool(options.pop("lattice", False))  # force the general lattice path (tests: it must reproduce the 1-d one)
     options.pop("tvalue", None)
     options.pop("prune", None)
     if options:
@@ -373,14 +431,54 @@ def lower(sequence, *, init=None, probe=None, options=None, dtype="f64", propaga
         rest = [vindex[v] for v in variables if v not in covered]
         tiles += [(rest[i:i + 3] + [-1, -1])[:3] for i in range(0, len(rest), 3)]
 
-    # ---- shifts: 1-d integers, or collinear integer vectors
+    # ---- shifts: 1-d integers, collinear integer vectors (exactly the 1-d problem) -- or a general integer lattice
     vecs = [op.k for op in seq if isinstance(op, S) and not common.isscalar(op.k)]
-    base = _unit_vector(vecs) if vecs else None
+    lattice = lattice_opt
+    base = None
+    if vecs and not lattice:
+        try:
+            base = _unit_vector(vecs)
+            for op in seq:
+                if isinstance(op, S):
+                    _multiple([op.k] if common.isscalar(op.k) else op.k, base)
+        except NotImplementedError as ex:
+            if "non-collinear" not in str(ex) and "different dimensions" not in str(ex):
+                raise
+            lattice, base = True, None
+    if lattice:
+        for v in vecs:
+            if not np.issubdtype(np.asarray(v).dtype, np.integer) or np.asarray(v).shape[:-1] not in ((), (1,)):
+                raise NotImplementedError("lattice shifts need one integer vector per operator (float shifts: shift-merge / "
+                                          "shift-prune, epgpy/shift.py:367-542, are outside the hot path)")
 
     def shift_count(op):
         if base is None:
             return int(op.k)
         return _multiple([op.k] if common.isscalar(op.k) else op.k, base)
+
+    # ---- lattice mode: walk the configuration lattice once (slot counts, gather maps of every shift)
+    lat_steps, lat = [], None
+    if lattice:
+        if sm.nstate != 0:
+            raise NotImplementedError("lattice shifts start from a state matrix without populated orders (nstate = 0)")
+        kdim_l = max([1] + [np.asarray(op.k).shape[-1] for op in seq if isinstance(op, S) and not common.isscalar(op.k)])
+        lat = _Lattice(kdim_l)
+        nmax_pts = 1
+        for op in seq:
+            if isinstance(op, S):
+                kv = [op.k] if common.isscalar(op.k) else np.asarray(op.k).reshape(-1)
+                cap = max_nstate or op.nmax or None
+                kz_before, n_before = lat.kzero, len(lat.coords)
+                maps = lat.shift(kv, cap)
+                lat_steps.append((maps, kz_before, n_before, list(lat.coords)))
+                nmax_pts = max(nmax_pts, len(lat.coords))
+            elif isinstance(op, Reset) or (isinstance(op, PD) and op.reset):
+                lat.reset()
+            elif isinstance(op, Spoiler):
+                lat.spoil()
+            elif isinstance(op, DiffOperator) and not isinstance(op, (ops_mod.E, ops_mod.P, ops_mod.R, ops_mod.Phi, ops_mod.ScalarOp)):
+                lat.mix()
+        lat = _Lattice(kdim_l)  # replayed by the main walk
 
     # ---- order schedule: maximum order of the whole tape
     init_n = sm.nstate
@@ -391,6 +489,8 @@ def lower(sequence, *, init=None, probe=None, options=None, dtype="f64", propaga
         crop, init_n = init_n - max_nstate, max_nstate
     n, max_order = init_n, init_n
     for op in seq:
+        if lattice:
+            break
         if isinstance(op, S):
             cap = max_nstate or op.nmax or None
             n = n + abs(shift_count(op)) if cap is None else min(n + abs(shift_count(op)), max(cap, 0))
@@ -399,6 +499,8 @@ def lower(sequence, *, init=None, probe=None, options=None, dtype="f64", propaga
             n = 0
     if init_n > max_order:
         max_order = init_n
+    if lattice:
+        max_order = nmax_pts - 1  # slots 0 .. max_order hold the lattice points
 
     # ---- init / equilibrium blocks (half storage: orders 0..init_n)
     st = sm.states[..., crop:sm.states.shape[-2] - crop, :]
@@ -412,14 +514,21 @@ def lower(sequence, *, init=None, probe=None, options=None, dtype="f64", propaga
     kdim = 1 if base is None else len(base)
     bvec = np.ones(1) if base is None else base.astype(float)
 
-    def diffusion_block(op):
+    def diffusion_block(op, coords=None):
+        nonlocal kdim
         m = np.arange(0, max_order + 1, dtype=float)
         tau = np.asarray(op.tau, dtype=float) * 1e-3
         Kp = m[:, None] * bvec[None, :] * kvalue * 1e-3   # order +m
+        if coords is not None:  # lattice mode: one row per slot, the wavenumber of its lattice point (unused slots: 0)
+            kdim = len(coords[0])
+            Kp = np.zeros((max_order + 1, kdim))
+            Kp[:len(coords)] = np.asarray(coords, dtype=float) * kvalue * 1e-3
         if op.k is None:
             sh = np.zeros(kdim)
         else:
             sh = np.asarray(op.k, dtype=float).reshape(-1)
+            if coords is not None and len(sh) < kdim:
+                sh = np.pad(sh, (0, kdim - len(sh)))
             if len(sh) != kdim:
                 raise ValueError("Incompatible numbers of dimensions for k1 and k2")
             sh = sh * kvalue * 1e-3
@@ -457,9 +566,14 @@ def lower(sequence, *, init=None, probe=None, options=None, dtype="f64", propaga
     alive_vars = set()     # order-1 variables injected so far
     seg_first = 0
 
-    def close_segment(shift, n_old, n_new, flags=0):
+    maps_all = []          # lattice mode: gather maps of all shifts, concatenated (F+ | F- | Z per shift)
+    lat_i = 0
+
+    def close_segment(shift, n_old, n_new, flags=0, rsv=0):
         nonlocal seg_first
-        segs.append([seg_first, len(bld.records) - seg_first, n_old, shift, n_old, n_new, flags])
+        if lattice:  # the pass covers every slot; order 0 sits at slot kzero (bits 16.. of the flags)
+            flags |= SEG_LATTICE | (lat.kzero << 16)
+        segs.append([seg_first, len(bld.records) - seg_first, n_old, shift, n_old, n_new, flags, rsv])
         seg_first = len(bld.records)
 
     def part_flag():
@@ -468,7 +582,18 @@ def lower(sequence, *, init=None, probe=None, options=None, dtype="f64", propaga
     for op in seq:
         if isinstance(op, Jacobian) and probes is not None:
             pass  # an in-sequence Jacobian is a probe like any other
-        if isinstance(op, S):
+        if isinstance(op, S) and lattice:
+            maps, kz_before, n_before, coords_after = lat_steps[lat_i]
+            lat_i += 1
+            off = len(maps_all)
+            for mp in maps:
+                maps_all.extend(mp)
+            assert lat.kzero == kz_before and len(lat.coords) == n_before
+            close_segment(2, n_before - 1, len(coords_after) - 1, 0, rsv=off)  # (flags carry the kzero of the pass just closed)
+            kv = [op.k] if common.isscalar(op.k) else np.asarray(op.k).reshape(-1)
+            lat.shift(kv, max_nstate or op.nmax or None)
+            n = len(lat.coords) - 1
+        elif isinstance(op, S):
             m = shift_count(op)
             cap = max_nstate or op.nmax or None
             for _ in range(abs(m)):
@@ -481,7 +606,11 @@ def lower(sequence, *, init=None, probe=None, options=None, dtype="f64", propaga
         elif isinstance(op, (X, D, Spoiler)):
             fl = F_BASE | (part_flag() if propagate_nondiff else 0)
             if isinstance(op, Spoiler):
+                if lattice:
+                    lat.spoil()
                 bld.record(OP_SPOIL, fl)
+            elif isinstance(op, D) and lattice:
+                bld.record(OP_D, fl, [bld.block(diffusion_block(op, lat.coords))])  # the table follows the current lattice
             elif isinstance(op, D):
                 key = (id(op), "D")
                 if key not in bld.cache:
@@ -510,12 +639,19 @@ def lower(sequence, *, init=None, probe=None, options=None, dtype="f64", propaga
             bld.record(OP_PD, F_BASE, [bld.block(np.atleast_1d(np.asarray(op.pd, dtype=float))[..., None])])
             if op.reset:
                 close_segment(0, n, n, SEG_RESET)
+                if lattice:
+                    lat.reset()
+                    n = 0
         elif isinstance(op, Reset):
             if nvar and alive and not propagate_nondiff:
                 raise NotImplementedError("RESET after a differentiated operator needs propagate_nondiff=True")
             close_segment(0, n, n, SEG_RESET)
+            if lattice:
+                lat.reset()
             n = 0
         elif isinstance(op, DiffOperator):
+            if lattice and not isinstance(op, (ops_mod.E, ops_mod.P, ops_mod.R, ops_mod.Phi, ops_mod.ScalarOp)):
+                lat.mix()
             key = (id(op), "form")
             if key not in bld.cache:
                 bld.cache[key] = op._lowered_form()
@@ -685,7 +821,7 @@ def lower(sequence, *, init=None, probe=None, options=None, dtype="f64", propaga
     recs = bld.records
     if fuse and not nvar:
         recs, segs = fuse_records(recs, segs)
-    if prune_unobservable:
+    if prune_unobservable and not lattice:
         reach = -1
         for i in range(len(segs) - 1, -1, -1):
             sg = segs[i]
@@ -709,7 +845,7 @@ def lower(sequence, *, init=None, probe=None, options=None, dtype="f64", propaga
     sega = np.zeros(len(segs), dtype=SEG_DTYPE)
     if segs:
         a = np.array(segs, dtype=np.int64)
-        for j, name in enumerate(("first", "count", "nact", "shift", "n_old", "n_new", "flags")):
+        for j, name in enumerate(("first", "count", "nact", "shift", "n_old", "n_new", "flags", "rsv")):
             sega[name] = a[:, j]
     segs = sega
 
@@ -726,6 +862,9 @@ def lower(sequence, *, init=None, probe=None, options=None, dtype="f64", propaga
     low.nvar1, low.pairs = nvar1, pairs
     low.tiles = np.array(tiles, dtype=np.int32).reshape(-1, 3) if tiles else np.zeros((0, 3), dtype=np.int32)
     low.final_n = n  # order count when the tape ends
+    low.lattice = lattice
+    low.maps = np.asarray(maps_all, dtype=np.int32)
+    low.coords = None if lat is None else np.asarray(lat.coords, dtype=np.int64)
     low.rows, low.times = rows_out, times
     low.nprobe = len(probes) if probes else 1
     low.keepalive = seq

@@ -46,7 +46,7 @@
 extern "C" {
 #endif
 
-#define EPGX_VERSION 105 /* 0.1.5: order-2 partial states (injection source sets, variable tiles), epgx_simulate_state, 4 pools */
+#define EPGX_VERSION 106 /* 0.1.6: configuration lattices (general integer n-d shifts as gather maps), order-2 partial states */
 #define EPGX_MAX_DIMS 8
 #define EPGX_MAX_PATTERNS 64
 #define EPGX_MAX_POOLS 4
@@ -148,7 +148,12 @@ typedef struct {
 enum {
   EPGX_SEG_RESET = 1 << 0, /* after the pass: state <- equilibrium, order <- 0 (operator.py:297-304) */
   /* the shift truncates at max_nstate (n_new == n_old): what moves above n_new must read as zero */
-  EPGX_SEG_MASK_TOP = 1 << 1
+  EPGX_SEG_MASK_TOP = 1 << 1,
+  /* general integer n-d shifts (shift.py:103-117, 297-364): the state is stored on a LATTICE of configurations, one
+   * slot per lattice point (full storage: k and -k), every slot 0..nact takes part in the pass and the order k = 0 sits
+   * at slot (flags >> 16).  shift == 2 closes such a segment with a gather: new slot j of F+ / F- / Z takes old slot
+   * maps[rsv + c (n_new + 1) + j], c = 0, 1, 2 (-1: empty).  Lattice tapes run in the shared-memory kernel. */
+  EPGX_SEG_LATTICE = 1 << 2
 };
 
 /* segment, 32 bytes: one pass over orders 0..nact applying records [first, first+count), then
@@ -162,7 +167,7 @@ typedef struct {
   int32_t n_old;
   int32_t n_new;
   int32_t flags;
-  int32_t rsv;
+  int32_t rsv;   /* EPGX_SEG_LATTICE with shift == 2: offset of the three gather maps in epgx_tape.maps */
 } epgx_segment;
 
 /* the lowered sequence (host memory, copied by epgx_plan_create) */
@@ -198,6 +203,8 @@ typedef struct {
    * (a, b, ab).  ntile == 0: consecutive variables (order-1 tapes). */
   int32_t ntile;
   const int32_t *tiles;
+  int64_t nmap; /* gather maps of the lattice shifts (EPGX_SEG_LATTICE), concatenated */
+  const int32_t *maps;
 } epgx_tape;
 
 typedef struct epgx_plan epgx_plan;

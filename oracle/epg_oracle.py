@@ -601,6 +601,35 @@ def shift_int(states, k, inplace=False):
     return out
 
 
+def shift_nd(states, coords, kvec, nmax=None, tol=1e-8):
+    """general integer n-d shift on a lattice of configurations (epgpy/shift.py:297-364, not in place):
+    F+ moves from k to k + dk, Z stays, F-(k) = conj F+(-k) is rebuilt from the symmetry; the union of old and moved
+    points is re-sorted (symmetric order: point j mirrors point N - 1 - j), cropped at nmax and pruned of rows that are
+    zero within `tol` for every atom.  states [..., N, 3], coords [N, d] -> (states', coords')"""
+    coords = np.asarray(coords, dtype=int)
+    kvec = np.asarray(kvec, dtype=int).reshape(1, -1)
+    n1 = coords.shape[0]
+    uniq, inv = np.unique(np.concatenate([coords, coords + kvec, coords - kvec]), axis=0, return_inverse=True)
+    inv = np.asarray(inv).reshape(-1)
+    idx_l, idx_t = inv[:n1], inv[n1:2 * n1]
+    keep_l = keep_t = slice(None)
+    if nmax is not None:
+        keep = np.all(np.abs(uniq) <= nmax, axis=-1)
+        if not np.all(keep):
+            uniq = uniq[keep]
+            remap = -np.ones(keep.size, dtype=int)
+            remap[keep] = np.arange(uniq.shape[0])
+            idx_t, idx_l = remap[idx_t], remap[idx_l]
+            keep_t, keep_l = idx_t >= 0, idx_l >= 0
+    new = np.zeros(states.shape[:-2] + (uniq.shape[0], 3), dtype=states.dtype)
+    new[..., idx_l[keep_l], 2] = states[..., keep_l, 2]
+    new[..., idx_t[keep_t], 0] = states[..., keep_t, 0]
+    new[..., 1] = new[..., ::-1, 0].conj()
+    nonzero = ~np.all(np.isclose(new, 0, atol=tol), axis=tuple(range(new.ndim - 2)) + (-1,))
+    nonzero[(uniq.shape[0] - 1) // 2] = True
+    return new[..., nonzero, :], uniq[nonzero]
+
+
 def bmatrix(tau, k1, k2=None):
     """b-matrix of a linear change k1 -> k2 (epgpy/diffusion.py:86-123). tau in ms, k in rad/m"""
     outer = lambda a, b: a[..., None] * b[..., None, :]
@@ -672,6 +701,7 @@ class _Sim:
         self.max_nstate = max_nstate
         self.kvalue = kvalue
         self.kvec = kvec  # base shift vector (collinear n-d shifts) or None
+        self.coords = None  # [N, d] integer lattice points of the stored rows (general n-d shifts), else None
 
     # -- helpers
     def all_states(self):
@@ -691,6 +721,8 @@ class _Sim:
 
     def wavenumbers(self):
         """k of every stored order, rad/m (epgpy/statematrix.py:177-186)"""
+        if self.coords is not None:
+            return self.coords.astype(float) * self.kvalue
         n = nstate(self.states)
         m = np.arange(-n, n + 1, dtype=float)
         if self.kvec is None:
@@ -827,6 +859,28 @@ def _apply_linear(sim, op):
 def _apply_shift(sim, op):
     """epgpy/shift.py:82-101"""
     k = op.k
+    if sim.coords is not None or (not isinstance(k, (int, np.integer)) and sim.kvec is None):
+        # general integer lattice (the reference's `shift-nd` method, epgpy/shift.py:103-117): every state set moves on
+        # the same lattice; rows are pruned only where ALL sets are empty so that they keep one common row order
+        kv = np.atleast_1d(np.asarray(k)).reshape(-1)
+        if sim.coords is None:
+            n = nstate(sim.states)
+            sim.coords = np.zeros((2 * n + 1, len(kv)), dtype=int)
+            sim.coords[:, 0] = np.arange(-n, n + 1)
+        if len(kv) < sim.coords.shape[1]:
+            kv = np.pad(kv, (0, sim.coords.shape[1] - len(kv)))
+        elif len(kv) > sim.coords.shape[1]:
+            sim.coords = np.pad(sim.coords, [(0, 0), (0, len(kv) - sim.coords.shape[1])])
+        nmax = sim.max_nstate or None
+        keys = [key for key, _ in sim.all_states()]
+        stacked = np.stack([st for _, st in sim.all_states()], axis=0)  # [sets, *grid, N, 3]
+        stacked, coords = shift_nd(stacked, sim.coords, kv, nmax=nmax, tol=1e-30)
+        for key, st in zip(keys, stacked):
+            sim.set(key, np.array(st))
+        eq = np.zeros(sim.states.shape, dtype=complex)
+        eq[..., (coords.shape[0] - 1) // 2, 2] = sim.eq[..., nstate(sim.eq), 2]
+        sim.eq, sim.coords = eq, coords
+        return
     if not isinstance(k, (int, np.integer)):
         kv = np.asarray(k).reshape(-1)
         if sim.kvec is None:
@@ -866,6 +920,8 @@ def _apply_diffusion(sim, op, propagate):
             sh = np.asarray(op.k, dtype=float).reshape(-1)
         if sh is None:
             raise ValueError("scalar D.k with vector shifts")
+        if sim.coords is not None and len(sh) < sim.coords.shape[1]:
+            sh = np.pad(sh, (0, sim.coords.shape[1] - len(sh)))
         sh = sh * sim.kvalue
         bT = bmatrix(tau, kk - sh, kk)
     DL, DT = diffusion_factors(bL, bT, op.D if np.ndim(op.D) else float(op.D))
@@ -943,6 +999,10 @@ def simulate(seq, *, init=None, density=1.0, max_nstate=None, kvalue=1.0, kvec=N
                     s[..., :2] = 0
                     sim.set(v, s)
         elif kind == "RESET":
+            if sim.coords is not None:  # back to the single lattice point k = 0
+                c = (sim.coords.shape[0] - 1) // 2
+                sim.eq = sim.eq[..., c:c + 1, :].copy()
+                sim.coords = np.zeros((1, sim.coords.shape[1]), dtype=int)
             sim.eq = resize(sim.eq, 0)
             sim.states = np.broadcast_to(sim.eq, sim.grid + (1, 3)).copy()
             for v in list(sim.partials):

@@ -425,7 +425,49 @@ def slice_profile(epg, nsample=41, nfreq=15):
     return dict(seq=[pulse, epg.P(-2.0, [freqs]), epg.ADC, epg.Adc("Z0")])
 
 
+def gre_lattice_2d(epg, ntr=16):
+    """general integer n-d shifts (the reference's `shift-nd` method, shift.py:103-117, 297-364): NON-collinear 2-d
+    gradient moments that come back to k = 0, with diffusion on the 2-d wavenumbers"""
+    T2 = np.array([40.0, 80.0])
+    ks = [[1, 0], [0, 1], [-1, 0], [0, -1], [1, 1], [-1, 1], [0, -2], [1, 0]]
+    seq = []
+    for i in range(ntr):
+        k = ks[i % 8]
+        seq += [epg.T(30 + 5 * i, 20.0 * i), epg.E(5, 800.0, T2), epg.ADC, epg.Adc("Z0"), epg.S(k), epg.D(4.0, 2e-3, k=k)]
+    return dict(seq=seq, options={"kvalue": 300.0})
+
+
+def gre_lattice_3d_cropped(epg, ntr=14):
+    """3-d lattice cropped at max_nstate = 2, a spoiler and a reset in between, B1 axis"""
+    B1 = np.array([[0.8, 1.0, 1.2]])
+    T2 = np.array([40.0, 80.0])
+    ks = [[1, 0, 0], [0, 1, -1], [-1, 0, 1], [0, -1, 0], [1, 1, 0], [-1, 0, 0]]
+    seq = []
+    for i in range(ntr):
+        k = ks[i % 6]
+        seq += [epg.T((25 + 4 * i) * B1, 35.0 * i), epg.E(6, 700.0, T2, 0.01), epg.ADC, epg.S(k)]
+        if i == 6:
+            seq += [epg.SPOILER]
+        if i == 10:
+            seq += [epg.RESET]
+    return dict(seq=seq, options={"max_nstate": 2})
+
+
+def lattice_jac(epg, ntr=10):
+    """derivatives on a 2-d lattice: the partial states move through the same gather maps"""
+    T2 = np.array([40.0, 80.0, 120.0])
+    ks = [[1, 0], [0, 1], [-1, 0], [0, -1], [1, -1]]
+    seq = []
+    for i in range(ntr):
+        seq += [epg.T(30 + 5 * i, 90.0, order1={"B1": {"alpha": 30.0 + 5 * i}}), epg.E(5, 800.0, T2, order1=["T2"]), epg.ADC,
+                epg.S(ks[i % 5])]
+    return dict(seq=seq, jac=["magnitude", "B1", "T2"])
+
+
 CASES["slice_profile"] = slice_profile
+CASES["gre_lattice_2d"] = gre_lattice_2d
+CASES["gre_lattice_3d_cropped"] = gre_lattice_3d_cropped
+CASES["lattice_jac"] = lattice_jac
 
 
 def probe_expr(epg):

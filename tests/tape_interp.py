@@ -72,7 +72,7 @@ def run(low, stream=None):
                 out.append(e)
         return out
 
-    st = {"m0": m0}
+    st = {"m0": m0, "kz": 0}  # kz: slot of the order k = 0 (lattice mode: epgx.h EPGX_SEG_LATTICE; else 0)
 
     def apply(rec, na):
         if True:
@@ -101,7 +101,7 @@ def run(low, stream=None):
                     o = [np.array(x) for x in o]
                     if affine is not None and src == 0 and (flags & L.F_AFFINE):
                         for x, a in zip(o, affine):
-                            x[..., 0] += a
+                            x[..., st["kz"]] += a
                     if s == "inject":
                         p[:, :, aux + 1] += o[0]; m[:, :, aux + 1] += o[1]; z[:, :, aux + 1] += o[2]
                     else:
@@ -152,7 +152,7 @@ def run(low, stream=None):
                 for s in sets:
                     eq = np.zeros((natoms, npool, na), dtype=complex)
                     if s == 0:
-                        eq[..., 0] = m0
+                        eq[..., st["kz"]] = m0
                     p[:, :, s] = np.einsum("aij,ajk->aik", mt, p[:, :, s])
                     m[:, :, s] = np.einsum("aij,ajk->aik", mt.conj(), m[:, :, s])
                     z[:, :, s] = np.einsum("aij,ajk->aik", ml, z[:, :, s] - eq) + eq
@@ -167,14 +167,21 @@ def run(low, stream=None):
                     f = cplx(blk(off[0], pat[0], 2), 0)
                 src = Z if flags & L.F_Z0 else P
                 if flags & L.F_BASE:
-                    sig[aux] = src[:, :, 0, 0] * f
+                    sig[aux] = src[:, :, 0, st["kz"]] * f
                 if flags & L.F_PARTIALS:
                     for v in range(low.nvar):
-                        jac[aux1, v] = src[:, :, 1 + v, 0] * f
-    def close(sh, n_old, n_new, sflags):
+                        jac[aux1, v] = src[:, :, 1 + v, st["kz"]] * f
+    def close(sh, n_old, n_new, sflags, rsv=0):
         if sflags & L.SEG_RESET:
             P[:] = 0; M[:] = 0; Z[:] = 0
             Z[:, :, 0, 0] = st["m0"]
+        elif sh == 2:  # lattice gather: new slot j <- old slot map[j] (-1: empty), per component
+            nn = n_new + 1
+            for arr, mp in zip((P, M, Z), (low.maps[rsv:rsv + nn], low.maps[rsv + nn:rsv + 2 * nn], low.maps[rsv + 2 * nn:rsv + 3 * nn])):
+                old = arr.copy()
+                arr[:] = 0
+                ok = mp >= 0
+                arr[..., np.nonzero(ok)[0]] = old[..., mp[ok]]
         elif sh:
             up, dn = (P, M) if sh > 0 else (M, P)
             new0 = dn[..., 1].conj() if (n_old >= 1 and C > 1) else 0 * dn[..., 0]
@@ -187,9 +194,10 @@ def run(low, stream=None):
 
     if stream is None:
         for seg in low.segs:
+            st["kz"] = (int(seg["flags"]) >> 16) if int(seg["flags"]) & L.SEG_LATTICE else 0
             for rec in expand(low.ops[seg["first"]: seg["first"] + seg["count"]]):
                 apply(rec, int(seg["nact"]) + 1)
-            close(int(seg["shift"]), int(seg["n_old"]), int(seg["n_new"]), int(seg["flags"]))
+            close(int(seg["shift"]), int(seg["n_old"]), int(seg["n_new"]), int(seg["flags"]), int(seg["rsv"]))
         return sig, jac
 
     # ---- the merged stream (internal codes: csrc/epgx_common.cuh)

@@ -29,7 +29,7 @@ def test_header_symbols_exported():
     assert set(syms) == set(engine.EXPORTS), (syms, engine.EXPORTS)
     for s in syms:
         assert getattr(L, s) is not None
-    assert L.epgx_version() == 105
+    assert L.epgx_version() == 106
 
 
 def test_struct_sizes_match_header():
@@ -37,7 +37,7 @@ def test_struct_sizes_match_header():
 
     assert lowering.OP_DTYPE.itemsize == 32 and lowering.SEG_DTYPE.itemsize == 32
     # epgx_tape: 8 + 64 + 8 + 64*8*4 + 64*4 + 6*8 + 8 + 4 + 4 + 4*4 + 3*4, padded to 8
-    assert ctypes.sizeof(engine._Tape) == 2488
+    assert ctypes.sizeof(engine._Tape) == 2504
     assert ctypes.sizeof(engine.Config) == 64
 
 

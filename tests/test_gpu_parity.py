@@ -106,7 +106,8 @@ def _run_variant(epg, case, dtype="f64", **variant):
 
 @pytest.mark.parametrize("lanes,atoms", [(1, 1), (1, 32), (2, 3), (8, 16), (32, 2), (64, 1), (128, 2), (256, 1)])
 @pytest.mark.parametrize("name", ["fisp_unbounded", "fisp_bounded", "misc_ops", "spgr_exchange", "fisp_jac_global",
-                                  "gre_diffusion_tensor", "init_states", "init_states_jac", "init_states_jac_complex"])
+                                  "gre_diffusion_tensor", "init_states", "init_states_jac", "init_states_jac_complex",
+                                  "gre_lattice_2d", "gre_lattice_3d_cropped", "lattice_jac"])
 def test_ring_kernel_variants(name, lanes, atoms, golden, epg):
     """ring kernel: every lanes-per-atom / atoms-per-CTA mapping gives the same answer (ragged tails included)"""
     ref = golden(name)
@@ -605,3 +606,15 @@ def test_pulsejac_kernel_is_refused_for_repeated_variables(epg):
     assert plan.config()["kernel"] != 5
     with pytest.raises(NotImplementedError):
         plan.set_variant(kernel=6)
+
+
+@pytest.mark.parametrize("name", ["fisp_bounded", "gre_diffusion_1d", "spgr_exchange", "mse_jac", "misc_ops"])
+def test_lattice_path_reproduces_the_1d_path(name, golden, epg):
+    """the general lattice machinery (gather maps, slot of k = 0, per-slot diffusion tables) forced on 1-d sequences must
+    give the 1-d answers: golden vectors of the reference"""
+    ref = golden(name)
+    case = cases.CASES[name](epg)
+    sig, jac = run_case(epg.simulate, epg, case, lattice=True)
+    assert rel_err(sig, ref["signal"]) < RTOL64
+    if "jacobian" in ref.files:
+        assert rel_err(jac, ref["jacobian"]) < RTOL64
