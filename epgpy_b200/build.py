@@ -39,6 +39,8 @@ def build(force=False, verbose=False, defines=(), out=None, only=None):
             continue
         cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", *defines,
                "-Xcompiler", "-fPIC", "-I" + os.path.join(ROOT, "include"), "-c", src, "-o", obj]
+        if os.path.basename(src) == "epgx_host.cu":  # host marshalling: AVX2 streaming stores (every x86 host of a B200 has them)
+            cmd[cmd.index("-Xcompiler") + 1] = "-fPIC,-mavx2"
         if verbose:
             cmd += ["-Xptxas", "-v"]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))

@@ -766,8 +766,16 @@ extern "C" int epgx_simulate(const epgx_plan *pl, const void *ws, int64_t atom_b
   return epgx_simulate_strided(pl, ws, atom_begin, atom_count, signal, atom_count, jacobian, atom_count, stream);
 }
 
+static bool real_signal_ok(const epgx_plan *pl) {
+  if (!pl || pl->cfg.kernel != 2 || pl->tape.nvar != 0) return false;
+  for (const epgx_op &o : pl->ops)
+    if (o.code == EPGX_OP_ADC && (o.flags & EPGX_FLAG_SCALE)) return false; // a complex read-out factor
+  return true;
+}
+
 static int run_range(const epgx_plan *pl, const void *ws, int64_t atom_begin, int64_t atom_count, void *signal,
-                     int64_t signal_stride, void *jacobian, int64_t jacobian_stride, void *state, void *stream) {
+                     int64_t signal_stride, void *jacobian, int64_t jacobian_stride, void *state, void *stream,
+                     bool out_real = false) {
   if (!pl || !ws) return fail(EPGX_ERR_INVALID, "null argument");
   if (signal_stride < atom_count || jacobian_stride < atom_count) return fail(EPGX_ERR_INVALID, "row stride < atom_count");
   if (atom_begin < 0 || atom_count < 0 || atom_begin + atom_count > pl->natoms)
@@ -794,6 +802,7 @@ static int run_range(const epgx_plan *pl, const void *ws, int64_t atom_begin, in
   kp.signal = signal;
   kp.jac = jacobian;
   kp.state = state;
+  kp.out_real = out_real ? 1 : 0;
   kp.atom_begin = atom_begin;
   kp.atom_count = atom_count;
   kp.sig_stride = signal_stride;
@@ -822,6 +831,14 @@ extern "C" int epgx_simulate_strided(const epgx_plan *pl, const void *ws, int64_
                                      void *signal, int64_t signal_stride, void *jacobian, int64_t jacobian_stride,
                                      void *stream) {
   return run_range(pl, ws, atom_begin, atom_count, signal, signal_stride, jacobian, jacobian_stride, nullptr, stream);
+}
+
+extern "C" int epgx_plan_real_signal(const epgx_plan *pl) { return real_signal_ok(pl) ? 1 : 0; }
+
+extern "C" int epgx_simulate_real(const epgx_plan *pl, const void *ws, int64_t atom_begin, int64_t atom_count, void *signal,
+                                  int64_t signal_stride, void *stream) {
+  if (!real_signal_ok(pl)) return fail(EPGX_ERR_UNSUPPORTED, "the signal of this plan is not real-valued (see epgx_plan_real_signal)");
+  return run_range(pl, ws, atom_begin, atom_count, signal, signal_stride, nullptr, atom_count, nullptr, stream, true);
 }
 
 extern "C" int epgx_simulate_state(const epgx_plan *pl, const void *ws, int64_t atom_begin, int64_t atom_count, void *signal,

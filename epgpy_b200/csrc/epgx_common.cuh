@@ -267,6 +267,7 @@ struct KParams {
   const int *tiles; // ring kernel: [gridDim.y][3] variables resident per tile (-1: empty), or null: consecutive
   const int *maps;  // ring kernel: gather maps of the lattice shifts (EPGX_SEG_LATTICE)
   int lattice;      // the tape has lattice segments: one more ring per atom as the gather's temporary
+  int out_real;     // real kernel: `signal` holds rows of reals (epgx_simulate_real)
   int bounded; // the tape has segments that truncate at max_nstate (EPGX_SEG_MASK_TOP)
   unsigned init_off, m0_off;
   int init_pat, m0_pat, init_n;

@@ -206,6 +206,7 @@ __global__ void __launch_bounds__(MAXT, real_min_blocks(sizeof(real) * NS, MAXT)
     }
   }
   real2 *sig = (real2 *)p.signal;
+  real *sigr = (real *)p.signal; // p.out_real: rows of REALS (the imaginary parts of this kernel's signal are exact zeros)
 
 #define SLOT_CASE(K, ...)                      \
   case (K) + 1:                                \
@@ -351,7 +352,10 @@ __global__ void __launch_bounds__(MAXT, real_min_blocks(sizeof(real) * NS, MAXT)
 #undef TRW
       __syncwarp();
       if (valid) // lane j (+ G, ...) stores the echoes of its TRs
-        for (int j = lane; j < TAPE_CHUNK / 2; j += G) sig[(long long)tb[4 * j + 2].y * p.sig_stride + a_rel] = real2{sb[j], real(0)};
+        for (int j = lane; j < TAPE_CHUNK / 2; j += G) {
+          const long long o = (long long)tb[4 * j + 2].y * p.sig_stride + a_rel;
+          if (p.out_real) sigr[o] = sb[j]; else sig[o] = real2{sb[j], real(0)};
+        }
       nact = tb[4 * (TAPE_CHUNK / 2 - 1) + 3].z;
       nslot = nact < 0 ? 0 : SLOTS_FOR(nact);
       continue;
@@ -408,7 +412,8 @@ __global__ void __launch_bounds__(MAXT, real_min_blocks(sizeof(real) * NS, MAXT)
             fr = ldc(c); fi = ldc(c + 1);
           }
           const real x = (flags & EPGX_FLAG_Z0) ? Z[0] : P[0];
-          sig[(long long)aux * p.sig_stride + a_rel] = real2{x * fr, x * fi};
+          const long long o = (long long)aux * p.sig_stride + a_rel;
+          if (p.out_real) sigr[o] = x * fr; else sig[o] = real2{x * fr, x * fi};
         }
         break;
       case EPGX_OP_SEG: {
@@ -425,7 +430,10 @@ __global__ void __launch_bounds__(MAXT, real_min_blocks(sizeof(real) * NS, MAXT)
                                            ldc(cb + 1), ldc(coef + (unsigned)q0.w + patoff[(q1.y >> 8) & 0xff]), false, m0);
         APPLY5(f.a, f.w, f.b, f.u, f.h)
         if (lane == 0 && nslot > 0) { P[0] += f.fz; M[0] += f.fz; Z[0] += f.zz; }
-        if (lane == 0 && valid) sig[(long long)q0.y * p.sig_stride + a_rel] = real2{P[0], real(0)};
+        if (lane == 0 && valid) {
+          const long long o = (long long)q0.y * p.sig_stride + a_rel;
+          if (p.out_real) sigr[o] = P[0]; else sig[o] = real2{P[0], real(0)};
+        }
         const int segw = (q0.x >> 16) & 0xffff; // (shift + 1) | segment flags << 2
         DO_SEG((segw & 3) - 1, (int)((unsigned)q1.x >> 16), (int)((unsigned)q1.x & 0xffff), segw >> 2, q1.z)
         ++r;

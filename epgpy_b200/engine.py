@@ -60,7 +60,8 @@ def _count(n=1):
 EXPORTS = [
     "epgx_version", "epgx_device_count", "epgx_last_error", "epgx_plan_create", "epgx_plan_destroy",
     "epgx_plan_config", "epgx_plan_stream", "epgx_plan_set_variant", "epgx_plan_workspace_bytes", "epgx_plan_upload",
-    "epgx_simulate", "epgx_simulate_strided", "epgx_simulate_state", "epgx_copy2d_to_host", "epgx_simulate_host", "epgx_reduce",
+    "epgx_simulate", "epgx_simulate_strided", "epgx_simulate_state", "epgx_plan_real_signal", "epgx_simulate_real",
+    "epgx_expand_real", "epgx_copy2d_to_host", "epgx_simulate_host", "epgx_reduce",
     "epgx_fma_peak",
 ]
 
@@ -90,6 +91,9 @@ def lib():
             L.epgx_simulate.argtypes = [vp, vp, i64, i64, vp, vp, vp]
             L.epgx_simulate_strided.argtypes = [vp, vp, i64, i64, vp, i64, vp, i64, vp]
             L.epgx_simulate_state.argtypes = [vp, vp, i64, i64, vp, i64, vp, i64, vp, vp]
+            L.epgx_plan_real_signal.argtypes = [vp]
+            L.epgx_simulate_real.argtypes = [vp, vp, i64, i64, vp, i64, vp]
+            L.epgx_expand_real.argtypes = [i32, vp, i64, vp, i64, i64, i64, i32]
             L.epgx_copy2d_to_host.argtypes = [vp, i64, vp, i64, i64, i64, vp]
             L.epgx_simulate_host.argtypes = [vp, i32, i64, i64, vp, vp]
             L.epgx_reduce.argtypes = [i32, vp, vp, i64, i64, i64, vp]
@@ -379,6 +383,104 @@ class Plan:
             copy.synchronize()
             compute.synchronize()
         return dev_signal, dev_jacobian
+
+    def real_signal(self):
+        """True when the signal of the plan is real-valued and the kernel can emit rows of reals (epgx_plan_real_signal)"""
+        return bool(lib().epgx_plan_real_signal(self._h))
+
+    def run_to_host_real(self, device, out_signal, atom_begin=0, atom_count=None, nchunk=16, host_col=0, host_atoms=None,
+                         nthreads=None, nstage=4):
+        """`run_to_host` for plans with a real-valued signal (`real_signal()`): only the real parts cross PCIe -- half the
+        bytes of the complex result, and the device->host copy is what bounds the end-to-end rate of a dictionary.
+        Pipeline per column chunk: kernel (rows of reals into one of two device buffers) -> D2H into a pinned staging
+        ring -> `epgx_expand_real` (host threads, streaming stores) into the complex result `out_signal`
+        [nadc][host_atoms][1].  The expansion of chunk i runs while chunk i + 1 is copied and chunk i + 2 computed.
+        Synchronises before returning."""
+        import queue
+        import threading as _th
+
+        import torch
+
+        require_cuda()
+        low = self.low
+        if not self.real_signal() or low.npool != 1:
+            raise EpgxError("this plan has no real-valued signal")
+        if atom_count is None:
+            atom_count = low.natoms - atom_begin
+        if host_atoms is None:
+            host_atoms = atom_count
+        if host_col < 0 or host_col + atom_count > host_atoms:
+            raise ValueError("host column range outside the host buffer")
+        self._check_buffer(out_signal, "out_signal", low.nadc, host_atoms)
+        if atom_count == 0 or low.nadc == 0:
+            return
+        if nthreads is None:
+            nthreads = int(os.environ.get("EPGX_HOST_THREADS", 0)) or max(1, min(16, (os.cpu_count() or 1) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", 1)))))
+        dev = torch.device("cuda", device)
+        rdt = torch.float64 if low.dtype == "f64" else torch.float32
+        rsz = 8 if low.dtype == "f64" else 4
+        L = lib()
+        per = -(-atom_count // max(1, nchunk))
+        nstage = max(2, nstage)
+        dst0 = (out_signal.data_ptr() if hasattr(out_signal, "data_ptr") else out_signal.ctypes.data) + host_col * 2 * rsz
+        with torch.cuda.device(dev):
+            ws = self.upload(device, force=True)
+            dbuf = [torch.empty((low.nadc, per), dtype=rdt, device=dev) for _ in range(2)]
+            stage = [torch.empty((low.nadc, per), dtype=rdt, pin_memory=True) for _ in range(nstage)]
+            compute = torch.cuda.current_stream(dev)
+            self._wait_upload(device, compute)
+            copy = torch.cuda.Stream(dev)
+            jobs, errors = queue.Queue(), []
+            free = [_th.Event() for _ in range(nstage)]
+            for ev in free:
+                ev.set()
+
+            def expander():
+                while True:
+                    job = jobs.get()
+                    if job is None:
+                        return
+                    slot, b, c, ev = job
+                    try:
+                        ev.synchronize()  # the D2H copy of this chunk has landed in the staging slot
+                        rc = L.epgx_expand_real(DTYPES[low.dtype], stage[slot].data_ptr(), per, dst0 + b * 2 * rsz, host_atoms,
+                                                low.nadc, c, nthreads)
+                        if rc != 0:
+                            errors.append(EpgxError(f"epgx_expand_real: {rc}"))
+                    except BaseException as ex:  # surfaced by the caller
+                        errors.append(ex)
+                    finally:
+                        free[slot].set()
+
+            worker = _th.Thread(target=expander, daemon=True)
+            worker.start()
+            copied = [None, None]  # event behind the copy that last read device buffer k
+            try:
+                for i, b in enumerate(range(0, atom_count, per)):
+                    c = min(per, atom_count - b)
+                    k, slot = i % 2, i % nstage
+                    if copied[k] is not None:
+                        compute.wait_event(copied[k])
+                    _check(L.epgx_simulate_real(self._h, ws.data_ptr(), atom_begin + b, c, dbuf[k].data_ptr(), per, compute.cuda_stream))
+                    _count()
+                    done = torch.cuda.Event()
+                    done.record(compute)
+                    free[slot].wait()   # the expansion that last used this staging slot is over
+                    free[slot].clear()
+                    copy.wait_event(done)
+                    with torch.cuda.stream(copy):
+                        stage[slot].copy_(dbuf[k], non_blocking=True)
+                        ev = torch.cuda.Event()
+                        ev.record(copy)
+                    copied[k] = ev
+                    jobs.put((slot, b, c, ev))
+            finally:
+                jobs.put(None)
+                worker.join()
+            copy.synchronize()
+            compute.synchronize()
+            if errors:
+                raise errors[0]
 
     def run_host(self, device, atom_begin, atom_count, signal, jacobian=None):
         """epgx_simulate_host: the plain C-ABI call on HOST numpy buffers (alloc + H2D + run + D2H)"""

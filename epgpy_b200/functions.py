@@ -74,7 +74,7 @@ def _host_buffer(shape, cdt):
         return torch.empty(shape, dtype=cdt)
 
 
-def run_lowered(low, plan=None, device=None, atom_range=None, nchunk=None, keep_device=None):
+def run_lowered(low, plan=None, device=None, atom_range=None, nchunk=None, keep_device=None, real_output=None):
     """run a lowered sequence on one or several devices of this process: the atom range is cut in one contiguous
     slab per device (no inter-device traffic) and every slab in column chunks, chunk i + 1 being computed while chunk i
     is copied into the pinned host result (engine.Plan.run_to_host).
@@ -108,9 +108,19 @@ def run_lowered(low, plan=None, device=None, atom_range=None, nchunk=None, keep_
         nchunk = int(min(16, max(1, per_dev // (32 << 20))))
     parts, errors = [None] * len(slabs), []
 
+    # a real-valued signal crosses PCIe as reals and is widened to complex on the host (engine.Plan.run_to_host_real), unless
+    # a row is reduced on the device (that needs the device slab) or the result is too small to matter
+    real_path = (real_output is not False and not has_jac and plan.real_signal() and low.npool == 1 and sig_t is not None
+                 and sig_t.is_pinned() and low.nbytes_out(natoms=count) >= (64 << 20)
+                 and not any(r.kind == "sig" and r.reduce is not None for rows in low.rows for r in rows))
+
     def work(i, d, b, c):
         try:
             col = b - begin
+            if real_path:
+                plan.run_to_host_real(d, sig_t, b, c, nchunk=max(nchunk, 8), host_col=col, host_atoms=count)
+                parts[i] = (d, b, c, None, None)
+                return
             sig_d, jac_d = plan.run_to_host(d, sig_t, b, c, nchunk=nchunk, out_jacobian=jac_t, host_col=col, host_atoms=count)
             parts[i] = (d, b, c, sig_d, jac_d)
         except BaseException as ex:  # re-raised in the calling thread

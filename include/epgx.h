@@ -46,7 +46,7 @@
 extern "C" {
 #endif
 
-#define EPGX_VERSION 106 /* 0.1.6: configuration lattices (general integer n-d shifts as gather maps), order-2 partial states */
+#define EPGX_VERSION 107 /* 0.1.7: real-valued signal rows (epgx_simulate_real / epgx_expand_real), lattices, order 2 */
 #define EPGX_MAX_DIMS 8
 #define EPGX_MAX_PATTERNS 64
 #define EPGX_MAX_POOLS 4
@@ -281,6 +281,19 @@ int epgx_simulate_strided(const epgx_plan *plan, const void *workspace, int64_t 
 int epgx_simulate_state(const epgx_plan *plan, const void *workspace, int64_t atom_begin, int64_t atom_count,
                         void *signal, int64_t signal_stride, void *jacobian, int64_t jacobian_stride, void *state,
                         void *stream);
+
+/* REAL-VALUED signal rows.  On real-valued phase graphs (kernel 2: +-90 degree pulses, no precession, real initial state,
+ * read-outs without a complex factor) the imaginary part of every sample is an exact zero; sending only the real parts
+ * halves the device->host traffic of a dictionary (8 instead of 16 GB for 1 M atoms x 1000 TRs in FP64), which is what
+ * bounds the end-to-end rate.  epgx_plan_real_signal tells whether a plan qualifies; epgx_simulate_real is
+ * epgx_simulate_strided with `signal` = real[nadc][signal_stride] (no Jacobian); epgx_expand_real widens rows of reals
+ * in HOST memory to the complex rows the reference's API returns (imaginary parts zero), with `nthreads` host threads
+ * and streaming stores:  dst[r * dst_pitch + c] = (src[r * src_pitch + c], 0),  pitches in elements. */
+int epgx_plan_real_signal(const epgx_plan *plan);
+int epgx_simulate_real(const epgx_plan *plan, const void *workspace, int64_t atom_begin, int64_t atom_count, void *signal,
+                       int64_t signal_stride, void *stream);
+int epgx_expand_real(int dtype, const void *src, int64_t src_pitch, void *dst, int64_t dst_pitch, int64_t rows, int64_t cols,
+                     int nthreads);
 
 /* asynchronous pitched device->host copy (cudaMemcpy2DAsync) of `height` rows of `width` bytes: brings a
  * column range of the signal slab to (pinned) host memory while the next range is computed */

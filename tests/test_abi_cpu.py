@@ -29,7 +29,7 @@ def test_header_symbols_exported():
     assert set(syms) == set(engine.EXPORTS), (syms, engine.EXPORTS)
     for s in syms:
         assert getattr(L, s) is not None
-    assert L.epgx_version() == 106
+    assert L.epgx_version() == 107
 
 
 def test_struct_sizes_match_header():
@@ -103,3 +103,23 @@ def test_no_cpu_fallback():
     plan = engine.Plan(lowering.lower(cases.readme_mse(epg)["seq"]))
     with pytest.raises(engine.EpgxError):
         plan.run_host(0, 0, 3, sig)
+
+
+def test_expand_real_rows_on_the_host():
+    """epgx_expand_real: rows of reals -> complex rows with zero imaginary parts, pitched source and destination, any
+    alignment, several threads (pure host marshalling: runs without a GPU)"""
+    import numpy as np
+
+    from epgpy_b200 import engine
+
+    L = engine.lib()
+    rng = np.random.RandomState(0)
+    for dt, cdt, code in ((np.float64, np.complex128, 0), (np.float32, np.complex64, 1)):
+        for rows, cols, sp, dp, off, nth in ((7, 1003, 1100, 5000, 3, 4), (1, 5, 5, 5, 0, 8), (33, 64, 64, 200, 1, 1)):
+            src = rng.rand(rows, sp).astype(dt)
+            dst = np.full((rows, dp), 1 + 1j, dtype=cdt)
+            assert L.epgx_expand_real(code, src.ctypes.data, sp, dst.ctypes.data + off * dst.itemsize, dp, rows, cols, nth) == 0
+            want = np.full((rows, dp), 1 + 1j, dtype=cdt)
+            want[:, off:off + cols] = src[:, :cols]
+            assert np.array_equal(dst, want)
+    assert L.epgx_expand_real(0, None, 1, None, 1, 1, 1, 1) < 0

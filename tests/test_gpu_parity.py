@@ -618,3 +618,25 @@ def test_lattice_path_reproduces_the_1d_path(name, golden, epg):
     assert rel_err(sig, ref["signal"]) < RTOL64
     if "jacobian" in ref.files:
         assert rel_err(jac, ref["jacobian"]) < RTOL64
+
+
+@pytest.mark.parametrize("dtype", ["f64", "f32"])
+def test_real_valued_signal_rows_path(dtype, epg):
+    """real-valued plans ship only the real parts over PCIe and widen them to complex on the host
+    (epgx_simulate_real + epgx_expand_real): bit-identical to the complex rows of the plain path, ragged chunks and a
+    column offset included"""
+    from epgpy_b200 import engine, functions, lowering
+
+    case = cases.fisp(epg, 150, sizes=(41, 37, 29))  # 44 k atoms x 150 rows x 16 B = 105 MB: above the small-result cut
+    low = lowering.lower(case["seq"], dtype=dtype)
+    plan = engine.Plan(low)
+    assert plan.real_signal()
+    a, _ = functions.run_lowered(low, plan=plan, real_output=False)
+    b, _ = functions.run_lowered(low, plan=plan)
+    assert b.parts[0][3] is None, "the real-rows path was not taken"
+    assert np.array_equal(a.sig_host, b.sig_host) and not np.any(b.sig_host.imag)
+    c, _ = functions.run_lowered(low, plan=plan, atom_range=(1234, 30011), nchunk=7)
+    assert np.array_equal(c.sig_host, a.sig_host[:, 1234:1234 + 30011])
+    # a complex plan refuses
+    low2 = lowering.lower(cases.readme_mse(epg)["seq"], dtype=dtype)
+    assert not engine.Plan(low2).real_signal()
