@@ -627,7 +627,7 @@ def test_real_valued_signal_rows_path(dtype, epg):
     column offset included"""
     from epgpy_b200 import engine, functions, lowering
 
-    case = cases.fisp(epg, 150, sizes=(41, 37, 29))  # 44 k atoms x 150 rows x 16 B = 105 MB: above the small-result cut
+    case = cases.fisp(epg, 200, sizes=(45, 41, 31))  # 57 k atoms x 200 rows x 8 B (FP32) = 91 MB: above the small-result cut
     low = lowering.lower(case["seq"], dtype=dtype)
     plan = engine.Plan(low)
     assert plan.real_signal()
