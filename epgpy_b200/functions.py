@@ -118,7 +118,7 @@ def run_lowered(low, plan=None, device=None, atom_range=None, nchunk=None, keep_
         try:
             col = b - begin
             if real_path:
-                plan.run_to_host_real(d, sig_t, b, c, nchunk=max(nchunk, 8), host_col=col, host_atoms=count)
+                plan.run_to_host_real(d, sig_t, b, c, nchunk=max(2 * nchunk, 8), host_col=col, host_atoms=count)
                 parts[i] = (d, b, c, None, None)
                 return
             sig_d, jac_d = plan.run_to_host(d, sig_t, b, c, nchunk=nchunk, out_jacobian=jac_t, host_col=col, host_atoms=count)
