@@ -333,7 +333,7 @@ def main():
             del out
             barrier()
             t_e2e = 0.0
-            l0 = engine.LAUNCHES
+            l0, h0, d0 = engine.LAUNCHES, engine.H2D_BYTES, engine.D2H_BYTES
             for i in range(args.steps):
                 flush.zero_()
                 barrier()
@@ -344,12 +344,18 @@ def main():
                     del out  # the pinned pages go back to torch's host cache and serve the next call
             launches += engine.LAUNCHES - l0
             t_e2e = rank_max(t_e2e)
+            real_rows = (engine.D2H_BYTES - d0) < args.steps * low.nadc * cnt * csz
             e2e = {"value": natoms * args.steps / t_e2e, "unit": "atoms/s",
-                   "h2d_bytes_per_step": int(plan.workspace_bytes()), "d2h_bytes_per_step": int(low.nadc * cnt * csz),
+                   # counted by the binding from the copies it issued (tape + tables in; result rows out: REAL parts only when
+                   # the signal is real-valued, widened to complex128 by host threads -- Plan.run_to_host_real)
+                   "h2d_bytes_per_step": int((engine.H2D_BYTES - h0) // args.steps), "d2h_bytes_per_step": int((engine.D2H_BYTES - d0) // args.steps),
+                   "real_rows_over_pcie": bool(real_rows),
                    "ms_per_step": 1e3 * t_e2e / args.steps, "first_call_ms": 1e3 * t_first,
                    "path": "epg.simulate(sequence" + (", shard=(rank, world))" if world > 1 else ")") +
-                           ": lowering + epgx_plan_create + epgx_plan_upload + epgx_simulate_strided x chunks overlapped with "
-                           "epgx_copy2d_to_host into the pinned result + zero-copy reshape; a fresh call per step (no plan cache)",
+                           ": lowering + epgx_plan_create + epgx_plan_upload + chunked kernel launches overlapped with the D2H copy of "
+                           "the previous chunk (real-valued signal: epgx_simulate_real -> pinned staging -> epgx_expand_real into "
+                           "the complex128 result; else epgx_simulate_strided -> epgx_copy2d_to_host) + zero-copy reshape; a fresh "
+                           "call per step (no plan cache)",
                    "host_lowering_ms": 1e3 * t_lower, "operator_construction_ms_outside": 1e3 * t_build,
                    "result_shape": list(out.shape), "result_dtype": str(out.dtype)}
             # ---- parity of the TIMED output: scattered atoms against the CPU oracle (outside the timed region)

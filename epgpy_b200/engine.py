@@ -51,11 +51,19 @@ class Config(ctypes.Structure):
 _lib = None
 _lock = threading.Lock()
 LAUNCHES = 0  # kernel launches issued through this binding (bench.py reports the count of its timed regions)
+H2D_BYTES = 0  # bytes this binding copied host -> device (tape + coefficient table uploads)
+D2H_BYTES = 0  # bytes this binding copied device -> host (result rows)
 
 
 def _count(n=1):
     global LAUNCHES
     LAUNCHES += n
+
+
+def _moved(h2d=0, d2h=0):
+    global H2D_BYTES, D2H_BYTES
+    H2D_BYTES += h2d
+    D2H_BYTES += d2h
 
 EXPORTS = [
     "epgx_version", "epgx_device_count", "epgx_last_error", "epgx_plan_create", "epgx_plan_destroy",
@@ -206,6 +214,7 @@ class Plan:
                         ws = torch.empty(self.workspace_bytes(), dtype=torch.uint8, device=dev)
                     stream = torch.cuda.current_stream(dev)
                     _check(lib().epgx_plan_upload(self._h, ws.data_ptr(), stream.cuda_stream))
+                    _moved(h2d=ws.numel())
                     ev = torch.cuda.Event()
                     ev.record(stream)
                 self._ws[device] = (ws, ev)
@@ -377,9 +386,11 @@ class Plan:
                 if low.nadc:
                     _check(L.epgx_copy2d_to_host(hs + colb, hpitch, dev_signal.data_ptr() + colb, pitch, c * low.npool * csz,
                                                  low.nadc, copy.cuda_stream))
+                    _moved(d2h=c * low.npool * csz * low.nadc)
                 if has_jac:
                     _check(L.epgx_copy2d_to_host(hj + colb, hpitch, dev_jacobian.data_ptr() + colb, pitch,
                                                  c * low.npool * csz, low.njac * low.nvar, copy.cuda_stream))
+                    _moved(d2h=c * low.npool * csz * low.njac * low.nvar)
             copy.synchronize()
             compute.synchronize()
         return dev_signal, dev_jacobian
@@ -470,6 +481,7 @@ class Plan:
                     copy.wait_event(done)
                     with torch.cuda.stream(copy):
                         stage[slot].copy_(dbuf[k], non_blocking=True)
+                        _moved(d2h=dbuf[k].numel() * rsz)
                         ev = torch.cuda.Event()
                         ev.record(copy)
                     copied[k] = ev
