@@ -36,7 +36,7 @@ def sync():
 
 
 res = {}
-for name in ("contiguous", "pitched_1000_rows"):
+for name in ("contiguous",):
     best = 0.0
     for _ in range(args.reps):
         sync()
