@@ -249,7 +249,15 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = local_rank
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", dev))
+        # NCCL's copy kernels on a HIGH-PRIORITY stream: the simulation fills every SM with CTAs that hold all its
+        # registers, and at equal priority the all-gather of chunk j only got its CTAs placed once the kernels of all later
+        # chunks had drained (measured: the whole gather time showed up as a tail behind the last kernel)
+        opts_pg = None
+        try:
+            opts_pg = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
+        except Exception:
+            pass
+        dist.init_process_group("nccl", device_id=torch.device("cuda", dev), pg_options=opts_pg)
 
     def barrier():
         if world > 1:

@@ -357,10 +357,6 @@ def lower(sequence, *, init=None, probe=None, options=None, dtype="f64", propaga
     seq = flatten_sequence(sequence)
     if need_probe and not any(isinstance(op, Probe) for op in seq):
         raise ValueError("Cannot simulate sequence without at least one Probe/ADC operator")
-    for key in ("kgrid",):
-        if options.get(key):
-            raise NotImplementedError(f"state-matrix option `{key}` belongs to the shift-merge method, outside the hot path")
-
     # ---- initial state
     if init is None:
         init = [0, 0, 1]
@@ -373,6 +369,7 @@ def lower(sequence, *, init=None, probe=None, options=None, dtype="f64", propaga
         sm = StateMatrix(init)
     max_nstate = options.pop("max_nstate", None) or None
     lattice_opt = bool(options.pop("lattice", False))  # force the general lattice path (tests: it must reproduce the 1-d one)
+    kgrid_opt = options.pop("kgrid", None)
     options.pop("tvalue", None)
     options.pop("prune", None)
     if options:
@@ -435,6 +432,32 @@ def lower(sequence, *, init=None, probe=None, options=None, dtype="f64", propaga
     vecs = [op.k for op in seq if isinstance(op, S) and not common.isscalar(op.k)]
     lattice = lattice_opt
     base = None
+    # float shifts (the reference's `shift-merge`, shift.py:119-145, 367-444): wavenumbers quantised on a grid `kgrid`.
+    # Shifts that are multiples of the grid never merge two different wavenumbers, and the method is then exactly the
+    # integer lattice in grid units -- that is the part lowered here; other float shifts merge states approximately
+    # (weighted mean wavenumbers, data dependent) and are refused.
+    kscale = None
+    if kgrid_opt is not None or any(not np.issubdtype(np.asarray(v).dtype, np.integer) for v in vecs):
+        grids = [kgrid_opt if kgrid_opt is not None else op.kgrid for op in seq if isinstance(op, S)]
+        if any(g is None for g in grids):
+            raise AttributeError("kgrid not set")
+        kdim_f = max([1] + [np.asarray(v).shape[-1] for v in vecs])
+        kscale = np.broadcast_to(np.asarray(grids[0], dtype=float), (kdim_f,)).copy()
+        if any(not np.allclose(np.broadcast_to(np.asarray(g, dtype=float), (kdim_f,)), kscale) for g in grids):
+            raise NotImplementedError("different kgrid values in one sequence")
+        lattice = True
+
+    def grid_units(k):
+        """shift in lattice (grid) units"""
+        kv = np.atleast_1d(np.asarray(k if not common.isscalar(k) else [k])).reshape(-1)
+        if kscale is None:
+            return kv
+        q = kv / kscale[:len(kv)]
+        if not np.allclose(q, np.round(q), atol=1e-6):
+            raise NotImplementedError("float shifts that are not multiples of kgrid merge states approximately (shift-merge / "
+                                      "shift-prune, epgpy/shift.py:367-542): outside the hot path")
+        return np.round(q).astype(int)
+
     if vecs and not lattice:
         try:
             base = _unit_vector(vecs)
@@ -447,9 +470,11 @@ def lower(sequence, *, init=None, probe=None, options=None, dtype="f64", propaga
             lattice, base = True, None
     if lattice:
         for v in vecs:
-            if not np.issubdtype(np.asarray(v).dtype, np.integer) or np.asarray(v).shape[:-1] not in ((), (1,)):
-                raise NotImplementedError("lattice shifts need one integer vector per operator (float shifts: shift-merge / "
-                                          "shift-prune, epgpy/shift.py:367-542, are outside the hot path)")
+            if np.asarray(v).shape[:-1] not in ((), (1,)):
+                raise NotImplementedError("lattice shifts need one vector per operator (per-atom shift vectors: shift-prune, "
+                                          "epgpy/shift.py:478-542, are outside the hot path)")
+            if kscale is None and not np.issubdtype(np.asarray(v).dtype, np.integer):
+                raise AttributeError("kgrid not set")
 
     def shift_count(op):
         if base is None:
@@ -466,8 +491,8 @@ def lower(sequence, *, init=None, probe=None, options=None, dtype="f64", propaga
         nmax_pts = 1
         for op in seq:
             if isinstance(op, S):
-                kv = [op.k] if common.isscalar(op.k) else np.asarray(op.k).reshape(-1)
-                cap = max_nstate or op.nmax or None
+                kv = grid_units(op.k)
+                cap = (max_nstate or op.nmax or None) if kscale is None else None  # (shift-merge does not crop)
                 kz_before, n_before = lat.kzero, len(lat.coords)
                 maps = lat.shift(kv, cap)
                 lat_steps.append((maps, kz_before, n_before, list(lat.coords)))
@@ -522,7 +547,7 @@ def lower(sequence, *, init=None, probe=None, options=None, dtype="f64", propaga
         if coords is not None:  # lattice mode: one row per slot, the wavenumber of its lattice point (unused slots: 0)
             kdim = len(coords[0])
             Kp = np.zeros((max_order + 1, kdim))
-            Kp[:len(coords)] = np.asarray(coords, dtype=float) * kvalue * 1e-3
+            Kp[:len(coords)] = np.asarray(coords, dtype=float) * (1.0 if kscale is None else kscale[:kdim]) * kvalue * 1e-3
         if op.k is None:
             sh = np.zeros(kdim)
         else:
@@ -590,8 +615,7 @@ def lower(sequence, *, init=None, probe=None, options=None, dtype="f64", propaga
                 maps_all.extend(mp)
             assert lat.kzero == kz_before and len(lat.coords) == n_before
             close_segment(2, n_before - 1, len(coords_after) - 1, 0, rsv=off)  # (flags carry the kzero of the pass just closed)
-            kv = [op.k] if common.isscalar(op.k) else np.asarray(op.k).reshape(-1)
-            lat.shift(kv, max_nstate or op.nmax or None)
+            lat.shift(grid_units(op.k), (max_nstate or op.nmax or None) if kscale is None else None)
             n = len(lat.coords) - 1
         elif isinstance(op, S):
             m = shift_count(op)

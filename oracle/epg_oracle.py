@@ -702,6 +702,7 @@ class _Sim:
         self.kvalue = kvalue
         self.kvec = kvec  # base shift vector (collinear n-d shifts) or None
         self.coords = None  # [N, d] integer lattice points of the stored rows (general n-d shifts), else None
+        self.kgrid = None   # float shifts (shift-merge, shift.py:119-145) on multiples of this grid: lattice units
 
     # -- helpers
     def all_states(self):
@@ -722,7 +723,7 @@ class _Sim:
     def wavenumbers(self):
         """k of every stored order, rad/m (epgpy/statematrix.py:177-186)"""
         if self.coords is not None:
-            return self.coords.astype(float) * self.kvalue
+            return self.coords.astype(float) * (1.0 if self.kgrid is None else self.kgrid) * self.kvalue
         n = nstate(self.states)
         m = np.arange(-n, n + 1, dtype=float)
         if self.kvec is None:
@@ -859,10 +860,15 @@ def _apply_linear(sim, op):
 def _apply_shift(sim, op):
     """epgpy/shift.py:82-101"""
     k = op.k
-    if sim.coords is not None or (not isinstance(k, (int, np.integer)) and sim.kvec is None):
+    if sim.coords is not None or sim.kgrid is not None or (not isinstance(k, (int, np.integer)) and sim.kvec is None):
         # general integer lattice (the reference's `shift-nd` method, epgpy/shift.py:103-117): every state set moves on
         # the same lattice; rows are pruned only where ALL sets are empty so that they keep one common row order
         kv = np.atleast_1d(np.asarray(k)).reshape(-1)
+        if sim.kgrid is not None:  # the quantisation of shift.py:401-404, exact for multiples of the grid
+            q = kv / sim.kgrid
+            if not np.allclose(q, np.round(q), atol=1e-6):
+                raise NotImplementedError("float shifts off the grid merge states approximately: outside the hot path")
+            kv = np.round(q).astype(int)
         if sim.coords is None:
             n = nstate(sim.states)
             sim.coords = np.zeros((2 * n + 1, len(kv)), dtype=int)
@@ -871,7 +877,7 @@ def _apply_shift(sim, op):
             kv = np.pad(kv, (0, sim.coords.shape[1] - len(kv)))
         elif len(kv) > sim.coords.shape[1]:
             sim.coords = np.pad(sim.coords, [(0, 0), (0, len(kv) - sim.coords.shape[1])])
-        nmax = sim.max_nstate or None
+        nmax = (sim.max_nstate or None) if sim.kgrid is None else None  # (shift-merge does not crop)
         keys = [key for key, _ in sim.all_states()]
         stacked = np.stack([st for _, st in sim.all_states()], axis=0)  # [sets, *grid, N, 3]
         stacked, coords = shift_nd(stacked, sim.coords, kv, nmax=nmax, tol=1e-30)
@@ -959,7 +965,7 @@ def _apply_exchange(sim, op, propagate):
 
 
 def simulate(seq, *, init=None, density=1.0, max_nstate=None, kvalue=1.0, kvec=None,
-             jacobian=None, jacobian_probe=None, hessian=None, propagate_nondiff=False, adc_time=False, grid=None):
+             jacobian=None, jacobian_probe=None, hessian=None, propagate_nondiff=False, adc_time=False, grid=None, kgrid=None):
     """forward simulation: values (nADC, *grid) complex128   (epgpy/functions.py:50-192)
 
     jacobian: list of variable names -> also returns (nADC, *grid, nvars)  (epgpy/diff.py:384-416)
@@ -977,6 +983,7 @@ def simulate(seq, *, init=None, density=1.0, max_nstate=None, kvalue=1.0, kvec=N
     if init is not None and np.ndim(init) > 2:
         shape = broadcast_left(shape, np.shape(init)[:-2])
     sim = _Sim(shape, init, density, max_nstate, kvalue, kvec)
+    sim.kgrid = kgrid
     nd = len(shape)
     if hessian is not None:
         v1s, v2s = hessian

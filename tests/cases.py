@@ -464,7 +464,36 @@ def lattice_jac(epg, ntr=10):
     return dict(seq=seq, jac=["magnitude", "B1", "T2"])
 
 
+def gre_lattice_float(epg, ntr=16):
+    """FLOAT shifts on multiples of `kgrid` (the reference's shift-merge method, shift.py:119-145, 367-444): exactly
+    the integer lattice in grid units"""
+    case = gre_lattice_2d(epg, ntr)
+    seq = []
+    for op in lowering_flatten(case["seq"]):
+        name = type(op).__name__
+        if name == "S" or (isinstance(op, dict) and op.get("kind") == "S"):
+            k = op.k if not isinstance(op, dict) else op["k"]
+            seq.append(epg.S([0.5 * float(x) for x in np.asarray(k).reshape(-1)]))
+        elif name == "D" or (isinstance(op, dict) and op.get("kind") == "D"):
+            k = op.k if not isinstance(op, dict) else op["k"]
+            seq.append(epg.D(4.0, 2e-3, k=[0.5 * float(x) for x in np.asarray(k).reshape(-1)]))
+        else:
+            seq.append(op)
+    return dict(seq=seq, options={"kvalue": 600.0, "kgrid": 0.25})
+
+
+def lowering_flatten(seq):
+    out = []
+    for item in seq:
+        if isinstance(item, (list, tuple)):
+            out.extend(lowering_flatten(item))
+        else:
+            out.append(item)
+    return out
+
+
 CASES["slice_profile"] = slice_profile
+CASES["gre_lattice_float"] = gre_lattice_float
 CASES["gre_lattice_2d"] = gre_lattice_2d
 CASES["gre_lattice_3d_cropped"] = gre_lattice_3d_cropped
 CASES["lattice_jac"] = lattice_jac

@@ -30,6 +30,7 @@ def run(case, **extra):
         density=case.get("density") if case.get("density") is not None else 1.0,
         jacobian=case.get("jac"),
         init=case.get("init"),
+        kgrid=opts.get("kgrid"),
     )
     kw.update(extra)
     res = O.simulate(case["seq"], **kw)

@@ -59,7 +59,9 @@ def test_random_jacobian(seed):
                                    propagate_nondiff=True)
     ss, sj = max(1.0, np.abs(rs).max()), max(1.0, np.abs(rj).max())
     for kernel in (0, 1, 4, 5):  # auto, ring, realjac (orders over warps), setjac (one warp per state set)
-        for dtype, tol in (("f64", 1e-10), ("f32", 1e-4)):
+        # FP32 bar of the derivative columns: 5e-5 = 5 x the 1e-5 signal bar, as in test_fp32_matches_reference (all
+        # variables of a random sequence share one scale here, hence the same factor for the whole array)
+        for dtype, tol in (("f64", 1e-10), ("f32", 5e-5)):
             for lanes in (0, 2, 32, 128):
                 try:
                     got, k = _run(epg, seq, opts, jac, dtype, kernel, lanes)

@@ -122,8 +122,10 @@ def test_errors_like_reference():
         epg.T(1, 2, duration=-1)
     with pytest.raises(ValueError):  # unknown derivative parameter (diff.py:197-199)
         epg.T(1, 2, order1="T2")
-    with pytest.raises(NotImplementedError):  # float shifts need shift-merge: outside the hot path
+    with pytest.raises(AttributeError):  # float shift without kgrid (shift.py:131-132)
         interp_simulate([epg.T(90, 90), epg.S([0.5, 0.1]), epg.ADC])
+    with pytest.raises(NotImplementedError):  # float shifts off the grid merge states approximately: outside the hot path
+        interp_simulate([epg.T(90, 90), epg.S([0.5, 0.1]), epg.ADC], kgrid=0.25)
     with pytest.raises(RuntimeError):  # X non-conserving khi (exchange.py:97-100)
         kmat = epg.exchange_matrix(1e-2, densities=[0.5, 0.5])
         interp_simulate([epg.T(30, 0), epg.X(5, kmat, T1=[1e3, 1e3], T2=[50, 10]), epg.Adc(reduce=0)],
