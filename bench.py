@@ -198,7 +198,9 @@ def main():
     ap.add_argument("--atoms-per-cta", type=int, default=0)
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"])
     ap.add_argument("--gather-chunks", type=int, default=8)
-    ap.add_argument("--no-gather", action="store_true", help="N > 1: leave the final NCCL all-gather out of the timed step")
+    ap.add_argument("--no-gather", action="store_true", help="N > 1: leave the final gather out of the timed step")
+    ap.add_argument("--gather-impl", default="p2p", choices=["p2p", "nccl"],
+                    help="p2p: copy-engine pushes into peer windows (CUDA IPC over NVLink); nccl: chunked all-gather")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extra", action="store_true")
@@ -289,12 +291,27 @@ def main():
 
     cdt = torch.complex128 if args.dtype == "f64" else torch.complex64
     csz = 16 if args.dtype == "f64" else 8
-    sig = torch.empty((low.nadc, natoms if gather else cnt, 1), dtype=cdt, device=f"cuda:{dev}")
+    window, gather_impl = None, None
+    if gather and args.gather_impl == "p2p":
+        try:  # every rank must agree: a failure anywhere sends all of them to the NCCL path
+            window = sharding.PeerWindow(low, dev)
+            ok = torch.ones(1, device=f"cuda:{dev}")
+        except Exception as ex:
+            window, ok = None, torch.zeros(1, device=f"cuda:{dev}")
+            print(f"rank {rank}: peer window unavailable ({type(ex).__name__}: {ex}); using the NCCL all-gather", file=sys.stderr)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if not bool(ok.item()) and window is not None:
+            window = None
+    if gather:
+        gather_impl = "p2p" if window is not None else "nccl"
+    sig = window.tensor if window is not None else torch.empty((low.nadc, natoms if gather else cnt, 1), dtype=cdt, device=f"cuda:{dev}")
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{dev}")  # > 126 MB L2
     plan.upload(dev)
 
     def step():
-        if gather:  # slab kernels in chunks + the one collective of the path: NCCL all-gather of the signal slabs
+        if window is not None:  # slab kernels in chunks, each finished chunk pushed into every peer's window (copy engines)
+            sharding.run_gather_p2p(plan, window, nchunk=args.gather_chunks)
+        elif gather:  # slab kernels in chunks + NCCL all-gather of the signal slabs
             sharding.run_gather(plan, dev, nchunk=args.gather_chunks, out=sig)
         else:
             plan.run(dev, a0, cnt, signal=sig)
@@ -501,9 +518,11 @@ def main():
             "config": {"workload": workload, "atoms_per_gpu": cnt, "atoms_total": natoms, "ntr": args.ntr,
                        "l2": "256 MB buffer written between timed iterations (L2 flush)", "kernel": cfg,
                        "state_updates_per_atom_executed": cfg["updates_per_atom"], "gather": bool(gather),
-                       "gather_note": ("NCCL all-gather of the signal slabs inside the timed step, in %d chunks overlapped with the "
-                                       "slab kernels; every rank ends with the whole [nadc][atoms] dictionary" % args.gather_chunks)
-                       if gather else None,
+                       "gather_impl": gather_impl,
+                       "gather_note": ("final gather of the signal slabs inside the timed step, in %d chunks overlapped with the slab "
+                                       "kernels (p2p: copy-engine pushes into CUDA-IPC peer windows over NVLink + a closing NCCL "
+                                       "barrier; nccl: chunked all-gather); every rank ends with the whole [nadc][atoms] dictionary"
+                                       % args.gather_chunks) if gather else None,
                        # what the reference (full storage, no pruning, no fusion) performs for the same output
                        "state_updates_per_atom_reference": 4002002 if (args.ntr == NTR and max_nstate is None) else None},
             "state_updates_per_s": cfg["updates_per_atom"] * value,
@@ -513,9 +532,9 @@ def main():
         print(json.dumps(line))
         if parity is not None and not parity["ok"]:
             print(f"PARITY FAILURE: max rel err {parity['parity_max_rel']:.3e} > {parity['tol']}", file=sys.stderr)
-            if world > 1:
-                dist.destroy_process_group()
             return 1
+    if window is not None:
+        window.close()
     if world > 1:
         dist.destroy_process_group()
     return 0

@@ -885,6 +885,48 @@ extern "C" int epgx_simulate_host(const epgx_plan *pl, int device, int64_t atom_
   return rc;
 }
 
+extern "C" int epgx_peer_alloc(int64_t bytes, void **ptr, char handle[64]) {
+  if (!ptr || !handle || bytes <= 0) return fail(EPGX_ERR_INVALID, "bad peer_alloc arguments");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
+  *ptr = nullptr;
+  CUDA_TRY(cudaMalloc(ptr, (size_t)bytes));
+  cudaIpcMemHandle_t h;
+  cudaError_t e = cudaIpcGetMemHandle(&h, *ptr);
+  if (e != cudaSuccess) {
+    cudaFree(*ptr);
+    *ptr = nullptr;
+    return fail(EPGX_ERR_CUDA, std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(e));
+  }
+  memcpy(handle, &h, 64);
+  return EPGX_OK;
+}
+
+extern "C" int epgx_peer_open(const char handle[64], void **ptr) {
+  if (!ptr || !handle) return fail(EPGX_ERR_INVALID, "null argument");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, 64);
+  CUDA_TRY(cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return EPGX_OK;
+}
+
+extern "C" int epgx_peer_close(void *ptr) {
+  if (ptr) CUDA_TRY(cudaIpcCloseMemHandle(ptr));
+  return EPGX_OK;
+}
+
+extern "C" int epgx_peer_free(void *ptr) {
+  if (ptr) CUDA_TRY(cudaFree(ptr));
+  return EPGX_OK;
+}
+
+extern "C" int epgx_copy2d_device(void *dst, int64_t dst_pitch, const void *src, int64_t src_pitch, int64_t width,
+                                  int64_t height, void *stream) {
+  if (!dst || !src) return fail(EPGX_ERR_INVALID, "null argument");
+  CUDA_TRY(cudaMemcpy2DAsync(dst, (size_t)dst_pitch, src, (size_t)src_pitch, (size_t)width, (size_t)height,
+                             cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return EPGX_OK;
+}
+
 extern "C" int epgx_copy2d_to_host(void *dst, int64_t dst_pitch, const void *src, int64_t src_pitch, int64_t width,
                                    int64_t height, void *stream) {
   if (!dst || !src) return fail(EPGX_ERR_INVALID, "null argument");

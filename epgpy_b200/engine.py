@@ -69,7 +69,8 @@ EXPORTS = [
     "epgx_version", "epgx_device_count", "epgx_last_error", "epgx_plan_create", "epgx_plan_destroy",
     "epgx_plan_config", "epgx_plan_stream", "epgx_plan_set_variant", "epgx_plan_workspace_bytes", "epgx_plan_upload",
     "epgx_simulate", "epgx_simulate_strided", "epgx_simulate_state", "epgx_plan_real_signal", "epgx_simulate_real",
-    "epgx_expand_real", "epgx_copy2d_to_host", "epgx_simulate_host", "epgx_reduce",
+    "epgx_expand_real", "epgx_peer_alloc", "epgx_peer_open", "epgx_peer_close", "epgx_peer_free", "epgx_copy2d_device",
+    "epgx_copy2d_to_host", "epgx_simulate_host", "epgx_reduce",
     "epgx_fma_peak",
 ]
 
@@ -102,6 +103,11 @@ def lib():
             L.epgx_plan_real_signal.argtypes = [vp]
             L.epgx_simulate_real.argtypes = [vp, vp, i64, i64, vp, i64, vp]
             L.epgx_expand_real.argtypes = [i32, vp, i64, vp, i64, i64, i64, i32]
+            L.epgx_peer_alloc.argtypes = [i64, ctypes.POINTER(vp), ctypes.c_char_p]
+            L.epgx_peer_open.argtypes = [ctypes.c_char_p, ctypes.POINTER(vp)]
+            L.epgx_peer_close.argtypes = [vp]
+            L.epgx_peer_free.argtypes = [vp]
+            L.epgx_copy2d_device.argtypes = [vp, i64, vp, i64, i64, i64, vp]
             L.epgx_copy2d_to_host.argtypes = [vp, i64, vp, i64, i64, i64, vp]
             L.epgx_simulate_host.argtypes = [vp, i32, i64, i64, vp, vp]
             L.epgx_reduce.argtypes = [i32, vp, vp, i64, i64, i64, vp]

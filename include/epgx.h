@@ -46,7 +46,7 @@
 extern "C" {
 #endif
 
-#define EPGX_VERSION 107 /* 0.1.7: real-valued signal rows (epgx_simulate_real / epgx_expand_real), lattices, order 2 */
+#define EPGX_VERSION 108 /* 0.1.8: peer windows (copy-engine gather over NVLink), real-valued signal rows, lattices, order 2 */
 #define EPGX_MAX_DIMS 8
 #define EPGX_MAX_PATTERNS 64
 #define EPGX_MAX_POOLS 4
@@ -294,6 +294,20 @@ int epgx_simulate_real(const epgx_plan *plan, const void *workspace, int64_t ato
                        int64_t signal_stride, void *stream);
 int epgx_expand_real(int dtype, const void *src, int64_t src_pitch, void *dst, int64_t dst_pitch, int64_t rows, int64_t cols,
                      int nthreads);
+
+/* PEER WINDOWS: the final gather of the signal slabs over NVLink without a collective kernel.  Every rank (one process per
+ * GPU) allocates its result buffer with epgx_peer_alloc, which also returns a 64-byte CUDA IPC handle; the ranks exchange
+ * the handles (any transport) and map each other's buffers with epgx_peer_open.  After the kernel of a column chunk has
+ * written the rank's own buffer, epgx_copy2d_device pushes the chunk into every peer's buffer with the COPY ENGINES
+ * (cudaMemcpy2DAsync device -> device), at its final place: no SM is taken from the simulation of the next chunk -- an
+ * NCCL all-gather's copy kernels only got their CTAs placed once the simulation had drained -- and no scatter pass
+ * follows. */
+int epgx_peer_alloc(int64_t bytes, void **ptr, char handle[64]);
+int epgx_peer_open(const char handle[64], void **ptr);
+int epgx_peer_close(void *ptr);
+int epgx_peer_free(void *ptr);
+int epgx_copy2d_device(void *dst, int64_t dst_pitch, const void *src, int64_t src_pitch, int64_t width, int64_t height,
+                       void *stream);
 
 /* asynchronous pitched device->host copy (cudaMemcpy2DAsync) of `height` rows of `width` bytes: brings a
  * column range of the signal slab to (pinned) host memory while the next range is computed */

@@ -44,6 +44,17 @@ def _worker(rank, world, port, ref, out):
             torch.cuda.synchronize()
             got = full.cpu().numpy().reshape((low.nadc,) + tuple(low.grid))
             res[f"run_gather{nchunk}"] = float(np.abs(got - ref).max() / np.abs(ref).max())
+        # the same gather with copy-engine pushes into CUDA-IPC peer windows
+        window = sharding.PeerWindow(low, rank)
+        for nchunk in (1, 3):
+            window.tensor.zero_()
+            torch.cuda.synchronize()
+            dist.barrier()
+            full = sharding.run_gather_p2p(plan, window, nchunk=nchunk)
+            torch.cuda.synchronize()
+            got = full.cpu().numpy().reshape((low.nadc,) + tuple(low.grid))
+            res[f"p2p{nchunk}"] = float(np.abs(got - ref).max() / np.abs(ref).max())
+        window.close()
         b, c = sharding.slab(low.natoms, rank, world)
         local, _ = plan.run(rank, b, c)
         full = sharding.gather_rows(local, low.natoms)
