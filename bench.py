@@ -494,12 +494,15 @@ def main():
             "kernel_ms_per_launch": kernel_ms, "kernel_share_of_step": kernel_ms / step_ms,
             # dram__bytes_read.sum + dram__bytes_write.sum of the ncu --set full capture in profiles/ (27 000-atom
             # launch), scaled to this launch's atom count
-            "traffic": 14492.0 * cnt if (args.ntr == NTR and args.dtype == "f64") else None,
-            "traffic_note": "scaled per atom from the 27 000-atom capture profiles/r01_real_kernel_f64_full.txt "
-                            "(2.7 MB read + 388.6 MB written; algorithmic: 16 kB per atom, the difference is dirty lines "
+            "traffic": 14545.0 * cnt if (args.ntr == NTR and args.dtype == "f64") else None,
+            "traffic_note": "scaled per atom from the 27 000-atom capture profiles/r02b_real_kernel_f64_full.txt "
+                            "(2.7 MB read + 390.0 MB written; algorithmic: 16 kB per atom, the difference is dirty lines "
                             "still in the 126 MB L2 when the kernel ends)",
             "peak_source": f"measured live on this GPU: dependent-FMA microbenchmark epgx_fma_peak({args.dtype})",
             "flops_per_atom_executed": cfg["flops_per_atom"],
+            # the real-valued kernels apply a pulse in 7 instructions / 11 flops per order since round 2 (shared
+            # q = b s + u Z); rounds 1 counted the row-by-row form, 14 flops per order: the same launch at that count
+            "frac_at_round1_flop_count": (achieved * 14.0 / 11.0 / peak if peak else None) if cfg["kernel"] == 2 else None,
             "hbm": {"achieved": bytes_alg / (kernel_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                     "frac": bytes_alg / (kernel_ms * 1e-3) / 1e9 / hbm_peak,
                     "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"},

@@ -88,11 +88,13 @@ static double form_flops(int code, int flags, int npool) {
 
 static const int kRegSlots[5] = {1, 2, 4, 8, 16};
 
-// flops per order in the real-valued kernels (three reals per order)
+// flops per order in the real-valued kernels (three reals per order).  A pulse / fused E.T.E takes seven instructions:
+// s = F+ + F- (1), u Z (1), q = b s + u Z (2), F+' = c F+ + q (2), F-' = c F- + q (2), h s (1), Z' = w Z + h s (2) = 11
+// flops (round 1 counted the row-by-row form: 14); scaled windows (epgx_real.cuh) drop the product u Z and execute 10
 static double form_flops_real(int code) {
   switch (code) {
   case EPGX_OP_T_RE:
-  case EPGX_OP_FUSED: return 14;
+  case EPGX_OP_FUSED: return 11;
   case EPGX_OP_E:
   case EPGX_OP_D:
   case EPGX_OP_DIAG: return 3;
@@ -195,7 +197,7 @@ static int choose_variant(const epgx_plan *pl, epgx_config &c, int kernel, int l
     for (int o : {2, 4, 8, 16, 32}) // register slots come in pairs: blocks of two orders per lane
       if (o >= need && !NS) NS = o;
     if (NS && NS <= ns_max) {
-      int A = atoms > 0 ? atoms : 128 / G;
+      int A = atoms > 0 ? atoms : (G == 32 ? 2 : 128 / G); // (one warp per atom: CTAs of two warps, measured 2 % faster than four)
       while (A * G > 256 && A > 1) --A;
       while (G >= 8 && A > 1 && A * 32 * 9 * rsz > 40 * 1024) --A; // staging rows of the whole-TR windows
       c.kernel = 2;
@@ -205,7 +207,11 @@ static int choose_variant(const epgx_plan *pl, epgx_config &c, int kernel, int l
       c.var_tiles = 1;
       c.atoms_per_cta = A;
       c.threads_per_cta = A * G;
-      c.smem_bytes = 2 * epgx::kTapeChunk * 32 + ((A * t.npattern + 3) & ~3) * 4 + (G >= 8 ? A * 32 * 9 * rsz : 0) + 32;
+      // tape windows (three when the next window's gathers are prefetched: G = 32), pattern offsets, staging rows +
+      // echoes of the whole-TR windows, a row of zeros, prefetched coefficient entries [A][32][12] (epgx_real.cuh)
+      const bool pf = epgx::kRealPrefetch && G == 32;
+      c.smem_bytes = (pf ? 3 : 2) * epgx::kTapeChunk * 32 + ((A * t.npattern + 3) & ~3) * 4 + (G >= 8 ? A * 32 * 9 * rsz : 0) +
+                     4 * rsz + (pf ? A * 32 * 12 * rsz : 0) + 32;
       c.ring = C;
       return EPGX_OK;
     }
@@ -632,11 +638,75 @@ extern "C" int epgx_plan_create(const epgx_tape *t, epgx_plan **out) {
       }
       st.push_back(seg_rec(sg.shift, sg.n_old, sg.n_new, sg.flags, next_nact));
     }
+    // plain whole-TR pair: unit shift +1, no segment flag but (possibly) the truncation at max_nstate
+    auto plain_tr = [&](const std::vector<epgx_op> &v, size_t k) {
+      return k + 1 < v.size() && v[k].code == EPGX_OP_TR && (v[k + 1].flags & ~(EPGX_SEG_MASK_TOP << 2)) == 2;
+    };
+    if (pl->real_ok) {
+      // Runs of plain whole-TR pairs start at a window boundary: the records in front of a run are padded with NOPs
+      // (the first one, aux = 1, tells the record loop to skip to the next window), the run fills whole windows and,
+      // unless the stream ends there, its last window is padded as well.  Windows hold an EVEN number of pairs (the
+      // fast path runs two TRs per iteration, epgx_real.cuh), so the first pair of an odd run stays in front of the
+      // padding as a generic record.  Without this the first and the last TRs of a FISP train -- 4 % of the TRs, where
+      // few orders are populated -- went through the record-at-a-time path and took 20 % of the kernel's time.
+      std::vector<epgx_op> in;
+      in.swap(st);
+      const size_t n = in.size();
+      auto pad_window = [&]() {
+        if (st.size() % CH == 0) return;
+        epgx_op skip = nop;
+        skip.aux = 1;
+        st.push_back(skip);
+        while (st.size() % CH) st.push_back(nop);
+      };
+      size_t i = 0;
+      while (i < n) {
+        if (in[i].code == EPGX_OP_NOP) { ++i; continue; } // alignment padding of the first pass
+        std::vector<size_t> run;
+        size_t j = i;
+        for (;;) {
+          while (j < n && in[j].code == EPGX_OP_NOP) ++j;
+          if (!plain_tr(in, j)) break;
+          run.push_back(j);
+          j += 2;
+        }
+        if (run.size() >= 4) {
+          size_t k = 0;
+          if (run.size() & 1) {
+            if (st.size() & 1) st.push_back(nop);
+            st.push_back(in[run[0]]);
+            st.push_back(in[run[0] + 1]);
+            k = 1;
+          }
+          pad_window();
+          for (; k < run.size(); ++k) { st.push_back(in[run[k]]); st.push_back(in[run[k] + 1]); }
+          i = j;
+          while (i < n && in[i].code == EPGX_OP_NOP) ++i;
+          if (i < n) pad_window();
+          continue;
+        }
+        const int code = in[i].code;
+        if (code == EPGX_OP_TR) { // (not plain, or a short run) a pair at an even position: never split by a window
+          if (st.size() & 1) st.push_back(nop);
+          st.push_back(in[i]);
+          st.push_back(in[i + 1]);
+          i += 2;
+          continue;
+        }
+        if (code == EPGX_OP_FUSED && (int)(st.size() % CH) == CH - 1) st.push_back(nop);
+        st.push_back(in[i++]);
+      }
+    }
+    for (size_t b0 = 0; b0 < st.size(); b0 += CH) {
+      // windows made of an even number of plain TR pairs followed by nothing but padding: the fast path of the real
+      // kernel; the pair count rides in rsv1 of the window's first record
+      int m = 0;
+      while (m < CH / 2 && plain_tr(st, b0 + 2 * m)) ++m;
+      bool pure = m >= 2 && m % 2 == 0;
+      for (size_t k = b0 + 2 * m; pure && k < b0 + CH && k < st.size(); ++k) pure = st[k].code == EPGX_OP_NOP;
+      if (pure) { st[b0].flags |= 0x8000; st[b0].rsv1 = m; }
+    }
     for (size_t b0 = 0; b0 + CH <= st.size(); b0 += CH) {
-      bool pure = true;
-      for (int j = 0; pure && j < CH; j += 2) // unit shift +1, no segment flag but (possibly) the truncation at max_nstate
-        pure = st[b0 + j].code == EPGX_OP_TR && (st[b0 + j + 1].flags & ~(EPGX_SEG_MASK_TOP << 2)) == 2;
-      if (pure) st[b0].flags |= 0x8000;
       bool purec = st[b0 + CH - 1].code == EPGX_OP_NOP;
       for (int j = 0; purec && j + 3 <= CH - 1; j += 3) purec = st[b0 + j].code == EPGX_OP_TRC && st[b0 + j + 1].flags == 2;
       if (purec) st[b0].flags |= 0x4000;

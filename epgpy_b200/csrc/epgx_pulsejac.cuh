@@ -133,14 +133,14 @@ __global__ void __launch_bounds__(PJ_THREADS, pj_min_blocks(3 * NO * sizeof(real
       const bool aff = (flags & EPGX_FLAG_AFFINE) && !partial;
       switch (code) {
       case EPGX_OP_T_RE: {
-        const real a = ca[0], w = ca[1], b = ca[2], u = ca[3], h = real(-0.5) * u;
+        const real a = ca[0], w = ca[1], b = ca[2], u = ca[3], h = real(-0.5) * u, c = a - b;
         if (mine) {
 #pragma unroll
-          for (int k = 0; k < NO; ++k) {
-            const real p_ = P[k], m_ = M[k], z_ = Z[k], t_ = u * z_;
-            P[k] = fma(a, p_, fma(b, m_, t_));
-            M[k] = fma(a, m_, fma(b, p_, t_));
-            Z[k] = fma(w, z_, h * (p_ + m_));
+          for (int k = 0; k < NO; ++k) { // seven instructions per order: q = b s + u Z shared by F+ and F- (epgx_real.cuh)
+            const real p_ = P[k], m_ = M[k], z_ = Z[k], s_ = p_ + m_, q_ = fma(b, s_, u * z_);
+            P[k] = fma(c, p_, q_);
+            M[k] = fma(c, m_, q_);
+            Z[k] = fma(w, z_, h * s_);
           }
         }
       } break;

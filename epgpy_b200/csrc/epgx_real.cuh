@@ -19,82 +19,131 @@
 #include "epgx_common.cuh"
 #include "epgx_reg.cuh"
 
+#ifndef EPGX_REAL_PREFETCH
+#define EPGX_REAL_PREFETCH 0
+#endif
+#ifndef EPGX_REAL_UNROLL
+#define EPGX_REAL_UNROLL 1 // iterations (of two TRs) unrolled in the whole-TR loop
+#endif
+#ifndef EPGX_REAL_AFF
+#define EPGX_REAL_AFF 0 // affine terms of order 0 through a per-lane pointer (1) or selects (0)
+#endif
+#ifndef EPGX_REAL_SCALED
+#define EPGX_REAL_SCALED 1 // 0: every whole-TR window runs the unscaled seven-instruction form (experiments)
+#endif
+
 namespace epgx {
+
+constexpr int RAW_REALS = 12; // prefetched coefficient entries per TR: T (a, w, b, u), E_pre (e1, r0, e2), E_post (e1, r0, e2), 2 pad
+
+// 1 / x to full precision without the division subroutine (|x| normal: the caller checks the range)
+__device__ __forceinline__ double rcp_newton(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  r = fma(fma(-x, r, 1.0), r, r);
+  return fma(fma(-x, r, 1.0), r, r);
+}
+__device__ __forceinline__ float rcp_newton(float x) { return __frcp_rn(x); }
 
 // One tape window of TAPE_CHUNK / 2 whole-TR records (fused E.T.E, plain ADC, unit shift +1) for one atom
 // per warp, with a COMPILE-TIME number KP of active register pairs: the per-TR body is a single basic block (no
 // slot dispatch), so the scheduler overlaps the coefficient loads, the 18 KP FMAs and the 2 KP shuffles /
 // selects of the shift.  KP is the largest pair count of the window; registers above the populated orders
 // hold zeros (or unobservable values), so over-covering changes nothing.  The fused coefficients of the
-// window's TRs wait in the warp's shared-memory rows cw[TR][8] (written by lane TR); lane 0 leaves the echo of
-// TR j in sb[j]; cw[TR][7] != 0 flags a shift that truncates at max_nstate.
+// window's TRs wait in the warp's shared-memory rows cw[TR][8] = (c, w | b, u | h, mask | fz, zz) (written by lane TR);
+// lane 0 leaves the echo of TR j in sb[j]; mask != 0 flags a shift that truncates at max_nstate.  The affine terms
+// (fz, zz) belong to order 0 only: lane 0 reads them from the row, every other lane from a row of zeros (af / afs:
+// per-lane base and stride -- one load instead of four selects per TR).
 //
 // Two TRs per iteration.  Even TR ("phase 0"): the even order of a block is in register 2 sp, the odd one in
 // 2 sp + 1 (canonical).  Its shift rotates the ODD F+ registers up one lane (they become the even orders of
 // the next block) and the EVEN F- registers down one lane (they become the odd orders of the previous block);
 // the other registers stay where they are and change role.  Odd TR ("phase 1"): roles swapped, its shift
 // rotates the even F+ and the odd F- registers and restores the canonical roles.  Z never moves.
-template <typename real, int NS, int KP, bool MASK>
+//
+// Arithmetic of one TR on one order (the fused E.T.E is the real matrix [[a b u] [b a u] [h h w]]):
+//   s = F+ + F-,  q = b s + u Z,  F+' = c F+ + q,  F-' = c F- + q,  Z' = w Z + h s      with c = a - b
+// -- SEVEN floating-point instructions (the row-by-row form takes eight: q is shared by F+ and F-, s by q and Z').
+// SC (scaled window): the lanes keep Zs = u_j Z instead of Z while the window runs (u_j: the coefficient of the TR
+// about to be applied), which removes the product u Z as well -- SIX instructions:
+//   q = b s + Zs,  Zs' = w~ Zs + h~ s,   w~ = u_(j+1) w / u_j,  h~ = u_(j+1) h,  zz~ = u_(j+1) zz   (staged by the prologue)
+// The last TR of a window takes u_(j+1) := 1 and leaves plain Z; a window with a vanishing u (a pulse of 0 or 180
+// degrees) runs unscaled.  Only Z is rescaled: rescaling F as well would remove h, but the two scales then grow
+// like prod 1 / (h u) -- not bounded over a window in FP32.
+template <typename real, int NS, int KP, bool MASK, bool SC>
 __device__ __forceinline__ void tr_window(real (&P)[NS], real (&M)[NS], real (&Z)[NS], const real *cw, real *sb, bool lane0,
-                                          bool is_first, bool is_last, int srcUp, int srcDn, unsigned mtop, int jbeg, int jend) {
+                                          bool is_first, bool is_last, int srcUp, int srcDn, unsigned mtop, int jbeg, int jend,
+                                          const real *af, int afs) {
   typedef typename vec2<real>::type real2;
   const unsigned FULL = 0xffffffffu;
   if constexpr (2 * KP <= NS) {
-#pragma unroll 1
+    if (SC && jbeg == 0) { // entering a scaled window: Zs = u_0 Z (registers above the pair count hold zeros or unobservable orders)
+      const real u0 = cw[3];
+#pragma unroll
+      for (int r = 0; r < 2 * KP; ++r) Z[r] *= u0;
+    }
+    constexpr int kUnroll = EPGX_REAL_UNROLL;
+#pragma unroll(kUnroll)
     for (int j = jbeg; j < jend; j += 2) {
 #pragma unroll
       for (int ph = 0; ph < 2; ++ph) {
-        // coefficients of the TR: broadcast loads from the warp's staging rows (a, w | b, u | h, fz | zz, -)
+        // coefficients of the TR: broadcast loads from the warp's staging rows
         const real2 c0 = ((const real2 *)cw)[4 * (j + ph)], c1v = ((const real2 *)cw)[4 * (j + ph) + 1],
                     c2 = ((const real2 *)cw)[4 * (j + ph) + 2];
-        const real a = c0.x, w = c0.y, b = c1v.x, u = c1v.y, h = c2.x;
+        const real c = c0.x, w = c0.y, b = c1v.x, u = c1v.y, h = c2.x;
         if constexpr (sizeof(real) == 4) {
           // FP32: the two orders of a block sit in adjacent registers and take the same coefficients -- Blackwell's
-          // packed FFMA2 / FMUL2 / FADD2 (sm_100: fma.rn.f32x2) update both at once, 8 instructions per register pair
-          // instead of 18; the scalar coefficients are broadcast operands and the role swap of the odd TRs is the
+          // packed FFMA2 / FMUL2 / FADD2 (sm_100: fma.rn.f32x2) update both at once, 7 (6 scaled) instructions per register
+          // pair; the scalar coefficients are broadcast operands and the role swap of the odd TRs is the
           // LO_HI operand swizzle on the Z pair (both free).  The kernel is issue-bound in FP32.
 #pragma unroll
           for (int sp = 0; sp < KP; ++sp) {
             const float2 p2 = make_float2(P[2 * sp], P[2 * sp + 1]), m2 = make_float2(M[2 * sp], M[2 * sp + 1]);
             const float2 z2 = ph ? make_float2(Z[2 * sp + 1], Z[2 * sp]) : make_float2(Z[2 * sp], Z[2 * sp + 1]);
-            const float2 a2 = make_float2(a, a), b2 = make_float2(b, b), u2 = make_float2(u, u), w2 = make_float2(w, w),
+            const float2 cc2 = make_float2(c, c), b2 = make_float2(b, b), u2 = make_float2(u, u), w2 = make_float2(w, w),
                          h2 = make_float2(h, h);
-            const float2 t2 = __fmul2_rn(u2, z2);
-            const float2 np = __ffma2_rn(a2, p2, __ffma2_rn(b2, m2, t2));
-            const float2 nm = __ffma2_rn(a2, m2, __ffma2_rn(b2, p2, t2));
-            const float2 nz = __ffma2_rn(w2, z2, __fmul2_rn(h2, __fadd2_rn(p2, m2)));
+            const float2 s2 = __fadd2_rn(p2, m2);
+            const float2 q2 = SC ? __ffma2_rn(b2, s2, z2) : __ffma2_rn(b2, s2, __fmul2_rn(u2, z2));
+            const float2 np = __ffma2_rn(cc2, p2, q2);
+            const float2 nm = __ffma2_rn(cc2, m2, q2);
+            const float2 nz = __ffma2_rn(w2, z2, __fmul2_rn(h2, s2));
             P[2 * sp] = np.x; P[2 * sp + 1] = np.y; M[2 * sp] = nm.x; M[2 * sp + 1] = nm.y;
             if (ph) { Z[2 * sp + 1] = nz.x; Z[2 * sp] = nz.y; } else { Z[2 * sp] = nz.x; Z[2 * sp + 1] = nz.y; }
           }
         } else {
-          const real fz0 = lane0 ? c2.y : real(0), zz0 = lane0 ? cw[8 * (j + ph) + 6] : real(0);
+#if EPGX_REAL_AFF
+          const real2 aff = *(const real2 *)(af + afs * (j + ph));
+          const real fz0 = aff.x, zz0 = aff.y;
+#else
+          const real fz0 = lane0 ? cw[8 * (j + ph) + 6] : real(0), zz0 = lane0 ? cw[8 * (j + ph) + 7] : real(0);
+#endif
 #pragma unroll
           for (int sp = 0; sp < KP; ++sp)
 #pragma unroll
             for (int i = 0; i < 2; ++i) {
               const int r = 2 * sp + (i ^ ph); // register of F+- (k = 2 b + i) in this phase; Z(k) is in 2 sp + i
               const real p_ = P[r], m_ = M[r], z_ = Z[2 * sp + i];
-              // eight FP64 instructions per order: the product u Z is shared by F+ and F- (written out with fma();
-              // the plain expressions contract left to right into 1 DMUL + 2 DFMA each, nine per order).  Order 0
-              // (pair 0, i = 0, lane 0) takes the affine terms of the two E operators as the addends of its first
-              // products, which costs two selects instead of three FP64 additions for the whole warp
+              // seven (scaled window: six) FP64 instructions per order, written out with fma().  Order 0 (pair 0,
+              // i = 0, lane 0) takes the affine terms of the two E operators as the addends of its first products,
+              // which costs two selects instead of three FP64 additions for the whole warp
+              const real s_ = p_ + m_;
               if (sp == 0 && i == 0) {
-                const real t_ = fma(u, z_, fz0);
-                P[r] = fma(a, p_, fma(b, m_, t_));
-                M[r] = fma(a, m_, fma(b, p_, t_));
-                Z[0] = fma(w, z_, fma(h, p_ + m_, zz0));
+                const real q_ = fma(b, s_, SC ? z_ + fz0 : fma(u, z_, fz0));
+                P[r] = fma(c, p_, q_);
+                M[r] = fma(c, m_, q_);
+                Z[0] = fma(w, z_, fma(h, s_, zz0));
               } else {
-                const real t_ = u * z_;
-                P[r] = fma(a, p_, fma(b, m_, t_));
-                M[r] = fma(a, m_, fma(b, p_, t_));
-                Z[2 * sp + i] = fma(w, z_, h * (p_ + m_));
+                const real q_ = SC ? fma(b, s_, z_) : fma(b, s_, u * z_);
+                P[r] = fma(c, p_, q_);
+                M[r] = fma(c, m_, q_);
+                Z[2 * sp + i] = fma(w, z_, h * s_);
               }
             }
           if (lane0) sb[j + ph] = P[ph]; // the echo of the TR; written to HBM by lane j + ph after the window
         }
         if constexpr (sizeof(real) == 4) {
           if (lane0) {
-            const real fz = c2.y, zz = cw[8 * (j + ph) + 6];
+            const real fz = cw[8 * (j + ph) + 6], zz = cw[8 * (j + ph) + 7];
             P[ph] += fz; M[ph] += fz; Z[0] += zz;
             sb[j + ph] = P[ph];
           }
@@ -122,7 +171,7 @@ __device__ __forceinline__ void tr_window(real (&P)[NS], real (&M)[NS], real (&Z
         // above the cap reads as zero.  mtop: bit of its canonical register in this lane (0: another lane / not held);
         // in the roles after this shift the register is (canonical ^ (1 - ph))
         if constexpr (MASK) {
-          if (cw[8 * (j + ph) + 7] != real(0)) { // (bit tests: an index comparison would turn P[] into a local array)
+          if (c2.y != real(0)) { // (bit tests: an index comparison would turn P[] into a local array)
 #pragma unroll
             for (int r = 0; r < 2 * KP; ++r) P[r] = ((mtop >> (r ^ (1 - ph))) & 1u) ? real(0) : P[r];
           }
@@ -164,11 +213,25 @@ __global__ void __launch_bounds__(MAXT, real_min_blocks(sizeof(real) * NS, MAXT)
   const long long atom = p.atom_begin + (valid ? a_rel : p.atom_count - 1);
   const real *__restrict__ coef = (const real *)p.coef;
 
+  // EPGX_REAL_PREFETCH (experiment, off): with one warp per atom (G = 32) the coefficient gathers of the NEXT whole-TR
+  // window are issued as cp.async copies into raw[TR][12] while this window runs (three tape buffers: the records of
+  // window w + 1 must be in shared memory during window w).  The window prologue spends 30 % of its samples waiting
+  // on those gathers, yet the kernel is SLOWER with the prefetch (FP64 228 ms against 213 ms, FP32 133 against 124:
+  // 28 kB instead of 13 kB of shared memory per CTA and 10 more LSU instructions per TR and lane) -- measured twice,
+  // in two implementations.
+  const bool pf = EPGX_REAL_PREFETCH && G == 32;
+  const int NB = pf ? 3 : 2;
   int4 *tbuf = (int4 *)smem_raw;
-  int *patoff = (int *)(tbuf + 2 * TAPE_CHUNK * 2) + al * p.npattern;
+  int *patoff = (int *)(tbuf + NB * TAPE_CHUNK * 2) + al * p.npattern;
   // whole-TR windows (G >= 8): per atom, coefficient rows [32][8] and the echoes of the window [32]
-  real *cw = (real *)((int *)(tbuf + 2 * TAPE_CHUNK * 2) + ((p.A * p.npattern + 3) & ~3)) + (size_t)al * (32 * 9);
+  real *cw0 = (real *)((int *)(tbuf + NB * TAPE_CHUNK * 2) + ((p.A * p.npattern + 3) & ~3));
+  real *cw = cw0 + (size_t)al * (32 * 9);
   real *sb = cw + 32 * 8;
+  real *zrow = cw0 + (G >= 8 ? (size_t)p.A * (32 * 9) : 0); // two zeros: the affine terms of the lanes that do not hold order 0
+  real *raw = zrow + 4 + (size_t)al * (32 * RAW_REALS);
+  if (tid < 4) zrow[tid] = real(0);
+  const real *af = lane == 0 ? cw + 6 : zrow;
+  const int afs = lane == 0 ? 8 : 0;
   {
     int idx[EPGX_MAX_DIMS];
     long long r = atom;
@@ -228,12 +291,12 @@ __global__ void __launch_bounds__(MAXT, real_min_blocks(sizeof(real) * NS, MAXT)
     break;                                                                                                  \
   }
 // F+' = a F+ + b F- + u Z ; F-' = b F+ + a F- + u Z ; Z' = w Z + h (F+ + F-)
-#define APPLY5(a, w, b, u, h)                  \
-  DUFF(nslot, {                                \
-    const real p_ = P[s], m_ = M[s], z_ = Z[s]; \
-    P[s] = a * p_ + b * m_ + u * z_;           \
-    M[s] = a * m_ + b * p_ + u * z_;           \
-    Z[s] = w * z_ + h * (p_ + m_);             \
+#define APPLY5(a, w, b, u, h)                                              \
+  DUFF(nslot, {                                                            \
+    const real p_ = P[s], m_ = M[s], z_ = Z[s], s_ = p_ + m_, q_ = fma(b, s_, u * z_); \
+    P[s] = fma(a - b, p_, q_);                                             \
+    M[s] = fma(a - b, m_, q_);                                             \
+    Z[s] = fma(w, z_, h * s_);                                             \
   })
 
 // close a segment (reset / unit shift) and open the next one (order count of the next pass)
@@ -296,20 +359,48 @@ __global__ void __launch_bounds__(MAXT, real_min_blocks(sizeof(real) * NS, MAXT)
 
   const int4 *stream = (const int4 *)p.stream;
   const int nthreads = blockDim.x;
-  for (int i = tid; i < 2 * TAPE_CHUNK && i < 2 * p.nstream; i += nthreads) __pipeline_memcpy_async(tbuf + i, stream + i, 16);
+  // tape windows: NB shared-memory buffers; window w + NB - 1 is fetched while window w runs
+  for (int i = tid; i < (NB - 1) * 2 * TAPE_CHUNK && i < 2 * p.nstream; i += nthreads) __pipeline_memcpy_async(tbuf + i, stream + i, 16);
+  __pipeline_commit();
+  // the coefficient gathers of the next window (cp.async into raw[TR][RAW_REALS]; lane j: TR j), issued once the rows of
+  // the current window have been consumed.  A pure window is never the first of the stream (which opens with a SEG
+  // record), so its gathers were always issued one window earlier.
+#define PREFETCH_NEXT(TN_)                                                                                 \
+  if (pf && ((TN_)[0].x & EPGX_CHUNK_PURE_TR) && lane < (TN_)[1].w) {                                      \
+    const int4 a0 = (TN_)[4 * lane], a1 = (TN_)[4 * lane + 1], b0 = (TN_)[4 * lane + 2], b1 = (TN_)[4 * lane + 3]; \
+    const real *ct = coef + (unsigned)a0.z + patoff[a1.y & 0xff];                                          \
+    const real *ca = coef + (unsigned)a0.w + patoff[(a1.y >> 8) & 0xff];                                   \
+    const real *ea = coef + (unsigned)a1.x + patoff[(a1.y >> 16) & 0xff];                                  \
+    const real *cb = coef + (unsigned)b0.z + patoff[b1.y & 0xff];                                          \
+    const real *eb = coef + (unsigned)b0.w + patoff[(b1.y >> 8) & 0xff];                                   \
+    real *rw = raw + RAW_REALS * lane;                                                                     \
+    _Pragma("unroll") for (int k = 0; k < 4; ++k) __pipeline_memcpy_async(rw + k, ct + k, sizeof(real));   \
+    __pipeline_memcpy_async(rw + 4, ca, sizeof(real));                                                     \
+    __pipeline_memcpy_async(rw + 5, ca + 1, sizeof(real));                                                 \
+    __pipeline_memcpy_async(rw + 6, ea, sizeof(real));                                                     \
+    __pipeline_memcpy_async(rw + 7, cb, sizeof(real));                                                     \
+    __pipeline_memcpy_async(rw + 8, cb + 1, sizeof(real));                                                 \
+    __pipeline_memcpy_async(rw + 9, eb, sizeof(real));                                                     \
+  }                                                                                                        \
   __pipeline_commit();
   int nact = -1, nslot = 0;
+  int bcur = 0; // tape buffer of the current window
   for (int base = 0, chunk = 0; base < p.nstream; base += TAPE_CHUNK, ++chunk) {
     __pipeline_wait_prior(0);
     __syncthreads();
     {
-      const int nb = base + TAPE_CHUNK;
-      int4 *dst = tbuf + ((chunk + 1) & 1) * 2 * TAPE_CHUNK;
+      const int nb = base + (NB - 1) * TAPE_CHUNK;
+      int bd = bcur + NB - 1;
+      if (bd >= NB) bd -= NB;
+      int4 *dst = tbuf + bd * 2 * TAPE_CHUNK;
       for (int i = tid; i < 2 * TAPE_CHUNK && nb * 2 + i < 2 * p.nstream; i += nthreads)
         __pipeline_memcpy_async(dst + i, stream + (size_t)nb * 2 + i, 16);
       __pipeline_commit();
     }
-    const int4 *tb = tbuf + (chunk & 1) * 2 * TAPE_CHUNK;
+    const int4 *tb = tbuf + bcur * 2 * TAPE_CHUNK;
+    const int4 *tnext = tbuf + (bcur + 1 >= NB ? 0 : bcur + 1) * 2 * TAPE_CHUNK; // (pf: the records of the next window)
+    const bool has_next = base + TAPE_CHUNK < p.nstream;
+    if (++bcur >= NB) bcur = 0;
     const int cnt = min(TAPE_CHUNK, p.nstream - base);
     if (G >= 8 && (tb[0].x & EPGX_CHUNK_PURE_TR)) {
       // ---- fast path: the window holds TAPE_CHUNK / 2 whole-TR records (shift +1, no flags).  Phase 1: the G lanes
@@ -320,30 +411,60 @@ __global__ void __launch_bounds__(MAXT, real_min_blocks(sizeof(real) * NS, MAXT)
       // (lowering.py) and need not move; nact of TR j is the "next nact" of TR j - 1
       // (the window runs as two halves of 16 TRs, each with its own pair count: 0.13 pair less per TR on average)
       constexpr int HALF = TAPE_CHUNK / 4;
+      const int ntr = tb[1].w; // whole-TR records of this window: TAPE_CHUNK / 2, or an even number below it (rest: NOP padding)
       int need0 = 0, need1 = 0;
-      for (int j = lane; j < TAPE_CHUNK / 2; j += G) {
+      bool bad = false;
+      for (int j = lane; j < ntr; j += G) {
         const int4 a0 = tb[4 * j], a1 = tb[4 * j + 1], b0 = tb[4 * j + 2], b1 = tb[4 * j + 3];
         const int fl = (a0.x >> 16) & 0xffff;
-        const real *ct = coef + (unsigned)a0.z + patoff[a1.y & 0xff];
-        const real *ca = coef + (unsigned)a0.w + patoff[(a1.y >> 8) & 0xff];
-        const real *cb = coef + (unsigned)b0.z + patoff[b1.y & 0xff];
-        const Fused5<real> fv = fuse5<real>(ldc(ct), ldc(ct + 1), ldc(ct + 2), ldc(ct + 3), fl & EPGX_FLAG_PRE, ldc(ca),
-                                            ldc(ca + 1), ldc(coef + (unsigned)a1.x + patoff[(a1.y >> 16) & 0xff]),
-                                            fl & EPGX_FLAG_POST, ldc(cb), ldc(cb + 1),
-                                            ldc(coef + (unsigned)b0.w + patoff[(b1.y >> 8) & 0xff]), false, m0);
+        real g[10]; // T (a, w, b, u), E_pre (e1, r0, e2), E_post (e1, r0, e2)
+        if (pf) {
+          const real2 *rw = (const real2 *)(raw + RAW_REALS * j);
+#pragma unroll
+          for (int k = 0; k < 5; ++k) { const real2 v = rw[k]; g[2 * k] = v.x; g[2 * k + 1] = v.y; }
+        } else {
+          const real *ct = coef + (unsigned)a0.z + patoff[a1.y & 0xff];
+          const real *ca = coef + (unsigned)a0.w + patoff[(a1.y >> 8) & 0xff];
+          const real *cb = coef + (unsigned)b0.z + patoff[b1.y & 0xff];
+          g[0] = ldc(ct); g[1] = ldc(ct + 1); g[2] = ldc(ct + 2); g[3] = ldc(ct + 3);
+          g[4] = ldc(ca); g[5] = ldc(ca + 1); g[6] = ldc(coef + (unsigned)a1.x + patoff[(a1.y >> 16) & 0xff]);
+          g[7] = ldc(cb); g[8] = ldc(cb + 1); g[9] = ldc(coef + (unsigned)b0.w + patoff[(b1.y >> 8) & 0xff]);
+        }
+        const Fused5<real> fv = fuse5<real>(g[0], g[1], g[2], g[3], fl & EPGX_FLAG_PRE, g[4], g[5], g[6], fl & EPGX_FLAG_POST, g[7],
+                                            g[8], g[9], false, m0);
         real2 *c = (real2 *)(cw + 8 * j);
-        c[0] = real2{fv.a, fv.w}; c[1] = real2{fv.b, fv.u}; c[2] = real2{fv.h, fv.fz};
-        c[3] = real2{fv.zz, ((b0.x >> 18) & EPGX_SEG_MASK_TOP) ? real(1) : real(0)};
+        c[0] = real2{fv.a - fv.b, fv.w}; c[1] = real2{fv.b, fv.u};
+        c[2] = real2{fv.h, ((b0.x >> 18) & EPGX_SEG_MASK_TOP) ? real(1) : real(0)}; c[3] = real2{fv.fz, fv.zz};
+        const real au = fabs(fv.u);
+        bad = bad || !(au >= (sizeof(real) == 4 ? real(1e-15) : real(1e-100)) && au <= real(4));
         const int cur = j == 0 ? nact : tb[4 * j - 1].z;
         const int nd = (max(max(min((int)((unsigned)b1.x & 0xffff), cur + 1), cur), 0) >> (lgG + 1)) + 1;
         if (j < HALF) need0 = max(need0, nd); else need1 = max(need1, nd);
       }
       need0 = __reduce_max_sync(FULL, need0);
       need1 = __reduce_max_sync(FULL, need1);
+      // scaled window (see tr_window): every u of the window usable as a scale for every atom of the warp
+      // (worth it when the orders in flight outweigh the division per TR of the second staging pass)
+      const bool sc = EPGX_REAL_SCALED && (need0 + need1) * G >= 96 && !__any_sync(FULL, bad);
       __syncwarp();
-#define TRW(K_) case K_: tr_window<real, NS, K_, BOUNDED>(P, M, Z, cw, sb, lane == 0, is_first, is_last, srcUp, srcDn, mtop, jb, jb + HALF); break;
+      if (has_next) { PREFETCH_NEXT(tnext) } // (raw[] of this window has been read)
+      if (sc) {
+        for (int j = lane; j < ntr; j += G) {
+          real *c = cw + 8 * j;
+          const real un = j + 1 < ntr ? c[8 + 3] : real(1);
+          c[1] = c[1] * (un * rcp_newton(c[3]));
+          c[4] *= un;
+          c[7] *= un;
+        }
+        __syncwarp();
+      }
+#define TRW(K_)                                                                                                              \
+  case K_:                                                                                                                   \
+    if (sc) tr_window<real, NS, K_, BOUNDED, true>(P, M, Z, cw, sb, lane == 0, is_first, is_last, srcUp, srcDn, mtop, jb, min(jb + HALF, ntr), af, afs); \
+    else tr_window<real, NS, K_, BOUNDED, false>(P, M, Z, cw, sb, lane == 0, is_first, is_last, srcUp, srcDn, mtop, jb, min(jb + HALF, ntr), af, afs); \
+    break;
 #pragma unroll 1
-      for (int jb = 0; jb < TAPE_CHUNK / 2; jb += HALF) {
+      for (int jb = 0; jb < ntr; jb += HALF) {
         switch (jb ? need1 : need0) {
           TRW(1) TRW(2) TRW(3) TRW(4) TRW(5) TRW(6) TRW(7) TRW(8) TRW(9) TRW(10) TRW(11) TRW(12) TRW(13) TRW(14) TRW(15) TRW(16)
         default: break;
@@ -352,14 +473,15 @@ __global__ void __launch_bounds__(MAXT, real_min_blocks(sizeof(real) * NS, MAXT)
 #undef TRW
       __syncwarp();
       if (valid) // lane j (+ G, ...) stores the echoes of its TRs
-        for (int j = lane; j < TAPE_CHUNK / 2; j += G) {
+        for (int j = lane; j < ntr; j += G) {
           const long long o = (long long)tb[4 * j + 2].y * p.sig_stride + a_rel;
           if (p.out_real) sigr[o] = sb[j]; else sig[o] = real2{sb[j], real(0)};
         }
-      nact = tb[4 * (TAPE_CHUNK / 2 - 1) + 3].z;
+      nact = tb[4 * (ntr - 1) + 3].z;
       nslot = nact < 0 ? 0 : SLOTS_FOR(nact);
       continue;
     }
+    if (has_next) { PREFETCH_NEXT(tnext) }
     for (int r = 0; r < cnt; ++r) {
       const int4 r0 = tb[2 * r], r1 = tb[2 * r + 1];
       const int code = r0.x & 0xffff, flags = (r0.x >> 16) & 0xffff, aux = r0.y;
@@ -367,6 +489,9 @@ __global__ void __launch_bounds__(MAXT, real_min_blocks(sizeof(real) * NS, MAXT)
       const int pat0 = r1.y & 0xff, pat1 = (r1.y >> 8) & 0xff, pat2 = (r1.y >> 16) & 0xff;
 
       switch (code) {
+      case EPGX_OP_NOP:
+        if (aux) r = cnt; // padding up to the next window (a run of whole-TR records starts there)
+        break;
       case EPGX_OP_FUSED: {
         const int4 q0 = tb[2 * r + 2], q1 = tb[2 * r + 3]; // the CONT record (never split from FUSED)
         const real *ct = coef + off0 + patoff[pat0];
@@ -444,6 +569,7 @@ __global__ void __launch_bounds__(MAXT, real_min_blocks(sizeof(real) * NS, MAXT)
     }
   }
 #undef APPLY5
+#undef PREFETCH_NEXT
 #undef DO_SEG
 #undef SHIFT_REAL
 #undef DUFF

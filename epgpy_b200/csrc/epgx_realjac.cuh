@@ -261,13 +261,13 @@ __device__ __forceinline__ void trj_assemble(const int4 *g, int part, const real
   out[7] = real(0);
 }
 
-// the per-TR arithmetic, K slots: 9 + 18 (SETS - 1) operations per order
+// the per-TR arithmetic, K slots: 7 + 14 (SETS - 1) floating-point instructions per order
 template <typename real, int NS, int SETS, int K>
 __device__ __forceinline__ void rj_trj(real (&P)[SETS][NS], real (&M)[SETS][NS], real (&Z)[SETS][NS], const real *cf) {
   typedef typename vec2<real>::type real2;
   if constexpr (K <= NS) {
     const real2 f0 = ((const real2 *)cf)[0], f1 = ((const real2 *)cf)[1], f2 = ((const real2 *)cf)[2];
-    const real a = f0.x, w = f0.y, b = f1.x, u = f1.y, h = f2.x;
+    const real a = f0.x, w = f0.y, b = f1.x, u = f1.y, h = f2.x, c = a - b;
 #pragma unroll
     for (int q = 1; q < SETS; ++q) {
       const real2 j0 = ((const real2 *)cf)[4 * q], j1 = ((const real2 *)cf)[4 * q + 1], j2 = ((const real2 *)cf)[4 * q + 2];
@@ -276,17 +276,21 @@ __device__ __forceinline__ void rj_trj(real (&P)[SETS][NS], real (&M)[SETS][NS],
       for (int s = 0; s < K; ++s) {
         const real xp = P[0][s], xm = M[0][s], xz = Z[0][s];
         const real p_ = P[q][s], m_ = M[q][s], z_ = Z[q][s];
-        P[q][s] = a * p_ + b * m_ + u * z_ + ja * xp + jb * xm + ju * xz;
-        M[q][s] = a * m_ + b * p_ + u * z_ + ja * xm + jb * xp + ju * xz;
-        Z[q][s] = w * z_ + h * (p_ + m_) + jw * xz + jh * (xp + xm);
+        // shared by the rows of F+ and F- (epgx_real.cuh): q = b s + u Z + jb xs + ju x_Z -- 14 instead of 18 per order
+        const real s_ = p_ + m_, xs = xp + xm;
+        const real q_ = fma(b, s_, fma(u, z_, fma(jb, xs, ju * xz)));
+        P[q][s] = fma(c, p_, fma(ja - jb, xp, q_));
+        M[q][s] = fma(c, m_, fma(ja - jb, xm, q_));
+        Z[q][s] = fma(w, z_, fma(h, s_, fma(jw, xz, jh * xs)));
       }
     }
 #pragma unroll
     for (int s = 0; s < K; ++s) {
       const real p_ = P[0][s], m_ = M[0][s], z_ = Z[0][s];
-      P[0][s] = a * p_ + b * m_ + u * z_;
-      M[0][s] = a * m_ + b * p_ + u * z_;
-      Z[0][s] = w * z_ + h * (p_ + m_);
+      const real s_ = p_ + m_, q_ = fma(b, s_, u * z_);
+      P[0][s] = fma(c, p_, q_);
+      M[0][s] = fma(c, m_, q_);
+      Z[0][s] = fma(w, z_, h * s_);
     }
   }
 }
