@@ -199,8 +199,10 @@ def main():
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"])
     ap.add_argument("--gather-chunks", type=int, default=8)
     ap.add_argument("--no-gather", action="store_true", help="N > 1: leave the final gather out of the timed step")
-    ap.add_argument("--gather-impl", default="p2p", choices=["p2p", "nccl"],
-                    help="p2p: copy-engine pushes into peer windows (CUDA IPC over NVLink); nccl: chunked all-gather")
+    ap.add_argument("--gather-impl", default="auto", choices=["auto", "p2p", "nccl"],
+                    help="p2p: copy-engine pushes into peer windows (CUDA IPC over NVLink); nccl: chunked all-gather; auto: p2p "
+                         "up to four ranks, nccl above (measured: 122.6 / 65.2 / 53.2 ms with p2p at N = 2 / 4 / 8 against "
+                         "129.9 / 71.6 / 43.8 ms with nccl, profiles/scale_r02.json and scale_r02b_p2p.json)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extra", action="store_true")
@@ -292,7 +294,7 @@ def main():
     cdt = torch.complex128 if args.dtype == "f64" else torch.complex64
     csz = 16 if args.dtype == "f64" else 8
     window, gather_impl = None, None
-    if gather and args.gather_impl == "p2p":
+    if gather and (args.gather_impl == "p2p" or (args.gather_impl == "auto" and world <= 4)):
         try:  # every rank must agree: a failure anywhere sends all of them to the NCCL path
             window = sharding.PeerWindow(low, dev)
             ok = torch.ones(1, device=f"cuda:{dev}")
@@ -495,7 +497,7 @@ def main():
             # dram__bytes_read.sum + dram__bytes_write.sum of the ncu --set full capture in profiles/ (27 000-atom
             # launch), scaled to this launch's atom count
             "traffic": 14545.0 * cnt if (args.ntr == NTR and args.dtype == "f64") else None,
-            "traffic_note": "scaled per atom from the 27 000-atom capture profiles/r02b_real_kernel_f64_full.txt "
+            "traffic_note": "scaled per atom from the 27 000-atom capture profiles/r02c_real_kernel_f64_full.txt "
                             "(2.7 MB read + 390.0 MB written; algorithmic: 16 kB per atom, the difference is dirty lines "
                             "still in the 126 MB L2 when the kernel ends)",
             "peak_source": f"measured live on this GPU: dependent-FMA microbenchmark epgx_fma_peak({args.dtype})",
