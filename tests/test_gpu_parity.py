@@ -186,6 +186,53 @@ def test_real_kernel_variants(lanes, atoms, dtype, max_nstate, epg):
     assert rel_err(ring[0], ref) < RTOL64
 
 
+def _tr_runs_sequence(epg, runs, zero_flip_at=(), sizes=(3, 2, 5)):
+    """FISP-like train cut into RUNS of whole-TR records by records that are not TRs (a spoiled inversion, a pause
+    without read-out, a reset): the stream builder aligns every run of >= 4 plain TR pairs to a tape window, keeps the
+    first pair of an odd run generic and pads partial windows (csrc/epgx.cu).  zero_flip_at: TR indices with a 0 degree
+    pulse (u = 0: the window must run unscaled, csrc/epgx_real.cuh)"""
+    T1 = np.linspace(300, 3000, sizes[0])
+    T2 = np.linspace(20, 300, sizes[1])[None, :]
+    B1 = np.linspace(0.7, 1.2, sizes[2])[None, None, :]
+    rng = np.random.RandomState(3)
+    seq, i = [epg.T(180, 0), epg.E(20, T1, T2)], 0
+    for r, n in enumerate(runs):
+        for _ in range(n):
+            fa = 0.0 if i in zero_flip_at else 10 + 50 * abs(np.sin(i * np.pi / 37))
+            tr = rng.uniform(11, 16)
+            seq.append([epg.T(fa * B1, 90), epg.E(3, T1, T2), epg.ADC, epg.E(tr - 3, T1, T2), epg.S(1)])
+            i += 1
+        if r % 3 == 0:
+            seq += [epg.E(40, T1, T2), epg.SPOILER, epg.T(180, 0), epg.E(15, T1, T2)]
+        elif r % 3 == 1:
+            seq += [epg.T(30 * B1, 90), epg.E(5, T1, T2), epg.S(1)]  # a TR without read-out: not a whole-TR record
+        else:
+            seq += [epg.RESET, epg.T(90 * B1, 90), epg.E(4, T1, T2)]
+    return seq
+
+
+@pytest.mark.parametrize("dtype", ["f64", "f32"])
+@pytest.mark.parametrize("lanes", [0, 2, 8, 32])
+@pytest.mark.parametrize("runs,zeros,max_nstate", [((1, 3, 4, 5, 33, 2, 64, 7, 38), (), None), ((70, 9), (12, 13, 50, 75), None),
+                                                   ((5, 67, 4), (40,), 6), ((32,), (), None), ((31,), (), None)])
+def test_real_kernel_whole_tr_runs(runs, zeros, max_nstate, lanes, dtype, epg):
+    """runs of whole-TR records of every length class (below the run threshold, odd, one window, several windows, partial
+    last window), separated by generic records, zero-flip pulses inside scaled windows, bounded and unbounded states:
+    real kernel (all lane counts) against the ring kernel and the oracle"""
+    opts = {"max_nstate": max_nstate} if max_nstate else {}
+    case = {"seq": _tr_runs_sequence(epg, runs, zeros), "options": opts}
+    ring, _ = _run_variant(epg, case, kernel=1)
+    try:
+        got, cfg = _run_variant(epg, case, dtype=dtype, kernel=3, lanes_per_atom=lanes)
+    except MemoryError:
+        pytest.skip("more orders than lanes x slots of any instance")
+    assert cfg["kernel"] == 2
+    assert rel_err(got[0], ring[0]) < (1e-12 if dtype == "f64" else RTOL32)
+    ref = oracle_api.O.simulate(_tr_runs_sequence(oracle_api.epg, runs, zeros), **opts)
+    assert rel_err(ring[0], ref) < RTOL64
+    assert rel_err(got[0], ref) < (RTOL64 if dtype == "f64" else RTOL32)
+
+
 @pytest.mark.parametrize("dtype", ["f64", "f32"])
 @pytest.mark.parametrize("lanes", [0, 1, 4, 32])
 @pytest.mark.parametrize("name", ["init_states_real", "init_states_cropped"])

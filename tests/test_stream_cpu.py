@@ -145,3 +145,53 @@ def test_whole_tr_groups_on_the_host(variables, max_nstate, epg):
     assert np.abs(s1 - s0).max() <= 1e-13 * max(1.0, np.abs(s0).max())
     for v in range(low.nvar):
         assert np.abs(j1[:, v] - j0[:, v]).max() <= 1e-12 * max(1e-30, np.abs(j0[:, v]).max())
+
+
+def test_whole_tr_runs_are_aligned_to_tape_windows(epg):
+    """real-valued plans: every run of >= 4 plain whole-TR pairs starts at a window boundary behind a skip mark, windows
+    hold an even number of pairs (count in rsv1 of the window's first record, flag 0x8000), the first pair of an odd run
+    stays in front of the padding, and every TR keeps its place in the order of the tape (csrc/epgx.cu)"""
+    from epgpy_b200 import engine, lowering
+    import test_gpu_parity as tgp
+
+    runs = (1, 3, 4, 5, 33, 2, 64, 7, 38)
+    low = lowering.lower(tgp._tr_runs_sequence(epg, runs))
+    plan = engine.Plan(low)
+    st = plan.stream()
+    assert plan.config()["kernel"] == 2
+    code, flags = st["code"], st["flags"]
+    fast = 0
+    for w0 in range(0, len(st), 64):
+        w = st[w0:w0 + 64]
+        if flags[w0] & 0x8000:
+            m = int(w["rsv1"][0])
+            assert 2 <= m <= 32 and m % 2 == 0
+            assert np.all(w["code"][0:2 * m:2] == OP_TR) and np.all(w["code"][1:2 * m:2] == OP_CONT)
+            assert np.all(w["code"][2 * m:] == OP_NOP)
+            if w0 > 0:  # the window in front ends with padding that opens with a skip mark, or is a full fast window
+                prev = st[w0 - 64:w0]
+                if not (flags[w0 - 64] & 0x8000 and int(prev["rsv1"][0]) == 32):
+                    pad = np.flatnonzero((prev["code"] == OP_NOP) & (prev["aux"] == 1))
+                    assert len(pad) and np.all(prev["code"][pad[-1]:] == OP_NOP)
+            fast += m
+    # the long runs (33, 64, 7, 38 TRs; a run loses its first / last TR to the generic path when the records around it
+    # fuse with them) take the fast path, and no run of four plain pairs is left in a generic window
+    assert fast >= 32 + 62 + 6 + 36
+    streak = 0
+    for w0 in range(0, len(st), 64):
+        if flags[w0] & 0x8000:
+            streak = 0
+            continue
+        i = w0
+        while i < min(w0 + 64, len(st)):
+            if code[i] == OP_TR and int(flags[i + 1]) & ~(2 << 2) == 2:
+                streak += 1
+                i += 2
+            else:
+                if code[i] != OP_NOP:
+                    streak = 0
+                i += 1
+            assert streak < 4
+    # read-out rows are visited in increasing order (no TR was moved across another)
+    rows = [int(st[i + 1]["aux"]) for i in np.flatnonzero(code == OP_TR)]
+    assert rows == sorted(rows) and len(rows) == len(set(rows))
