@@ -10,8 +10,8 @@ from .utils import Axes, get_wavenumber
 from .operators import (
     Operator, MultiOperator, EmptyOperator, Spoiler, Wait, Offset, Reset, PD, System,
     DiffOperator, MatrixOp, ScalarOp,
-    Probe, Adc, Jacobian, Hessian, PartialsPruner,
-    E, P, R, T, Tx, Ty, Phi, S, D,
+    Probe, Adc, DFT, Imaging, Jacobian, Hessian, PartialsPruner,
+    E, P, R, T, Tx, Ty, Phi, S, G, C, D,
     ADC, NULL, SPOILER, RESET,
 )
 from .exchange import X, exchange_matrix

@@ -315,7 +315,7 @@ __global__ void __launch_bounds__(256) ring_kernel(const KParams p) {
             for (int q = 0; q < NP; ++q) m0[q] = ldc(coef + off0 + POFF(pat0, q));
             break;
           case EPGX_OP_ADC:
-            if (k == kz && valid) {
+            if (k == ((flags & EPGX_FLAG_SLOT) ? aux1 : kz) && valid) { // (EPGX_FLAG_SLOT: any lattice slot, base state only)
 #pragma unroll
               for (int q = 0; q < NP; ++q) {
                 real fr = real(1), fi = real(0);

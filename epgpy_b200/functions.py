@@ -220,6 +220,21 @@ def _assemble(low, res, count=None, asarray=True):
                 if row.post is not None:
                     arr = np.asarray(row.post(arr)).astype(cdt, copy=False)
                 values[ip].append(arr)
+            elif row.kind == "lin":
+                # weighted sum of configuration rows (accumulated-time F0: statematrix.py:149-156)
+                nrow, wts, scale = row.jac
+                arr = sum(wts[i] * to_grid(sig_host[row.index + i].reshape(-1)) for i in range(nrow))
+                if scale is not None:
+                    arr = arr * common.left(np.atleast_1d(scale), arr.ndim)
+                if row.post is not None:
+                    arr = np.asarray(row.post(arr)).astype(cdt, copy=False)
+                values[ip].append(np.asarray(arr).astype(cdt, copy=False))
+            elif row.kind == "fourier":
+                # DFT / Imaging (probe.py:168-219): F [*grid, nslot] read by the device, weights applied here
+                nrow, kphys, tacc, probe, system = row.jac
+                F = np.stack([to_grid(sig_host[row.index + i].reshape(-1)) for i in range(nrow)], axis=-1)
+                val = probe.combine(F, kphys, tacc, system, low.kdim)
+                values[ip].append(row.post(val) if row.post is not None else val)
             elif row.kind == "expr":
                 val = row.jac._eval(to_grid(sig_host[row.index].reshape(-1)), to_grid(sig_host[row.index + 1].reshape(-1)))
                 values[ip].append(row.post(val) if row.post is not None else val)

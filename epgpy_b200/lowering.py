@@ -26,7 +26,7 @@ from .statematrix import StateMatrix
 # opcodes / flags (include/epgx.h)
 (OP_NOP, OP_T_GEN, OP_T_RE, OP_T_IM, OP_E, OP_DIAG, OP_MATRIX, OP_D, OP_X, OP_SPOIL, OP_PD, OP_ADC, OP_FUSED,
  OP_CONT) = range(14)
-F_BASE, F_PARTIALS, F_INJECT, F_G, F_AFFINE, F_Z0, F_SCALE, F_PRE, F_POST, F_IM, F_GEN, F_P1, F_P2 = (1 << i for i in range(13))
+F_BASE, F_PARTIALS, F_INJECT, F_G, F_AFFINE, F_Z0, F_SCALE, F_PRE, F_POST, F_IM, F_GEN, F_P1, F_P2, F_SLOT = (1 << i for i in range(14))
 SEG_RESET, SEG_MASK_TOP, SEG_LATTICE = 1, 2, 4
 MAX_DIMS, MAX_PATTERNS, MAX_POOLS = 8, 64, 4
 
@@ -370,7 +370,9 @@ def lower(sequence, *, init=None, probe=None, options=None, dtype="f64", propaga
     max_nstate = options.pop("max_nstate", None) or None
     lattice_opt = bool(options.pop("lattice", False))  # force the general lattice path (tests: it must reproduce the 1-d one)
     kgrid_opt = options.pop("kgrid", None)
-    options.pop("tvalue", None)
+    tvalue = options.pop("tvalue", None)
+    if tvalue is None:
+        tvalue = getattr(sm, "tvalue", 1.0)
     options.pop("prune", None)
     if options:
         raise TypeError(f"unknown simulate option(s): {sorted(options)}")
@@ -430,13 +432,15 @@ def lower(sequence, *, init=None, probe=None, options=None, dtype="f64", propaga
 
     # ---- shifts: 1-d integers, collinear integer vectors (exactly the 1-d problem) -- or a general integer lattice
     vecs = [op.k for op in seq if isinstance(op, S) and not common.isscalar(op.k)]
-    lattice = lattice_opt
+    lattice = lattice_opt or any(isinstance(pb, (ops_mod.DFT, ops_mod.Imaging)) for pb in list(seq) + list(probes or []))
     base = None
     # float shifts (the reference's `shift-merge`, shift.py:119-145, 367-444): wavenumbers quantised on a grid `kgrid`.
     # Shifts that are multiples of the grid never merge two different wavenumbers, and the method is then exactly the
     # integer lattice in grid units -- that is the part lowered here; other float shifts merge states approximately
     # (weighted mean wavenumbers, data dependent) and are refused.
-    kscale = None
+    # The reference quantises WAVENUMBERS, i.e. shifts times ktvalue = (kvalue, kvalue, kvalue, tvalue)
+    # (statematrix.py:203-211; shift.py:136-141): the grid units of a shift are k * ktvalue / kgrid.
+    kscale = ktv = None
     if kgrid_opt is not None or any(not np.issubdtype(np.asarray(v).dtype, np.integer) for v in vecs):
         grids = [kgrid_opt if kgrid_opt is not None else op.kgrid for op in seq if isinstance(op, S)]
         if any(g is None for g in grids):
@@ -445,6 +449,8 @@ def lower(sequence, *, init=None, probe=None, options=None, dtype="f64", propaga
         kscale = np.broadcast_to(np.asarray(grids[0], dtype=float), (kdim_f,)).copy()
         if any(not np.allclose(np.broadcast_to(np.asarray(g, dtype=float), (kdim_f,)), kscale) for g in grids):
             raise NotImplementedError("different kgrid values in one sequence")
+        kv3 = [float(kvalue)] * 3 if common.isscalar(kvalue) else [float(x) for x in list(kvalue)[:3]]
+        ktv = np.asarray(kv3[:min(kdim_f, 3)] + [float(tvalue)] * (kdim_f == 4))
         lattice = True
 
     def grid_units(k):
@@ -452,10 +458,10 @@ def lower(sequence, *, init=None, probe=None, options=None, dtype="f64", propaga
         kv = np.atleast_1d(np.asarray(k if not common.isscalar(k) else [k])).reshape(-1)
         if kscale is None:
             return kv
-        q = kv / kscale[:len(kv)]
+        q = kv * ktv[:len(kv)] / kscale[:len(kv)]
         if not np.allclose(q, np.round(q), atol=1e-6):
-            raise NotImplementedError("float shifts that are not multiples of kgrid merge states approximately (shift-merge / "
-                                      "shift-prune, epgpy/shift.py:367-542): outside the hot path")
+            raise NotImplementedError("float shifts whose wavenumbers (k * kvalue) are not multiples of kgrid merge states "
+                                      "approximately (shift-merge / shift-prune, epgpy/shift.py:367-542): outside the hot path")
         return np.round(q).astype(int)
 
     if vecs and not lattice:
@@ -545,9 +551,11 @@ def lower(sequence, *, init=None, probe=None, options=None, dtype="f64", propaga
         tau = np.asarray(op.tau, dtype=float) * 1e-3
         Kp = m[:, None] * bvec[None, :] * kvalue * 1e-3   # order +m
         if coords is not None:  # lattice mode: one row per slot, the wavenumber of its lattice point (unused slots: 0)
-            kdim = len(coords[0])
+            kdim = min(len(coords[0]), 3)  # (a fourth coordinate is accumulated time: no diffusion weighting)
             Kp = np.zeros((max_order + 1, kdim))
-            Kp[:len(coords)] = np.asarray(coords, dtype=float) * (1.0 if kscale is None else kscale[:kdim]) * kvalue * 1e-3
+            cs = np.asarray(coords, dtype=float)[:, :kdim]
+            # integer lattice: coordinates are shift counts (x kvalue); float lattice: grid units of WAVENUMBERS (x kgrid)
+            Kp[:len(coords)] = cs * (kvalue if kscale is None else kscale[:kdim]) * 1e-3
         if op.k is None:
             sh = np.zeros(kdim)
         else:
@@ -603,6 +611,35 @@ def lower(sequence, *, init=None, probe=None, options=None, dtype="f64", propaga
 
     def part_flag():
         return F_PARTIALS if (nvar and (alive or alive2)) else 0
+
+    def lattice_slots(zero_k=False):
+        """slots of the current lattice that can hold F+ (all of them, or those with zero wavenumber), their
+        wavenumbers (rad/m, first three coordinates) and accumulated times (fourth coordinate, x tvalue)"""
+        if not lattice:
+            raise NotImplementedError("this probe reads configurations other than k = 0: it needs the lattice path")
+        if nvar:
+            raise NotImplementedError("derivatives of probes over several configurations")
+        cs = np.asarray(lat.coords, dtype=float).reshape(len(lat.coords), lat.kdim)
+        unit = np.ones(lat.kdim)
+        if kscale is not None:  # float lattice: grid units of wavenumbers / of t * tvalue
+            unit = kscale[:lat.kdim].copy()
+        else:
+            unit[:min(lat.kdim, 3)] = (np.broadcast_to(np.asarray(kvalue, dtype=float), (3,)))[:min(lat.kdim, 3)]
+            if lat.kdim == 4:
+                unit[3] = float(tvalue)
+        phys = cs * unit
+        kphys = np.zeros((len(cs), 3))
+        kphys[:, :min(lat.kdim, 3)] = phys[:, :3]
+        tacc = phys[:, 3] if lat.kdim == 4 else np.zeros(len(cs))
+        keep = [i for i, c in enumerate(lat.coords) if lat.occ[c][0] and (not zero_k or not any(c[:3]))]
+        if not keep:
+            keep = [lat.kzero]
+        return keep, kphys[keep], tacc[keep]
+
+    system = {}
+
+    def system_now():
+        return dict(system)
 
     for op in seq:
         if isinstance(op, Jacobian) and probes is not None:
@@ -741,7 +778,11 @@ def lower(sequence, *, init=None, probe=None, options=None, dtype="f64", propaga
                     _emit_or_reuse(bld, op, form, F_BASE)
         elif isinstance(op, Probe):
             pass
-        elif isinstance(op, (EmptyOperator, ops_mod.System)):
+        elif isinstance(op, ops_mod.System):
+            if any(k in ("kvalue", "tvalue") for k in op.properties):
+                raise NotImplementedError("System(kvalue=..., tvalue=...) in mid-sequence: pass them as simulate options")
+            system.update(op.properties)
+        elif isinstance(op, EmptyOperator):
             pass
         else:
             raise NotImplementedError(f"operator {op!r} ({type(op).__name__}) has no device implementation")
@@ -805,8 +846,34 @@ def lower(sequence, *, init=None, probe=None, options=None, dtype="f64", propaga
                     bld.record(OP_ADC, F_BASE | F_Z0, [], aux=nadc + 1)
                     rows.append(Row("expr", nadc, post=(op._post if isinstance(op, Adc) else custom_post), jac=eff))
                     nadc += 2
+                elif isinstance(eff, (ops_mod.DFT, ops_mod.Imaging)):
+                    # Fourier probes (probe.py:168-219): every configuration that can hold transverse magnetisation is read
+                    # into a row of its own (EPGX_FLAG_SLOT) and the host applies the probe's weights to the rows
+                    slots, kphys, tacc = lattice_slots()
+                    for i, sl in enumerate(slots):
+                        bld.record(OP_ADC, F_BASE | F_SLOT, [], aux=nadc + i, aux1=sl)
+                    rows.append(Row("fourier", nadc, post=custom_post, jac=(len(slots), kphys, tacc, eff, system_now())))
+                    nadc += len(slots)
+                elif lattice and lat.kdim == 4 and eff.attr in ("F0", "F0t"):
+                    # configurations with an accumulated-time coordinate (shift.py:188-210): F0 is the sum of
+                    # exp(-|t|) F over the configurations with zero wavenumber (statematrix.py:149-156)
+                    if eff.reduce not in (None, False):
+                        raise NotImplementedError("Adc(reduce=...) with accumulated-time coordinates")
+                    if eff.attr == "F0t":
+                        raise NotImplementedError("Adc('F0t'): one value per configuration; probe F0")
+                    slots, _, tacc = lattice_slots(zero_k=True)
+                    for i, sl in enumerate(slots):
+                        bld.record(OP_ADC, F_BASE | F_SLOT, [], aux=nadc + i, aux1=sl)
+                    wts = np.exp(-np.abs(tacc)).astype(complex)
+                    scale = None if eff.weights is None else np.asarray(eff.weights, dtype=complex)
+                    if phase is not None:
+                        scale = np.exp(1j * np.asarray(phase, dtype=float) * common.DEG) * (1 if scale is None else scale)
+                    rows.append(Row("lin", nadc, post=custom_post, jac=(len(slots), wts, scale)))
+                    nadc += len(slots)
                 else:
                     attr = eff.attr
+                    if lattice and lat.kdim == 4:
+                        raise NotImplementedError(f"Adc('{attr}') with accumulated-time coordinates: probe F0")
                     if attr not in ("F0", "Z0"):
                         raise NotImplementedError(f"Adc('{attr}'): only F0 and Z0 can be probed on the device")
                     red = eff.reduce
@@ -887,6 +954,7 @@ def lower(sequence, *, init=None, probe=None, options=None, dtype="f64", propaga
     low.tiles = np.array(tiles, dtype=np.int32).reshape(-1, 3) if tiles else np.zeros((0, 3), dtype=np.int32)
     low.final_n = n  # order count when the tape ends
     low.lattice = lattice
+    low.kdim = lat.kdim if lattice else 1
     low.maps = np.asarray(maps_all, dtype=np.int32)
     low.coords = None if lat is None else np.asarray(lat.coords, dtype=np.int64)
     low.rows, low.times = rows_out, times

@@ -17,6 +17,8 @@ Coefficient "forms" (see include/epgx.h for the device-side layout); every block
 
 import numpy as np
 
+from .utils import get_wavenumber
+
 from . import common
 from .common import DEG, asparam, expand_left, get_shape, isscalar, op_shape
 
@@ -1049,6 +1051,35 @@ class S(DiffOperator):
         return 1 if isscalar(self.k) else self.k.shape[-1]
 
 
+class G(S):
+    """gradient lobe (epgpy/shift.py:163-185): a shift by the wavenumber k = 2 pi gamma tau gradient (rad/m; tau in ms,
+    gradient in mT/m, scalar or up to three components).  A float shift: it runs on the lattice when `kgrid` divides
+    k * kvalue (lowering.py)."""
+
+    def __init__(self, tau, gradient, *, duration=None, **kwargs):
+        tau, gradient = np.asarray(tau, dtype=float), np.asarray(gradient, dtype=float)
+        if np.any(tau < 0):
+            raise ValueError("Cannot have negative time")
+        if gradient.ndim and gradient.shape[-1] > 3:
+            raise ValueError("Only 3d gradients are allowed")
+        self.tau, self.gradient = tau, gradient
+        super().__init__(get_wavenumber(tau, gradient), duration=tau if duration is True else duration, **kwargs)
+
+
+class C(S):
+    """time accumulation for temporal dephasing (epgpy/shift.py:188-210): a shift of tau * R2 along the FOURTH
+    coordinate of the configurations (the first three are the wavenumber).  Configurations that differ only in accumulated
+    time stay apart: F0 is the state refocused in space AND time."""
+
+    def __init__(self, tau, R2=1, *, duration=None, **kwargs):
+        tau, R2 = np.asarray(tau, dtype=float), np.asarray(R2, dtype=float)
+        if np.any(tau < 0):
+            raise ValueError("Cannot have negative time")
+        evol = tau * R2
+        self.tau, self.R2 = tau, R2
+        super().__init__(np.stack([0 * evol] * 3 + [evol], axis=-1), duration=tau if duration is True else duration, **kwargs)
+
+
 class D(Operator):
     """diffusion attenuation (epgpy/diffusion.py:14-79): tau in ms, D in mm^2/s (scalar or kdim x kdim),
     k (rad/m per unit shift) the shift of the S operator that immediately precedes it, if any"""
@@ -1171,6 +1202,61 @@ class Adc(Probe):
 
 
 ADC = Adc()
+
+
+class _FourierProbe(Probe):
+    """probes that are linear functionals of ALL transverse configurations (epgpy/probe.py:168-219).  The engine reads
+    the configurations (one row per lattice slot, EPGX_FLAG_SLOT) and `combine` applies the probe's weights on the host."""
+
+    def __init__(self, coords=None, *, name=None, **opts):
+        self.attr = self.expr = None
+        self.coords = None if coords is None else np.asarray(coords)
+        self.opts = opts
+        self.phase = self.reduce = self.weights = None
+        self._post = None
+        self._kwargs = {}
+        EmptyOperator.__init__(self, name=name or type(self).__name__)
+
+    @staticmethod
+    def _like_reference(F, k, t):
+        """wavenumbers / accumulated times with the leading grid axes of the reference's sm.k / sm.t (statematrix.py:177-200)"""
+        lead = (1,) * (np.ndim(F) - 1)
+        return np.reshape(k, lead + np.shape(k)), np.reshape(t, lead + np.shape(t))
+
+    def _coords(self, system):
+        coords = self.coords if self.coords is not None else system.get("coords")
+        if coords is None:
+            raise ValueError(f"{type(self).__name__}: no coordinates (argument `coords` or System(coords=...))")
+        return np.asarray(coords)
+
+
+class DFT(_FourierProbe):
+    """discrete Fourier transform of the F states at the positions `coords` (epgpy/probe.py:168-181): (*grid, *positions)"""
+
+    def __init__(self, coords=None, *, name=None):
+        super().__init__(coords, name=name)
+
+    def combine(self, F, k, t, system, kdim):
+        from .utils import dft
+
+        k, t = self._like_reference(F, k, t)
+        return dft(self._coords(system), F, k)
+
+
+class Imaging(_FourierProbe):
+    """imaging read-out (epgpy/probe.py:184-219): voxel shape, T2' / off-resonance modulation over the accumulated time,
+    weights, reduction (`utils.imaging`); coordinates, modulation and weights default to the System arrays"""
+
+    def combine(self, F, k, t, system, kdim):
+        from .utils import imaging
+
+        k, t = self._like_reference(F, k, t)
+        opts = dict(self.opts)
+        modulation = opts.pop("modulation", None)
+        weights = opts.pop("weights", None)
+        return imaging(self._coords(system), F, k, acctime=t if kdim == 4 else None,
+                       modulation=system.get("modulation") if modulation is None else modulation,
+                       weights=system.get("weights") if weights is None else weights, **opts)
 
 
 class Jacobian(Probe):

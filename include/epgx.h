@@ -46,7 +46,7 @@
 extern "C" {
 #endif
 
-#define EPGX_VERSION 108 /* 0.1.8: peer windows (copy-engine gather over NVLink), real-valued signal rows, lattices, order 2 */
+#define EPGX_VERSION 109 /* 0.1.9: EPGX_FLAG_SLOT (read-outs of any lattice slot: accumulated-time F0, DFT / Imaging probes); 0.1.8: peer windows, real-valued signal rows, lattices, order 2 */
 #define EPGX_MAX_DIMS 8
 #define EPGX_MAX_PATTERNS 64
 #define EPGX_MAX_POOLS 4
@@ -130,7 +130,12 @@ enum {
    * order-2 ones (variables >= nvar1): an operator is applied to the order-2 states, then their injections are made
    * from the PRE-operator order-1 states, then the order-1 states follow (diff.py:119-131) */
   EPGX_FLAG_P1 = 1 << 11,
-  EPGX_FLAG_P2 = 1 << 12
+  EPGX_FLAG_P2 = 1 << 12,
+  /* ADC in a lattice segment (EPGX_SEG_LATTICE), base state only: read the lattice slot aux1 instead of the slot of
+   * k = 0.  Probes that are linear functionals of ALL configurations -- the reference's F0 with accumulated time
+   * (statematrix.py:149-156: sum of exp(-|t|) F over the states with zero wavenumber), DFT and Imaging (probe.py:168-219) --
+   * read the slots they need into rows of `signal` and the host combines the rows with weights it knows from the lattice */
+  EPGX_FLAG_SLOT = 1 << 13
 };
 
 /* tape record, 32 bytes */

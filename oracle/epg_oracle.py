@@ -703,6 +703,7 @@ class _Sim:
         self.kvec = kvec  # base shift vector (collinear n-d shifts) or None
         self.coords = None  # [N, d] integer lattice points of the stored rows (general n-d shifts), else None
         self.kgrid = None   # float shifts (shift-merge, shift.py:119-145) on multiples of this grid: lattice units
+        self.tvalue = 1.0   # scale of the fourth (accumulated time) coordinate (statematrix.py:203-211)
 
     # -- helpers
     def all_states(self):
@@ -723,7 +724,9 @@ class _Sim:
     def wavenumbers(self):
         """k of every stored order, rad/m (epgpy/statematrix.py:177-186)"""
         if self.coords is not None:
-            return self.coords.astype(float) * (1.0 if self.kgrid is None else self.kgrid) * self.kvalue
+            c3 = self.coords[:, :3].astype(float)  # (a fourth coordinate is accumulated time: statematrix.py:177-186)
+            # integer lattice: shift counts x kvalue; float lattice: grid units of the WAVENUMBERS k * kvalue
+            return c3 * self.kvalue if self.kgrid is None else c3 * self.kgrid
         n = nstate(self.states)
         m = np.arange(-n, n + 1, dtype=float)
         if self.kvec is None:
@@ -864,8 +867,11 @@ def _apply_shift(sim, op):
         # general integer lattice (the reference's `shift-nd` method, epgpy/shift.py:103-117): every state set moves on
         # the same lattice; rows are pruned only where ALL sets are empty so that they keep one common row order
         kv = np.atleast_1d(np.asarray(k)).reshape(-1)
-        if sim.kgrid is not None:  # the quantisation of shift.py:401-404, exact for multiples of the grid
-            q = kv / sim.kgrid
+        if sim.kgrid is not None:
+            # the quantisation of shift.py:401-404 acts on wavenumbers = shifts x ktvalue (shift.py:136-141,
+            # statematrix.py:203-211): (kvalue, kvalue, kvalue, tvalue); exact for multiples of the grid
+            ktv = np.asarray(([float(sim.kvalue)] * 3 + [float(sim.tvalue)])[:len(kv)] if len(kv) == 4 else [float(sim.kvalue)] * len(kv))
+            q = kv * ktv / sim.kgrid
             if not np.allclose(q, np.round(q), atol=1e-6):
                 raise NotImplementedError("float shifts off the grid merge states approximately: outside the hot path")
             kv = np.round(q).astype(int)
@@ -926,8 +932,8 @@ def _apply_diffusion(sim, op, propagate):
             sh = np.asarray(op.k, dtype=float).reshape(-1)
         if sh is None:
             raise ValueError("scalar D.k with vector shifts")
-        if sim.coords is not None and len(sh) < sim.coords.shape[1]:
-            sh = np.pad(sh, (0, sim.coords.shape[1] - len(sh)))
+        if sim.coords is not None and len(sh) < min(sim.coords.shape[1], 3):
+            sh = np.pad(sh, (0, min(sim.coords.shape[1], 3) - len(sh)))
         sh = sh * sim.kvalue
         bT = bmatrix(tau, kk - sh, kk)
     DL, DT = diffusion_factors(bL, bT, op.D if np.ndim(op.D) else float(op.D))
@@ -965,7 +971,8 @@ def _apply_exchange(sim, op, propagate):
 
 
 def simulate(seq, *, init=None, density=1.0, max_nstate=None, kvalue=1.0, kvec=None,
-             jacobian=None, jacobian_probe=None, hessian=None, propagate_nondiff=False, adc_time=False, grid=None, kgrid=None):
+             jacobian=None, jacobian_probe=None, hessian=None, propagate_nondiff=False, adc_time=False, grid=None, kgrid=None,
+             tvalue=1.0):
     """forward simulation: values (nADC, *grid) complex128   (epgpy/functions.py:50-192)
 
     jacobian: list of variable names -> also returns (nADC, *grid, nvars)  (epgpy/diff.py:384-416)
@@ -983,7 +990,7 @@ def simulate(seq, *, init=None, density=1.0, max_nstate=None, kvalue=1.0, kvec=N
     if init is not None and np.ndim(init) > 2:
         shape = broadcast_left(shape, np.shape(init)[:-2])
     sim = _Sim(shape, init, density, max_nstate, kvalue, kvec)
-    sim.kgrid = kgrid
+    sim.kgrid, sim.tvalue = kgrid, tvalue
     nd = len(shape)
     if hessian is not None:
         v1s, v2s = hessian
@@ -1032,7 +1039,7 @@ def simulate(seq, *, init=None, density=1.0, max_nstate=None, kvalue=1.0, kvec=N
             raise ValueError(f"unknown op kind {kind}")
         tic = tic + op.duration
         if kind == "ADC":
-            values.append(_acquire(sim.states, op, op.attr))
+            values.append(_acquire(sim.states, op, op.attr, sim))
             times.append(tic)
             if jacobian is not None:
                 attr = jacobian_probe or "F0"
@@ -1069,11 +1076,19 @@ def simulate(seq, *, init=None, density=1.0, max_nstate=None, kvalue=1.0, kvec=N
     return res[0] if len(res) == 1 else res
 
 
-def _acquire(states, op, attr):
+def _acquire(states, op, attr, sim=None):
     """epgpy/probe.py:138-165, statematrix.py:148-175"""
     n = nstate(states)
     col = {"F0": 0, "Z0": 2}[attr]
-    arr = states[..., n, col]
+    if sim is not None and sim.coords is not None and sim.coords.shape[1] == 4:
+        # accumulated-time coordinate (statematrix.py:136-156): F0 sums exp(-|t|) F over the rows with zero wavenumber
+        if attr != "F0":
+            raise NotImplementedError("Z0 with accumulated-time coordinates")
+        i0 = np.all(sim.coords[:, :3] == 0, axis=-1)
+        t = sim.coords[:, 3].astype(float) * (sim.tvalue if sim.kgrid is None else np.broadcast_to(np.asarray(sim.kgrid, dtype=float), (4,))[3])
+        arr = (states[..., 0] * (i0 * np.exp(-np.abs(t)))).sum(axis=-1)
+    else:
+        arr = states[..., n, col]
     if op.weights is not None:
         w = op.weights
         if w.size > 1 and w.ndim < arr.ndim:

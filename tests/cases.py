@@ -482,6 +482,24 @@ def gre_lattice_float(epg, ntr=16):
     return dict(seq=seq, options={"kvalue": 600.0, "kgrid": 0.25})
 
 
+def gre_gradient_time(epg, necho=8):
+    """gradient lobes `G` (float wavenumbers, two spatial components) and time accumulation `C` (fourth coordinate) in a
+    multi spin echo with imperfect refocusing, on a grid that divides k * kvalue and t * tvalue but NOT k itself (the
+    reference quantises wavenumbers, i.e. shifts times ktvalue: shift.py:136-141, statematrix.py:203-211).  F0 is the
+    state refocused in space AND time (shift.py:163-210): the gradient-recalled read-out between two spin echoes sees
+    only the pathways whose accumulated time is zero as well."""
+    T1 = np.array([600.0, 1100.0, 1600.0])
+    T2 = np.array([40.0, 90.0])[None, :]
+    g0 = 0.1 / (2 * np.pi * 42576.0 * 1e-3)   # gradient (mT/m) whose 1 ms lobe shifts k by 0.1 rad/m
+    seq = [epg.T(90, 90)]
+    for i in range(necho):
+        seq += [epg.G(1.0, [2 * g0, g0]), epg.C(1.5), epg.E(4, T1, T2), epg.T(150 - 4 * i, 0), epg.G(1.0, [2 * g0, g0]), epg.C(1.5),
+                epg.E(4, T1, T2), epg.ADC,
+                epg.G(0.5, [-8 * g0, 4 * g0]), epg.C(0.5), epg.D(6.0, 1.5e-3), epg.G(0.5, [8 * g0, -4 * g0]), epg.C(0.5),
+                epg.E(2, T1, T2), epg.Adc(phase=15.0 * i)]
+    return dict(seq=seq, options={"kvalue": 2.5, "tvalue": 2.0, "kgrid": 0.25})
+
+
 def lowering_flatten(seq):
     out = []
     for item in seq:
@@ -494,6 +512,7 @@ def lowering_flatten(seq):
 
 CASES["slice_profile"] = slice_profile
 CASES["gre_lattice_float"] = gre_lattice_float
+CASES["gre_gradient_time"] = gre_gradient_time
 CASES["gre_lattice_2d"] = gre_lattice_2d
 CASES["gre_lattice_3d_cropped"] = gre_lattice_3d_cropped
 CASES["lattice_jac"] = lattice_jac
@@ -504,6 +523,45 @@ def probe_expr(epg):
     case = misc_ops(epg)
     case["probe"] = ["abs(F0)", "Z0.real + 2 * F0", "F0"]
     return case
+
+
+# ---- Fourier probes (probe.py:168-219): DFT / Imaging read every transverse configuration
+
+
+def dft_gre_1d(epg, ntr=12):
+    """RF-spoiled GRE with integer unit shifts; `DFT` probes at 21 positions after every pulse (magnetisation profile
+    across the voxel) next to the plain ADC"""
+    T1 = np.array([500.0, 1200.0])
+    T2 = np.array([40.0, 80.0, 160.0])[None, :]
+    x = np.linspace(-0.5e-3, 0.5e-3, 21)  # m
+    seq = []
+    for i in range(ntr):
+        seq += [epg.T(30, 117 * i * (i + 1) / 2), epg.E(3, T1, T2), epg.DFT(x), epg.ADC, epg.E(7, T1, T2), epg.S(1)]
+    return dict(seq=seq, options={"kvalue": 2 * np.pi * 1e3})
+
+
+def imaging_gradients_2d(epg, necho=5):
+    """gradient lobes in two dimensions + accumulated time; `Imaging` probes: box voxels, T2' and off-resonance
+    modulation (complex), positions on a 5 x 4 grid, not reduced; a second probe reduced over everything"""
+    T1 = np.array([600.0, 1100.0, 1600.0])
+    T2 = np.array([40.0, 90.0])[None, :]
+    g0 = 0.1 / (2 * np.pi * 42576.0 * 1e-3)
+    pos = np.stack(np.meshgrid(np.linspace(-2.0, 2.0, 5), np.linspace(-1.0, 1.5, 4), indexing="ij"), axis=-1)  # (5, 4, 2), m
+    seq = [epg.T(90, 90)]
+    for i in range(necho):
+        seq += [epg.G(1.0, [2 * g0, g0]), epg.C(1.5), epg.E(4, T1, T2), epg.T(150 - 4 * i, 0), epg.G(1.0, [2 * g0, g0]), epg.C(1.5),
+                epg.E(4, T1, T2), epg.Imaging(pos, voxel_size=0.8, modulation=0.3 + 0.05j, reduce=False),
+                epg.G(0.5, [-8 * g0, 4 * g0]), epg.C(0.5), epg.G(0.5, [8 * g0, -4 * g0]), epg.C(0.5),
+                epg.E(2, T1, T2), epg.Imaging(pos[:, 0], voxel_shape="point", modulation=0.2)]
+    return dict(seq=seq, options={"kvalue": 2.5, "tvalue": 2.0, "kgrid": 0.25})
+
+
+FOURIER_CASES = {"dft_gre_1d": dft_gre_1d, "imaging_gradients_2d": imaging_gradients_2d}
+
+
+def run_probes(epg, case):
+    """values of every probe of the sequence, in order of appearance, as a list of arrays / lists"""
+    return epg.simulate(case["seq"], asarray=False, **case["options"])
 
 
 def namespace(pkg):

@@ -67,6 +67,12 @@ def main():
         np.savez_compressed(os.path.join(HERE, f"{name}.npz"), signal=sig, hessian=hes)
         print(f"{name:20s} signal {sig.shape} hessian {hes.shape}")
 
+    # ---- Fourier probes (DFT / Imaging) and gradient / time-accumulation shifts: one array per probe event
+    for name, fn in cases.FOURIER_CASES.items():
+        vals = cases.run_probes(ns, fn(ns))
+        np.savez_compressed(os.path.join(HERE, f"{name}.npz"), **{f"probe{i}": np.asarray(v) for i, v in enumerate(vals)})
+        print(f"{name:20s}", len(vals), "probe events", sorted({np.asarray(v).shape for v in vals}))
+
     # ---- `probe=` expressions
     case = cases.probe_expr(ns)
     vals = epgpy.simulate(case["seq"], probe=case["probe"])

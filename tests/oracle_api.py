@@ -13,8 +13,18 @@ if ROOT not in sys.path:
 
 from oracle import epg_oracle as O  # noqa: E402
 
+def _gradient(tau, gradient, **kw):
+    """gradient lobe = shift by k = 2 pi gamma tau gradient (epgpy/shift.py:163-185, utils.py:157-169)"""
+    return O.S(2 * np.pi * 42576.0 * np.asarray(gradient, dtype=float) * 1e-3 * float(tau), **kw)
+
+
+def _time_accumulation(tau, R2=1, **kw):
+    """shift of tau * R2 along the fourth (time) coordinate (epgpy/shift.py:188-210)"""
+    return O.S(np.array([0.0, 0.0, 0.0, float(tau) * float(R2)]), **kw)
+
+
 epg = types.SimpleNamespace(
-    T=O.T, Phi=O.Phi, E=O.E, P=O.P, R=O.R, S=O.S, D=O.D, X=O.X,
+    T=O.T, Phi=O.Phi, E=O.E, P=O.P, R=O.R, S=O.S, D=O.D, X=O.X, G=_gradient, C=_time_accumulation,
     Adc=O.ADC, ADC=O.ADC(), SPOILER=O.SPOILER(), RESET=O.RESET(), PD=O.PD, Wait=O.WAIT,
     exchange_matrix=O.kinetic_matrix,
 )
@@ -31,6 +41,7 @@ def run(case, **extra):
         jacobian=case.get("jac"),
         init=case.get("init"),
         kgrid=opts.get("kgrid"),
+        tvalue=opts.get("tvalue", 1.0),
     )
     kw.update(extra)
     res = O.simulate(case["seq"], **kw)

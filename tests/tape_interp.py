@@ -167,7 +167,7 @@ def run(low, stream=None):
                     f = cplx(blk(off[0], pat[0], 2), 0)
                 src = Z if flags & L.F_Z0 else P
                 if flags & L.F_BASE:
-                    sig[aux] = src[:, :, 0, st["kz"]] * f
+                    sig[aux] = src[:, :, 0, aux1 if flags & L.F_SLOT else st["kz"]] * f
                 if flags & L.F_PARTIALS:
                     for v in range(low.nvar):
                         jac[aux1, v] = src[:, :, 1 + v, st["kz"]] * f
@@ -319,6 +319,7 @@ def simulate(epg_mod, sequence, **kw):
     probe = kw.pop("probe", None)
     propagate = kw.pop("propagate_nondiff", False)
     prune = kw.pop("prune_unobservable", True)
+    asarray = kw.pop("asarray", True)
     extra = {k: kw.pop(k) for k in ("fuse", "pre_inject") if k in kw}
     low = L.lower(sequence, init=init, probe=probe, options=kw, propagate_nondiff=propagate, prune_unobservable=prune,
                   **extra)
@@ -343,7 +344,7 @@ def simulate(epg_mod, sequence, **kw):
     saved = functions.engine.device_reduce
     functions.engine.device_reduce = lambda t, axis: _T(t.a.sum(axis=axis))
     try:
-        values = functions._assemble(low, [(0, 0, low.natoms, _T(sig), _T(jac))])
+        values = functions._assemble(low, [(0, 0, low.natoms, _T(sig), _T(jac))], asarray=asarray)
     finally:
         functions.engine.device_reduce = saved
     return values[0] if len(values) == 1 else values

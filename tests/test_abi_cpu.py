@@ -29,7 +29,7 @@ def test_header_symbols_exported():
     assert set(syms) == set(engine.EXPORTS), (syms, engine.EXPORTS)
     for s in syms:
         assert getattr(L, s) is not None
-    assert L.epgx_version() == 108
+    assert L.epgx_version() == 109
 
 
 def test_struct_sizes_match_header():

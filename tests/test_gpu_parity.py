@@ -87,6 +87,22 @@ def test_probe_expressions(golden, epg):
         assert rel_err(np.asarray(v), ref[f"probe{i}"]) < RTOL64
 
 
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+@pytest.mark.parametrize("name", sorted(cases.FOURIER_CASES))
+def test_fourier_probes(name, dtype, golden, epg):
+    """DFT / Imaging probes through the engine: the ring kernel reads every transverse configuration of the lattice
+    (EPGX_FLAG_SLOT rows), the host applies the probe's weights (probe.py:168-219, utils.py:12-115)"""
+    ref = golden(name)
+    case = cases.FOURIER_CASES[name](epg)
+    vals = epg.simulate(case["seq"], asarray=False, dtype=dtype, **case["options"])
+    assert len(vals) == len(ref.files)
+    tol = RTOL64 if dtype == "float64" else 20 * RTOL32
+    for i, v in enumerate(vals):
+        want = ref[f"probe{i}"]
+        assert np.shape(v) == want.shape
+        assert np.abs(np.asarray(v) - want).max() <= tol * max(np.abs(want).max(), 1e-30)
+
+
 def _run_variant(epg, case, dtype="f64", **variant):
     from epgpy_b200 import engine, functions, lowering
 

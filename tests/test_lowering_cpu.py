@@ -78,6 +78,38 @@ def test_probe_expressions(golden):
         assert rel_err(np.asarray(v), ref[f"probe{i}"]) < RTOL64
 
 
+@pytest.mark.parametrize("name", sorted(cases.FOURIER_CASES))
+def test_fourier_probes(name, golden):
+    """DFT / Imaging probes (probe.py:168-219): every transverse configuration read into a row of its own
+    (EPGX_FLAG_SLOT), the probe's weights applied on the host -- against the reference, probe event by probe event"""
+    ref = golden(name)
+    case = cases.FOURIER_CASES[name](product_namespace())
+    vals = interp_simulate(case["seq"], asarray=False, **case["options"])
+    assert len(vals) == len(ref.files)
+    for i, v in enumerate(vals):
+        want = ref[f"probe{i}"]
+        assert np.shape(v) == want.shape
+        assert np.abs(np.asarray(v) - want).max() <= 1e-10 * max(np.abs(want).max(), 1e-30)
+
+
+def test_gradient_and_time_operators_like_the_reference():
+    """G / C constructors (shift.py:163-210): wavenumber of a gradient lobe, time on the fourth coordinate, errors"""
+    epg = product_namespace()
+    assert np.allclose(epg.G(1.0, [1.0, 2.0]).k, 2 * np.pi * 42576.0 * 1e-3 * np.array([[1.0, 2.0]]))
+    assert np.array_equal(epg.C(1.5, 2.0).k, [[0, 0, 0, 3.0]]) and epg.C(1.5).kdim == 4
+    assert epg.G(2.0, 3.0, duration=True).duration == 2.0
+    with pytest.raises(ValueError):
+        epg.G(-1.0, 1.0)
+    with pytest.raises(ValueError):
+        epg.C(-1.0)
+    with pytest.raises(ValueError):
+        epg.G(1.0, [1.0, 2.0, 3.0, 4.0])
+    with pytest.raises(AttributeError):  # float shift without kgrid (shift.py:131-132)
+        interp_simulate([epg.T(30, 0), epg.G(1.0, 1.0), epg.ADC])
+    with pytest.raises(NotImplementedError):  # wavenumbers off the grid merge approximately: not lowered
+        interp_simulate([epg.T(30, 0), epg.G(1.0, 1.0), epg.ADC], kgrid=1.0)
+
+
 def test_in_sequence_jacobian_survives_probe_none():
     """probe=[None, ...] keeps the in-sequence probes: an in-sequence Jacobian must still see its variables
     (round-1 advisor finding: the derivatives silently came back as zeros)"""

@@ -124,7 +124,7 @@ def test_merged_stream_reproduces_the_tape(name, epg):
     their fused five-coefficient algebra, hopped E records) gives what the plain tape gives"""
     case = cases.CASES[name](epg)
     init = epg.StateMatrix(density=case["density"]) if case.get("density") is not None else None
-    if name in ("gre_lattice_2d", "gre_lattice_3d_cropped", "lattice_jac", "gre_lattice_float"):
+    if name in ("gre_lattice_2d", "gre_lattice_3d_cropped", "lattice_jac", "gre_lattice_float", "gre_gradient_time"):
         pytest.skip("lattice tapes run in the shared-memory kernel only: the register kernels' stream is not used")
     if case.get("init") is not None:
         init = np.array(case["init"])
