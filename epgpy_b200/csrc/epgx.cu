@@ -199,7 +199,7 @@ static int choose_variant(const epgx_plan *pl, epgx_config &c, int kernel, int l
     if (NS && NS <= ns_max) {
       int A = atoms > 0 ? atoms : (G == 32 ? 2 : 128 / G); // (one warp per atom: CTAs of two warps, measured 2 % faster than four)
       while (A * G > 256 && A > 1) --A;
-      while (G >= 8 && A > 1 && A * 32 * 9 * rsz > 40 * 1024) --A; // staging rows of the whole-TR windows
+      while (G >= 8 && A > 1 && A * 32 * (epgx::kRealWindows + 8 * (G == 32 ? epgx::kRealWindows : 1)) * rsz > 48 * 1024) --A; // staging rows of the whole-TR windows
       c.kernel = 2;
       c.lanes_per_atom = G;
       c.slots_per_lane = NS;
@@ -207,11 +207,10 @@ static int choose_variant(const epgx_plan *pl, epgx_config &c, int kernel, int l
       c.var_tiles = 1;
       c.atoms_per_cta = A;
       c.threads_per_cta = A * G;
-      // tape windows (three when the next window's gathers are prefetched: G = 32), pattern offsets, staging rows +
-      // echoes of the whole-TR windows, a row of zeros, prefetched coefficient entries [A][32][12] (epgx_real.cuh)
-      const bool pf = epgx::kRealPrefetch && G == 32;
-      c.smem_bytes = (pf ? 3 : 2) * epgx::kTapeChunk * 32 + ((A * t.npattern + 3) & ~3) * 4 + (G >= 8 ? A * 32 * 9 * rsz : 0) +
-                     4 * rsz + (pf ? A * 32 * 12 * rsz : 0) + 32;
+      // tape windows (two buffers of kRealWindows host windows), pattern offsets, staging rows + echoes of the whole-TR
+      // windows [A][32 kRealWindows][9], a row of zeros (epgx_real.cuh)
+      const int kw = G == 32 ? epgx::kRealWindows : 1;
+      c.smem_bytes = 2 * epgx::kRealWindows * epgx::kTapeChunk * 32 + ((A * t.npattern + 3) & ~3) * 4 + (G >= 8 ? A * 32 * (epgx::kRealWindows + 8 * kw) * rsz : 0) + 4 * rsz + 32;
       c.ring = C;
       return EPGX_OK;
     }

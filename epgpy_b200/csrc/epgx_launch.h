@@ -13,10 +13,10 @@ template <typename real> cudaError_t launch_realjac(int slots, const KParams &kp
 template <typename real> cudaError_t launch_setjac(int slots, const KParams &kp, dim3 grid, int threads, int smem, cudaStream_t st);
 template <typename real> cudaError_t launch_pulsejac(int orders, const KParams &kp, dim3 grid, int threads, int smem, cudaStream_t st);
 constexpr int kTapeChunk = 64;      // == TAPE_CHUNK of epgx_reg.cuh (checked there)
-#ifndef EPGX_REAL_PREFETCH
-#define EPGX_REAL_PREFETCH 0 // experiment of epgx_real.cuh (cp.async prefetch of the next window's coefficients): off
+#ifndef EPGX_REAL_WINDOWS
+#define EPGX_REAL_WINDOWS 2 // real kernel: tape windows joined into one kernel window (one coefficient-staging pass for 64 TRs)
 #endif
-constexpr bool kRealPrefetch = EPGX_REAL_PREFETCH != 0;
+constexpr int kRealWindows = EPGX_REAL_WINDOWS;
 constexpr int kTrcPerWindow = 21;   // == TRC_PER_WINDOW
 constexpr int kTrcReals = 14;       // == TRC_REALS
 constexpr int kTrjPerWindow = 12;   // == TRJ_PER_WINDOW of epgx_realjac.cuh

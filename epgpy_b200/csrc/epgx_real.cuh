@@ -19,9 +19,6 @@
 #include "epgx_common.cuh"
 #include "epgx_reg.cuh"
 
-#ifndef EPGX_REAL_PREFETCH
-#define EPGX_REAL_PREFETCH 0
-#endif
 #ifndef EPGX_REAL_UNROLL
 #define EPGX_REAL_UNROLL 1 // iterations (of two TRs) unrolled in the whole-TR loop
 #endif
@@ -33,8 +30,6 @@
 #endif
 
 namespace epgx {
-
-constexpr int RAW_REALS = 12; // prefetched coefficient entries per TR: T (a, w, b, u), E_pre (e1, r0, e2), E_post (e1, r0, e2), 2 pad
 
 // 1 / x to full precision without the division subroutine (|x| normal: the caller checks the range)
 __device__ __forceinline__ double rcp_newton(double x) {
@@ -213,22 +208,22 @@ __global__ void __launch_bounds__(MAXT, real_min_blocks(sizeof(real) * NS, MAXT)
   const long long atom = p.atom_begin + (valid ? a_rel : p.atom_count - 1);
   const real *__restrict__ coef = (const real *)p.coef;
 
-  // EPGX_REAL_PREFETCH (experiment, off): with one warp per atom (G = 32) the coefficient gathers of the NEXT whole-TR
-  // window are issued as cp.async copies into raw[TR][12] while this window runs (three tape buffers: the records of
-  // window w + 1 must be in shared memory during window w).  The window prologue spends 30 % of its samples waiting
-  // on those gathers, yet the kernel is SLOWER with the prefetch (FP64 228 ms against 213 ms, FP32 133 against 124:
-  // 28 kB instead of 13 kB of shared memory per CTA and 10 more LSU instructions per TR and lane) -- measured twice,
-  // in two implementations.
-  const bool pf = EPGX_REAL_PREFETCH && G == 32;
-  const int NB = pf ? 3 : 2;
+  // The kernel steps through the tape KW host windows at a time (kRealWindows = 2: 128 records, double-buffered): two
+  // consecutive whole-TR windows run as ONE window of 64 TRs -- one prologue (decode, gathers, fusing, staging: its
+  // latencies took 18 % of the kernel with 32-TR windows) for twice the TRs.
+  // (one warp per atom only: with several atoms per warp the staging rows of a 64-TR window cost CTAs -- measured
+  // FP32 122.3 -> 118.8 ms, FP64 unchanged, but max_nstate = 32 at 8 lanes per atom 61.4 -> 65.6 ms when joined)
+  constexpr int KW = kRealWindows, RCH = KW * TAPE_CHUNK;
+  const int WTR = (G == 32 ? KW : 1) * (TAPE_CHUNK / 2); // rows of the staging buffers: windows are joined for G = 32 only
   int4 *tbuf = (int4 *)smem_raw;
-  int *patoff = (int *)(tbuf + NB * TAPE_CHUNK * 2) + al * p.npattern;
-  // whole-TR windows (G >= 8): per atom, coefficient rows [32][8] and the echoes of the window [32]
-  real *cw0 = (real *)((int *)(tbuf + NB * TAPE_CHUNK * 2) + ((p.A * p.npattern + 3) & ~3));
-  real *cw = cw0 + (size_t)al * (32 * 9);
-  real *sb = cw + 32 * 8;
-  real *zrow = cw0 + (G >= 8 ? (size_t)p.A * (32 * 9) : 0); // two zeros: the affine terms of the lanes that do not hold order 0
-  real *raw = zrow + 4 + (size_t)al * (32 * RAW_REALS);
+  int *patoff = (int *)(tbuf + 2 * RCH * 2) + al * p.npattern;
+  // whole-TR windows (G >= 8): per atom, the echoes of the window [KW * 32] then the coefficient rows [WTR][8] (the echo
+  // buffer first: at a compile-time distance from the rows)
+  constexpr int SBN = KW * (TAPE_CHUNK / 2);
+  real *cw0 = (real *)((int *)(tbuf + 2 * RCH * 2) + ((p.A * p.npattern + 3) & ~3));
+  real *sb = cw0 + (size_t)al * (SBN + WTR * 8);
+  real *cw = sb + SBN;
+  real *zrow = cw0 + (G >= 8 ? (size_t)p.A * (SBN + WTR * 8) : 0); // two zeros: the affine terms of the lanes that do not hold order 0
   if (tid < 4) zrow[tid] = real(0);
   const real *af = lane == 0 ? cw + 6 : zrow;
   const int afs = lane == 0 ? 8 : 0;
@@ -359,70 +354,52 @@ __global__ void __launch_bounds__(MAXT, real_min_blocks(sizeof(real) * NS, MAXT)
 
   const int4 *stream = (const int4 *)p.stream;
   const int nthreads = blockDim.x;
-  // tape windows: NB shared-memory buffers; window w + NB - 1 is fetched while window w runs
-  for (int i = tid; i < (NB - 1) * 2 * TAPE_CHUNK && i < 2 * p.nstream; i += nthreads) __pipeline_memcpy_async(tbuf + i, stream + i, 16);
-  __pipeline_commit();
-  // the coefficient gathers of the next window (cp.async into raw[TR][RAW_REALS]; lane j: TR j), issued once the rows of
-  // the current window have been consumed.  A pure window is never the first of the stream (which opens with a SEG
-  // record), so its gathers were always issued one window earlier.
-#define PREFETCH_NEXT(TN_)                                                                                 \
-  if (pf && ((TN_)[0].x & EPGX_CHUNK_PURE_TR) && lane < (TN_)[1].w) {                                      \
-    const int4 a0 = (TN_)[4 * lane], a1 = (TN_)[4 * lane + 1], b0 = (TN_)[4 * lane + 2], b1 = (TN_)[4 * lane + 3]; \
-    const real *ct = coef + (unsigned)a0.z + patoff[a1.y & 0xff];                                          \
-    const real *ca = coef + (unsigned)a0.w + patoff[(a1.y >> 8) & 0xff];                                   \
-    const real *ea = coef + (unsigned)a1.x + patoff[(a1.y >> 16) & 0xff];                                  \
-    const real *cb = coef + (unsigned)b0.z + patoff[b1.y & 0xff];                                          \
-    const real *eb = coef + (unsigned)b0.w + patoff[(b1.y >> 8) & 0xff];                                   \
-    real *rw = raw + RAW_REALS * lane;                                                                     \
-    _Pragma("unroll") for (int k = 0; k < 4; ++k) __pipeline_memcpy_async(rw + k, ct + k, sizeof(real));   \
-    __pipeline_memcpy_async(rw + 4, ca, sizeof(real));                                                     \
-    __pipeline_memcpy_async(rw + 5, ca + 1, sizeof(real));                                                 \
-    __pipeline_memcpy_async(rw + 6, ea, sizeof(real));                                                     \
-    __pipeline_memcpy_async(rw + 7, cb, sizeof(real));                                                     \
-    __pipeline_memcpy_async(rw + 8, cb + 1, sizeof(real));                                                 \
-    __pipeline_memcpy_async(rw + 9, eb, sizeof(real));                                                     \
-  }                                                                                                        \
+  for (int i = tid; i < 2 * RCH && i < 2 * p.nstream; i += nthreads) __pipeline_memcpy_async(tbuf + i, stream + i, 16);
   __pipeline_commit();
   int nact = -1, nslot = 0;
-  int bcur = 0; // tape buffer of the current window
-  for (int base = 0, chunk = 0; base < p.nstream; base += TAPE_CHUNK, ++chunk) {
+  for (int base0 = 0, chunk = 0; base0 < p.nstream; base0 += RCH, ++chunk) {
     __pipeline_wait_prior(0);
     __syncthreads();
     {
-      const int nb = base + (NB - 1) * TAPE_CHUNK;
-      int bd = bcur + NB - 1;
-      if (bd >= NB) bd -= NB;
-      int4 *dst = tbuf + bd * 2 * TAPE_CHUNK;
-      for (int i = tid; i < 2 * TAPE_CHUNK && nb * 2 + i < 2 * p.nstream; i += nthreads)
+      const int nb = base0 + RCH;
+      int4 *dst = tbuf + ((chunk + 1) & 1) * 2 * RCH;
+      for (int i = tid; i < 2 * RCH && nb * 2 + i < 2 * p.nstream; i += nthreads)
         __pipeline_memcpy_async(dst + i, stream + (size_t)nb * 2 + i, 16);
       __pipeline_commit();
     }
-    const int4 *tb = tbuf + bcur * 2 * TAPE_CHUNK;
-    const int4 *tnext = tbuf + (bcur + 1 >= NB ? 0 : bcur + 1) * 2 * TAPE_CHUNK; // (pf: the records of the next window)
-    const bool has_next = base + TAPE_CHUNK < p.nstream;
-    if (++bcur >= NB) bcur = 0;
+    const int4 *tb0 = tbuf + (chunk & 1) * 2 * RCH;
+    // host windows of this kernel window that are whole-TR windows, joined while the previous one is full
+    int joined = 0; // host windows consumed by the joined fast path that starts at sub-window `h`
+    for (int h = 0; h < KW; h += joined > 0 ? joined : 1) {
+    const int base = base0 + h * TAPE_CHUNK;
+    if (base >= p.nstream) break;
+    const int4 *tb = tb0 + h * 2 * TAPE_CHUNK;
     const int cnt = min(TAPE_CHUNK, p.nstream - base);
+    joined = 0;
     if (G >= 8 && (tb[0].x & EPGX_CHUNK_PURE_TR)) {
-      // ---- fast path: the window holds TAPE_CHUNK / 2 whole-TR records (shift +1, no flags).  Phase 1: the G lanes
+      // ---- fast path: the window holds whole-TR records (shift +1, no flags).  Phase 1: the G lanes
       // of an atom decode the TRs (lane, lane + G, ...), gather their coefficients, fuse them and stage them in the
-      // atom's shared-memory rows -- one vectorised pass for 32 TRs.  Phase 2 (tr_window) runs the TRs in order: no
+      // atom's shared-memory rows -- one vectorised pass for the window.  Phase 2 (tr_window) runs the TRs in order: no
       // global load and no decode on the per-TR path.  need: register pairs (2 G orders each) the window needs -- a TR
       // applies to orders 0..nact and shifts orders 0..min(n_new, nact + 1); what lies above nact + 1 is unobservable
       // (lowering.py) and need not move; nact of TR j is the "next nact" of TR j - 1
-      // (the window runs as two halves of 16 TRs, each with its own pair count: 0.13 pair less per TR on average)
+      // (the window runs in parts of 16 TRs, each with its own pair count: 0.13 pair less per TR on average)
       constexpr int HALF = TAPE_CHUNK / 4;
-      const int ntr = tb[1].w; // whole-TR records of this window: TAPE_CHUNK / 2, or an even number below it (rest: NOP padding)
-      int need0 = 0, need1 = 0;
+      static_assert(kRealWindows == 1 || kRealWindows == 2, "one or two host windows per kernel window");
+      // whole-TR records of this window: TAPE_CHUNK / 2, or an even number below it (rest: NOP padding); the next host
+      // window joins when this one is full and the run goes on (the TR records are contiguous then)
+      const int ntr0 = tb[1].w;
+      const bool join = KW == 2 && G == 32 && h == 0 && ntr0 == TAPE_CHUNK / 2 && base + TAPE_CHUNK < p.nstream &&
+                        (tb[2 * TAPE_CHUNK].x & EPGX_CHUNK_PURE_TR);
+      const int ntr = join ? ntr0 + tb[2 * TAPE_CHUNK + 1].w : ntr0;
+      joined = join ? 2 : 1;
+      int need0 = 0, need1 = 0, need2 = 0, need3 = 0;
       bool bad = false;
       for (int j = lane; j < ntr; j += G) {
         const int4 a0 = tb[4 * j], a1 = tb[4 * j + 1], b0 = tb[4 * j + 2], b1 = tb[4 * j + 3];
         const int fl = (a0.x >> 16) & 0xffff;
         real g[10]; // T (a, w, b, u), E_pre (e1, r0, e2), E_post (e1, r0, e2)
-        if (pf) {
-          const real2 *rw = (const real2 *)(raw + RAW_REALS * j);
-#pragma unroll
-          for (int k = 0; k < 5; ++k) { const real2 v = rw[k]; g[2 * k] = v.x; g[2 * k + 1] = v.y; }
-        } else {
+        {
           const real *ct = coef + (unsigned)a0.z + patoff[a1.y & 0xff];
           const real *ca = coef + (unsigned)a0.w + patoff[(a1.y >> 8) & 0xff];
           const real *cb = coef + (unsigned)b0.z + patoff[b1.y & 0xff];
@@ -439,15 +416,18 @@ __global__ void __launch_bounds__(MAXT, real_min_blocks(sizeof(real) * NS, MAXT)
         bad = bad || !(au >= (sizeof(real) == 4 ? real(1e-15) : real(1e-100)) && au <= real(4));
         const int cur = j == 0 ? nact : tb[4 * j - 1].z;
         const int nd = (max(max(min((int)((unsigned)b1.x & 0xffff), cur + 1), cur), 0) >> (lgG + 1)) + 1;
-        if (j < HALF) need0 = max(need0, nd); else need1 = max(need1, nd);
+        if (j < HALF) need0 = max(need0, nd); else if (j < 2 * HALF) need1 = max(need1, nd);
+        else if (j < 3 * HALF) need2 = max(need2, nd); else need3 = max(need3, nd);
       }
       need0 = __reduce_max_sync(FULL, need0);
       need1 = __reduce_max_sync(FULL, need1);
+      need2 = __reduce_max_sync(FULL, need2);
+      need3 = __reduce_max_sync(FULL, need3);
+      const int needsum = need0 + need1 + need2 + need3;
       // scaled window (see tr_window): every u of the window usable as a scale for every atom of the warp
-      // (worth it when the orders in flight outweigh the division per TR of the second staging pass)
-      const bool sc = EPGX_REAL_SCALED && (need0 + need1) * G >= 96 && !__any_sync(FULL, bad);
+      // (worth it when the orders in flight outweigh the reciprocal per TR of the second staging pass)
+      const bool sc = EPGX_REAL_SCALED && needsum * G * 2 >= 96 * ((ntr + HALF - 1) / HALF) && !__any_sync(FULL, bad);
       __syncwarp();
-      if (has_next) { PREFETCH_NEXT(tnext) } // (raw[] of this window has been read)
       if (sc) {
         for (int j = lane; j < ntr; j += G) {
           real *c = cw + 8 * j;
@@ -465,7 +445,7 @@ __global__ void __launch_bounds__(MAXT, real_min_blocks(sizeof(real) * NS, MAXT)
     break;
 #pragma unroll 1
       for (int jb = 0; jb < ntr; jb += HALF) {
-        switch (jb ? need1 : need0) {
+        switch (jb < HALF ? need0 : jb < 2 * HALF ? need1 : jb < 3 * HALF ? need2 : need3) {
           TRW(1) TRW(2) TRW(3) TRW(4) TRW(5) TRW(6) TRW(7) TRW(8) TRW(9) TRW(10) TRW(11) TRW(12) TRW(13) TRW(14) TRW(15) TRW(16)
         default: break;
         }
@@ -481,7 +461,6 @@ __global__ void __launch_bounds__(MAXT, real_min_blocks(sizeof(real) * NS, MAXT)
       nslot = nact < 0 ? 0 : SLOTS_FOR(nact);
       continue;
     }
-    if (has_next) { PREFETCH_NEXT(tnext) }
     for (int r = 0; r < cnt; ++r) {
       const int4 r0 = tb[2 * r], r1 = tb[2 * r + 1];
       const int code = r0.x & 0xffff, flags = (r0.x >> 16) & 0xffff, aux = r0.y;
@@ -567,9 +546,9 @@ __global__ void __launch_bounds__(MAXT, real_min_blocks(sizeof(real) * NS, MAXT)
         break;
       }
     }
+    } // host windows of this kernel window
   }
 #undef APPLY5
-#undef PREFETCH_NEXT
 #undef DO_SEG
 #undef SHIFT_REAL
 #undef DUFF

@@ -9,6 +9,7 @@ template <typename K> static void carve(K kernel, int smem, int threads, int max
   const int ctas = blocks * (threads > 0 && maxt / threads > 1 ? maxt / threads : 1);
   const int pct = (int)(((long long)(smem + 1024) * ctas * 100 + 228 * 1024 - 1) / (228 * 1024));
   cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct > 100 ? 100 : pct);
+  if (smem > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); // (opt-in above 48 kB)
 }
 #define LAUNCH(NS, MAXT)                                                                                       \
   if (kp.bounded) {                                                                                            \
