@@ -497,7 +497,7 @@ def main():
             # dram__bytes_read.sum + dram__bytes_write.sum of the ncu --set full capture in profiles/ (27 000-atom
             # launch), scaled to this launch's atom count
             "traffic": 14545.0 * cnt if (args.ntr == NTR and args.dtype == "f64") else None,
-            "traffic_note": "scaled per atom from the 27 000-atom capture profiles/r02c_real_kernel_f64_full.txt "
+            "traffic_note": "scaled per atom from the 27 000-atom capture profiles/r02d_real_kernel_f64_full.txt "
                             "(2.7 MB read + 390.0 MB written; algorithmic: 16 kB per atom, the difference is dirty lines "
                             "still in the 126 MB L2 when the kernel ends)",
             "peak_source": f"measured live on this GPU: dependent-FMA microbenchmark epgx_fma_peak({args.dtype})",
