@@ -25,56 +25,58 @@ def cexp(arr):
     return np.cos(arr) + 1j * np.sin(arr)
 
 
+def _negligible(w, tol):
+    """configurations whose weight stays below `tol` for every atom and position (the reference drops them before the
+    transform, utils.py:50-53, 63-66: part of its result at the 1e-8 level, so it is reproduced)"""
+    return ~np.any(np.abs(w) > tol, axis=tuple(range(w.ndim - 1)))
+
+
 def imaging(positions, states, wavenumbers, acctime=None, *, phase=None, weights=None, modulation=None, voxel_shape="box",
             voxel_size=1, expand=True, reduce=True, tol=1e-8):
-    """inverse discrete Fourier transform of the transverse configurations (epgpy/utils.py:12-95):
-    states [..., nstate], wavenumbers [..., nstate, ndim] (rad/m), positions [..., ndim]; voxel shape (sinc of a box),
-    modulation exp(-|t| Re m + 2 pi i t Im m) over the accumulated time `acctime`, phase (degrees), weights, reduction"""
-    F = np.asarray(states)
-    k = np.asarray(wavenumbers, dtype=float)
-    t = np.asarray(acctime, dtype=float) if acctime is not None else None
-    pos = np.asarray(positions, dtype=float)
-    pos = pos if pos.ndim > 1 else pos[..., None]
-    if expand:  # insert the position axes into F and k
-        dims = np.arange(pos.ndim - 1)
-        F = np.expand_dims(F, tuple(-2 - dims))
-        k = np.expand_dims(k, tuple(-3 - dims))
+    """image-space signal of the transverse configurations (epgpy/utils.py:12-95): sum over the configurations of
+        F * voxel(k) * modulation(t) * exp(i k.x)
+    with voxel(k) = prod sinc(k size / 2 pi) for box voxels (1 for points), modulation(t) = exp(-|t| Re m + 2 pi i t Im m)
+    over the accumulated time t (when given), an optional phase (degrees) and weights, then the reduction.
+    Shapes: states [..., nstate], wavenumbers [..., nstate, ndim] (rad/m), positions [..., ndim]; with `expand` the
+    position axes are inserted in front of the configuration axis."""
+    x = np.asarray(positions, dtype=float)
+    if x.ndim == 1:
+        x = x[:, None]
+    F, k = np.asarray(states), np.asarray(wavenumbers, dtype=float)
+    t = None if acctime is None else np.asarray(acctime, dtype=float)
+    if expand:
+        npos_axes = x.ndim - 1
+        F = F.reshape(F.shape[:-1] + (1,) * npos_axes + F.shape[-1:])
+        k = k.reshape(k.shape[:-2] + (1,) * npos_axes + k.shape[-2:])
         if t is not None:
-            t = np.expand_dims(t, tuple(-2 - dims))
-    if voxel_shape == "point":
-        voxel = 1.0
-    elif voxel_shape == "box":
-        voxel = np.sinc(k * voxel_size / 2 / np.pi).prod(-1)
-        kmask = np.any(np.abs(voxel) > tol, axis=tuple(range(F.ndim - 1)))
-        F, k, voxel = F[..., kmask], k[..., kmask, :], voxel[..., kmask]
-        if t is not None:
-            t = t[..., kmask]
-    else:
+            t = t.reshape(t.shape[:-1] + (1,) * npos_axes + t.shape[-1:])
+    if voxel_shape not in ("point", "box"):
         raise ValueError(f"Unknown voxel shape: {voxel_shape}")
+    amp = F
+    if voxel_shape == "box":
+        vox = np.prod(np.sinc(k * voxel_size / (2 * np.pi)), axis=-1)
+        drop = _negligible(vox, tol)
+        keep = ~drop if drop.ndim else slice(None)
+        amp, k, vox = amp[..., keep], k[..., keep, :], vox[..., keep]
+        t = None if t is None else t[..., keep]
+        amp = amp * vox
     if t is not None:
-        modulation = np.asarray(modulation if modulation is not None else 1.0)
-        mod = np.exp(-np.abs(t) * modulation.real[..., None])
-        mmask = np.any(mod > tol, axis=tuple(range(F.ndim - 1)))
-        F, k, mod = F[..., mmask], k[..., mmask, :], mod[..., mmask]
-        if getattr(voxel, "shape", None):
-            voxel = voxel[..., mmask]
-        if np.iscomplexobj(modulation):
-            mod = mod * cexp(t[..., mmask] * 2 * np.pi * modulation.imag[..., None])
-    else:
-        mod = 1.0
+        m = np.asarray(1.0 if modulation is None else modulation)
+        decay = np.exp(-np.abs(t) * m.real[..., None])
+        keep = ~_negligible(decay, tol)
+        amp, k, t, decay = amp[..., keep], k[..., keep, :], t[..., keep], decay[..., keep]
+        amp = amp * decay
+        if np.iscomplexobj(m):
+            amp = amp * cexp(2 * np.pi * t * m.imag[..., None])
     if phase is not None:
-        mod = mod * np.exp(1j * phase * np.pi / 180)
-    kdim = pos.shape[-1]
-    f = voxel * mod * F
-    kp = np.matmul(k[..., :kdim], pos[..., None])[..., 0]
-    im = np.matmul(f[..., None, :], cexp(kp)[..., None])[..., 0, 0]
+        amp = amp * np.exp(1j * np.pi / 180 * phase)
+    ndim = x.shape[-1]
+    im = np.sum(amp * cexp(np.sum(k[..., :ndim] * x[..., None, :], axis=-1)), axis=-1)
     if weights is not None:
         im = im * np.asarray(weights)
     if reduce is True:
         return im.sum()
-    if reduce is not False:
-        return im.sum(axis=reduce)
-    return im
+    return im if reduce is False else im.sum(axis=reduce)
 
 
 def dft(coords, states, wavenumbers, *, reduce=False):
