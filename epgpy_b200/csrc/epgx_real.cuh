@@ -19,11 +19,14 @@
 #include "epgx_common.cuh"
 #include "epgx_reg.cuh"
 
+// Compile-time switches of measured experiments.  The rejected variants stay in the source on
+// purpose: ptxas' register assignment in the whole-TR loops is sensitive to the surrounding code -- removing the unused
+// per-lane affine pointer (EPGX_REAL_AFF) changed the loop bodies and cost 2 % in FP32 (120.7 against 118.2 ms).
 #ifndef EPGX_REAL_UNROLL
-#define EPGX_REAL_UNROLL 1 // iterations (of two TRs) unrolled in the whole-TR loop
+#define EPGX_REAL_UNROLL 1 // iterations (of two TRs) unrolled in the whole-TR loop; 2: measured 10 % slower
 #endif
 #ifndef EPGX_REAL_AFF
-#define EPGX_REAL_AFF 0 // affine terms of order 0 through a per-lane pointer (1) or selects (0)
+#define EPGX_REAL_AFF 0 // affine terms of order 0 through a per-lane pointer (1: measured 2 % slower) or selects (0)
 #endif
 #ifndef EPGX_REAL_SCALED
 #define EPGX_REAL_SCALED 1 // 0: every whole-TR window runs the unscaled seven-instruction form (experiments)
