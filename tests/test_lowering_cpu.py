@@ -92,6 +92,35 @@ def test_fourier_probes(name, golden):
         assert np.abs(np.asarray(v) - want).max() <= 1e-10 * max(np.abs(want).max(), 1e-30)
 
 
+def test_fourier_probe_variants():
+    """coordinates / weights from System arrays, a DFT given through `probe=`, and what is refused: derivatives of probes over
+    several configurations, Z0 / reductions with an accumulated-time coordinate"""
+    epg = product_namespace()
+    x = np.linspace(-1e-3, 1e-3, 7)
+    base = [epg.T(40, 30), epg.E(3, 900.0, 70.0), epg.S(1), epg.T(25, 10), epg.E(3, 900.0, 70.0), epg.S(1)]
+    a = interp_simulate(base + [epg.DFT(x)], kvalue=3000.0)
+    b = interp_simulate([epg.System(coords=x)] + base + [epg.DFT()], kvalue=3000.0)
+    c = interp_simulate(base + [epg.ADC], probe=epg.DFT(x), kvalue=3000.0)
+    assert np.shape(a) == (1, 1, 7) and np.allclose(a, b, rtol=0, atol=1e-15) and np.allclose(a, c, rtol=0, atol=1e-15)
+    # the k = 0 term of the transform is the plain read-out
+    f0 = interp_simulate(base + [epg.ADC], kvalue=3000.0)
+    assert np.allclose(interp_simulate(base + [epg.DFT(np.zeros(1))], kvalue=0.0)[..., 0], interp_simulate(
+        base + [epg.Imaging(np.zeros(1), voxel_shape="point", reduce=False)], kvalue=0.0)[..., 0])
+    assert np.abs(f0).max() > 0
+    w = interp_simulate([epg.System(coords=x, weights=np.arange(7.0))] + base + [epg.Imaging(voxel_shape="point", reduce=False)],
+                        kvalue=3000.0)
+    assert np.allclose(w, np.asarray(a) * np.arange(7.0))
+    with pytest.raises(NotImplementedError):
+        interp_simulate([epg.T(40, 30, order1="alpha")] + base[1:] + [epg.DFT(x)], probe=[None, epg.Jacobian("alpha")], kvalue=3000.0)
+    timed = [epg.T(40, 30), epg.C(1.0), epg.E(3, 900.0, 70.0)]
+    with pytest.raises(NotImplementedError):
+        interp_simulate(timed + [epg.Adc("Z0")], kgrid=0.5)
+    with pytest.raises(NotImplementedError):
+        interp_simulate(timed + [epg.Adc(reduce=True)], kgrid=0.5)
+    with pytest.raises(ValueError):
+        interp_simulate(base + [epg.DFT()], kvalue=3000.0)  # no coordinates anywhere
+
+
 def test_gradient_and_time_operators_like_the_reference():
     """G / C constructors (shift.py:163-210): wavenumber of a gradient lobe, time on the fourth coordinate, errors"""
     epg = product_namespace()
