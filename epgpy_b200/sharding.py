@@ -189,12 +189,11 @@ def run_gather_p2p(plan, window, nchunk=8):
             plan.run_strided(device, begin + b, c, _Ptr(window.ptr.value + col), low.natoms)
             done = torch.cuda.Event()
             done.record(cur)
-            k = 0
-            for r in range(world):
-                if r == rank:
-                    continue
+            # peers in ROTATED order (rank + 1, rank + 2, ...): at any moment every window receives from one rank instead
+            # of all ranks writing into window 0 first, then window 1, ... (the schedule of an all-to-all)
+            for k, d in enumerate(range(1, world)):
+                r = (rank + d) % world
                 st = window.streams[k % len(window.streams)]
-                k += 1
                 st.wait_event(done)
                 engine._check(L.epgx_copy2d_device(window.peers[r] + col, pitch, window.ptr.value + col, pitch, c * csz, low.nadc,
                                                    st.cuda_stream))
