@@ -2,7 +2,7 @@
 
 `from_reference(sequence)` reads only PUBLIC attributes of the reference's operators (SURVEY.md 8b:
 `T.alpha/phi`, `E.tau/T1/T2/g`, `P.tau/g`, `R.rT/rL/r0`, `S.k/nmax`, `D.tau/D/k`, `X.tau/khi/axis/T1/T2/g`,
-`Adc.attr/phase/reduce/weights`, `PD.pd/reset`, `op.order1`, `op.duration`, generic `MatrixOp.mat/mat0/dmats`,
+`Adc.attr/phase/reduce/weights`, `DFT.coords`, `Imaging.coords/opts`, `System.properties`, `PD.pd/reset`, `op.order1`, `op.duration`, generic `MatrixOp.mat/mat0/dmats`,
 `ScalarOp.arr/arr0/darrs`) and rebuilds the sequence with `epgpy_b200.operators`, so a script written against
 `epgpy` can hand its existing operator list to the B200 engine:
 
@@ -52,9 +52,15 @@ def _convert(op):
         return ops.P(op.tau, op.g, **_diff(op), duration=dur, name=op.name)
     if name == "R":
         return ops.R(op.rT, op.rL, r0=op.r0, **_diff(op), duration=dur, name=op.name)
-    if name == "S":
+    if name in ("S", "G", "C"):  # (G and C are shifts by their wavenumber / accumulated time: shift.py:163-210)
         k = op.k if isinstance(op.k, (int, np.integer)) else np.asarray(op.k)
-        return ops.S(k, nmax=op.nmax, duration=dur, name=op.name)
+        return ops.S(k, nmax=op.nmax, kgrid=getattr(op, "kgrid", None), duration=dur, name=op.name)
+    if name == "DFT":
+        return ops.DFT(None if op.coords is None else np.asarray(op.coords), name=op.name)
+    if name == "Imaging":
+        return ops.Imaging(None if op.coords is None else np.asarray(op.coords), name=op.name, **dict(op.opts))
+    if name == "System":
+        return ops.System(name=op.name, **dict(op.properties))
     if name == "D":
         return ops.D(op.tau, op.D, op.k, duration=dur, name=op.name)
     if name == "X":

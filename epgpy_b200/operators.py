@@ -1245,7 +1245,9 @@ class DFT(_FourierProbe):
 
 class Imaging(_FourierProbe):
     """imaging read-out (epgpy/probe.py:184-219): voxel shape, T2' / off-resonance modulation over the accumulated time,
-    weights, reduction (`utils.imaging`); coordinates, modulation and weights default to the System arrays"""
+    weights, reduction (`utils.imaging`); coordinates, modulation and weights default to the System arrays.
+    (The reference POPS `modulation` / `weights` from the probe's options at its first acquisition, probe.py:205-210, so an
+    Imaging object acquired twice loses them the second time; here the options are kept.)"""
 
     def combine(self, F, k, t, system, kdim):
         from .utils import imaging

@@ -43,7 +43,7 @@ ENGINES = ["interp", pytest.param("cuda", marks=pytest.mark.gpu)]
 
 
 NAMES = ["readme_mse", "mse_grid", "fisp_bounded", "fisp_jac_global", "mse_jac", "jac_all_params", "gre_diffusion_1d",
-         "gre_diffusion_tensor", "bssfp_mt", "spgr_exchange", "hyperecho", "misc_ops", "adc_reduce"]
+         "gre_diffusion_tensor", "bssfp_mt", "spgr_exchange", "hyperecho", "misc_ops", "adc_reduce", "gre_gradient_time"]
 
 
 @pytest.mark.parametrize("engine", ENGINES)
@@ -72,6 +72,23 @@ def test_reference_objects_run_on_the_engine_path(name, engine, ref):
     assert len(got_t) == len(want_t)
     for a, b in zip(got_t, want_t):
         assert np.allclose(np.asarray(a, dtype=float), np.asarray(b, dtype=float), rtol=1e-13, atol=0)
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+@pytest.mark.parametrize("name", sorted(cases.FOURIER_CASES))
+def test_reference_fourier_probes_run_on_the_engine_path(name, engine, ref):
+    """sequences built with the reference's own G / C / DFT / Imaging objects, converted and run on the engine path"""
+    from epgpy_b200 import compat
+
+    rns = cases.namespace(ref)
+    case = cases.FOURIER_CASES[name](rns)
+    seq = compat.from_reference(case["seq"])  # (before the reference runs: its Imaging._acquire POPS modulation / weights
+    want = cases.run_probes(rns, case)        # from the probe's options, probe.py:205-210)
+    got = _engine_simulate(engine)(seq, asarray=False, **case["options"])
+    assert len(got) == len(want)
+    for g, w in zip(got, want):
+        w = np.asarray(w)
+        assert np.shape(g) == w.shape and np.abs(np.asarray(g) - w).max() <= 1e-10 * max(np.abs(w).max(), 1e-30)
 
 
 def test_identity_is_preserved(ref):
