@@ -91,6 +91,58 @@ def test_reference_fourier_probes_run_on_the_engine_path(name, engine, ref):
         assert np.shape(g) == w.shape and np.abs(np.asarray(g) - w).max() <= 1e-10 * max(np.abs(w).max(), 1e-30)
 
 
+def _random_lattice_sequence(R, seed):
+    """random gradient / time-accumulation train of the REFERENCE's operators with spoilers, resets, and DFT / Imaging /
+    Adc probes in one to three dimensions (wavenumbers on the grid: k * kvalue = multiples of kgrid)"""
+    rng = np.random.RandomState(seed)
+    g0 = 0.1 / (2 * np.pi * 42576.0 * 1e-3)
+    T1, T2 = np.array([500.0, 1200.0]), np.array([40.0, 80.0, 160.0])[None, :]
+    use_c, kdim = rng.rand() < 0.6, int(rng.choice([1, 2, 3]))
+    x = rng.uniform(-2, 2, (4, kdim))
+    seq = []
+    for _ in range(rng.randint(4, 9)):
+        seq.append(R.T(rng.uniform(10, 170), rng.uniform(-180, 180)))
+        for _ in range(rng.randint(1, 3)):
+            gv = [int(v) * g0 for v in rng.randint(-3, 4, kdim)]
+            if any(gv):
+                seq.append(R.G(1.0, gv))
+            if use_c and rng.rand() < 0.7:
+                seq.append(R.C(float(rng.choice([0.5, 1.0, 1.5]))))
+        seq.append(R.E(rng.uniform(1, 8), T1, T2))
+        r = rng.rand()
+        if r < 0.15:
+            seq.append(R.SPOILER)
+        elif r < 0.22:
+            seq.append(R.RESET)
+        r = rng.rand()
+        if r < 0.4:
+            seq.append(R.DFT(x))
+        elif r < 0.7:
+            mod = complex(rng.uniform(0, 0.5), rng.uniform(-0.1, 0.1)) if use_c else None
+            seq.append(R.Imaging(x, voxel_size=float(rng.uniform(0.2, 1.5)), modulation=mod, reduce=False))
+        else:
+            seq.append(R.Adc(phase=float(rng.uniform(-90, 90))))
+    return seq, dict(kvalue=2.5, tvalue=2.0, kgrid=0.25)
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+@pytest.mark.parametrize("seed", range(12))
+def test_random_gradient_trains_with_fourier_probes(seed, engine, ref):
+    """fuzz of the configuration lattice with accumulated time and of the probes over several configurations against the
+    unmodified reference (shift-merge on the grid, statematrix.F0 with a time coordinate, probe.DFT / Imaging)"""
+    from epgpy_b200 import compat
+
+    seq, opts = _random_lattice_sequence(ref.core, seed)
+    conv = compat.from_reference(seq)
+    want = ref.simulate(seq, asarray=False, **opts)
+    got = _engine_simulate(engine)(conv, asarray=False, **opts)
+    assert len(got) == len(want)
+    for g, w in zip(got, want):
+        w = np.asarray(w)
+        assert np.shape(g) == w.shape
+        assert np.abs(np.asarray(g) - w).max() <= 1e-10 * max(np.abs(w).max(), 1e-3)
+
+
 def test_identity_is_preserved(ref):
     from epgpy_b200 import compat
 
