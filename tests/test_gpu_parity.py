@@ -96,7 +96,7 @@ def test_fourier_probes(name, dtype, golden, epg):
     case = cases.FOURIER_CASES[name](epg)
     vals = epg.simulate(case["seq"], asarray=False, dtype=dtype, **case["options"])
     assert len(vals) == len(ref.files)
-    tol = RTOL64 if dtype == "float64" else 20 * RTOL32
+    tol = RTOL64 if dtype == "float64" else RTOL32  # (measured FP32: 1.0e-6 and 2.5e-7)
     for i, v in enumerate(vals):
         want = ref[f"probe{i}"]
         assert np.shape(v) == want.shape
