@@ -108,3 +108,23 @@ class RFPulse(ops.MultiOperator):
         for key, val in info.items():
             setattr(self, key, val)
         super().__init__(seq, name=name, duration=duration)
+
+
+def encode_phase(pulse, gradient, fov, *, expand=True, rewind=None, npoint=101, gamma=None):
+    """slice-selective version of a shaped pulse (epgpy/rfpulse.py:321-345): the positions `fov` (mm; a scalar field of
+    view becomes `npoint` positions across it) see the off-resonance of `gradient` (mT/m) during every sample of the
+    pulse -- a new grid axis behind the pulse's own unless expand=False -- and `rewind` (True: one half) appends the
+    rephasing precession.  Returns the list of operators (an n = 0 tape on the engine: DESIGN.md section 2.2)."""
+    from . import utils
+
+    if not isinstance(pulse, RFPulse):
+        raise TypeError("Can only use RFPulse operators")
+    if np.isscalar(fov):
+        fov = utils.spatial_range(fov, npoint)
+    freqs = utils.space_to_freq(gradient, fov, gamma=utils.gamma_1H if gamma is None else gamma)
+    if expand:
+        freqs = np.reshape(freqs, (1,) * len(pulse.shape) + np.shape(freqs))
+    out = functions.modify(pulse, g=freqs, expand=False)
+    if rewind is not None:
+        out.append(ops.P(pulse.duration * (0.5 if rewind is True else float(rewind)), g=-freqs, duration=0))
+    return out

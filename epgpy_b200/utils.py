@@ -19,6 +19,32 @@ def get_wavenumber(grad, duration, gamma=gamma_1H):
     return 2 * np.pi * gamma * np.asarray(grad) * 1e-3 * np.asarray(duration)
 
 
+def spatial_range(fov, nvalue=100):
+    """`nvalue` positions across a field of view `fov` (mm), centred (epgpy/utils.py:175-183)"""
+    return fov * np.linspace(-0.5, 0.5, nvalue)
+
+
+def space_to_freq(grad, positions, *, gamma=gamma_1H):
+    """off-resonance (kHz) of positions (mm) under a gradient (mT/m) (epgpy/utils.py:186-208)"""
+    return grad * 1e-6 * gamma * (positions if np.isscalar(positions) else np.asarray(positions))
+
+
+def freq_to_space(grad, frequencies, *, gamma=gamma_1H):
+    """positions (mm) of off-resonances (kHz) under a gradient (mT/m) (epgpy/utils.py:211-213)"""
+    return frequencies / grad / gamma * 1e6
+
+
+def check_states(states):
+    """F-(k) = conj F+(-k), Z(k) = conj Z(-k) (epgpy/utils.py:118-121)"""
+    states = np.asarray(states)
+    return np.allclose(states, states[..., ::-1, [1, 0, 2]].conj())
+
+
+def get_norm(states):
+    """norm of the transverse + longitudinal states without the F+ column (epgpy/utils.py:152-154)"""
+    return np.sqrt(np.sum(np.abs(np.asarray(states)[..., 1:]) ** 2, axis=(-2, -1)))
+
+
 def cexp(arr):
     """exp(1j * arr) (epgpy/utils.py:124-131)"""
     arr = np.asarray(arr, dtype=float)

@@ -143,6 +143,35 @@ def test_random_gradient_trains_with_fourier_probes(seed, engine, ref):
         assert np.abs(np.asarray(g) - w).max() <= 1e-10 * max(np.abs(w).max(), 1e-3)
 
 
+@pytest.mark.parametrize("engine", ENGINES)
+def test_slice_selective_pulse_like_the_reference(engine, ref):
+    """`rfpulse.encode_phase` (rfpulse.py:321-345) and the small `utils` helpers it uses: excitation profile of a windowed
+    sinc across a slice, with and without rephasing, against the reference's own helper + simulate"""
+    import epgpy_b200
+    from epgpy import rfpulse as rrf
+    from epgpy_b200 import rfpulse as brf, utils as butils
+
+    simulate = _engine_simulate(engine)
+    t = np.linspace(-3, 3, 31)
+    values = np.sinc(t) * np.hanning(31)
+    for fov, kw in ((20.0, dict(rewind=True)), (20.0, dict(rewind=0.4, npoint=21)), (np.linspace(-8, 8, 13), dict(expand=False))):
+        rs = rrf.encode_phase(rrf.RFPulse(values, 3.0, alpha=70, phi=15.0), 12.0, fov, **kw)
+        bs = brf.encode_phase(brf.RFPulse(values, 3.0, alpha=70, phi=15.0), 12.0, fov, **kw)
+        want = np.asarray(ref.simulate(list(rs) + [ref.core.ADC, ref.core.Adc("Z0")]))
+        got = np.asarray(simulate(list(bs) + [epgpy_b200.epg.ADC, epgpy_b200.epg.Adc("Z0")]))
+        assert got.shape == want.shape and rel_err(got, want) < RTOL64
+    with pytest.raises(TypeError):
+        brf.encode_phase(epgpy_b200.epg.T(30, 0), 12.0, 20.0)
+    x = np.linspace(-3, 3, 7)
+    assert np.allclose(butils.freq_to_space(9.0, butils.space_to_freq(9.0, x)), x)
+    assert np.allclose(butils.space_to_freq(9.0, x), ref.utils.space_to_freq(9.0, x))
+    assert np.allclose(butils.spatial_range(30.0, 11), ref.utils.spatial_range(30.0, 11))
+    sm = np.zeros((2, 5, 3), dtype=complex)
+    sm[:, 2, 2] = 1
+    sm[:, 3, 0], sm[:, 1, 1] = 0.3 + 0.1j, 0.3 - 0.1j
+    assert butils.check_states(sm) and np.allclose(butils.get_norm(sm), ref.utils.get_norm(sm))
+
+
 def test_identity_is_preserved(ref):
     from epgpy_b200 import compat
 
